@@ -1,0 +1,28 @@
+"""CPU oracle for the DINO-Tracker inference hot path.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs
+of ``bench.py`` may import anything from this package, and only as the checker
+or as the timed CPU baseline -- never as the thing shipped.  The product path
+(``dino_tracker_b200``) never imports it and fails loudly if its CUDA library is
+missing.
+
+Every function is a plain PyTorch-fp32 (CPU) restatement of one reference
+function and cites the reference ``file:line`` it follows (paths are relative to
+the reference repo root, AssafSinger94/dino-tracker @ 5b0f2b0).
+
+Pinning status (see DESIGN.md "Oracle"):
+  * tracker / inference / delta-DINO / best-buddies rows:
+    pinned.  ``oracle/make_golden.py`` imports the *live reference modules* in
+    the build container (behind the three in-memory shims of
+    ``oracle/ref_harness.py``), runs them on seeded synthetic inputs and commits
+    inputs-by-seed + reference outputs under ``tests/golden/``; the CPU test
+    suite checks this oracle against those vectors.
+  * ViT row (a1): PARITY UNPINNED.  The DINOv2 block arithmetic lives in a
+    third-party module (facebookresearch/dinov2, fetched by torch.hub at an
+    unpinned ref, ``models/extractor.py:26``) that is absent from the reference
+    tree and from this image.  ``oracle/vit.py`` restates the public DINOv2
+    ViT definition plus everything the reference itself defines (stride patch,
+    pos-embed interpolation, tap point); it is cross-checked against
+    ``transformers.models.dinov2`` with shared random weights only.
+"""

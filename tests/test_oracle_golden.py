@@ -1,0 +1,101 @@
+"""CPU suite: the oracle restatement against the reference's own outputs (tests/golden)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import best_buddies as obb
+from oracle import delta_dino as od
+from oracle import inference as oi
+from oracle import synth
+from oracle import tracker as ot
+from oracle.tracker import Geometry
+
+from golden_util import GOLDEN_DIR, TRACK_CASES, load_track_case
+
+XY_TOL = 1e-3  # px, BASELINE.json north_star
+
+
+@pytest.mark.parametrize("name", sorted(TRACK_CASES))
+def test_inference_matches_reference(name):
+    cfg, geo, feats, head, g = load_track_case(name)
+    q = torch.from_numpy(g["query_points"])
+    traj, occ, aux = oi.infer(feats, q, head, geo, 0.7, 0.6, batch_size=cfg["batch"], return_all=True)
+    assert np.abs(aux["trajs"].numpy() - g["trajectories"]).max() <= XY_TOL
+    assert np.abs(aux["cos_sims"].numpy() - g["cos_sims"]).max() <= 2e-5  # follows the 1e-3 px budget
+    assert np.array_equal(occ.numpy(), g["occlusion"])
+    for n in range(q.shape[0]):
+        m = int(g["n_anchors"][n])
+        assert aux["anchors"][n].shape[0] == m
+        assert np.abs(aux["anchors"][n].numpy() - g["anchors"][n, :m]).max() <= XY_TOL
+
+
+@pytest.mark.parametrize("name", ["track_small_well", "track_small_fallback"])
+def test_forward_matches_reference(name):
+    cfg, geo, feats, head, g = load_track_case(name)
+    q = torch.from_numpy(g["query_points"])
+    inp = oi.trajectory_input(q[0], cfg["T"], 0, cfg["T"])
+    for faithful in (False, True):
+        out = ot.tracker_forward(feats, inp, head, geo, faithful=faithful)
+        assert np.abs(out.numpy() - g["forward0"]).max() <= 2e-6  # normalised [-1, 1] units
+
+
+def test_fallback_branch_is_exercised():
+    cfg, geo, feats, head, g = load_track_case("track_small_fallback")
+    q = torch.from_numpy(g["query_points"])
+    inp = oi.trajectory_input(q[0], cfg["T"], 0, cfg["T"])
+    frames = feats[inp[-1].long()]
+    pn = ot.normalize_points_for_sampling(inp[0], geo)
+    d = ot.sample_descriptors(frames, torch.cat([pn[:, :2], inp[1][:, None].float()], 1))
+    _, aux = ot.head_forward(torch.relu(ot.corr_maps(d, frames, inp[2])), head, geo, return_aux=True)
+    assert aux["fallback"].any()
+
+
+def test_explicit_sampler_equals_grid_sample():
+    torch.manual_seed(0)
+    feats = torch.randn(7, 5, 13, 17)
+    pts = torch.rand(200, 3) * 2.4 - 1.2
+    pts[:, 2] = torch.randint(0, 7, (200,)).float()
+    mine = ot.sample_descriptors(feats, pts)
+    vol = feats.permute(1, 0, 2, 3)[None]
+    s = pts[None, None, :, None].clone()
+    s[..., 2] = s[..., 2] / 6 * 2 - 1
+    ref = torch.nn.functional.grid_sample(vol, s, align_corners=True, padding_mode="border")
+    ref = ref.squeeze().permute(1, 0)
+    assert torch.allclose(mine, ref, atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("name", ["delta_small", "delta_full_geom"])
+def test_delta_dino_matches_reference(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    H, W, T = (int(v) for v in g["HWT"])
+    channels = [int(c) for c in g["channels"]]
+    seed = int(g["seed"])
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")}
+    video = synth.random_video(T, H, W, seed=seed)
+    geo = Geometry(H=H, W=W)
+    dino = synth.random_features(T, channels[-1], geo.h, geo.w, seed=seed + 1)
+    refined = od.refined_features(video, dino, sd).numpy()
+    if "refined" in g:
+        assert np.abs(refined - g["refined"]).max() <= 2e-5
+        assert np.abs(od.delta_cnn(video, sd).numpy() - g["cnn_out"]).max() <= 2e-5
+    else:
+        assert np.abs(refined.reshape(-1)[g["refined_idx"]] - g["refined_vals"]).max() <= 2e-5
+        assert abs(np.abs(refined.astype(np.float64)).sum() - g["refined_sum"][1]) <= 1e-6 * g["refined_sum"][1]
+
+
+def test_best_buddies_matches_reference():
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "bb_small.npz")))
+    H, W, T, C = (int(v) for v in g["HWTC"])
+    feats = torch.from_numpy(g["features"])
+    res = obb.best_buddies(feats, H, W)
+    assert len(res) == T * (T - 1)
+    for k, v in res.items():
+        assert np.array_equal(v["source_coords"].numpy(), g[f"{k}.source_coords"])
+        assert np.array_equal(v["target_coords"].numpy(), g[f"{k}.target_coords"])
+        assert np.abs(v["cos_sims"].numpy() - g[f"{k}.cos_sims"]).max() <= 1e-6
+    # (t, s) is (s, t) with source/target swapped: one GEMM serves both
+    a, b = res["0_1"], res["1_0"]
+    ia = np.lexsort(a["target_coords"].numpy().T[::-1])
+    assert np.array_equal(a["target_coords"].numpy()[ia], b["source_coords"].numpy())
