@@ -25,6 +25,7 @@ TRACK_CASES = {
     "track_small_fallback": dict(H=98, W=126, T=5, C=32, seed=14, head="default", nq=(2, 2), tq=[0, 1, 2, 4], batch=None, noise=0.15),
     "track_small_mixed": dict(H=98, W=126, T=5, C=32, seed=15, head="mixed", nq=(2, 2), tq=[0, 1, 2, 4], batch=None, noise=0.15),
     "track_small_noisy": dict(H=98, W=126, T=8, C=48, seed=16, head="sharp", nq=(3, 3), tq=[0, 1, 2, 3, 4, 5, 6, 7, 0], batch=None, noise=0.9),
+    "track_full_fallback": dict(H=476, W=854, T=3, C=16, seed=18, head="default", nq=(2, 2), tq=[0, 1, 2, 1], batch=None, noise=0.15),
     "track_full_geom":   dict(H=476, W=854, T=4, C=32, seed=17, head="sharp", nq=(2, 2), tq=[0, 1, 2, 3], batch=None, noise=0.15),
 }
 

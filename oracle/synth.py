@@ -53,8 +53,14 @@ def head_weights(kind="well", seed=0):
         sd = {"cnn_refiner.0.weight": u(0.2, 1, 16, 1, 3, 3), "cnn_refiner.0.bias": u(0.2, 1, 16),
               "cnn_refiner.2.weight": u(0.2, 1, 1, 16, 3, 3), "cnn_refiner.2.bias": u(0.2, 1, 1)}
     elif kind == "default":
-        sd = {"cnn_refiner.0.weight": u(-1 / 3, 1 / 3, 16, 1, 3, 3), "cnn_refiner.0.bias": u(-1 / 3, 1 / 3, 16),
-              "cnn_refiner.2.weight": u(-1 / 12, 1 / 12, 1, 16, 3, 3), "cnn_refiner.2.bias": u(-1 / 12, 1 / 12, 1)}
+        # mixed-sign kernels whose spatial sums are tiny (like PyTorch-default init in the probe of
+        # SURVEY.md 8d): normalisation blows the gain up, the softmax collapses onto a spot unrelated
+        # to the pre-CNN arg-max, and the disc mass drops below 1e-8 -> fallback branch.
+        def tiny_sum(o, i, total):
+            r = u(-1, 1, o, i, 3, 3)
+            return r - r.mean(dim=(2, 3), keepdim=True) + total / 9
+        sd = {"cnn_refiner.0.weight": tiny_sum(16, 1, 0.05), "cnn_refiner.0.bias": u(-1 / 3, 1 / 3, 16),
+              "cnn_refiner.2.weight": tiny_sum(1, 16, 0.05), "cnn_refiner.2.bias": u(-1 / 12, 1 / 12, 1)}
     elif kind == "mixed":
         w1 = u(-0.5, 1, 16, 1, 3, 3); w2 = u(-0.5, 1, 1, 16, 3, 3)
         sd = {"cnn_refiner.0.weight": w1, "cnn_refiner.0.bias": u(-0.2, 0.2, 16),

@@ -31,7 +31,7 @@ def test_inference_matches_reference(name):
         assert np.abs(aux["anchors"][n].numpy() - g["anchors"][n, :m]).max() <= XY_TOL
 
 
-@pytest.mark.parametrize("name", ["track_small_well", "track_small_fallback"])
+@pytest.mark.parametrize("name", ["track_small_well", "track_small_fallback", "track_full_fallback"])
 def test_forward_matches_reference(name):
     cfg, geo, feats, head, g = load_track_case(name)
     q = torch.from_numpy(g["query_points"])
@@ -42,7 +42,7 @@ def test_forward_matches_reference(name):
 
 
 def test_fallback_branch_is_exercised():
-    cfg, geo, feats, head, g = load_track_case("track_small_fallback")
+    cfg, geo, feats, head, g = load_track_case("track_full_fallback")
     q = torch.from_numpy(g["query_points"])
     inp = oi.trajectory_input(q[0], cfg["T"], 0, cfg["T"])
     frames = feats[inp[-1].long()]
@@ -97,5 +97,6 @@ def test_best_buddies_matches_reference():
         assert np.abs(v["cos_sims"].numpy() - g[f"{k}.cos_sims"]).max() <= 1e-6
     # (t, s) is (s, t) with source/target swapped: one GEMM serves both
     a, b = res["0_1"], res["1_0"]
-    ia = np.lexsort(a["target_coords"].numpy().T[::-1])
+    tc = a["target_coords"].numpy()
+    ia = np.lexsort((tc[:, 0], tc[:, 1]))  # ascending token order = (y, x)
     assert np.array_equal(a["target_coords"].numpy()[ia], b["source_coords"].numpy())
