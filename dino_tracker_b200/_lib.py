@@ -1,0 +1,113 @@
+"""ctypes binding of libdinotrk.so (include/dinotrk.h).  There is NO fallback: if the CUDA library is
+missing or fails to load, importing the product path raises."""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_ulonglong, c_void_p
+
+import torch
+
+from . import build as _build
+
+_LIB = None
+
+
+class Geom(Structure):
+    _fields_ = [("H", c_int), ("W", c_int), ("patch", c_int), ("stride", c_int), ("radius", c_int),
+                ("h", c_int), ("w", c_int)]
+
+
+class HeadWeights(Structure):
+    _fields_ = [("w1", c_float * 9 * 16), ("b1", c_float * 16), ("w2", c_float * 9 * 16), ("b2", c_float)]
+
+
+class DinotrkError(RuntimeError):
+    pass
+
+
+# every exported symbol of include/dinotrk.h: name -> (restype, argtypes)
+_P = c_void_p
+SIGNATURES = {
+    "dinotrk_version": (c_int, []),
+    "dinotrk_last_error": (c_char_p, []),
+    "dinotrk_launch_count": (c_ulonglong, []),
+    "dinotrk_make_geom": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(Geom)]),
+    "dinotrk_pack_features": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "dinotrk_unpack_features": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "dinotrk_token_norms": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
+    "dinotrk_sample_descriptors": (c_int, [_P, c_int, c_int, POINTER(Geom), _P, c_int, _P, c_int, c_int, _P, _P, _P]),
+    "dinotrk_corr_track_workspace_bytes": (c_size_t, [c_int, c_int, POINTER(Geom)]),
+    "dinotrk_corr_track": (c_int, [_P, _P, c_int, c_int, POINTER(Geom), POINTER(HeadWeights), _P, _P, _P, _P, _P, _P,
+                                   c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_size_t, _P]),
+    "dinotrk_map_stride": (c_int, [POINTER(Geom)]),
+    "dinotrk_corr_maps": (c_int, [_P, _P, c_int, c_int, POINTER(Geom), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int,
+                                  _P, _P, c_size_t, _P]),
+    "dinotrk_head": (c_int, [_P, c_int, POINTER(Geom), POINTER(HeadWeights), _P, _P, c_int, c_int, _P, _P]),
+    "dinotrk_infer_workspace_bytes": (c_size_t, [c_int, c_int, POINTER(Geom), c_int, c_int]),
+    "dinotrk_infer": (c_int, [_P, _P, c_int, c_int, POINTER(Geom), POINTER(HeadWeights), _P, c_int, c_float, c_float,
+                              c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "dinotrk_traj_cos_sims": (c_int, [_P, c_int, c_int, POINTER(Geom), _P, _P, c_int, _P, _P, c_size_t, _P]),
+    "dinotrk_delta_workspace_bytes": (c_size_t, [c_int, c_int, c_int, POINTER(c_int)]),
+    "dinotrk_delta_refine": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), POINTER(c_void_p), POINTER(c_void_p), _P,
+                                     _P, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "dinotrk_occlusion": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
+}
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load(build_if_missing=True):
+    """Load (building in-tree if needed) libdinotrk.so.  Raises if that is impossible."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise DinotrkError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _build.build()
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dinotrk_version() < 100:
+        raise DinotrkError("libdinotrk.so is older than the Python binding")
+    _LIB = lib
+    return lib
+
+
+def check(rc, what="dinotrk"):
+    if rc != 0:
+        raise DinotrkError(f"{what} failed ({rc}): {load().dinotrk_last_error().decode()}")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device pointers must come from contiguous CUDA tensors"
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(device):
+    if not torch.cuda.is_available():
+        raise DinotrkError("dino_tracker_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise DinotrkError(f"dino_tracker_b200 runs on CUDA only, got device={device!r}")
+    return dev
+
+
+def make_geom(H, W, patch=14, stride=7, radius=35):
+    g = Geom()
+    check(load().dinotrk_make_geom(H, W, patch, stride, radius, ctypes.byref(g)), "make_geom")
+    return g
+
+
+def launch_count():
+    return int(load().dinotrk_launch_count())

@@ -1,0 +1,266 @@
+// Cosine-correlation maps: descriptors x all tokens of a frame (models/tracker.py:158-169, :173).
+//
+//   corr[j][p] = relu( <d_j, F[frame][p]> / max(|d_j| * |F[frame][p]|, 1e-8) )
+//
+// Two exact-fp32 kernels over the token-major feature video [T][P][C]:
+//   * corr_gemm_kernel   -- grouped SGEMM (128 x 128 x 16 tiles, cp.async 3-stage ring) for groups with
+//                           many descriptors per frame (anchor phase, wide trajectory batches);
+//   * corr_stream_kernel -- HBM-streaming mat-vec for thin groups (<= STREAM_MAX_M descriptors per frame):
+//                           every token row is read once, descriptors live in shared memory.
+// The reference instead runs einsum("bc,nchw->bnhw") over all B x N pairs and keeps the diagonal.
+#include "common.cuh"
+#include "corr.cuh"
+
+namespace dtk {
+
+constexpr int BM = 128, BN = 128, BK = 16, KPAD = 20, STAGES = 3;
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_SMEM = STAGES * (BM + BN) * KPAD * 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// prefix of 128-row tiles per group; thin groups (m <= stream_max) get 0 GEMM tiles.
+__global__ void corr_plan_kernel(const int* __restrict__ grp_m, int n_groups, int stream_max,
+                                 int* __restrict__ tile_start) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < n_groups; ++k) {
+      tile_start[k] = acc;
+      int m = grp_m[k];
+      if (m > stream_max) acc += (m + BM - 1) / BM;
+    }
+    tile_start[n_groups] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+corr_gemm_kernel(const float* __restrict__ tpc, const float* __restrict__ norms, int C, int P,
+                 const float* __restrict__ desc, const float* __restrict__ desc_norm,
+                 const int* __restrict__ grp_frame, const int* __restrict__ grp_row0,
+                 const int* __restrict__ grp_m, const int* __restrict__ grp_map0,
+                 const int* __restrict__ tile_start, int n_groups, float* __restrict__ maps, int map_stride) {
+  extern __shared__ __align__(16) float smem[];
+  const int mt = blockIdx.x;
+  if (mt >= tile_start[n_groups]) return;
+  // binary search: last group k with tile_start[k] <= mt and a non-empty tile range
+  int lo = 0, hi = n_groups - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (tile_start[mid] <= mt) lo = mid; else hi = mid - 1;
+  }
+  const int g = lo;  // groups with zero tiles share a start with their successor; "last <=" skips them
+  const int m_grp = grp_m[g];
+  const int m0 = (mt - tile_start[g]) * BM;
+  const int n0 = blockIdx.y * BN;
+  const float* A = desc + (size_t)(grp_row0[g] + m0) * C;
+  const float* B = tpc + ((size_t)grp_frame[g] * P + n0) * C;
+  const int m_valid = min(BM, m_grp - m0), n_valid = min(BN, P - n0);
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int KT = (C + BK - 1) / BK;
+  auto load_stage = [&](int kt, int s) {
+    float* sa = smem + s * (BM + BN) * KPAD;
+    float* sb = sa + BM * KPAD;
+    const int k0 = kt * BK;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      int ch = tid + it * GEMM_THREADS;   // 0..511: row = ch / 4, chunk = ch % 4
+      int r = ch >> 2, c4 = (ch & 3) * 4;
+      bool kin = (k0 + c4) < C;
+      bool va = kin && r < m_valid, vb = kin && r < n_valid;  // invalid chunks: zero-fill, in-bounds dummy src
+      cp_async16(sa + r * KPAD + c4, va ? A + (size_t)r * C + k0 + c4 : A, va);
+      cp_async16(sb + r * KPAD + c4, vb ? B + (size_t)r * C + k0 + c4 : B, vb);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_stage(s, s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nk = kt + STAGES - 1;
+      if (nk < KT) load_stage(nk, nk % STAGES);
+      cp_async_commit();
+    }
+    const float* sa = smem + (kt % STAGES) * (BM + BN) * KPAD;
+    const float* sb = sa + BM * KPAD;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(sa + (ty + 16 * i) * KPAD + kk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = *reinterpret_cast<const float4*>(sb + (tx + 16 * j) * KPAD + kk);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i][j] = fmaf(a[i].x, b.x, acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, b.y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, b.z, acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, b.w, acc[i][j]);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: cosine-normalise (clamp 1e-8), ReLU, store
+  const float* fn = norms + (size_t)grp_frame[g] * P + n0;
+  const float* dn = desc_norm + grp_row0[g] + m0;
+  float fnv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) fnv[j] = (tx + 16 * j) < n_valid ? fn[tx + 16 * j] : 1.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int r = ty + 16 * i;
+    if (r >= m_valid) continue;
+    float dnv = dn[r];
+    float* out = maps + (size_t)(grp_map0[g] + m0 + r) * map_stride + n0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = tx + 16 * j;
+      if (c < n_valid) {
+        float v = __fdiv_rn(acc[i][j], fmaxf(__fmul_rn(dnv, fnv[j]), 1e-8f));
+        out[c] = fmaxf(v, 0.f);
+      }
+    }
+  }
+}
+
+// ---- thin groups: stream every token row once --------------------------------------------------
+constexpr int STREAM_THREADS = 256;
+constexpr int STREAM_TOK = 64;  // tokens per CTA (8 per warp)
+
+template <int MAXM>
+__global__ void __launch_bounds__(STREAM_THREADS)
+corr_stream_kernel(const float* __restrict__ tpc, const float* __restrict__ norms, int C, int P,
+                   const float* __restrict__ desc, const float* __restrict__ desc_norm,
+                   const int* __restrict__ grp_frame, const int* __restrict__ grp_row0,
+                   const int* __restrict__ grp_m, const int* __restrict__ grp_map0, int stream_max,
+                   float* __restrict__ maps, int map_stride) {
+  extern __shared__ __align__(16) float sdesc[];  // [MAXM][C]
+  const int g = blockIdx.y;
+  const int m = grp_m[g];
+  if (m <= 0 || m > stream_max) return;
+  const int frame = grp_frame[g], row0 = grp_row0[g], map0 = grp_map0[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C4 = C >> 2;
+  for (int mb = 0; mb < m; mb += MAXM) {
+    const int mc = min(MAXM, m - mb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < mc * C4; i += STREAM_THREADS)
+      reinterpret_cast<float4*>(sdesc)[i] = __ldg(reinterpret_cast<const float4*>(desc + (size_t)(row0 + mb) * C) + i);
+    __syncthreads();
+    for (int t = warp; t < STREAM_TOK; t += STREAM_THREADS / 32) {
+      const int p = blockIdx.x * STREAM_TOK + t;
+      if (p >= P) break;
+      const float4* row = reinterpret_cast<const float4*>(tpc + ((size_t)frame * P + p) * C);
+      float acc[MAXM];
+#pragma unroll
+      for (int q = 0; q < MAXM; ++q) acc[q] = 0.f;
+      for (int i = lane; i < C4; i += 32) {
+        float4 f = __ldg(row + i);
+#pragma unroll
+        for (int q = 0; q < MAXM; ++q) {
+          if (q < mc) {
+            float4 d = reinterpret_cast<const float4*>(sdesc + q * C)[i];
+            acc[q] = fmaf(f.x, d.x, acc[q]); acc[q] = fmaf(f.y, d.y, acc[q]);
+            acc[q] = fmaf(f.z, d.z, acc[q]); acc[q] = fmaf(f.w, d.w, acc[q]);
+          }
+        }
+      }
+      const float fn = norms[(size_t)frame * P + p];
+#pragma unroll
+      for (int q = 0; q < MAXM; ++q) {
+        float s = warp_sum(acc[q]);
+        if (lane == 0 && q < mc) {
+          float v = __fdiv_rn(s, fmaxf(__fmul_rn(desc_norm[row0 + mb + q], fn), 1e-8f));
+          maps[(size_t)(map0 + mb + q) * map_stride + p] = fmaxf(v, 0.f);
+        }
+      }
+    }
+  }
+}
+
+size_t corr_plan_bytes(int n_groups) { return align_up((size_t)(n_groups + 1) * sizeof(int), 256); }
+
+int launch_corr_maps(const float* tpc, const float* norms, int C, int P, const float* desc,
+                     const float* desc_norm, const int* grp_frame, const int* grp_row0, const int* grp_m,
+                     const int* grp_map0, int n_groups, int total_maps, int max_group_m, float* maps,
+                     int map_stride, int* tile_start, cudaStream_t st) {
+  if (n_groups <= 0 || total_maps <= 0) return DINOTRK_OK;
+  const int stream_max = STREAM_MAX_M;
+  if (max_group_m > stream_max) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      DTK_CUDA(cudaFuncSetAttribute(corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+      attr_set = true;
+    }
+    corr_plan_kernel<<<1, 32, 0, st>>>(grp_m, n_groups, stream_max, tile_start);
+    DTK_LAUNCHED();
+    // upper bound on sum ceil(m_k / BM) over the wide groups
+    int max_tiles = total_maps / BM + n_groups;
+    dim3 grid(max_tiles, cdiv(P, BN));
+    corr_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame,
+                                                            grp_row0, grp_m, grp_map0, tile_start, n_groups,
+                                                            maps, map_stride);
+    DTK_LAUNCHED();
+  }
+  {
+    // thin groups (there may be none; CTAs of wide groups exit at once)
+    constexpr int MAXM = 8;
+    size_t smem = (size_t)MAXM * C * sizeof(float);
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+      DTK_CUDA(cudaFuncSetAttribute(corr_stream_kernel<MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
+    }
+    dim3 grid(cdiv(P, STREAM_TOK), n_groups);
+    corr_stream_kernel<MAXM><<<grid, STREAM_THREADS, smem, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame,
+                                                                grp_row0, grp_m, grp_map0, stream_max, maps,
+                                                                map_stride);
+    DTK_LAUNCHED();
+  }
+  return DINOTRK_OK;
+}
+
+}  // namespace dtk
+
+using namespace dtk;
+
+extern "C" {
+
+int dinotrk_map_stride(const dinotrk_geom* g) { return g ? (int)align_up((size_t)g->h * g->w, 4) : 0; }
+
+int dinotrk_corr_maps(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+                      const float* desc, const float* desc_norm, const int* grp_frame, const int* grp_row0,
+                      const int* grp_m, const int* grp_map0, int n_groups, int total_maps, int max_group_m,
+                      float* maps, void* workspace, size_t workspace_bytes, void* stream) {
+  DTK_CHECK_ARG(tpc && norms && g && desc && desc_norm && grp_frame && grp_row0 && grp_m && grp_map0 && maps,
+                "corr_maps: null pointer");
+  DTK_CHECK_ARG(T > 0 && C > 0 && C % 4 == 0 && n_groups >= 0 && total_maps >= 0, "corr_maps: bad sizes");
+  DTK_CHECK_ARG(workspace && workspace_bytes >= corr_plan_bytes(n_groups), "corr_maps: workspace too small");
+  return launch_corr_maps(tpc, norms, C, g->h * g->w, desc, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
+                          n_groups, total_maps, max_group_m, maps, dinotrk_map_stride(g), (int*)workspace,
+                          (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,284 @@
+// Delta-DINO: 4 x [conv5x5 (reflect pad, dilation d) + BatchNorm(eval) (+ ReLU + BlurPool)] and the
+// resampling of its output onto the ViT token grid, fused with the residual add
+// (models/networks/delta_dino.py:8-61, models/utils.py:7-45, models/tracker.py:113-129).
+//
+// Activations are NHWC fp32.  Each convolution is an implicit GEMM (M = output pixels, N = C_out,
+// K = 25 taps x C_in, K-major weights with the BatchNorm folded in on the host) on the same
+// 128 x 128 x 16 cp.async pipeline as the correlation GEMM; the im2col gather (reflection, dilation)
+// happens in the cp.async address computation, nothing is materialised.
+#include <utility>
+
+#include "common.cuh"
+
+namespace dtk {
+
+constexpr int CBM = 128, CBN = 128, CBK = 16, CKPAD = 20, CSTAGES = 3;
+constexpr int CONV_THREADS = 256;
+constexpr int CONV_SMEM = CSTAGES * (CBM + CBN) * CKPAD * 4;
+
+__device__ __forceinline__ void cp16(void* smem, const void* gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+
+struct ConvShape {
+  int B, H, W, Cin, Cout, dil;  // Cin is the padded (multiple of 4) channel count of the NHWC input
+  int relu;
+};
+
+__device__ __forceinline__ int reflect(int v, int n) {
+  v = v < 0 ? -v : v;
+  return v >= n ? 2 * (n - 1) - v : v;
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 2)
+conv5x5_kernel(const float* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ bias,
+               float* __restrict__ out, ConvShape cs) {
+  extern __shared__ __align__(16) float smem[];
+  const int M = cs.B * cs.H * cs.W, K = 25 * cs.Cin;
+  const int m0 = blockIdx.x * CBM, n0 = blockIdx.y * CBN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+  // the two A rows (output pixels) this thread gathers, and the two B rows (output channels)
+  int pb[2], py[2], px[2];
+  bool pv[2];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    int r = (tid + it * CONV_THREADS) >> 2;
+    int m = m0 + r;
+    pv[it] = m < M;
+    int mm = pv[it] ? m : 0;
+    pb[it] = mm / (cs.H * cs.W);
+    int rem = mm - pb[it] * cs.H * cs.W;
+    py[it] = rem / cs.W;
+    px[it] = rem - py[it] * cs.W;
+  }
+  const int c4 = (tid & 3) * 4;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int KT = (K + CBK - 1) / CBK;
+  auto load_stage = [&](int kt, int s) {
+    float* sa = smem + s * (CBM + CBN) * CKPAD;
+    float* sb = sa + CBM * CKPAD;
+    const int k = kt * CBK + c4;
+    const bool kin = k < K;
+    const int tap = kin ? k / cs.Cin : 0;
+    const int ci = kin ? k - tap * cs.Cin : 0;
+    const int ky = tap / 5, kx = tap - ky * 5;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      int r = (tid + it * CONV_THREADS) >> 2;
+      int sy = reflect(py[it] + (ky - 2) * cs.dil, cs.H), sx = reflect(px[it] + (kx - 2) * cs.dil, cs.W);
+      const float* src = in + (((size_t)pb[it] * cs.H + sy) * cs.W + sx) * cs.Cin + ci;
+      bool va = kin && pv[it];
+      cp16(sa + r * CKPAD + c4, va ? src : in, va);
+      int n = n0 + r;
+      bool vb = kin && n < cs.Cout;
+      cp16(sb + r * CKPAD + c4, vb ? wgt + (size_t)n * K + k : wgt, vb);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < CSTAGES - 1; ++s) {
+    if (s < KT) load_stage(s, s);
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+  for (int kt = 0; kt < KT; ++kt) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(CSTAGES - 2));
+    __syncthreads();
+    {
+      int nk = kt + CSTAGES - 1;
+      if (nk < KT) load_stage(nk, nk % CSTAGES);
+      asm volatile("cp.async.commit_group;\n" ::);
+    }
+    const float* sa = smem + (kt % CSTAGES) * (CBM + CBN) * CKPAD;
+    const float* sb = sa + CBM * CKPAD;
+#pragma unroll
+    for (int kk = 0; kk < CBK; kk += 4) {
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(sa + (ty + 16 * i) * CKPAD + kk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = *reinterpret_cast<const float4*>(sb + (tx + 16 * j) * CKPAD + kk);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i][j] = fmaf(a[i].x, b.x, acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, b.y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, b.z, acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, b.w, acc[i][j]);
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+
+  float bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bv[j] = (n0 + tx + 16 * j) < cs.Cout ? bias[n0 + tx + 16 * j] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + ty + 16 * i;
+    if (m >= M) continue;
+    float* o = out + (size_t)m * cs.Cout + n0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = tx + 16 * j;
+      if (n0 + c < cs.Cout) {
+        float v = acc[i][j] + bv[j];
+        o[c] = cs.relu ? fmaxf(v, 0.f) : v;
+      }
+    }
+  }
+}
+
+// RGB frames [B][3][H][W] (reference layout) -> NHWC with a zero 4th channel
+__global__ void rgb_to_nhwc4_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int HW) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * HW) return;
+  size_t b = i / HW, p = i - b * HW;
+  const float* s = in + b * 3 * HW + p;
+  reinterpret_cast<float4*>(out)[i] = make_float4(s[0], s[HW], s[2 * HW], 0.f);
+}
+
+// antialiased_cnns.BlurPool(stride 2, filt 4): reflect pad (1,2,1,2), depthwise outer([1,3,3,1])/64.
+__global__ void blurpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C,
+                                int Ho, int Wo) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*Ho*Wo*(C/4)
+  const int C4 = C >> 2;
+  size_t total = (size_t)B * Ho * Wo * C4;
+  if (i >= total) return;
+  int c4 = (int)(i % C4);
+  size_t p = i / C4;
+  int ox = (int)(p % Wo);
+  size_t q = p / Wo;
+  int oy = (int)(q % Ho);
+  int b = (int)(q / Ho);
+  const float f[4] = {1.f / 8.f, 3.f / 8.f, 3.f / 8.f, 1.f / 8.f};
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    int sy = reflect(2 * oy + ky - 1, H);
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      int sx = reflect(2 * ox + kx - 1, W);
+      float wv = f[ky] * f[kx];  // exact: (1|3)*(1|3)/64
+      float4 v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + sy) * W + sx) * C) + c4);
+      acc.x = fmaf(v.x, wv, acc.x); acc.y = fmaf(v.y, wv, acc.y);
+      acc.z = fmaf(v.z, wv, acc.z); acc.w = fmaf(v.w, wv, acc.w);
+    }
+  }
+  reinterpret_cast<float4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C)[c4] = acc;
+}
+
+// refined[t][p][:] = dino[t][p][:] + bilinear(cnn[t], iy[r], ix[c])   (grid_sample border, align_corners=True)
+// ix/iy: un-normalised, clipped source coordinates per token column / row (computed on the host with the
+// reference's fp32 arithmetic, models/utils.py:31-43).
+__global__ void align_add_kernel(const float* __restrict__ cnn, const float* __restrict__ dino,
+                                 float* __restrict__ refined, const float* __restrict__ ixs,
+                                 const float* __restrict__ iys, int Hc, int Wc, int C, int h, int w) {
+  const int p = blockIdx.x, b = blockIdx.y;
+  const int r = p / w, c = p - r * w;
+  const float ix = ixs[c], iy = iys[r];
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+  // ATen grid_sampler_2d: nw = (ix_se - ix) * (iy_se - iy), ne = (ix - ix_sw) * (iy_sw - iy), ...
+  const float wnw = (x0f + 1.f - ix) * (y0f + 1.f - iy), wne = (ix - x0f) * (y0f + 1.f - iy);
+  const float wsw = (x0f + 1.f - ix) * (iy - y0f), wse = (ix - x0f) * (iy - y0f);
+  const bool okx1 = x1 <= Wc - 1, oky1 = y1 <= Hc - 1;
+  const float4* base = reinterpret_cast<const float4*>(cnn + (size_t)b * Hc * Wc * C);
+  const int C4 = C >> 2;
+  const float4* pnw = base + ((size_t)y0 * Wc + x0) * C4;
+  const float4* pne = base + ((size_t)y0 * Wc + (okx1 ? x1 : x0)) * C4;
+  const float4* psw = base + ((size_t)(oky1 ? y1 : y0) * Wc + x0) * C4;
+  const float4* pse = base + ((size_t)(oky1 ? y1 : y0) * Wc + (okx1 ? x1 : x0)) * C4;
+  const float4* d = reinterpret_cast<const float4*>(dino + ((size_t)b * h * w + p) * C);
+  float4* o = reinterpret_cast<float4*>(refined + ((size_t)b * h * w + p) * C);
+  for (int i = threadIdx.x; i < C4; i += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = __ldg(pnw + i);
+    acc.x = fmaf(v.x, wnw, acc.x); acc.y = fmaf(v.y, wnw, acc.y); acc.z = fmaf(v.z, wnw, acc.z); acc.w = fmaf(v.w, wnw, acc.w);
+    if (okx1) { v = __ldg(pne + i); acc.x = fmaf(v.x, wne, acc.x); acc.y = fmaf(v.y, wne, acc.y); acc.z = fmaf(v.z, wne, acc.z); acc.w = fmaf(v.w, wne, acc.w); }
+    if (oky1) { v = __ldg(psw + i); acc.x = fmaf(v.x, wsw, acc.x); acc.y = fmaf(v.y, wsw, acc.y); acc.z = fmaf(v.z, wsw, acc.z); acc.w = fmaf(v.w, wsw, acc.w); }
+    if (okx1 && oky1) { v = __ldg(pse + i); acc.x = fmaf(v.x, wse, acc.x); acc.y = fmaf(v.y, wse, acc.y); acc.z = fmaf(v.z, wse, acc.z); acc.w = fmaf(v.w, wse, acc.w); }
+    float4 dv = __ldg(d + i);
+    o[i] = make_float4(dv.x + acc.x, dv.y + acc.y, dv.z + acc.z, dv.w + acc.w);
+  }
+}
+
+static int launch_conv(const float* in, const float* wgt, const float* bias, float* out, ConvShape cs, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    DTK_CUDA(cudaFuncSetAttribute(conv5x5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
+    attr = true;
+  }
+  dim3 grid(cdiv(cs.B * cs.H * cs.W, CBM), cdiv(cs.Cout, CBN));
+  conv5x5_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(in, wgt, bias, out, cs);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+}  // namespace dtk
+
+using namespace dtk;
+
+extern "C" {
+
+size_t dinotrk_delta_workspace_bytes(int B, int H, int W, const int* channels) {
+  // ping-pong NHWC buffers: the largest activation is conv0's output (B x H x W x C1)
+  size_t a = (size_t)B * H * W * (channels[1] > 4 ? channels[1] : 4) * sizeof(float);
+  return 2 * align_up(a, 256) + 4096;
+}
+
+int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* channels, const float* const* wgt,
+                         const float* const* bias, const float* dino_tpc, const float* ixs, const float* iys,
+                         int h, int w, float* refined_tpc, float* norms, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  DTK_CHECK_ARG(frames && channels && wgt && bias && dino_tpc && ixs && iys && refined_tpc, "delta_refine: null pointer");
+  DTK_CHECK_ARG(channels[0] == 3, "delta_refine: input must be RGB");
+  for (int l = 1; l <= 4; ++l) DTK_CHECK_ARG(channels[l] % 4 == 0, "delta_refine: channel counts must be multiples of 4");
+  DTK_CHECK_ARG(workspace && workspace_bytes >= dinotrk_delta_workspace_bytes(B, H, W, channels),
+                "delta_refine: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ar(workspace, workspace_bytes);
+  size_t half = (size_t)B * H * W * (channels[1] > 4 ? channels[1] : 4);
+  float* buf0 = ar.take<float>(half);
+  float* buf1 = ar.take<float>(half);
+
+  {
+    size_t n = (size_t)B * H * W;
+    rgb_to_nhwc4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(frames, buf0, B, H * W);
+    DTK_LAUNCHED();
+  }
+  int ch = H, cw = W, cin = 4;
+  float* cur = buf0;
+  float* oth = buf1;
+  const int dil[4] = {1, 1, 1, 2};
+  for (int l = 0; l < 4; ++l) {
+    ConvShape cs{B, ch, cw, cin, channels[l + 1], dil[l], l < 3 ? 1 : 0};
+    int rc = launch_conv(cur, wgt[l], bias[l], oth, cs, st);
+    if (rc) return rc;
+    std::swap(cur, oth);
+    cin = channels[l + 1];
+    if (l < 3) {
+      int ho = (ch - 1) / 2 + 1, wo = (cw - 1) / 2 + 1;
+      size_t tot = (size_t)B * ho * wo * (cin / 4);
+      blurpool_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur, oth, B, ch, cw, cin, ho, wo);
+      DTK_LAUNCHED();
+      std::swap(cur, oth);
+      ch = ho; cw = wo;
+    }
+  }
+  align_add_kernel<<<dim3(h * w, B), 128, 0, st>>>(cur, dino_tpc, refined_tpc, ixs, iys, ch, cw, cin, h, w);
+  DTK_LAUNCHED();
+  if (norms) return dinotrk_token_norms(refined_tpc, norms, B, cin, h * w, stream);
+  return DINOTRK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+// Tracker head: arg-max, 2-layer normalised-conv refiner, spatial softmax, disc-masked soft-argmax
+// with the numerical-stability fallback (models/networks/tracker_head.py:107-121, :68-98, :100-105;
+// conv_norm.py:34-46; data/dataset.py:21-53).
+//
+// One persistent CTA per SM; one warp per 4-row band of the map, one lane per 4x4-pixel tile
+// (band = 32 tiles = 128 columns >= w).  Per hidden channel a lane computes its 16 hidden values from
+// the 6x6 input window it keeps in registers, publishes its top/bottom rows to shared memory (the only
+// cross-warp traffic), takes the side/corner halo from its lane neighbours by shuffle and
+// accumulates the second convolution into 16 registers.  The next map is prefetched with cp.async
+// while the current one is being refined.
+#include "common.cuh"
+#include "corr.cuh"
+
+namespace dtk {
+
+constexpr int HEAD_MAX_W = 128, HEAD_MAX_H = 128;
+
+struct HeadParams {
+  int h, w, P, map_stride;
+  int stride_px, half_patch, radius2;  // pixel geometry: centre = half_patch + stride * index
+  float normW, normH;                  // W - 1, H - 1
+  int out_stride, out_mode;
+};
+
+__device__ __forceinline__ void cp_async16_head(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+
+template <typename T>
+__device__ __forceinline__ T block_bcast_reduce(T v, T* red, int warp, int lane, int nwarps, T (*op)(T, T)) {
+  // warp-level then cross-warp; every thread returns the result
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  T r = red[0];
+  for (int k = 1; k < nwarps; ++k) r = op(r, red[k]);
+  return r;
+}
+__device__ __forceinline__ float opmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float opadd(float a, float b) { return a + b; }
+// arg-max key: larger value wins, ties -> smaller index (torch.argmax returns the first maximum).
+// Values are >= 0 (ReLU'd), so the float bit pattern orders like the value.
+__device__ __forceinline__ unsigned long long opkey(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_head_weights wts,
+            const int* __restrict__ out_index, float* __restrict__ out, int* __restrict__ aux) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int h = hp.h, w = hp.w, P = hp.P;
+  const int lin_elems = (hp.map_stride + 3) & ~3;
+  float* sm_lin[2] = {smem, smem + lin_elems};
+  float* sm_hid = smem + 2 * lin_elems;                   // [2 buffers][nwarps][2 rows][128]
+  float* sm_red = sm_hid + 2 * nwarps * 2 * 128;          // [nwarps] floats
+  unsigned long long* sm_red64 = reinterpret_cast<unsigned long long*>(sm_red + 32);  // [nwarps]
+
+  const int r0 = warp * 4, c0 = lane * 4;  // this lane's tile
+  const int nchunks = hp.map_stride / 4;
+
+  int map = blockIdx.x;
+  if (map < n_maps) {
+    const float4* src = reinterpret_cast<const float4*>(maps + (size_t)map * hp.map_stride);
+    for (int i = threadIdx.x; i < nchunks; i += blockDim.x) cp_async16_head(sm_lin[0] + 4 * i, src + i);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+
+  for (int it = 0; map < n_maps; map += gridDim.x, ++it) {
+    const float* lin = sm_lin[it & 1];
+    {  // prefetch the next map into the other buffer
+      int nmap = map + gridDim.x;
+      if (nmap < n_maps) {
+        const float4* src = reinterpret_cast<const float4*>(maps + (size_t)nmap * hp.map_stride);
+        float* dst = sm_lin[(it + 1) & 1];
+        for (int i = threadIdx.x; i < nchunks; i += blockDim.x) cp_async16_head(dst + 4 * i, src + i);
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    }
+    __syncthreads();
+
+    // ---- arg-max of the (already ReLU'd) map: first maximal index ----------------------------
+    unsigned long long key = 0ull;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      float v = lin[i] + 0.f;  // -0.0 -> +0.0 so that the bit pattern orders like the value
+      unsigned long long k = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(0x7fffffff - i);
+      key = k > key ? k : key;
+    }
+    key = block_bcast_reduce<unsigned long long>(key, sm_red64, warp, lane, nwarps, opkey);
+    const int amax = 0x7fffffff - (int)(key & 0xffffffffu);
+    const int arow = amax / w, acol = amax - arow * w;
+
+    // ---- 6x6 input window (zero outside the map = conv zero padding) -------------------------
+    float m[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      int r = r0 - 1 + i;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        int c = c0 - 1 + j;
+        m[i][j] = (r >= 0 && r < h && c >= 0 && c < w) ? lin[r * w + c] : 0.f;
+      }
+    }
+    bool valid[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) valid[i][j] = (r0 + i < h) && (c0 + j < w);
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = wts.b2;
+
+#pragma unroll 1
+    for (int o = 0; o < 16; ++o) {
+      float w1[9], w2[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { w1[k] = wts.w1[o][k]; w2[k] = wts.w2[o][k]; }
+      const float b1 = wts.b1[o];
+      // hidden window: hid[1..4][1..4] own, ring = halo
+      float hid[6][6];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = b1;
+#pragma unroll
+          for (int ki = 0; ki < 3; ++ki)
+#pragma unroll
+            for (int kj = 0; kj < 3; ++kj) a = fmaf(w1[ki * 3 + kj], m[i + ki][j + kj], a);
+          hid[i + 1][j + 1] = valid[i][j] ? fmaxf(a, 0.f) : 0.f;  // hidden is zero-padded outside the map
+        }
+      float* hb = sm_hid + ((o & 1) * nwarps + warp) * 2 * 128;
+      *reinterpret_cast<float4*>(hb + c0) = make_float4(hid[1][1], hid[1][2], hid[1][3], hid[1][4]);
+      *reinterpret_cast<float4*>(hb + 128 + c0) = make_float4(hid[4][1], hid[4][2], hid[4][3], hid[4][4]);
+      __syncthreads();
+      float4 top = make_float4(0.f, 0.f, 0.f, 0.f), bot = top;
+      if (warp > 0) top = *reinterpret_cast<const float4*>(sm_hid + ((o & 1) * nwarps + warp - 1) * 2 * 128 + 128 + c0);
+      if (warp + 1 < nwarps) bot = *reinterpret_cast<const float4*>(sm_hid + ((o & 1) * nwarps + warp + 1) * 2 * 128 + c0);
+      hid[0][1] = top.x; hid[0][2] = top.y; hid[0][3] = top.z; hid[0][4] = top.w;
+      hid[5][1] = bot.x; hid[5][2] = bot.y; hid[5][3] = bot.z; hid[5][4] = bot.w;
+      // side + corner halo from lane neighbours (lane 0 / 31: outside the band -> zero padding)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        float l = __shfl_up_sync(0xffffffffu, hid[i][4], 1);
+        float r = __shfl_down_sync(0xffffffffu, hid[i][1], 1);
+        hid[i][0] = lane > 0 ? l : 0.f;
+        hid[i][5] = lane < 31 ? r : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = acc[i][j];
+#pragma unroll
+          for (int ki = 0; ki < 3; ++ki)
+#pragma unroll
+            for (int kj = 0; kj < 3; ++kj) a = fmaf(w2[ki * 3 + kj], hid[i + ki][j + kj], a);
+          acc[i][j] = a;
+        }
+    }
+
+    // ---- softmax statistics over the whole map -----------------------------------------------
+    float zmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (valid[i][j]) zmax = fmaxf(zmax, acc[i][j]);
+    zmax = block_bcast_reduce<float>(zmax, sm_red, warp, lane, nwarps, opmax);
+    float e[4][4];
+    float ssum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        e[i][j] = valid[i][j] ? expf(acc[i][j] - zmax) : 0.f;
+        ssum += e[i][j];
+      }
+    ssum = block_bcast_reduce<float>(ssum, sm_red, warp, lane, nwarps, opadd);
+
+    // ---- disc-masked soft-argmax (mask: |token centre - argmax centre| <= radius px) ----------
+    float s = 0.f, sx = 0.f, sy = 0.f, gx = 0.f, gy = 0.f, cnt = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int dr = (r0 + i - arow) * hp.stride_px, dc = (c0 + j - acol) * hp.stride_px;
+        if (valid[i][j] && dr * dr + dc * dc <= hp.radius2) {
+          float p = __fdiv_rn(e[i][j], ssum);
+          float x = (float)(hp.half_patch + (c0 + j) * hp.stride_px), y = (float)(hp.half_patch + (r0 + i) * hp.stride_px);
+          s += p; sx = fmaf(x, p, sx); sy = fmaf(y, p, sy);
+          gx += x; gy += y; cnt += 1.f;
+        }
+      }
+    s = block_bcast_reduce<float>(s, sm_red, warp, lane, nwarps, opadd);
+    sx = block_bcast_reduce<float>(sx, sm_red, warp, lane, nwarps, opadd);
+    sy = block_bcast_reduce<float>(sy, sm_red, warp, lane, nwarps, opadd);
+    const bool fallback = s < 1e-8f;
+    if (fallback) {  // heatmap <- (heatmap + 1/|mask|) * mask  (tracker_head.py:87-94), block-uniform branch
+      gx = block_bcast_reduce<float>(gx, sm_red, warp, lane, nwarps, opadd);
+      gy = block_bcast_reduce<float>(gy, sm_red, warp, lane, nwarps, opadd);
+      cnt = block_bcast_reduce<float>(cnt, sm_red, warp, lane, nwarps, opadd);
+      float u = __fdiv_rn(1.f, cnt);
+      s = fmaf(cnt, u, s); sx = fmaf(gx, u, sx); sy = fmaf(gy, u, sy);
+    }
+    if (threadIdx.x == 0) {
+      float px = __fdiv_rn(sx, s), py = __fdiv_rn(sy, s);
+      // RangeNormalizer((W, H)) dst=(-1,1): x / (W-1); * 2; + (-1)      (data/dataset.py:33-35)
+      float nx = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(px, hp.normW)), -1.f);
+      float ny = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(py, hp.normH)), -1.f);
+      if (hp.out_mode == 0) {  // unnormalize(src=(-1,1)): (v - (-1)) / 2 * (W-1)   (data/dataset.py:50-52)
+        nx = __fmul_rn(__fdiv_rn(__fadd_rn(nx, 1.f), 2.f), hp.normW);
+        ny = __fmul_rn(__fdiv_rn(__fadd_rn(ny, 1.f), 2.f), hp.normH);
+      }
+      size_t oi = (size_t)(out_index ? out_index[map] : map) * hp.out_stride;
+      out[oi] = nx; out[oi + 1] = ny;
+      if (aux) { aux[2 * map] = amax; aux[2 * map + 1] = fallback ? 1 : 0; }
+    }
+    __syncthreads();  // lin / sm_hid are reused by the next iteration
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
+int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geom& g,
+                const dinotrk_head_weights& hw, const int* out_index, float* out, int out_stride, int out_mode,
+                int* aux, cudaStream_t st) {
+  if (n_maps <= 0) return DINOTRK_OK;
+  DTK_CHECK_ARG(g.w <= HEAD_MAX_W && g.h <= HEAD_MAX_H, "head: token grid %dx%d exceeds the supported %dx%d",
+                g.h, g.w, HEAD_MAX_H, HEAD_MAX_W);
+  HeadParams hp;
+  hp.h = g.h; hp.w = g.w; hp.P = g.h * g.w; hp.map_stride = map_stride;
+  hp.stride_px = g.stride; hp.half_patch = g.patch / 2; hp.radius2 = g.radius * g.radius;
+  hp.normW = (float)(g.W - 1); hp.normH = (float)(g.H - 1);
+  hp.out_stride = out_stride; hp.out_mode = out_mode;
+  const int nwarps = cdiv(g.h, 4);
+  const int threads = nwarps * 32;
+  const int lin_elems = (map_stride + 3) & ~3;
+  size_t smem = (size_t)(2 * lin_elems + 2 * nwarps * 2 * 128 + 32) * sizeof(float) + 32 * sizeof(unsigned long long);
+  static size_t attr_smem[2] = {0, 0};
+  const int variant = threads <= 576 ? 0 : 1;  // <= 576 threads: 112 registers/thread; else 64
+  if (smem > attr_smem[variant]) {
+    if (variant == 0) DTK_CUDA(cudaFuncSetAttribute(head_kernel<576>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else DTK_CUDA(cudaFuncSetAttribute(head_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[variant] = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = n_maps < sms ? n_maps : sms;
+  if (variant == 0) head_kernel<576><<<grid, threads, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux);
+  else head_kernel<1024><<<grid, threads, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+}  // namespace dtk
+
+using namespace dtk;
+
+extern "C" int dinotrk_head(const float* maps, int n_maps, const dinotrk_geom* g, const dinotrk_head_weights* hw,
+                            const int* out_index, float* out, int out_stride, int out_mode, int* aux, void* stream) {
+  DTK_CHECK_ARG(maps && g && hw && out, "head: null pointer");
+  DTK_CHECK_ARG(out_stride >= 2 && (out_mode == 0 || out_mode == 1), "head: bad out_stride/out_mode");
+  return launch_head(maps, n_maps, dinotrk_map_stride(g), *g, *hw, out_index, out, out_stride, out_mode, aux,
+                     (cudaStream_t)stream);
+}

@@ -1,0 +1,422 @@
+// Inference driver on the device: trajectories, trajectory cosine similarities, anchor re-tracking and
+// occlusion (models/model_inference.py:8-216) + the generic grouped correlation/head entry point behind
+// Tracker.forward (models/tracker.py:303-325).
+//
+// The reference walks query points and anchor frames in Python, one model() call per (query, anchor):
+// each call gathers (T+1) x C x h x w twice and runs a B x N einsum.  Here every phase is a handful of
+// launches over work lists grouped by target frame:
+//   A  trajectories : descriptors s_n (N of them)          x every frame t        -> traj[n][t]
+//   B  cos-sims     : d[n][i] sampled along the trajectory . d[n][t_q]            -> cos[n][i]
+//   C  anchors      : for every anchor frame a, descriptors e[n][i] (a in A_n)    -> anchors[n][a][i]
+//   D  occlusion    : lower medians over anchors, threshold, OR with cos < th     -> occ[n][i]
+#include <vector>
+
+#include "common.cuh"
+#include "corr.cuh"
+#include "sample.cuh"
+
+namespace dtk {
+
+// ---------------------------------------------------------------------------------- phase A helpers
+// descriptors of the query points: frames_set = [t_q, s..e-1], set index 0 (model_inference.py:8-34)
+__global__ void sample_query_kernel(const float* __restrict__ tpc, int T, int C, int P, int h, int w, PointAffine pa,
+                                    const float* __restrict__ qp, float* __restrict__ desc, float* __restrict__ dnorm) {
+  int n = blockIdx.x;
+  float x = __fadd_rn(__fmul_rn(pa.aw, qp[n * 3 + 0]), pa.bw);
+  float y = __fadd_rn(__fmul_rn(pa.ah, qp[n * 3 + 1]), pa.bh);
+  int tq = (int)qp[n * 3 + 2];
+  tq = min(max(tq, 0), T - 1);
+  // set index 0 of a set with N >= 2 slots: t_n = -1 exactly -> slot 0 with weight 1, slot 1 with weight 0.
+  // The weight-0 corner is skipped (0 * finite), so only frame t_q contributes.
+  TriCorners c = tri_setup(x, y, 0.f, 2, h, w);
+  sample_point(tpc, C, P, c, tq, -1, desc + (size_t)n * C, dnorm + n);
+}
+
+// out_index / t column for phase A maps of one chunk: map j -> group k -> (n, t)
+__global__ void index_traj_kernel(const int* __restrict__ grp_frame, const int* __restrict__ grp_row0,
+                                  const int* __restrict__ grp_map0, int n_groups, int n_maps, int T,
+                                  int* __restrict__ out_index, float* __restrict__ traj) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_maps) return;
+  int lo = 0, hi = n_groups - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (grp_map0[mid] <= j) lo = mid; else hi = mid - 1;
+  }
+  int n = grp_row0[lo] + (j - grp_map0[lo]);
+  int t = grp_frame[lo];
+  out_index[j] = n * T + t;
+  traj[((size_t)n * T + t) * 3 + 2] = (float)t;
+}
+
+// ---------------------------------------------------------------------------------- phase B
+// cos[n][i] = F.cosine_similarity(d[n][t_q], d[n][i]) with d sampled from the full T-frame set
+// (model_inference.py:110-126): x / max(|x|, eps) . y / max(|y|, eps), eps = 1e-8.
+__global__ void traj_cos_kernel(const float* __restrict__ tpc, int T, int C, int P, int h, int w, PointAffine pa,
+                                const float* __restrict__ traj, const float* __restrict__ qp,
+                                float* __restrict__ cos_out) {
+  extern __shared__ __align__(16) float sm[];  // dq[C], di[C]
+  __shared__ float nrm[2];
+  __shared__ float red[SAMPLE_THREADS / 32];
+  const int n = blockIdx.y, i = blockIdx.x;
+  int tq = (int)qp[n * 3 + 2];
+  tq = min(max(tq, 0), T - 1);
+  for (int which = 0; which < 2; ++which) {
+    const float* pt = traj + ((size_t)n * T + (which == 0 ? tq : i)) * 3;
+    float x = __fadd_rn(__fmul_rn(pa.aw, pt[0]), pa.bw);
+    float y = __fadd_rn(__fmul_rn(pa.ah, pt[1]), pa.bh);
+    TriCorners c = tri_setup(x, y, pt[2], T, h, w);  // frames_set = identity over the T frames
+    sample_point(tpc, C, P, c, c.z0, c.z1, sm + which * C, nrm + which);
+    __syncthreads();
+  }
+  const float nq = fmaxf(nrm[0], 1e-8f), ni = fmaxf(nrm[1], 1e-8f);
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < C; c += SAMPLE_THREADS) acc = fmaf(__fdiv_rn(sm[c], nq), __fdiv_rn(sm[C + c], ni), acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < SAMPLE_THREADS / 32; ++k) s += red[k];
+    cos_out[(size_t)n * T + i] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------- phase C helpers
+// per anchor frame a: ordered list of the query points n with cos[n][a] >= th, and its length
+__global__ void anchor_lists_kernel(const float* __restrict__ cos_sims, int N, int T, float th,
+                                    int* __restrict__ cnt, int* __restrict__ qlist) {
+  const int a = blockIdx.x;
+  __shared__ int base;
+  __shared__ int wcount[32];
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int n0 = 0; n0 < N; n0 += blockDim.x) {
+    int n = n0 + threadIdx.x;
+    bool v = n < N && cos_sims[(size_t)n * T + a] >= th;
+    unsigned bal = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) wcount[warp] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int k = 0; k < warp; ++k) off += wcount[k];
+    if (v) qlist[(size_t)a * N + off + __popc(bal & ((1u << lane) - 1))] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int k = 0; k < nw; ++k) tot += wcount[k];
+      base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cnt[a] = base;
+}
+
+// descriptors of one chunk of anchor work items.  Group k of the chunk covers items
+// [grp_item0[k], grp_item0[k] + grp_m[k]) of anchor frame grp_frame[k]; item u = (query slot u / T, frame u % T).
+// Source point traj[n][i] lives in frame i; frames_set = [a, i0..e-1] (model_inference.py:138-143).
+__global__ void sample_anchor_kernel(const float* __restrict__ tpc, int T, int C, int P, int h, int w, PointAffine pa,
+                                     const float* __restrict__ traj, const int* __restrict__ qlist, int N,
+                                     const int* __restrict__ grp_frame, const int* __restrict__ grp_map0,
+                                     const int* __restrict__ grp_item0, int n_groups, int frame_batch,
+                                     float* __restrict__ desc, float* __restrict__ dnorm, int* __restrict__ out_index) {
+  const int j = blockIdx.x;
+  int lo = 0, hi = n_groups - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (grp_map0[mid] <= j) lo = mid; else hi = mid - 1;
+  }
+  const int a = grp_frame[lo];
+  const int u = grp_item0[lo] + (j - grp_map0[lo]);
+  const int slot = u / T, i = u - slot * T;
+  const int n = qlist[(size_t)a * N + slot];
+  const int i0 = (i / frame_batch) * frame_batch, e = min(i0 + frame_batch, T);
+  const int Nset = e - i0 + 1;
+  const float* pt = traj + ((size_t)n * T + i) * 3;
+  float x = __fadd_rn(__fmul_rn(pa.aw, pt[0]), pa.bw);
+  float y = __fadd_rn(__fmul_rn(pa.ah, pt[1]), pa.bh);
+  TriCorners c = tri_setup(x, y, (float)(i - i0 + 1), Nset, h, w);
+  int f0 = c.z0 == 0 ? a : i0 + c.z0 - 1;
+  int f1 = c.z1 < 0 ? -1 : (c.z1 == 0 ? a : i0 + c.z1 - 1);
+  sample_point(tpc, C, P, c, f0, f1, desc + (size_t)j * C, dnorm + j);
+  if (threadIdx.x == 0) out_index[j] = (n * T + a) * T + i;
+}
+
+// ---------------------------------------------------------------------------------- phase D
+// model_inference.py:169-177.  One block per query point, one warp per column i.
+// D[a][i] = |anchors[n][a][i] - traj[n][a]| for a in A_n; med[i] = lower median over a
+// (torch.median: sorted position (M-1)/2); th = max_{i in A_n} med[i];
+// occ[i] = med[i] > th || cos[n][i] < cos_th.
+constexpr int OCC_THREADS = 256;
+__global__ void occlusion_kernel(const float* __restrict__ traj, const float* __restrict__ cos_sims,
+                                 const float* __restrict__ anchors, int T, float anchor_th, float cos_th,
+                                 uint8_t* __restrict__ occ) {
+  extern __shared__ float sm[];  // med[T] | alist[T] | ax[T] | ay[T] | col[nwarps][T]
+  float* med = sm;
+  int* alist = reinterpret_cast<int*>(sm + T);
+  float* ax = sm + 2 * T;
+  float* ay = sm + 3 * T;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = OCC_THREADS / 32;
+  float* col = sm + 4 * T + warp * T;
+  __shared__ int M;
+  __shared__ float th_s;
+  const int n = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int m = 0;
+    for (int a = 0; a < T; ++a)
+      if (cos_sims[(size_t)n * T + a] >= anchor_th) {
+        alist[m] = a;
+        ax[m] = traj[((size_t)n * T + a) * 3 + 0];
+        ay[m] = traj[((size_t)n * T + a) * 3 + 1];
+        ++m;
+      }
+    M = m;
+  }
+  __syncthreads();
+  const int m = M, want = (m - 1) / 2;
+  for (int i = warp; i < T; i += nw) {
+    for (int p = lane; p < m; p += 32) {
+      const float* g = anchors + (((size_t)n * T + alist[p]) * T + i) * 2;
+      float dx = __fsub_rn(g[0], ax[p]), dy = __fsub_rn(g[1], ay[p]);
+      col[p] = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    }
+    __syncwarp();
+    for (int p = lane; p < m; p += 32) {
+      const float dp = col[p];
+      int rank = 0;
+      for (int q = 0; q < m; ++q) {
+        float dq = col[q];
+        rank += (dq < dp) || (dq == dp && q < p);
+      }
+      if (rank == want) med[i] = dp;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float th = -INFINITY;
+    for (int p = 0; p < m; ++p) th = fmaxf(th, med[alist[p]]);
+    th_s = th;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T; i += blockDim.x)
+    occ[(size_t)n * T + i] = (m > 0 && (med[i] > th_s || cos_sims[(size_t)n * T + i] < cos_th)) ? 1 : 0;
+}
+
+struct GroupBuf {  // host mirror of the per-chunk group arrays: [frame | row0 | m | map0 | item0] x cap
+  std::vector<int> v;
+  int cap, n;
+  explicit GroupBuf(int c) : v((size_t)5 * c), cap(c), n(0) {}
+  void clear() { n = 0; }
+  void push(int frame, int row0, int m, int map0, int item0) {
+    v[n] = frame; v[cap + n] = row0; v[2 * cap + n] = m; v[3 * cap + n] = map0; v[4 * cap + n] = item0; ++n;
+  }
+};
+
+}  // namespace dtk
+
+using namespace dtk;
+
+extern "C" {
+
+size_t dinotrk_corr_track_workspace_bytes(int total_maps, int n_groups, const dinotrk_geom* g) {
+  if (!g) return 0;
+  return align_up((size_t)total_maps * dinotrk_map_stride(g) * sizeof(float), 256) + corr_plan_bytes(n_groups) + 1024;
+}
+
+int dinotrk_corr_track(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+                       const dinotrk_head_weights* hw, const float* desc, const float* desc_norm,
+                       const int* grp_frame, const int* grp_row0, const int* grp_m, const int* grp_map0,
+                       int n_groups, int total_maps, int max_group_m, const int* out_index, float* out,
+                       int out_stride, int out_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  DTK_CHECK_ARG(tpc && norms && g && hw && desc && desc_norm && grp_frame && grp_row0 && grp_m && grp_map0 && out,
+                "corr_track: null pointer");
+  DTK_CHECK_ARG(T > 0 && C > 0 && C % 4 == 0 && n_groups >= 0 && total_maps >= 0, "corr_track: bad sizes");
+  DTK_CHECK_ARG(workspace && workspace_bytes >= dinotrk_corr_track_workspace_bytes(total_maps, n_groups, g),
+                "corr_track: workspace too small");
+  if (total_maps == 0) return DINOTRK_OK;
+  Arena ar(workspace, workspace_bytes);
+  const int ms = dinotrk_map_stride(g);
+  float* maps = ar.take<float>((size_t)total_maps * ms);
+  int* plan = ar.take<int>(n_groups + 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_corr_maps(tpc, norms, C, g->h * g->w, desc, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
+                            n_groups, total_maps, max_group_m, maps, ms, plan, st);
+  if (rc) return rc;
+  return launch_head(maps, total_maps, ms, *g, *hw, out_index, out, out_stride, out_mode, nullptr, st);
+}
+
+static int infer_chunk_maps(int chunk_maps) { return chunk_maps > 0 ? chunk_maps : 4096; }
+
+size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N, int chunk_maps) {
+  if (!g) return 0;
+  const size_t ch = infer_chunk_maps(chunk_maps), ms = dinotrk_map_stride(g);
+  const int gcap = T + 2;
+  size_t b = 0;
+  b += align_up((size_t)N * C * 4, 256) + align_up((size_t)N * 4, 256);   // descA, normA
+  b += align_up(ch * ms * 4, 256);                                         // maps chunk
+  b += align_up(ch * C * 4, 256) + align_up(ch * 4, 256);                  // descC, normC
+  b += align_up(ch * 4, 256);                                              // out_index
+  b += align_up((size_t)5 * gcap * 4, 256) + align_up((size_t)(gcap + 1) * 4, 256);  // groups, plan
+  b += align_up((size_t)T * 4, 256) + align_up((size_t)T * N * 4, 256);    // cnt, qlist
+  return b + 4096;
+}
+
+int dinotrk_traj_cos_sims(const float* tpc, int T, int C, const dinotrk_geom* g, const float* traj,
+                          const float* query_points, int N, float* cos_sims, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  DTK_CHECK_ARG(tpc && g && traj && query_points && cos_sims, "traj_cos_sims: null pointer");
+  DTK_CHECK_ARG(T > 0 && C > 0 && C % 4 == 0 && N >= 0, "traj_cos_sims: bad sizes");
+  if (N == 0) return DINOTRK_OK;
+  size_t smem = (size_t)2 * C * sizeof(float);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    DTK_CUDA(cudaFuncSetAttribute(traj_cos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  traj_cos_kernel<<<dim3(T, N), SAMPLE_THREADS, smem, (cudaStream_t)stream>>>(
+      tpc, T, C, g->h * g->w, g->h, g->w, make_point_affine(*g), traj, query_points, cos_sims);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+int dinotrk_occlusion(const float* traj, const float* cos_sims, const float* anchors, int N, int T,
+                      float anchor_th, float cos_th, uint8_t* occ, void* stream) {
+  DTK_CHECK_ARG(traj && cos_sims && anchors && occ && N >= 0 && T > 0, "occlusion: bad args");
+  if (N == 0) return DINOTRK_OK;
+  size_t smem = (size_t)(4 + OCC_THREADS / 32) * T * sizeof(float);
+  DTK_CHECK_ARG(smem <= 200 * 1024, "occlusion: T=%d too large", T);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    DTK_CUDA(cudaFuncSetAttribute(occlusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  occlusion_kernel<<<N, OCC_THREADS, smem, (cudaStream_t)stream>>>(traj, cos_sims, anchors, T, anchor_th, cos_th, occ);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+                  const dinotrk_head_weights* hw, const float* query_points, int N, float anchor_th, float cos_th,
+                  int frame_batch, int start_phase, int stop_after, int chunk_maps, float* traj, float* cos_sims,
+                  float* anchors,
+                  uint8_t* occ, void* workspace, size_t workspace_bytes, void* stream) {
+  DTK_CHECK_ARG(tpc && norms && g && hw && query_points && traj, "infer: null pointer");
+  DTK_CHECK_ARG(T > 0 && C > 0 && C % 4 == 0 && N >= 0, "infer: bad sizes");
+  DTK_CHECK_ARG(start_phase >= 0 && start_phase <= stop_after && stop_after <= 3,
+                "infer: need 0 <= start_phase <= stop_after <= 3");
+  DTK_CHECK_ARG((stop_after < 1 || cos_sims) && (stop_after < 2 || anchors) && (stop_after < 3 || occ),
+                "infer: missing output buffer for the requested phases");
+  DTK_CHECK_ARG(workspace && workspace_bytes >= dinotrk_infer_workspace_bytes(T, C, g, N, chunk_maps),
+                "infer: workspace too small (%zu < %zu)", workspace_bytes,
+                dinotrk_infer_workspace_bytes(T, C, g, N, chunk_maps));
+  if (N == 0) return DINOTRK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = g->h * g->w, ms = dinotrk_map_stride(g);
+  const int ch = infer_chunk_maps(chunk_maps);
+  const int fb = frame_batch > 0 ? (frame_batch < T ? frame_batch : T) : T;
+  const int gcap = T + 2;
+  const PointAffine pa = make_point_affine(*g);
+
+  Arena ar(workspace, workspace_bytes);
+  float* descA = ar.take<float>((size_t)N * C);
+  float* normA = ar.take<float>(N);
+  float* maps = ar.take<float>((size_t)ch * ms);
+  float* descC = ar.take<float>((size_t)ch * C);
+  float* normC = ar.take<float>(ch);
+  int* out_index = ar.take<int>(ch);
+  int* d_grp = ar.take<int>((size_t)5 * gcap);
+  int* plan = ar.take<int>(gcap + 1);
+  int* d_cnt = ar.take<int>(T);
+  int* d_qlist = ar.take<int>((size_t)T * N);
+  DTK_CHECK_ARG(ar.ok(), "infer: workspace arena overflow");
+
+  GroupBuf gb(gcap);
+  auto upload_groups = [&]() -> int {
+    DTK_CUDA(cudaMemcpyAsync(d_grp, gb.v.data(), (size_t)5 * gcap * sizeof(int), cudaMemcpyHostToDevice, st));
+    return DINOTRK_OK;
+  };
+  const int *gf = d_grp, *gr = d_grp + gcap, *gm = d_grp + 2 * gcap, *gmap = d_grp + 3 * gcap, *gitem = d_grp + 4 * gcap;
+
+  // ---- phase A: trajectories -------------------------------------------------------------------
+  if (start_phase <= 0) {
+  sample_query_kernel<<<N, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, query_points, descA, normA);
+  DTK_LAUNCHED();
+  {
+    int t = 0, row = 0;  // next work item: (frame t, query row)
+    while (t < T) {
+      gb.clear();
+      int used = 0, maxm = 0;
+      while (t < T && used < ch && gb.n < gcap) {
+        int m = N - row;
+        if (m > ch - used) m = ch - used;
+        gb.push(t, row, m, used, 0);
+        used += m; row += m;
+        if (m > maxm) maxm = m;
+        if (row == N) { row = 0; ++t; }
+      }
+      int rc = upload_groups();
+      if (rc) return rc;
+      index_traj_kernel<<<cdiv(used, 256), 256, 0, st>>>(gf, gr, gmap, gb.n, used, T, out_index, traj);
+      DTK_LAUNCHED();
+      rc = launch_corr_maps(tpc, norms, C, P, descA, normA, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, st);
+      if (rc) return rc;
+      rc = launch_head(maps, used, ms, *g, *hw, out_index, traj, 3, 0, nullptr, st);
+      if (rc) return rc;
+    }
+  }
+  }
+  if (stop_after < 1) return DINOTRK_OK;
+
+  // ---- phase B: cosine similarities along the trajectories --------------------------------------
+  if (start_phase <= 1) {
+    int rc = dinotrk_traj_cos_sims(tpc, T, C, g, traj, query_points, N, cos_sims, nullptr, 0, stream);
+    if (rc) return rc;
+  }
+  if (stop_after < 2) return DINOTRK_OK;
+
+  // ---- phase C: anchor re-tracking ---------------------------------------------------------------
+  if (start_phase <= 2) {
+  anchor_lists_kernel<<<T, 256, 0, st>>>(cos_sims, N, T, anchor_th, d_cnt, d_qlist);
+  DTK_LAUNCHED();
+  std::vector<int> cnt(T);
+  DTK_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DTK_CUDA(cudaStreamSynchronize(st));  // the one host sync: sizes of the anchor work lists
+  {
+    int a = 0;
+    long long item = 0;  // next work item: anchor frame a, item index within a (slot * T + i)
+    while (a < T) {
+      gb.clear();
+      int used = 0, maxm = 0;
+      while (a < T && used < ch && gb.n < gcap) {
+        long long tot = (long long)cnt[a] * T;
+        long long m = tot - item;
+        if (m > ch - used) m = ch - used;
+        if (m > 0) {
+          gb.push(a, used, (int)m, used, (int)item);
+          used += (int)m; item += m;
+          if ((int)m > maxm) maxm = (int)m;
+        }
+        if (item >= tot) { item = 0; ++a; }
+      }
+      if (used == 0) break;
+      int rc = upload_groups();
+      if (rc) return rc;
+      sample_anchor_kernel<<<used, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, traj, d_qlist, N, gf, gmap,
+                                                           gitem, gb.n, fb, descC, normC, out_index);
+      DTK_LAUNCHED();
+      rc = launch_corr_maps(tpc, norms, C, P, descC, normC, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, st);
+      if (rc) return rc;
+      rc = launch_head(maps, used, ms, *g, *hw, out_index, anchors, 2, 0, nullptr, st);
+      if (rc) return rc;
+    }
+  }
+  }
+  if (stop_after < 3) return DINOTRK_OK;
+
+  // ---- phase D: occlusion --------------------------------------------------------------------------
+  return dinotrk_occlusion(traj, cos_sims, anchors, N, T, anchor_th, cos_th, occ, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+/*
+ * dinotrk.h -- C ABI of libdinotrk.so, the B200 (sm_100a) implementation of the
+ * DINO-Tracker inference hot path.
+ *
+ * The reference (AssafSinger94/dino-tracker) has no FFI layer: its boundary is the Python
+ * class surface of models/tracker.py + models/model_inference.py.  The host
+ * mirror of that surface lives in dino_tracker_b200/ and reaches the kernels only through
+ * the entry points declared here (ctypes).  Every entry point
+ *   - is extern "C", takes raw device pointers, sizes and a cudaStream_t (as void*);
+ *   - never allocates device memory: big scratch is a caller-provided workspace whose size
+ *     comes from the matching *_workspace_bytes query;
+ *   - only enqueues work on `stream` unless stated otherwise ("syncs" below);
+ *   - returns 0 on success or a negative code; dinotrk_last_error() gives the message
+ *     (thread-local).
+ *
+ * Layouts.  "tpc" = token-major feature video  [T][P][C] fp32, P = h*w tokens row-major
+ * (r*w + c), C contiguous: the ViT's natural output order, K-major for every contraction
+ * and coalesced for bilinear descriptor sampling.  "chw" = the reference's T x C x h x w
+ * (models/tracker.py:64-71).  Pixel coordinates are in the model frame (x in [0,W-1]).
+ */
+#ifndef DINOTRK_H_
+#define DINOTRK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DINOTRK_VERSION 100
+
+#define DINOTRK_OK 0
+#define DINOTRK_EINVAL (-22)
+#define DINOTRK_ECUDA (-5)
+#define DINOTRK_ENOMEM (-12)
+
+/* Video / token-grid geometry.  h = 1 + (H - patch) / stride, w likewise
+ * (models/extractor.py:171-177); radius = TrackerHead.argmax_radius (tracker_head.py:47). */
+typedef struct dinotrk_geom {
+  int H, W, patch, stride, radius;
+  int h, w;
+} dinotrk_geom;
+
+/* Refiner weights AFTER the spatial-sum normalisation of models/networks/conv_norm.py:34-46
+ * (done once per weight load on the host): w1[16][9], b1[16], w2[16][9] (out=1, in=16), b2. */
+typedef struct dinotrk_head_weights {
+  float w1[16][9];
+  float b1[16];
+  float w2[16][9];
+  float b2;
+} dinotrk_head_weights;
+
+int dinotrk_version(void);
+const char* dinotrk_last_error(void);
+/* Fills *g from (H, W, patch, stride, radius); returns DINOTRK_EINVAL on bad sizes. */
+int dinotrk_make_geom(int H, int W, int patch, int stride, int radius, dinotrk_geom* g);
+
+/* ---- feature cache (models/tracker.py:64-71,131-135) --------------------------------- */
+/* chw [T][C][P] -> tpc [T][P][C] and per-token L2 norms [T][P]
+ * (frame_embeddings_set.norm(dim=1), models/tracker.py:162). */
+int dinotrk_pack_features(const float* chw, float* tpc, float* norms, int T, int C, int P,
+                          void* stream);
+int dinotrk_unpack_features(const float* tpc, float* chw, int T, int C, int P, void* stream);
+int dinotrk_token_norms(const float* tpc, float* norms, int T, int C, int P, void* stream);
+
+/* ---- descriptor sampling (models/tracker.py:77-111, utils.py:75-101) ------------------- */
+/* points [B][3] = (x_px, y_px, set_index) ; frames_set [N] int32 = frame of each set slot.
+ * Reproduces normalize_points_for_sampling + the 5-D grid_sample (border, align_corners),
+ * including the fp32 temporal-weight leak.  points_normalized != 0: x,y already in [-1,1]
+ * (Tracker.sample_embeddings semantics).  out desc [B][C], desc_norm [B] (may be NULL). */
+int dinotrk_sample_descriptors(const float* tpc, int T, int C, const dinotrk_geom* g,
+                               const float* points, int B, const int* frames_set, int N,
+                               int points_normalized, float* desc, float* desc_norm,
+                               void* stream);
+
+/* ---- correlation + head (models/tracker.py:158-180, tracker_head.py:107-121) ----------- */
+/* Generic grouped form.  Group k (k < n_groups) correlates descriptor rows
+ * [row0[k], row0[k] + m[k]) of `desc` with every token of frame frame[k]; its maps are
+ * numbered map0[k] + r.  For map j the (x, y) result is written to out[out_index[j] * out_stride
+ * + {0,1}] (out_index == NULL: j).  out_mode 0: pixels (after RangeNormalizer.unnormalize,
+ * models/model_inference.py:52), 1: normalised [-1,1] (Tracker.forward).
+ * group arrays are device int32[n_groups]; total_maps = sum m.  Syncs: no. */
+size_t dinotrk_corr_track_workspace_bytes(int total_maps, int n_groups, const dinotrk_geom* g);
+int dinotrk_corr_track(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+                       const dinotrk_head_weights* hw, const float* desc, const float* desc_norm,
+                       const int* grp_frame, const int* grp_row0, const int* grp_m,
+                       const int* grp_map0, int n_groups, int total_maps, int max_group_m,
+                       const int* out_index, float* out, int out_stride, int out_mode,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Correlation maps only (ReLU'd cosine maps, [total_maps][map_stride] fp32,
+ * map_stride = dinotrk_map_stride(g)) -- the volume the fused path never keeps. */
+int dinotrk_map_stride(const dinotrk_geom* g);
+int dinotrk_corr_maps(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+                      const float* desc, const float* desc_norm, const int* grp_frame,
+                      const int* grp_row0, const int* grp_m, const int* grp_map0, int n_groups,
+                      int total_maps, int max_group_m, float* maps, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* Head only: maps -> (x, y) (tracker_head.py:107-121).  aux (may be NULL) receives per map
+ * {argmax index, fallback flag} as int32[2]. */
+int dinotrk_head(const float* maps, int n_maps, const dinotrk_geom* g,
+                 const dinotrk_head_weights* hw, const int* out_index, float* out,
+                 int out_stride, int out_mode, int* aux, void* stream);
+
+/* ---- inference driver (models/model_inference.py:97-216) ------------------------------- */
+/* query_points [N][3] (x, y, t) px; frame_batch = the reference's --batch-size (0 = whole
+ * video).  Outputs: traj [N][T][3] (x, y, t); cos_sims [N][T]; anchors [N][T(a)][T(i)][2] valid
+ * where cos_sims[n][a] >= anchor_th; occ [N][T] uint8.  Any of the last three may be NULL only
+ * together with stop_after < 3 / 2 / 1.  Phases 0 = trajectories (compute_trajectories),
+ * 1 = cos-sims, 2 = anchors, 3 = occlusion; phases start_phase..stop_after run (0..3 = infer), and
+ * the outputs of earlier phases are then inputs.  SYNCS the stream once when phase 2 runs (reads
+ * the per-frame anchor counts back to size the anchor work lists). */
+size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N, int chunk_maps);
+int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+                  const dinotrk_head_weights* hw, const float* query_points, int N,
+                  float anchor_th, float cos_th, int frame_batch, int start_phase, int stop_after,
+                  int chunk_maps,
+                  float* traj, float* cos_sims, float* anchors, uint8_t* occ,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* Piecewise entry points behind ModelInference.compute_* (same arithmetic as dinotrk_infer). */
+int dinotrk_traj_cos_sims(const float* tpc, int T, int C, const dinotrk_geom* g,
+                          const float* traj, const float* query_points, int N, float* cos_sims,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int dinotrk_occlusion(const float* traj, const float* cos_sims, const float* anchors, int N, int T,
+                      float anchor_th, float cos_th, uint8_t* occ, void* stream);
+
+/* ---- Delta-DINO refinement (models/tracker.py:113-135, delta_dino.py:8-61, models/utils.py:7-45) */
+/* frames [B][3][H][W] raw RGB in [0,1]; channels[5] = {3, c1, c2, c3, C} (c* multiples of 4);
+ * wgt[l] = conv l weights with BatchNorm(eval) folded in, K-major [C_out][5][5][C_in_pad]
+ * (C_in_pad = 4 for l = 0, else C_in); bias[l] [C_out] likewise folded.  dino_tpc [B][h*w][C];
+ * ixs[w] / iys[h] = un-normalised clipped CNN-grid sampling coordinates of the token columns / rows
+ * (models/utils.py:31-43).  Writes refined_tpc [B][h*w][C] = dino + aligned residual and
+ * (optional) per-token norms [B][h*w]. */
+size_t dinotrk_delta_workspace_bytes(int B, int H, int W, const int* channels);
+int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* channels,
+                         const float* const* wgt, const float* const* bias, const float* dino_tpc,
+                         const float* ixs, const float* iys, int h, int w, float* refined_tpc,
+                         float* norms, void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+unsigned long long dinotrk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DINOTRK_H_ */

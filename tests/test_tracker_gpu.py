@@ -1,0 +1,199 @@
+"""GPU parity suite: CUDA kernels (through the C ABI / the reference-facing classes) against the oracle
+and the committed reference vectors.  Tolerances: |dxy| <= 1e-3 px (BASELINE.json north_star),
+occlusion masks bit-exact."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inference as oi
+from oracle import synth
+from oracle import tracker as ot
+from oracle.tracker import Geometry
+
+from golden_util import TRACK_CASES, load_track_case
+
+pytestmark = pytest.mark.gpu
+XY_TOL = 1e-3
+DEV = "cuda:0"
+
+
+def make_model(geo, feats, head, T=None):
+    from dino_tracker_b200 import Tracker
+    T = feats.shape[0]
+    video = torch.zeros(T, 3, geo.H, geo.W, device=DEV)
+    m = Tracker(video=video, dino_embed_video=feats, device=DEV, delta_channels=[3, 4, 4, 4, feats.shape[1]])
+    m.tracker_head.load_state_dict(head)
+    return m
+
+
+def test_pack_unpack_and_norms():
+    from dino_tracker_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    chw = torch.randn(3, 40, 13 * 17, device=DEV)
+    tpc = torch.empty(3, 13 * 17, 40, device=DEV)
+    norms = torch.empty(3, 13 * 17, device=DEV)
+    _lib.check(lib.dinotrk_pack_features(_lib.ptr(chw), _lib.ptr(tpc), _lib.ptr(norms), 3, 40, 221, _lib.stream_ptr()))
+    assert torch.equal(tpc, chw.permute(0, 2, 1).contiguous())
+    assert torch.allclose(norms, chw.norm(dim=1), rtol=2e-7, atol=0)
+    back = torch.empty_like(chw)
+    _lib.check(lib.dinotrk_unpack_features(_lib.ptr(tpc), _lib.ptr(back), 3, 40, 221, _lib.stream_ptr()))
+    assert torch.equal(back, chw)
+
+
+@pytest.mark.parametrize("geo", [Geometry(H=98, W=126), Geometry(H=476, W=854)])
+def test_sample_descriptors_matches_oracle(geo):
+    torch.manual_seed(1)
+    T, C = 5, 64
+    feats = torch.randn(T, C, geo.h, geo.w)
+    m = make_model(geo, feats, synth.head_weights("well"))
+    B = 300
+    pts = torch.rand(B, 3) * torch.tensor([geo.W + 40.0, geo.H + 40.0, 1.0]) - torch.tensor([20.0, 20.0, 0.0])
+    frames_set = torch.tensor([3, 0, 1, 2, 4, 2], dtype=torch.int32)
+    pts[:, 2] = torch.randint(0, frames_set.shape[0], (B,)).float()
+    desc, dn = m._sample(m._dino_tpc, pts, frames_set, normalized=False)
+    pn = ot.normalize_points_for_sampling(pts, geo)
+    ref = ot.sample_descriptors(feats[frames_set.long()], pn)
+    assert (desc.cpu() - ref).abs().max().item() <= 2e-6
+    assert torch.allclose(dn.cpu(), ref.norm(dim=1), rtol=1e-6)
+    # Tracker.sample_embeddings semantics (already-normalised x, y; full frame set)
+    pn2 = pn.clone(); pn2[:, 2] = torch.randint(0, T, (B,)).float()
+    out = m.sample_embeddings(feats.to(DEV), pn2.to(DEV))
+    assert (out.cpu() - ot.sample_descriptors(feats, pn2)).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("m_per_frame", [3, 8, 9, 150])
+def test_corr_maps_match_oracle(m_per_frame):
+    """stream kernel (<= 8 descriptors per frame) and grouped GEMM (> 8), incl. ragged tiles."""
+    from dino_tracker_b200 import _lib
+    lib = _lib.load()
+    geo = Geometry(H=98, W=126)
+    torch.manual_seed(2)
+    T, C = 3, 48
+    feats = torch.randn(T, C, geo.h, geo.w)
+    model = make_model(geo, feats, synth.head_weights("well"))
+    frames = [2, 0, 1]
+    ms = [m_per_frame, max(1, m_per_frame - 2), m_per_frame + 1]
+    total = sum(ms)
+    desc = torch.randn(total, C)
+    desc[0] = 0  # zero descriptor: clamp(min=1e-8) path
+    row0 = np.cumsum([0] + ms[:-1]).astype(np.int32)
+    grp = torch.tensor(np.stack([frames, row0, ms, row0]).astype(np.int32), device=DEV)
+    dn = desc.norm(dim=1).to(DEV)
+    stride = lib.dinotrk_map_stride(ctypes.byref(model._geom))
+    maps = torch.zeros(total, stride, device=DEV)
+    ws = torch.empty(4096, device=DEV, dtype=torch.uint8)
+    d_dev = desc.to(DEV)
+    _lib.check(lib.dinotrk_corr_maps(_lib.ptr(model._dino_tpc), _lib.ptr(model._refined_norms_or_dino()), T, C,
+                                     ctypes.byref(model._geom), _lib.ptr(d_dev), _lib.ptr(dn), _lib.ptr(grp[0]),
+                                     _lib.ptr(grp[1]), _lib.ptr(grp[2]), _lib.ptr(grp[3]), 3, total, max(ms),
+                                     _lib.ptr(maps), _lib.ptr(ws), 4096, _lib.stream_ptr()))
+    tgt = torch.tensor(sum([[f] * m for f, m in zip(frames, ms)], []))
+    ref = torch.relu(ot.corr_maps(desc, feats, tgt))[:, 0].reshape(total, -1)
+    got = maps[:, : geo.P].cpu()
+    assert (got - ref).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("kind", ["well", "sharp", "mixed", "default"])
+@pytest.mark.parametrize("geo", [Geometry(H=98, W=126), Geometry(H=476, W=854)])
+def test_head_matches_oracle(kind, geo):
+    from dino_tracker_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(3)
+    n = 24
+    maps = np.maximum(rs.standard_normal((n, geo.h, geo.w)).astype(np.float32) * 0.2, 0)
+    for k in range(n):  # plant peaks (some at the borders / corners)
+        r, c = rs.randint(0, geo.h), rs.randint(0, geo.w)
+        if k % 6 == 0:
+            r, c = (0, 0) if k % 12 == 0 else (geo.h - 1, geo.w - 1)
+        maps[k, r, c] = 0.9 + 0.01 * k
+    maps[1] = 0.0  # all-zero map: arg-max index 0
+    maps[2, 3, 4] = maps[2, 5, 6] = 0.95  # exact tie: first index wins
+    head = synth.head_weights(kind, seed=7)
+    model = make_model(geo, torch.zeros(2, 8, geo.h, geo.w), head)
+    stride = lib.dinotrk_map_stride(ctypes.byref(model._geom))
+    buf = torch.zeros(n, stride, device=DEV)
+    buf[:, : geo.P] = torch.from_numpy(maps.reshape(n, -1)).to(DEV)
+    out = torch.empty(n, 2, device=DEV)
+    aux = torch.empty(n, 2, device=DEV, dtype=torch.int32)
+    _lib.check(lib.dinotrk_head(_lib.ptr(buf), n, ctypes.byref(model._geom), ctypes.byref(model.head_weights()), None,
+                                _lib.ptr(out), 2, 1, _lib.ptr(aux), _lib.stream_ptr()))
+    ref, raux = ot.head_forward(torch.from_numpy(maps)[:, None], head, geo, return_aux=True)
+    assert torch.equal(aux[:, 0].cpu().long(), raux["argmax"])
+    assert torch.equal(aux[:, 1].cpu().bool(), raux["fallback"])
+    if kind == "default" and geo.H == 476:
+        assert raux["fallback"].any()
+    scale = torch.tensor([geo.W - 1, geo.H - 1]) / 2  # normalised units -> px
+    assert ((out.cpu() - ref).abs() * scale).max().item() <= XY_TOL
+
+
+@pytest.mark.parametrize("name", ["track_small_well", "track_small_fallback", "track_full_fallback"])
+def test_forward_matches_reference_vectors(name):
+    from dino_tracker_b200 import generate_trajectory_input
+    cfg, geo, feats, head, g = load_track_case(name)
+    model = make_model(geo, feats, head)
+    model.cache_refined_embeddings()
+    q = torch.from_numpy(g["query_points"]).to(DEV)
+    inp = generate_trajectory_input(q[0], model.video)
+    out = model(inp)
+    scale = np.array([geo.W - 1, geo.H - 1]) / 2
+    assert (np.abs(out.cpu().numpy() - g["forward0"]) * scale).max() <= XY_TOL
+    # anchor-style input: sources in their own frames, one target
+    T = cfg["T"]
+    preds = torch.from_numpy(g["trajectories"][1]).to(DEV)
+    fs = torch.cat([torch.tensor([2]), torch.arange(T)]).int().to(DEV)
+    inp2 = (preds, torch.arange(1, T + 1, device=DEV), torch.zeros(T, dtype=torch.long, device=DEV), fs)
+    out2 = model(inp2).cpu()
+    ref2 = ot.tracker_forward(feats, (preds.cpu(), torch.arange(1, T + 1), torch.zeros(T, dtype=torch.long), fs.cpu()),
+                              head, geo)
+    assert ((out2 - ref2).abs() * torch.from_numpy(scale).float()).max().item() <= XY_TOL
+
+
+@pytest.mark.parametrize("name", sorted(TRACK_CASES))
+def test_infer_matches_reference_vectors(name):
+    from dino_tracker_b200 import ModelInference
+    cfg, geo, feats, head, g = load_track_case(name)
+    model = make_model(geo, feats, head)
+    mi = ModelInference(model, model.range_normalizer, 0.7, 0.6)
+    assert torch.equal(model.refined_features.cpu(), feats)  # default delta-DINO: exactly zero residual
+    q = torch.from_numpy(g["query_points"]).to(DEV)
+    r = mi.infer_all(q, cfg["batch"])
+    traj, occ = mi.infer(q, cfg["batch"])
+    assert np.abs(r["traj"].cpu().numpy() - g["trajectories"]).max() <= XY_TOL
+    assert np.abs(r["cos_sims"].cpu().numpy() - g["cos_sims"]).max() <= 2e-5
+    assert np.array_equal(occ.cpu().numpy(), g["occlusion"])
+    assert np.array_equal(traj.cpu().numpy(), r["traj"][..., :2].cpu().numpy())
+    vis = g["cos_sims"] >= 0.7
+    for n in range(q.shape[0]):
+        m = int(g["n_anchors"][n])
+        got = r["anchors"][n].cpu().numpy()[vis[n]]
+        assert got.shape[0] == m
+        assert np.abs(got - g["anchors"][n, :m]).max() <= XY_TOL
+    # piecewise API
+    t2 = mi.compute_trajectories(q, cfg["batch"])
+    c2 = mi.compute_trajectory_cos_sims(t2, q)
+    a2 = mi.compute_anchor_trajectories(t2, c2, cfg["batch"])
+    o2 = mi.compute_occlusion(t2, c2, a2)
+    assert torch.equal(t2, r["traj"]) and torch.equal(c2, r["cos_sims"])
+    assert np.array_equal(o2.cpu().numpy(), g["occlusion"])
+    assert all(a2[n].shape == (int(g["n_anchors"][n]), cfg["T"], 2) for n in range(q.shape[0]))
+
+
+def test_infer_medium_against_oracle():
+    """Full token geometry, wider batch (GEMM path, several chunks) against the oracle run here."""
+    from dino_tracker_b200 import ModelInference
+    geo = Geometry()
+    T, C = 6, 128
+    feats, _ = synth.shifted_field_features(T, C, geo.h, geo.w, seed=40, noise=0.2, max_shift=2)
+    head = synth.head_weights("sharp", seed=40)
+    q = synth.lattice_query_points(5, 4, geo.H, geo.W, t_q=[i % T for i in range(20)], margin=30.0, jitter_seed=40)
+    model = make_model(geo, feats, head)
+    mi = ModelInference(model, model.range_normalizer, 0.7, 0.6)
+    r = mi.infer_all(q.to(DEV))
+    t_ref, o_ref, aux = oi.infer(feats, q, head, geo, 0.7, 0.6, return_all=True)
+    assert (r["traj"].cpu() - aux["trajs"]).abs().max().item() <= XY_TOL
+    assert torch.equal(r["occ"].bool().cpu(), o_ref)
+    assert (r["cos_sims"].cpu() - aux["cos_sims"]).abs().max().item() <= 2e-5
