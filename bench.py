@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- query-points/sec of the DINO-Tracker inference hot path on B200 (BASELINE.json metric).
+
+One "step" = one ``ModelInference.infer`` over one synthetic 854x476, T=50 video with 256 query points
+(BASELINE.json configs[1]): trajectories, cos-sims, anchor re-tracking, occlusion.  1 query-point = one
+row of ``infer`` output (T-frame trajectory + T-frame occlusion mask), SURVEY.md 8d.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+* ``value``  : whole-job query-points/s, inputs resident in HBM, device-timed (CUDA events), max over ranks.
+* ``e2e``    : same metric through the public API with HOST buffers: pinned query points H2D, result D2H
+               inside the timed region.
+* ``roofline``: dominant kernel of the step (per-kernel CUDA-event times recorded inside the timed region).
+* ``cpu_baseline`` / ``--impl reference``: the oracle's faithful restatement of the reference's PyTorch
+  path (same einsum / gathers per model() call) on the host cores, on a bounded sample of the workload.
+
+N > 1 (torchrun, one rank per GPU): video-parallel -- every rank tracks its own video of the same shape
+(BASELINE configs[2] style), no data-path collective; weak scaling.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 476, 854
+GEO_H, GEO_W = 67, 121
+P = GEO_H * GEO_W
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--T", type=int, default=50)
+    ap.add_argument("--C", type=int, default=1024, help="feature dim: 1024 = ViT-L/14@15 (shipped config), 768 = ViT-B/14")
+    ap.add_argument("--nq", type=int, default=256)
+    ap.add_argument("--noise", type=float, default=0.25)
+    ap.add_argument("--chunk-maps", type=int, default=4096)
+    ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the cpu_baseline leg")
+    ap.add_argument("--stream-probe", type=int, default=1, help="0: skip the dedicated corr_stream HBM probe")
+    return ap.parse_args()
+
+
+def synth_video_features(T, C, device, seed, noise):
+    """Shifted smooth descriptor field + per-frame noise (same construction as oracle/synth.py, drawn with
+    torch's generator on the target device so that 1.7 GB of features need no host pass)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    pad = 8
+    base = torch.randn(C, GEO_H + 2 * pad, GEO_W + 2 * pad, device=device, generator=g)
+    sm = base.clone()
+    sm[:, 1:-1, 1:-1] = base[:, 1:-1, 1:-1] * 0.5 + 0.125 * (base[:, :-2, 1:-1] + base[:, 2:, 1:-1] +
+                                                             base[:, 1:-1, :-2] + base[:, 1:-1, 2:])
+    cg = torch.Generator().manual_seed(seed)
+    shifts = torch.zeros(T, 2, dtype=torch.long)
+    for t in range(1, T):
+        shifts[t] = (shifts[t - 1] + torch.randint(-1, 2, (2,), generator=cg)).clamp(-3, 3)
+    feats = torch.empty(T, C, GEO_H, GEO_W, device=device)
+    for t in range(T):
+        dy, dx = int(shifts[t, 0]), int(shifts[t, 1])
+        feats[t] = sm[:, pad + dy: pad + dy + GEO_H, pad + dx: pad + dx + GEO_W]
+        feats[t] += noise * torch.randn(C, GEO_H, GEO_W, device=device, generator=g)
+    return feats
+
+
+def query_lattice(nq, seed):
+    side = int(round(nq ** 0.5))
+    assert side * side == nq, "--nq must be a square number"
+    from bench_inputs import lattice  # not the oracle: the product arm never imports it
+    return lattice(side, side, H, W, 0, 30.0, seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if not (t0 <= ts <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "which": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "which": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+_CPU_FEATS = {}
+
+
+def cpu_reference_sample(T, C, nq, noise, seed=0, max_anchor_calls=6):
+    """Times the oracle's FAITHFUL restatement of the reference path on the host cores, on a bounded sample:
+    one query point -- its trajectory call (1 model() call over T+1 frames), the cos-sim pass, up to
+    ``max_anchor_calls`` anchor model() calls (extrapolated to this query point's anchor count) and the
+    occlusion step.  Returns (query-points/s, cores, description)."""
+    from oracle import inference as oi
+    from oracle.tracker import Geometry
+    from bench_inputs import sharp_head
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    geo = Geometry()
+    key = (T, C, seed, noise)
+    if key not in _CPU_FEATS:
+        _CPU_FEATS[key] = synth_video_features(T, C, "cpu", seed, noise)
+    feats = _CPU_FEATS[key]
+    head = sharp_head(0)
+    q = query_lattice(nq, seed)[nq // 2 + 3: nq // 2 + 4].clone()
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        traj = oi.compute_trajectories(feats, q, head, geo, None, faithful=True)
+        t_a = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        cos = oi.compute_trajectory_cos_sims(feats, traj, q, geo)
+        t_b = time.perf_counter() - t0
+        anchors = torch.arange(T)[cos[0] >= 0.7]
+        m = int(anchors.numel())
+        k = min(m, max_anchor_calls)
+        t0 = time.perf_counter()
+        part = oi.anchor_predictions(feats, traj[0], anchors[:k], head, geo, None, faithful=True)
+        t_c = (time.perf_counter() - t0) * (m / max(k, 1))
+        t0 = time.perf_counter()
+        green = part.repeat((m + k - 1) // max(k, 1), 1, 1)[:m] if k else part
+        oi.occlusion_for_query(green, traj[0, :, :2], cos[0], 0.7, 0.6)
+        t_d = time.perf_counter() - t0
+    total = t_a + t_b + t_c + t_d
+    desc = (f"1 query point of the T={T}, C={C} workload: trajectory model() call {t_a:.2f}s + cos-sims {t_b:.2f}s + "
+            f"{k} of {m} anchor model() calls (extrapolated x{m / max(k, 1):.1f}) {t_c:.2f}s + occlusion {t_d:.3f}s")
+    return 1.0 / total, cores, desc, total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, descs = [], None
+    for i in range(args.warmup + args.steps):
+        v, cores, desc, total = cpu_reference_sample(args.T, args.C, args.nq, args.noise, seed=0,
+                                                     max_anchor_calls=3)
+        if i >= args.warmup:
+            vals.append(v)
+        descs = desc
+    value = statistics.mean(vals) if vals else 0.0
+    line = {"impl": "reference", "metric": "query-points/sec (854x476, T=%d)" % args.T, "value": value,
+            "unit": "query-points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / value if value else None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "T": args.T, "C": args.C, "query_points": args.nq},
+            "cpu_baseline": {"value": value, "unit": "query-points/s", "cores": cores, "kind": "port", "sample": descs},
+            "e2e": {"value": value, "unit": "query-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return (f"TAP-Vid-DAVIS-shape single video 854x476, T={args.T}, {args.nq} query points (16x16 lattice, t_q=0), "
+            f"C={args.C} ({'ViT-L/14@15' if args.C == 1024 else 'ViT-B/14' if args.C == 768 else 'custom'} features), "
+            f"shifted-field synthetic features (noise {args.noise}), refined features cached in HBM")
+
+
+# ------------------------------------------------------------------------------------------ product arm
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if dist is not None:
+        dist.barrier()
+    from dino_tracker_b200 import ModelInference, Tracker, _lib
+    lib = _lib.load()
+
+    T, C, nq = args.T, args.C, args.nq
+    feats = synth_video_features(T, C, dev, 1234 + rank, args.noise)
+    video = torch.zeros(T, 3, H, W, device=dev)  # frames only feed delta-DINO (default init: zero residual)
+    model = Tracker(video=video, dino_embed_video=feats, device=dev, delta_channels=[3, 4, 4, 4, C])
+    del feats
+    from bench_inputs import sharp_head
+    model.tracker_head.load_state_dict(sharp_head(0))
+    mi = ModelInference(model, model.range_normalizer, 0.7, 0.6)
+    q_host = query_lattice(nq, 0).pin_memory()
+    q_dev = q_host.to(dev)
+
+    def step_resident():
+        return mi.infer(q_dev)
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+
+    # workload facts (anchors per query) from one un-timed call
+    r = mi.infer_all(q_dev)
+    n_anch = (r["cos_sims"] >= 0.7).sum(dim=1).float()
+    maps_per_step = int(nq * T + n_anch.sum().item() * T)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    _lib.profile_enable(True)
+    _lib.profile_collect()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    clocks = sampler.stop(t_wall0, t_wall1)
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        qd = q_host.to(dev, non_blocking=True)
+        traj, occ = mi.infer(qd)
+        traj_h, occ_h = traj.cpu(), occ.cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = q_host.numel() * 4
+    d2h = traj_h.numel() * 4 + occ_h.numel()
+
+    if dist is not None:
+        tt = torch.tensor([ms, e2e_s * 1000.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = tt[0].item(), tt[1].item()
+    else:
+        e2e_ms = e2e_s * 1000.0
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    value = world * nq * args.steps / (ms / 1000.0)
+    e2e_value = world * nq * args.steps / (e2e_ms / 1000.0)
+
+    # ---- roofline of the dominant kernel (per-class CUDA-event times from inside the timed region)
+    total_prof = sum(v[0] for v in prof.values()) or 1.0
+    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
+                   "share": v[0] / total_prof} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
+    roofline = kernel_roofline(dom, prof[dom], args, maps_per_step, peaks, clocks)
+    extra = {k: kernel_roofline(k, prof[k], args, maps_per_step, peaks, clocks)
+             for k in ("corr_gemm", "head", "corr_stream") if k in prof and k != dom}
+    if args.stream_probe:
+        extra["corr_stream_probe"] = stream_probe(model, mi, lib, _lib, args, peaks)
+
+    line = {"metric": "query-points/sec (854x476, T=%d)" % T, "value": value, "unit": "query-points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "T": T, "C": C, "query_points": nq,
+                       "anchors_per_query_mean": n_anch.mean().item(), "corr_maps_per_step": maps_per_step,
+                       "parallelism": f"video-parallel x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (1.66 GB feature video per step; no explicit flush)",
+                       "chunk_maps": args.chunk_maps},
+            "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": extra,
+            "kernels": kernels, "peaks": peaks}
+    if args.cpu_baseline and world == 1:
+        v, cores, desc, _ = cpu_reference_sample(T, C, nq, args.noise, seed=0, max_anchor_calls=3)
+        line["cpu_baseline"] = {"value": v, "unit": "query-points/s", "cores": cores, "kind": "port", "sample": desc}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks):
+    """Algorithmic work per launch / average launch time for one kernel class."""
+    ms_total, launches = stat
+    avg_s = ms_total / 1000.0 / max(launches, 1)
+    maps_per_launch = maps_per_step * args.steps / max(launches, 1)
+    if name in ("corr_gemm", "best_buddies", "vit_gemm", "delta_conv"):
+        flops = 2.0 * maps_per_launch * P * args.C  # <d, F[p]> for every token of the target frame
+        ach = flops / avg_s / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tf_sustained"], "traffic": None,
+                "note": "algorithmic FLOPs = 2*maps*P*C per launch; peak = sustained cuBLAS bf16 (%s); this kernel is "
+                        "exact-fp32 FFMA (CUDA cores), so its own ceiling is the fp32 pipe, see fp32_frac" % peaks["which"],
+                "fp32_frac": ach / fp32_peak_tflops(clocks)}
+    if name == "head":
+        flops = 4.67e6 * maps_per_launch  # 2 x (144 + 144) FMA per token, SURVEY.md 8a row a7
+        ach = flops / avg_s / 1e12
+        pk = fp32_peak_tflops(clocks)
+        return {"kernel": name, "bound": "fp32-cuda-core", "achieved": ach, "peak": pk, "unit": "TFLOP/s",
+                "frac": ach / pk, "traffic": None,
+                "note": "refiner convs are exact-fp32 CUDA-core work; peak = 148 SMs x 128 lanes x 2 x max SM clock"}
+    # HBM-bound streaming kernels: feature bytes read once per launch
+    nbytes = maps_per_launch * 0  # filled by the dedicated probe
+    return {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
+            "traffic": None, "note": "see roofline_other.corr_stream_probe"}
+
+
+def fp32_peak_tflops(clocks):
+    mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    return 148 * 128 * 2 * mhz * 1e6 / 1e12
+
+
+def stream_probe(model, mi, lib, _lib, args, peaks):
+    """The HBM-bound correlation kernel of SURVEY.md 8d on its own: Q_b descriptors x all T frames in one
+    launch (trajectory phase of a small query batch).  Algorithmic bytes per pass =
+    T*P*C*4 + T*P*4 + Q_b*C*4 + Q_b*T*8."""
+    import ctypes
+    dev = model._dev
+    T, C = args.T, args.C
+    out = {}
+    for qb in (1, 8):
+        desc = torch.randn(qb, C, device=dev)
+        dn = desc.norm(dim=1).contiguous()
+        grp = torch.stack([torch.arange(T), torch.zeros(T, dtype=torch.long), torch.full((T,), qb),
+                           torch.arange(T) * qb]).to(torch.int32).to(dev).contiguous()
+        stride = lib.dinotrk_map_stride(ctypes.byref(model._geom))
+        maps = torch.empty(T * qb, stride, device=dev)
+        ws = torch.empty(1 << 16, device=dev, dtype=torch.uint8)
+
+        def run():
+            _lib.check(lib.dinotrk_corr_maps(_lib.ptr(model._refined_tpc), _lib.ptr(model._refined_norms), T, C,
+                                             ctypes.byref(model._geom), _lib.ptr(desc), _lib.ptr(dn), _lib.ptr(grp[0]),
+                                             _lib.ptr(grp[1]), _lib.ptr(grp[2]), _lib.ptr(grp[3]), T, T * qb, qb,
+                                             _lib.ptr(maps), _lib.ptr(ws), 1 << 16, _lib.stream_ptr()))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        _lib.profile_enable(True); _lib.profile_collect()
+        for _ in range(5):
+            run()
+        prof = _lib.profile_collect(); _lib.profile_enable(False)
+        ms_total, n = prof["corr_stream"]
+        nbytes = T * P * C * 4 + T * P * 4 + qb * C * 4 + qb * T * 8
+        gbs = nbytes / (ms_total / n / 1000.0) / 1e9
+        out[f"Q_b={qb}"] = {"kernel": "corr_stream", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                            "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                            "bytes_per_launch": nbytes, "ms_per_launch": ms_total / n}
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

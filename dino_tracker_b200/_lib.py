@@ -49,6 +49,10 @@ SIGNATURES = {
     "dinotrk_delta_workspace_bytes": (c_size_t, [c_int, c_int, c_int, POINTER(c_int)]),
     "dinotrk_delta_refine": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), POINTER(c_void_p), POINTER(c_void_p), _P,
                                      _P, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "dinotrk_profile_classes": (c_int, []),
+    "dinotrk_profile_class_name": (c_char_p, [c_int]),
+    "dinotrk_profile_enable": (None, [c_int]),
+    "dinotrk_profile_collect": (c_int, [POINTER(ctypes.c_double), POINTER(c_ulonglong), c_int]),
     "dinotrk_occlusion": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, _P, _P]),
 }
 
@@ -107,6 +111,20 @@ def make_geom(H, W, patch=14, stride=7, radius=35):
     g = Geom()
     check(load().dinotrk_make_geom(H, W, patch, stride, radius, ctypes.byref(g)), "make_geom")
     return g
+
+
+def profile_enable(on=True):
+    load().dinotrk_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """-> {class name: (total ms, launches)} since the previous collect."""
+    lib = load()
+    n = lib.dinotrk_profile_classes()
+    ms = (ctypes.c_double * n)()
+    cnt = (c_ulonglong * n)()
+    check(lib.dinotrk_profile_collect(ms, cnt, n), "profile_collect")
+    return {lib.dinotrk_profile_class_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}
 
 
 def launch_count():

@@ -36,6 +36,22 @@ extern unsigned long long g_launches;
     DTK_CUDA(cudaPeekAtLastError());   \
   } while (0)
 
+// ---- optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline) ----
+enum ProfClass {
+  PROF_SAMPLE = 0, PROF_CORR_GEMM, PROF_CORR_STREAM, PROF_HEAD, PROF_COS, PROF_ANCHOR_LIST, PROF_OCCLUSION,
+  PROF_PACK, PROF_CONV, PROF_BLUR, PROF_ALIGN, PROF_MISC, PROF_BB, PROF_VIT_GEMM, PROF_VIT_ATTN, PROF_VIT_MISC,
+  PROF_COUNT
+};
+extern bool g_prof_on;
+void prof_begin(int cls, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfRange {
+  cudaStream_t st;
+  bool on;
+  ProfRange(int cls, cudaStream_t s) : st(s), on(g_prof_on) { if (on) prof_begin(cls, st); }
+  ~ProfRange() { if (on) prof_end(st); }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

@@ -214,11 +214,15 @@ int launch_corr_maps(const float* tpc, const float* norms, int C, int P, const f
       DTK_CUDA(cudaFuncSetAttribute(corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
       attr_set = true;
     }
-    corr_plan_kernel<<<1, 32, 0, st>>>(grp_m, n_groups, stream_max, tile_start);
-    DTK_LAUNCHED();
+    {
+      ProfRange pr(PROF_MISC, st);
+      corr_plan_kernel<<<1, 32, 0, st>>>(grp_m, n_groups, stream_max, tile_start);
+      DTK_LAUNCHED();
+    }
     // upper bound on sum ceil(m_k / BM) over the wide groups
     int max_tiles = total_maps / BM + n_groups;
     dim3 grid(max_tiles, cdiv(P, BN));
+    ProfRange pr(PROF_CORR_GEMM, st);
     corr_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame,
                                                             grp_row0, grp_m, grp_map0, tile_start, n_groups,
                                                             maps, map_stride);
@@ -234,6 +238,7 @@ int launch_corr_maps(const float* tpc, const float* norms, int C, int P, const f
       attr_smem = smem;
     }
     dim3 grid(cdiv(P, STREAM_TOK), n_groups);
+    ProfRange pr(PROF_CORR_STREAM, st);
     corr_stream_kernel<MAXM><<<grid, STREAM_THREADS, smem, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame,
                                                                 grp_row0, grp_m, grp_map0, stream_max, maps,
                                                                 map_stride);

@@ -219,6 +219,7 @@ static int launch_conv(const float* in, const float* wgt, const float* bias, flo
     attr = true;
   }
   dim3 grid(cdiv(cs.B * cs.H * cs.W, CBM), cdiv(cs.Cout, CBN));
+  ProfRange pr(PROF_CONV, st);
   conv5x5_kernel<<<grid, CONV_THREADS, CONV_SMEM, st>>>(in, wgt, bias, out, cs);
   DTK_LAUNCHED();
   return DINOTRK_OK;
@@ -253,6 +254,7 @@ int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* ch
 
   {
     size_t n = (size_t)B * H * W;
+    ProfRange pr(PROF_MISC, st);
     rgb_to_nhwc4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(frames, buf0, B, H * W);
     DTK_LAUNCHED();
   }
@@ -269,14 +271,20 @@ int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* ch
     if (l < 3) {
       int ho = (ch - 1) / 2 + 1, wo = (cw - 1) / 2 + 1;
       size_t tot = (size_t)B * ho * wo * (cin / 4);
-      blurpool_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur, oth, B, ch, cw, cin, ho, wo);
-      DTK_LAUNCHED();
+      {
+        ProfRange pr(PROF_BLUR, st);
+        blurpool_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur, oth, B, ch, cw, cin, ho, wo);
+        DTK_LAUNCHED();
+      }
       std::swap(cur, oth);
       ch = ho; cw = wo;
     }
   }
-  align_add_kernel<<<dim3(h * w, B), 128, 0, st>>>(cur, dino_tpc, refined_tpc, ixs, iys, ch, cw, cin, h, w);
-  DTK_LAUNCHED();
+  {
+    ProfRange pr(PROF_ALIGN, st);
+    align_add_kernel<<<dim3(h * w, B), 128, 0, st>>>(cur, dino_tpc, refined_tpc, ixs, iys, ch, cw, cin, h, w);
+    DTK_LAUNCHED();
+  }
   if (norms) return dinotrk_token_norms(refined_tpc, norms, B, cin, h * w, stream);
   return DINOTRK_OK;
 }

@@ -2,6 +2,8 @@
 //   reference: models/tracker.py:64-71 (cache), :77-111 (sampling), utils.py:75-101.
 #include <stdarg.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "sample.cuh"
 
@@ -16,6 +18,21 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; int cls; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int cls, cudaStream_t st) {
+  ProfRec r{prof_event(), prof_event(), cls};
+  cudaEventRecord(r.a, st);
+  g_prof_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof_recs.back().b, st); }
 
 // ---- [T][C][P] <-> [T][P][C] tiled transposes -------------------------------------------------
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int S) {
@@ -76,6 +93,26 @@ int dinotrk_version(void) { return DINOTRK_VERSION; }
 const char* dinotrk_last_error(void) { return dtk::g_err; }
 unsigned long long dinotrk_launch_count(void) { return dtk::g_launches; }
 
+static const char* kProfNames[PROF_COUNT] = {"sample", "corr_gemm", "corr_stream", "head", "traj_cos", "anchor_lists",
+                                              "occlusion", "pack", "delta_conv", "delta_blur", "delta_align", "misc",
+                                              "best_buddies", "vit_gemm", "vit_attn", "vit_misc"};
+int dinotrk_profile_classes(void) { return PROF_COUNT; }
+const char* dinotrk_profile_class_name(int cls) { return (cls >= 0 && cls < PROF_COUNT) ? kProfNames[cls] : ""; }
+void dinotrk_profile_enable(int on) { dtk::g_prof_on = on != 0; }
+int dinotrk_profile_collect(double* ms, unsigned long long* launches, int n) {
+  DTK_CHECK_ARG(ms && launches && n >= PROF_COUNT, "profile_collect: need %d slots", (int)PROF_COUNT);
+  for (int i = 0; i < n; ++i) { ms[i] = 0; launches[i] = 0; }
+  for (auto& r : g_prof_recs) {
+    DTK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    DTK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t; launches[r.cls] += 1;
+    g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+  }
+  g_prof_recs.clear();
+  return DINOTRK_OK;
+}
+
 int dinotrk_make_geom(int H, int W, int patch, int stride, int radius, dinotrk_geom* g) {
   DTK_CHECK_ARG(g != nullptr, "geom: null output");
   DTK_CHECK_ARG(patch > 0 && stride > 0 && H >= patch && W >= patch && radius >= 0,
@@ -89,6 +126,7 @@ int dinotrk_make_geom(int H, int W, int patch, int stride, int radius, dinotrk_g
 int dinotrk_token_norms(const float* tpc, float* norms, int T, int C, int P, void* stream) {
   DTK_CHECK_ARG(tpc && norms && T > 0 && P > 0 && C > 0 && C % 4 == 0, "token_norms: bad args (C must be a multiple of 4)");
   size_t n = (size_t)T * P;
+  ProfRange pr(PROF_PACK, (cudaStream_t)stream);
   token_norm_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(tpc, norms, n, C);
   DTK_LAUNCHED();
   return DINOTRK_OK;
@@ -97,8 +135,11 @@ int dinotrk_token_norms(const float* tpc, float* norms, int T, int C, int P, voi
 int dinotrk_pack_features(const float* chw, float* tpc, float* norms, int T, int C, int P, void* stream) {
   DTK_CHECK_ARG(chw && tpc && T > 0 && P > 0 && C > 0 && C % 4 == 0, "pack_features: bad args (C must be a multiple of 4)");
   dim3 grid(cdiv(P, 32), cdiv(C, 32), T), block(32, 8);
-  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(chw, tpc, C, P);
-  DTK_LAUNCHED();
+  {
+    ProfRange pr(PROF_PACK, (cudaStream_t)stream);
+    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(chw, tpc, C, P);
+    DTK_LAUNCHED();
+  }
   if (norms) return dinotrk_token_norms(tpc, norms, T, C, P, stream);
   return DINOTRK_OK;
 }
@@ -117,6 +158,7 @@ int dinotrk_sample_descriptors(const float* tpc, int T, int C, const dinotrk_geo
   DTK_CHECK_ARG(tpc && g && points && frames_set && desc, "sample_descriptors: null pointer");
   DTK_CHECK_ARG(T > 0 && C > 0 && C % 4 == 0 && N > 0 && B >= 0, "sample_descriptors: bad sizes");
   if (B == 0) return DINOTRK_OK;
+  ProfRange pr(PROF_SAMPLE, (cudaStream_t)stream);
   sample_kernel<<<B, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(tpc, C, g->h * g->w, g->h, g->w,
                                                               make_point_affine(*g), points, frames_set, N,
                                                               points_normalized, desc, desc_norm);

@@ -252,6 +252,7 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = n_maps < sms ? n_maps : sms;
+  ProfRange pr(PROF_HEAD, st);
   if (variant == 0) head_kernel<576><<<grid, threads, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux);
   else head_kernel<1024><<<grid, threads, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux);
   DTK_LAUNCHED();

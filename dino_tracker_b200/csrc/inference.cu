@@ -275,6 +275,7 @@ int dinotrk_traj_cos_sims(const float* tpc, int T, int C, const dinotrk_geom* g,
     DTK_CUDA(cudaFuncSetAttribute(traj_cos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
+  ProfRange pr(PROF_COS, (cudaStream_t)stream);
   traj_cos_kernel<<<dim3(T, N), SAMPLE_THREADS, smem, (cudaStream_t)stream>>>(
       tpc, T, C, g->h * g->w, g->h, g->w, make_point_affine(*g), traj, query_points, cos_sims);
   DTK_LAUNCHED();
@@ -292,6 +293,7 @@ int dinotrk_occlusion(const float* traj, const float* cos_sims, const float* anc
     DTK_CUDA(cudaFuncSetAttribute(occlusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
+  ProfRange pr(PROF_OCCLUSION, (cudaStream_t)stream);
   occlusion_kernel<<<N, OCC_THREADS, smem, (cudaStream_t)stream>>>(traj, cos_sims, anchors, T, anchor_th, cos_th, occ);
   DTK_LAUNCHED();
   return DINOTRK_OK;
@@ -341,8 +343,11 @@ int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dino
 
   // ---- phase A: trajectories -------------------------------------------------------------------
   if (start_phase <= 0) {
-  sample_query_kernel<<<N, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, query_points, descA, normA);
-  DTK_LAUNCHED();
+  {
+    ProfRange pr(PROF_SAMPLE, st);
+    sample_query_kernel<<<N, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, query_points, descA, normA);
+    DTK_LAUNCHED();
+  }
   {
     int t = 0, row = 0;  // next work item: (frame t, query row)
     while (t < T) {
@@ -358,8 +363,11 @@ int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dino
       }
       int rc = upload_groups();
       if (rc) return rc;
-      index_traj_kernel<<<cdiv(used, 256), 256, 0, st>>>(gf, gr, gmap, gb.n, used, T, out_index, traj);
-      DTK_LAUNCHED();
+      {
+        ProfRange pr(PROF_MISC, st);
+        index_traj_kernel<<<cdiv(used, 256), 256, 0, st>>>(gf, gr, gmap, gb.n, used, T, out_index, traj);
+        DTK_LAUNCHED();
+      }
       rc = launch_corr_maps(tpc, norms, C, P, descA, normA, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, st);
       if (rc) return rc;
       rc = launch_head(maps, used, ms, *g, *hw, out_index, traj, 3, 0, nullptr, st);
@@ -378,8 +386,11 @@ int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dino
 
   // ---- phase C: anchor re-tracking ---------------------------------------------------------------
   if (start_phase <= 2) {
-  anchor_lists_kernel<<<T, 256, 0, st>>>(cos_sims, N, T, anchor_th, d_cnt, d_qlist);
-  DTK_LAUNCHED();
+  {
+    ProfRange pr(PROF_ANCHOR_LIST, st);
+    anchor_lists_kernel<<<T, 256, 0, st>>>(cos_sims, N, T, anchor_th, d_cnt, d_qlist);
+    DTK_LAUNCHED();
+  }
   std::vector<int> cnt(T);
   DTK_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost, st));
   DTK_CUDA(cudaStreamSynchronize(st));  // the one host sync: sizes of the anchor work lists
@@ -403,9 +414,12 @@ int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dino
       if (used == 0) break;
       int rc = upload_groups();
       if (rc) return rc;
-      sample_anchor_kernel<<<used, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, traj, d_qlist, N, gf, gmap,
-                                                           gitem, gb.n, fb, descC, normC, out_index);
-      DTK_LAUNCHED();
+      {
+        ProfRange pr(PROF_SAMPLE, st);
+        sample_anchor_kernel<<<used, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, traj, d_qlist, N, gf, gmap,
+                                                             gitem, gb.n, fb, descC, normC, out_index);
+        DTK_LAUNCHED();
+      }
       rc = launch_corr_maps(tpc, norms, C, P, descC, normC, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, st);
       if (rc) return rc;
       rc = launch_head(maps, used, ms, *g, *hw, out_index, anchors, 2, 0, nullptr, st);

@@ -138,6 +138,13 @@ int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* ch
                          const float* ixs, const float* iys, int h, int w, float* refined_tpc,
                          float* norms, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- per-kernel-class device timing (CUDA events on the launching stream; bench.py roofline) ------ */
+int dinotrk_profile_classes(void);
+const char* dinotrk_profile_class_name(int cls);
+void dinotrk_profile_enable(int on);
+/* Waits for the recorded events; ms[cls] / launches[cls] accumulate since the previous collect. */
+int dinotrk_profile_collect(double* ms, unsigned long long* launches, int n);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long dinotrk_launch_count(void);
 
