@@ -231,10 +231,20 @@ using namespace dtk;
 
 extern "C" {
 
+static size_t delta_max_activation(int B, int H, int W, const int* channels) {
+  // largest NHWC activation over the stack (input padded to 4 channels, conv outputs, blur outputs)
+  size_t best = (size_t)B * H * W * 4;
+  int ch = H, cw = W;
+  for (int l = 0; l < 4; ++l) {
+    size_t a = (size_t)B * ch * cw * channels[l + 1];
+    if (a > best) best = a;
+    if (l < 3) { ch = (ch - 1) / 2 + 1; cw = (cw - 1) / 2 + 1; }
+  }
+  return best;
+}
+
 size_t dinotrk_delta_workspace_bytes(int B, int H, int W, const int* channels) {
-  // ping-pong NHWC buffers: the largest activation is conv0's output (B x H x W x C1)
-  size_t a = (size_t)B * H * W * (channels[1] > 4 ? channels[1] : 4) * sizeof(float);
-  return 2 * align_up(a, 256) + 4096;
+  return 2 * align_up(delta_max_activation(B, H, W, channels) * sizeof(float), 256) + 4096;
 }
 
 int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* channels, const float* const* wgt,
@@ -248,7 +258,7 @@ int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* ch
                 "delta_refine: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   Arena ar(workspace, workspace_bytes);
-  size_t half = (size_t)B * H * W * (channels[1] > 4 ? channels[1] : 4);
+  size_t half = delta_max_activation(B, H, W, channels);
   float* buf0 = ar.take<float>(half);
   float* buf1 = ar.take<float>(half);
 
