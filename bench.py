@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--nq", type=int, default=256)
     ap.add_argument("--noise", type=float, default=0.25)
     ap.add_argument("--chunk-maps", type=int, default=4096)
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "fp32"],
+                    help="wide correlation groups: tcgen05 3xTF32 tensor cores, or the exact-fp32 FFMA GEMM")
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the cpu_baseline leg")
     ap.add_argument("--stream-probe", type=int, default=1, help="0: skip the dedicated corr_stream HBM probe")
     return ap.parse_args()
@@ -228,7 +230,8 @@ def run_b200(args):
     T, C, nq = args.T, args.C, args.nq
     feats = synth_video_features(T, C, dev, 1234 + rank, args.noise)
     video = torch.zeros(T, 3, H, W, device=dev)  # frames only feed delta-DINO (default init: zero residual)
-    model = Tracker(video=video, dino_embed_video=feats, device=dev, delta_channels=[3, 4, 4, 4, C])
+    model = Tracker(video=video, dino_embed_video=feats, device=dev, delta_channels=[3, 4, 4, 4, C],
+                    corr_precision=args.precision)
     del feats
     from bench_inputs import sharp_head
     model.tracker_head.load_state_dict(sharp_head(0))
@@ -321,7 +324,7 @@ def run_b200(args):
                        "anchors_per_query_mean": n_anch.mean().item(), "corr_maps_per_step": maps_per_step,
                        "parallelism": f"video-parallel x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (1.66 GB feature video per step; no explicit flush)",
-                       "chunk_maps": args.chunk_maps},
+                       "chunk_maps": args.chunk_maps, "corr_precision": args.precision},
             "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": extra,
@@ -380,13 +383,14 @@ def stream_probe(model, mi, lib, _lib, args, peaks):
                            torch.arange(T) * qb]).to(torch.int32).to(dev).contiguous()
         stride = lib.dinotrk_map_stride(ctypes.byref(model._geom))
         maps = torch.empty(T * qb, stride, device=dev)
-        ws = torch.empty(1 << 16, device=dev, dtype=torch.uint8)
+        nb = lib.dinotrk_corr_maps_workspace_bytes(T * qb, T, C)
+        ws = torch.empty(nb, device=dev, dtype=torch.uint8)
+        feat = model.features_struct(model._refined_tpc, model._refined_norms)
 
         def run():
-            _lib.check(lib.dinotrk_corr_maps(_lib.ptr(model._refined_tpc), _lib.ptr(model._refined_norms), T, C,
-                                             ctypes.byref(model._geom), _lib.ptr(desc), _lib.ptr(dn), _lib.ptr(grp[0]),
-                                             _lib.ptr(grp[1]), _lib.ptr(grp[2]), _lib.ptr(grp[3]), T, T * qb, qb,
-                                             _lib.ptr(maps), _lib.ptr(ws), 1 << 16, _lib.stream_ptr()))
+            _lib.check(lib.dinotrk_corr_maps(ctypes.byref(feat), ctypes.byref(model._geom), _lib.ptr(desc), _lib.ptr(dn),
+                                             _lib.ptr(grp[0]), _lib.ptr(grp[1]), _lib.ptr(grp[2]), _lib.ptr(grp[3]), T,
+                                             T * qb, qb, _lib.ptr(maps), _lib.ptr(ws), nb, _lib.stream_ptr()))
         for _ in range(3):
             run()
         torch.cuda.synchronize()

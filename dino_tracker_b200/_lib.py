@@ -20,6 +20,10 @@ class HeadWeights(Structure):
     _fields_ = [("w1", c_float * 9 * 16), ("b1", c_float * 16), ("w2", c_float * 9 * 16), ("b2", c_float)]
 
 
+class Features(Structure):
+    _fields_ = [("tpc", c_void_p), ("norms", c_void_p), ("hi", c_void_p), ("lo", c_void_p), ("T", c_int), ("C", c_int)]
+
+
 class DinotrkError(RuntimeError):
     pass
 
@@ -35,15 +39,17 @@ SIGNATURES = {
     "dinotrk_unpack_features": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "dinotrk_token_norms": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "dinotrk_sample_descriptors": (c_int, [_P, c_int, c_int, POINTER(Geom), _P, c_int, _P, c_int, c_int, _P, _P, _P]),
-    "dinotrk_corr_track_workspace_bytes": (c_size_t, [c_int, c_int, POINTER(Geom)]),
-    "dinotrk_corr_track": (c_int, [_P, _P, c_int, c_int, POINTER(Geom), POINTER(HeadWeights), _P, _P, _P, _P, _P, _P,
+    "dinotrk_split_tf32": (c_int, [_P, _P, _P, c_size_t, _P]),
+    "dinotrk_corr_track_workspace_bytes": (c_size_t, [c_int, c_int, c_int, POINTER(Geom)]),
+    "dinotrk_corr_track": (c_int, [POINTER(Features), POINTER(Geom), POINTER(HeadWeights), _P, _P, _P, _P, _P, _P,
                                    c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_size_t, _P]),
+    "dinotrk_corr_maps_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dinotrk_map_stride": (c_int, [POINTER(Geom)]),
-    "dinotrk_corr_maps": (c_int, [_P, _P, c_int, c_int, POINTER(Geom), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int,
+    "dinotrk_corr_maps": (c_int, [POINTER(Features), POINTER(Geom), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int,
                                   _P, _P, c_size_t, _P]),
     "dinotrk_head": (c_int, [_P, c_int, POINTER(Geom), POINTER(HeadWeights), _P, _P, c_int, c_int, _P, _P]),
     "dinotrk_infer_workspace_bytes": (c_size_t, [c_int, c_int, POINTER(Geom), c_int, c_int]),
-    "dinotrk_infer": (c_int, [_P, _P, c_int, c_int, POINTER(Geom), POINTER(HeadWeights), _P, c_int, c_float, c_float,
+    "dinotrk_infer": (c_int, [POINTER(Features), POINTER(Geom), POINTER(HeadWeights), _P, c_int, c_float, c_float,
                               c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "dinotrk_traj_cos_sims": (c_int, [_P, c_int, c_int, POINTER(Geom), _P, _P, c_int, _P, _P, c_size_t, _P]),
     "dinotrk_delta_workspace_bytes": (c_size_t, [c_int, c_int, c_int, POINTER(c_int)]),
@@ -105,6 +111,16 @@ def require_cuda(device):
     if dev.type != "cuda":
         raise DinotrkError(f"dino_tracker_b200 runs on CUDA only, got device={device!r}")
     return dev
+
+
+def make_features(tpc, norms, hi=None, lo=None):
+    f = Features()
+    f.tpc, f.norms = tpc.data_ptr(), norms.data_ptr()
+    f.hi = hi.data_ptr() if hi is not None else None
+    f.lo = lo.data_ptr() if lo is not None else None
+    f.T, f.C = tpc.shape[0], tpc.shape[2]
+    f._keep = (tpc, norms, hi, lo)  # keep the tensors alive as long as the struct
+    return f
 
 
 def make_geom(H, W, patch=14, stride=7, radius=35):

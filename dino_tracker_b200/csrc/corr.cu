@@ -202,18 +202,16 @@ corr_stream_kernel(const float* __restrict__ tpc, const float* __restrict__ norm
 
 size_t corr_plan_bytes(int n_groups) { return align_up((size_t)(n_groups + 1) * sizeof(int), 256); }
 
-int launch_corr_maps(const float* tpc, const float* norms, int C, int P, const float* desc,
-                     const float* desc_norm, const int* grp_frame, const int* grp_row0, const int* grp_m,
-                     const int* grp_map0, int n_groups, int total_maps, int max_group_m, float* maps,
-                     int map_stride, int* tile_start, cudaStream_t st) {
+int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const float* desc_norm,
+                     const int* grp_frame, const int* grp_row0, const int* grp_m, const int* grp_map0, int n_groups,
+                     int total_maps, int max_group_m, float* maps, int map_stride, int* tile_start, float* split_ws,
+                     cudaStream_t st) {
   if (n_groups <= 0 || total_maps <= 0) return DINOTRK_OK;
+  const float* tpc = fv.tpc;
+  const float* norms = fv.norms;
+  const int C = fv.C, P = fv.P;
   const int stream_max = STREAM_MAX_M;
   if (max_group_m > stream_max) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      DTK_CUDA(cudaFuncSetAttribute(corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-      attr_set = true;
-    }
     {
       ProfRange pr(PROF_MISC, st);
       corr_plan_kernel<<<1, 32, 0, st>>>(grp_m, n_groups, stream_max, tile_start);
@@ -221,12 +219,23 @@ int launch_corr_maps(const float* tpc, const float* norms, int C, int P, const f
     }
     // upper bound on sum ceil(m_k / BM) over the wide groups
     int max_tiles = total_maps / BM + n_groups;
-    dim3 grid(max_tiles, cdiv(P, BN));
-    ProfRange pr(PROF_CORR_GEMM, st);
-    corr_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame,
-                                                            grp_row0, grp_m, grp_map0, tile_start, n_groups,
-                                                            maps, map_stride);
-    DTK_LAUNCHED();
+    if (fv.tensor()) {
+      int rc = launch_corr_gemm_tc(fv.hi, fv.lo, norms, fv.T, C, P, desc, desc_rows, desc_norm, grp_frame, grp_row0,
+                                   grp_m, grp_map0, tile_start, n_groups, max_tiles, maps, map_stride, split_ws, st);
+      if (rc) return rc;
+    } else {
+      static bool attr_set = false;
+      if (!attr_set) {
+        DTK_CUDA(cudaFuncSetAttribute(corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        attr_set = true;
+      }
+      dim3 grid(max_tiles, cdiv(P, BN));
+      ProfRange pr(PROF_CORR_GEMM, st);
+      corr_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame,
+                                                              grp_row0, grp_m, grp_map0, tile_start, n_groups,
+                                                              maps, map_stride);
+      DTK_LAUNCHED();
+    }
   }
   {
     // thin groups (there may be none; CTAs of wide groups exit at once)
@@ -255,16 +264,26 @@ extern "C" {
 
 int dinotrk_map_stride(const dinotrk_geom* g) { return g ? (int)align_up((size_t)g->h * g->w, 4) : 0; }
 
-int dinotrk_corr_maps(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
-                      const float* desc, const float* desc_norm, const int* grp_frame, const int* grp_row0,
-                      const int* grp_m, const int* grp_map0, int n_groups, int total_maps, int max_group_m,
-                      float* maps, void* workspace, size_t workspace_bytes, void* stream) {
-  DTK_CHECK_ARG(tpc && norms && g && desc && desc_norm && grp_frame && grp_row0 && grp_m && grp_map0 && maps,
-                "corr_maps: null pointer");
-  DTK_CHECK_ARG(T > 0 && C > 0 && C % 4 == 0 && n_groups >= 0 && total_maps >= 0, "corr_maps: bad sizes");
-  DTK_CHECK_ARG(workspace && workspace_bytes >= corr_plan_bytes(n_groups), "corr_maps: workspace too small");
-  return launch_corr_maps(tpc, norms, C, g->h * g->w, desc, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
-                          n_groups, total_maps, max_group_m, maps, dinotrk_map_stride(g), (int*)workspace,
+size_t dinotrk_corr_maps_workspace_bytes(int total_maps, int n_groups, int C) {
+  return corr_plan_bytes(n_groups) + corr_tc_workspace_bytes(total_maps, C) + 1024;
+}
+
+int dinotrk_corr_maps(const dinotrk_features* feat, const dinotrk_geom* g, const float* desc, const float* desc_norm,
+                      const int* grp_frame, const int* grp_row0, const int* grp_m, const int* grp_map0, int n_groups,
+                      int total_maps, int max_group_m, float* maps, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  DTK_CHECK_ARG(feat && feat->tpc && feat->norms && g && desc && desc_norm && grp_frame && grp_row0 && grp_m &&
+                grp_map0 && maps, "corr_maps: null pointer");
+  DTK_CHECK_ARG(feat->T > 0 && feat->C > 0 && feat->C % 4 == 0 && n_groups >= 0 && total_maps >= 0, "corr_maps: bad sizes");
+  DTK_CHECK_ARG((feat->hi == nullptr) == (feat->lo == nullptr), "corr_maps: hi and lo must be given together");
+  DTK_CHECK_ARG(workspace && workspace_bytes >= dinotrk_corr_maps_workspace_bytes(total_maps, n_groups, feat->C),
+                "corr_maps: workspace too small");
+  Arena ar(workspace, workspace_bytes);
+  int* plan = ar.take<int>(n_groups + 1);
+  float* split = ar.take<float>(corr_tc_workspace_bytes(total_maps, feat->C) / 4);
+  // rows of desc = total_maps here (one descriptor row per map is the generic contract)
+  return launch_corr_maps(make_view(*feat, *g), desc, total_maps, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
+                          n_groups, total_maps, max_group_m, maps, dinotrk_map_stride(g), plan, split,
                           (cudaStream_t)stream);
 }
 

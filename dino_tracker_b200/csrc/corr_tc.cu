@@ -1,0 +1,162 @@
+// Tensor-core correlation GEMM (tcgen05, 3xTF32) + TF32 operand splitting + TMA tensor-map helpers.
+//
+//   corr[j][p] = relu( <d_j, F[frame][p]> / max(|d_j| |F[frame][p]|, 1e-8) )     (models/tracker.py:158-173)
+//
+// The contraction runs as hi*hi + hi*lo + lo*hi on TF32 tensor cores with fp32 accumulation in TMEM
+// (operands pre-split into exactly-representable TF32 parts), which keeps the products faithful to
+// ~2^-21; the cosine normalisation and ReLU are the epilogue on the accumulator as it leaves TMEM.
+#include "common.cuh"
+#include "corr.cuh"
+#include "tcgemm.cuh"
+
+namespace dtk {
+
+// ---- driver entry point for cuTensorMapEncodeTiled (resolved once; no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box, int elem_bytes) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return DINOTRK_ECUDA; }
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(map, dt, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DINOTRK_ECUDA; }
+  return DINOTRK_OK;
+}
+
+int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
+                 int elem_bytes) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  return encode(map, base, 2, dims, strides, box, elem_bytes);
+}
+int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                 uint32_t box_cols, int elem_bytes) {
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {cols * (uint64_t)elem_bytes, rows * cols * (uint64_t)elem_bytes};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  return encode(map, base, 3, dims, strides, box, elem_bytes);
+}
+
+// x = hi + lo (+ residual < 2^-22 |x|): hi = x with the 13 low mantissa bits cleared, lo = (x - hi) likewise
+__global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 v = __ldg(x + i), h, l;
+    auto sp = [](float a, float& ah, float& al) {
+      ah = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+      al = __uint_as_float(__float_as_uint(__fsub_rn(a, ah)) & 0xffffe000u);
+    };
+    sp(v.x, h.x, l.x); sp(v.y, h.y, l.y); sp(v.z, h.z, l.z); sp(v.w, h.w, l.w);
+    hi[i] = h; lo[i] = l;
+  }
+}
+
+int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
+  if (n == 0) return DINOTRK_OK;
+  DTK_CHECK_ARG(n % 4 == 0, "split_tf32: length must be a multiple of 4");
+  size_t n4 = n / 4;
+  unsigned grid = (unsigned)((n4 + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  ProfRange pr(PROF_MISC, st);
+  split_tf32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi),
+                                          reinterpret_cast<float4*>(lo), n4);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+struct CorrEpi {
+  const float* norms;      // [T][P]
+  const float* desc_norm;  // [rows]
+  const int* grp_frame;
+  const int* grp_row0;
+  const int* grp_map0;
+  float* maps;
+  int map_stride, P;
+  __device__ __forceinline__ void operator()(int g, int r, int col0, const float (&f)[32], int ncols) const {
+    const float dn = desc_norm[grp_row0[g] + r];
+    const float* fn = norms + (size_t)grp_frame[g] * P + col0;
+    float* out = maps + (size_t)(grp_map0[g] + r) * map_stride + col0;
+    if (ncols == 32) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        // norms rows are only 4-byte aligned (P is odd): scalar broadcast loads
+        float4 n4 = make_float4(__ldg(fn + i), __ldg(fn + i + 1), __ldg(fn + i + 2), __ldg(fn + i + 3));
+        float4 o;
+        o.x = fmaxf(__fdiv_rn(f[i + 0], fmaxf(__fmul_rn(dn, n4.x), 1e-8f)), 0.f);
+        o.y = fmaxf(__fdiv_rn(f[i + 1], fmaxf(__fmul_rn(dn, n4.y), 1e-8f)), 0.f);
+        o.z = fmaxf(__fdiv_rn(f[i + 2], fmaxf(__fmul_rn(dn, n4.z), 1e-8f)), 0.f);
+        o.w = fmaxf(__fdiv_rn(f[i + 3], fmaxf(__fmul_rn(dn, n4.w), 1e-8f)), 0.f);
+        *reinterpret_cast<float4*>(out + i) = o;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols) out[i] = fmaxf(__fdiv_rn(f[i], fmaxf(__fmul_rn(dn, fn[i]), 1e-8f)), 0.f);
+    }
+  }
+};
+
+size_t corr_tc_workspace_bytes(int total_rows, int C) { return 2 * align_up((size_t)total_rows * C * 4, 256); }
+
+// wide groups on tensor cores; tile_start must already hold the plan (corr_plan_kernel).
+int launch_corr_gemm_tc(const float* tpc_hi, const float* tpc_lo, const float* norms, int T, int C, int P,
+                        const float* desc, int desc_rows, const float* desc_norm, const int* grp_frame,
+                        const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
+                        int max_tiles, float* maps, int map_stride, float* desc_split_ws, cudaStream_t st) {
+  using Cfg = TcCfg<TcMode::TF32X3>;
+  DTK_CHECK_ARG(((size_t)P * C * 4) % 16 == 0 && C % 4 == 0, "corr_tc: C must be a multiple of 4");
+  float* d_hi = desc_split_ws;
+  float* d_lo = desc_split_ws + align_up((size_t)desc_rows * C * 4, 256) / 4;
+  int rc = launch_split_tf32(desc, d_hi, d_lo, (size_t)desc_rows * C, st);
+  if (rc) return rc;
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  if ((rc = make_tmap_2d(&tmA_hi, d_hi, desc_rows, C, TC_BM, Cfg::kBK, 4))) return rc;
+  if ((rc = make_tmap_2d(&tmA_lo, d_lo, desc_rows, C, TC_BM, Cfg::kBK, 4))) return rc;
+  if ((rc = make_tmap_3d(&tmB_hi, tpc_hi, T, P, C, TC_BN, Cfg::kBK, 4))) return rc;
+  if ((rc = make_tmap_3d(&tmB_lo, tpc_lo, T, P, C, TC_BN, Cfg::kBK, 4))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    DTK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TcMode::TF32X3, CorrEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmem));
+    attr = true;
+  }
+  TcProblem pb{grp_frame, grp_row0, grp_m, tile_start, n_groups, P, C};
+  CorrEpi epi{norms, desc_norm, grp_frame, grp_row0, grp_map0, maps, map_stride, P};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int tiles_bound = max_tiles * cdiv(P, TC_BN);
+  int grid = tiles_bound < sms ? tiles_bound : sms;
+  if (grid < 1) grid = 1;
+  ProfRange pr(PROF_CORR_GEMM, st);
+  tc_gemm_kernel<TcMode::TF32X3, CorrEpi><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, pb, epi);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+}  // namespace dtk
+
+using namespace dtk;
+
+extern "C" int dinotrk_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
+  DTK_CHECK_ARG(x && hi && lo, "split_tf32: null pointer");
+  return launch_split_tf32(x, hi, lo, n, (cudaStream_t)stream);
+}

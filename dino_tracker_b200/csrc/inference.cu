@@ -219,29 +219,33 @@ using namespace dtk;
 
 extern "C" {
 
-size_t dinotrk_corr_track_workspace_bytes(int total_maps, int n_groups, const dinotrk_geom* g) {
+size_t dinotrk_corr_track_workspace_bytes(int total_maps, int n_groups, int C, const dinotrk_geom* g) {
   if (!g) return 0;
-  return align_up((size_t)total_maps * dinotrk_map_stride(g) * sizeof(float), 256) + corr_plan_bytes(n_groups) + 1024;
+  return align_up((size_t)total_maps * dinotrk_map_stride(g) * sizeof(float), 256) + corr_plan_bytes(n_groups) +
+         corr_tc_workspace_bytes(total_maps, C) + 1024;
 }
 
-int dinotrk_corr_track(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+int dinotrk_corr_track(const dinotrk_features* feat, const dinotrk_geom* g,
                        const dinotrk_head_weights* hw, const float* desc, const float* desc_norm,
                        const int* grp_frame, const int* grp_row0, const int* grp_m, const int* grp_map0,
                        int n_groups, int total_maps, int max_group_m, const int* out_index, float* out,
                        int out_stride, int out_mode, void* workspace, size_t workspace_bytes, void* stream) {
-  DTK_CHECK_ARG(tpc && norms && g && hw && desc && desc_norm && grp_frame && grp_row0 && grp_m && grp_map0 && out,
-                "corr_track: null pointer");
-  DTK_CHECK_ARG(T > 0 && C > 0 && C % 4 == 0 && n_groups >= 0 && total_maps >= 0, "corr_track: bad sizes");
-  DTK_CHECK_ARG(workspace && workspace_bytes >= dinotrk_corr_track_workspace_bytes(total_maps, n_groups, g),
+  DTK_CHECK_ARG(feat && feat->tpc && feat->norms && g && hw && desc && desc_norm && grp_frame && grp_row0 && grp_m &&
+                grp_map0 && out, "corr_track: null pointer");
+  const int C = feat->C;
+  DTK_CHECK_ARG(feat->T > 0 && C > 0 && C % 4 == 0 && n_groups >= 0 && total_maps >= 0, "corr_track: bad sizes");
+  DTK_CHECK_ARG((feat->hi == nullptr) == (feat->lo == nullptr), "corr_track: hi and lo must be given together");
+  DTK_CHECK_ARG(workspace && workspace_bytes >= dinotrk_corr_track_workspace_bytes(total_maps, n_groups, C, g),
                 "corr_track: workspace too small");
   if (total_maps == 0) return DINOTRK_OK;
   Arena ar(workspace, workspace_bytes);
   const int ms = dinotrk_map_stride(g);
   float* maps = ar.take<float>((size_t)total_maps * ms);
   int* plan = ar.take<int>(n_groups + 1);
+  float* split = ar.take<float>(corr_tc_workspace_bytes(total_maps, C) / 4);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_corr_maps(tpc, norms, C, g->h * g->w, desc, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
-                            n_groups, total_maps, max_group_m, maps, ms, plan, st);
+  int rc = launch_corr_maps(make_view(*feat, *g), desc, total_maps, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
+                            n_groups, total_maps, max_group_m, maps, ms, plan, split, st);
   if (rc) return rc;
   return launch_head(maps, total_maps, ms, *g, *hw, out_index, out, out_stride, out_mode, nullptr, st);
 }
@@ -259,6 +263,7 @@ size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N,
   b += align_up(ch * 4, 256);                                              // out_index
   b += align_up((size_t)5 * gcap * 4, 256) + align_up((size_t)(gcap + 1) * 4, 256);  // groups, plan
   b += align_up((size_t)T * 4, 256) + align_up((size_t)T * N * 4, 256);    // cnt, qlist
+  b += corr_tc_workspace_bytes((int)(ch > (size_t)N ? ch : (size_t)N), C) + 256;  // TF32 split of the descriptors
   return b + 4096;
 }
 
@@ -299,13 +304,17 @@ int dinotrk_occlusion(const float* traj, const float* cos_sims, const float* anc
   return DINOTRK_OK;
 }
 
-int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
                   const dinotrk_head_weights* hw, const float* query_points, int N, float anchor_th, float cos_th,
                   int frame_batch, int start_phase, int stop_after, int chunk_maps, float* traj, float* cos_sims,
                   float* anchors,
                   uint8_t* occ, void* workspace, size_t workspace_bytes, void* stream) {
-  DTK_CHECK_ARG(tpc && norms && g && hw && query_points && traj, "infer: null pointer");
+  DTK_CHECK_ARG(feat && feat->tpc && feat->norms && g && hw && query_points && traj, "infer: null pointer");
+  const float* tpc = feat->tpc;
+  const int T = feat->T, C = feat->C;
   DTK_CHECK_ARG(T > 0 && C > 0 && C % 4 == 0 && N >= 0, "infer: bad sizes");
+  DTK_CHECK_ARG((feat->hi == nullptr) == (feat->lo == nullptr), "infer: hi and lo must be given together");
+  const FeatView fv = make_view(*feat, *g);
   DTK_CHECK_ARG(start_phase >= 0 && start_phase <= stop_after && stop_after <= 3,
                 "infer: need 0 <= start_phase <= stop_after <= 3");
   DTK_CHECK_ARG((stop_after < 1 || cos_sims) && (stop_after < 2 || anchors) && (stop_after < 3 || occ),
@@ -332,6 +341,7 @@ int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dino
   int* plan = ar.take<int>(gcap + 1);
   int* d_cnt = ar.take<int>(T);
   int* d_qlist = ar.take<int>((size_t)T * N);
+  float* split = ar.take<float>(corr_tc_workspace_bytes(ch > N ? ch : N, C) / 4);
   DTK_CHECK_ARG(ar.ok(), "infer: workspace arena overflow");
 
   GroupBuf gb(gcap);
@@ -368,7 +378,7 @@ int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dino
         index_traj_kernel<<<cdiv(used, 256), 256, 0, st>>>(gf, gr, gmap, gb.n, used, T, out_index, traj);
         DTK_LAUNCHED();
       }
-      rc = launch_corr_maps(tpc, norms, C, P, descA, normA, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, st);
+      rc = launch_corr_maps(fv, descA, N, normA, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, split, st);
       if (rc) return rc;
       rc = launch_head(maps, used, ms, *g, *hw, out_index, traj, 3, 0, nullptr, st);
       if (rc) return rc;
@@ -420,7 +430,7 @@ int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dino
                                                              gitem, gb.n, fb, descC, normC, out_index);
         DTK_LAUNCHED();
       }
-      rc = launch_corr_maps(tpc, norms, C, P, descC, normC, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, st);
+      rc = launch_corr_maps(fv, descC, used, normC, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, split, st);
       if (rc) return rc;
       rc = launch_head(maps, used, ms, *g, *hw, out_index, anchors, 2, 0, nullptr, st);
       if (rc) return rc;

@@ -1,0 +1,199 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:   D[m][n] = sum_k A[m][k] * B[n][k]
+// (both operands K-major: A = [rows][K], B = [batch][N][K]), 128 x 256 output tiles, accumulators in
+// TMEM (two 256-column buffers so the epilogue of tile i overlaps the MMAs of tile i+1), operands
+// staged by TMA into 128B-swizzled shared memory through an mbarrier ring.
+//
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocation + MMA issue (one elected lane), tcgen05.commit -> barriers
+//   warps 2..5  : epilogue (tcgen05.ld of the warp's 32-lane quadrant -> Epi functor -> global)
+//
+// Modes:
+//   TF32X3 : fp32-faithful "3xTF32": operands pre-split into exactly-representable TF32 hi / lo parts,
+//            hi*hi + hi*lo + lo*hi accumulated in fp32 (error ~2^-21 per product before accumulation)
+//   TF32   : single pass on fp32 data (the tensor core reads the top 19 bits)
+//   BF16   : single pass on bf16 data
+// Work = grouped tiles: group g covers A rows [row0[g], row0[g] + m[g]) against B batch item batch[g];
+// m-tiles are numbered through the prefix array tile_start[] (device), n-tiles cover N.
+#pragma once
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace dtk {
+
+enum class TcMode { TF32X3 = 0, TF32 = 1, BF16 = 2 };
+
+constexpr int TC_BM = 128, TC_BN = 256;
+constexpr int TC_THREADS = 192;
+
+template <TcMode MODE>
+struct TcCfg {
+  static constexpr int kElem = (MODE == TcMode::BF16) ? 2 : 4;
+  static constexpr int kBK = 128 / kElem;                         // elements per 128-byte swizzle row
+  static constexpr int kOps = (MODE == TcMode::TF32X3) ? 2 : 1;   // hi (+ lo) tiles per operand
+  static constexpr int kUmmaK = 32 / kElem;                       // K per tcgen05.mma
+  static constexpr int kABytes = TC_BM * 128, kBBytes = TC_BN * 128;
+  static constexpr int kStageBytes = kOps * (kABytes + kBBytes);
+  static constexpr int kStages = (MODE == TcMode::TF32X3) ? 2 : 4;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr bool kTF32 = MODE != TcMode::BF16;
+  static constexpr uint32_t kIdesc = tc::make_idesc(kTF32 ? 2 : 1, TC_BM, TC_BN);
+};
+
+struct TcProblem {
+  const int* grp_batch;    // [n_groups] B batch item (frame) of each group
+  const int* grp_row0;     // [n_groups] first A row
+  const int* grp_m;        // [n_groups] number of A rows
+  const int* tile_start;   // [n_groups + 1] prefix of ceil(m / 128)
+  int n_groups;
+  int N, K;                // B rows per batch item, reduction length
+};
+
+// Epi must provide:  __device__ void operator()(int g, int r_in_group, int col0, const float (&v)[32], int ncols_valid)
+// for one row (r_in_group) and 32 consecutive columns starting at col0.
+template <TcMode MODE, class Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcProblem pb,
+               Epi epi) {
+  using Cfg = TcCfg<MODE>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles_n = (pb.N + TC_BN - 1) / TC_BN;
+  const int total_tiles = pb.tile_start[pb.n_groups] * n_tiles_n;
+  const int KB = (pb.K + Cfg::kBK - 1) / Cfg::kBK;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA_hi); tc::prefetch_tmap(&tmB_hi);
+    if (Cfg::kOps == 2) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); }
+    for (int s = 0; s < Cfg::kStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], 4); }
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile id -> (group, m0, n0): m-tile index is the slow dimension so that CTAs that run together share
+  // the same B rows (frame) in L2
+  auto decode = [&](int tile, int& g, int& m0, int& n0) {
+    int mt = tile / n_tiles_n;
+    n0 = (tile - mt * n_tiles_n) * TC_BN;
+    int lo = 0, hi = pb.n_groups - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (pb.tile_start[mid] <= mt) lo = mid; else hi = mid - 1;
+    }
+    g = lo;
+    m0 = (mt - pb.tile_start[g]) * TC_BM;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (tc::elect_one()) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int g, m0, n0;
+        decode(tile, g, m0, n0);
+        const int arow = pb.grp_row0[g] + m0, batch = pb.grp_batch[g];
+        for (int kb = 0; kb < KB; ++kb) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * Cfg::kStageBytes;
+          tc::mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+          const int k0 = kb * Cfg::kBK;
+          tc::tma_load_2d(&tmA_hi, &full[stage], st, k0, arow);
+          if (Cfg::kOps == 2) tc::tma_load_2d(&tmA_lo, &full[stage], st + Cfg::kABytes, k0, arow);
+          uint8_t* sb = st + Cfg::kOps * Cfg::kABytes;
+          tc::tma_load_3d(&tmB_hi, &full[stage], sb, k0, n0, batch);
+          if (Cfg::kOps == 2) tc::tma_load_3d(&tmB_lo, &full[stage], sb + Cfg::kBBytes, k0, n0, batch);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1, aphase = (it >> 1) & 1;
+      tc::mbar_wait(&tempty[buf], aphase ^ 1);
+      tc::fence_after_sync();
+      const uint32_t tmem_d = tmem_base + buf * TC_BN;
+      for (int kb = 0; kb < KB; ++kb) {
+        tc::mbar_wait(&full[stage], phase);
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t sa = tc::smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kOps * Cfg::kABytes;
+#pragma unroll
+          for (int ks = 0; ks < Cfg::kBK / Cfg::kUmmaK; ++ks) {
+            const uint32_t koff = ks * 32;  // bytes inside the 128-byte swizzle row
+            const uint64_t a_hi = tc::smem_desc_sw128(sa + koff), b_hi = tc::smem_desc_sw128(sb + koff);
+            const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+            if (Cfg::kOps == 2) {
+              const uint64_t a_lo = tc::smem_desc_sw128(sa + Cfg::kABytes + koff);
+              const uint64_t b_lo = tc::smem_desc_sw128(sb + Cfg::kBBytes + koff);
+              // small terms first, then the dominant hi*hi
+              tc::mma_ss<true>(tmem_d, a_lo, b_hi, Cfg::kIdesc, first);
+              tc::mma_ss<true>(tmem_d, a_hi, b_lo, Cfg::kIdesc, 1u);
+              tc::mma_ss<true>(tmem_d, a_hi, b_hi, Cfg::kIdesc, 1u);
+            } else {
+              tc::mma_ss<Cfg::kTF32>(tmem_d, a_hi, b_hi, Cfg::kIdesc, first);
+            }
+          }
+          tc::mma_commit(&empty[stage]);                 // smem slot reusable once these MMAs have read it
+          if (kb == KB - 1) tc::mma_commit(&tfull[buf]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
+    const int quad = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1, aphase = (it >> 1) & 1;
+      int g, m0, n0;
+      decode(tile, g, m0, n0);
+      const int r = m0 + quad * 32 + lane;       // row inside the group
+      const bool row_ok = r < pb.grp_m[g];
+      tc::mbar_wait(&tfull[buf], aphase);
+      tc::fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN;
+#pragma unroll 1
+      for (int c = 0; c < TC_BN; c += 32) {
+        uint32_t v[32];
+        tc::tmem_ld32(taddr + c, v);
+        tc::tmem_ld_wait();
+        const int ncols = min(32, pb.N - (n0 + c));
+        if (row_ok && ncols > 0) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          epi(g, r, n0 + c, f, ncols);
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace dtk

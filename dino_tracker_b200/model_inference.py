@@ -82,8 +82,9 @@ def _run_phases(model: Tracker, query_points, start, stop, batch_size, anchor_th
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         model.__dict__["_infer_ws"] = ws
     fb = 0 if batch_size is None else int(batch_size)
+    feat = model.features_struct(tpc, norms)
     _lib.check(lib.dinotrk_infer(
-        _lib.ptr(tpc), _lib.ptr(norms), T, C, ctypes.byref(geom), ctypes.byref(model.head_weights()), _lib.ptr(q), N,
+        ctypes.byref(feat), ctypes.byref(geom), ctypes.byref(model.head_weights()), _lib.ptr(q), N,
         float(anchor_th), float(cos_th), fb, start, stop, chunk_maps, _lib.ptr(traj), _lib.ptr(cos_sims),
         _lib.ptr(anchors), _lib.ptr(occ), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "infer")
     return {"traj": traj, "cos_sims": cos_sims, "anchors": anchors, "occ": occ}

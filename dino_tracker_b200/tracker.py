@@ -31,7 +31,7 @@ def _as_f32(t, device):
 class Tracker(nn.Module):
     def __init__(self, video=None, ckpt_path="", dino_embed_path="", dino_patch_size=14, stride=7,
                  device="cuda:0", cyc_n_frames=4, cyc_batch_size_per_frame=256, cyc_fg_points_ratio=0.7,
-                 cyc_thresh=4, dino_embed_video=None, delta_channels=None):
+                 cyc_thresh=4, dino_embed_video=None, delta_channels=None, corr_precision="tf32x3"):
         super().__init__()
         self.device = device
         self._dev = _lib.require_cuda(device)
@@ -47,8 +47,13 @@ class Tracker(nn.Module):
         self.video = video
         t, c, h, w = video.shape
         self._geom = _lib.make_geom(h, w, dino_patch_size, stride, 35)
+        assert corr_precision in ("tf32x3", "fp32")
+        # "tf32x3": wide correlation groups on tcgen05 tensor cores (3xTF32, fp32-faithful);
+        # "fp32"  : exact-fp32 FFMA GEMM on the CUDA cores (validation path)
+        self.corr_precision = corr_precision
         self._refined_tpc = None
         self._refined_norms = None
+        self._split_cache = {}
         self._head_cache = (None, None)
 
         if dino_embed_video is not None:      # in-process features (ViT stage of this package)
@@ -80,6 +85,18 @@ class Tracker(nn.Module):
         _lib.check(self._lib.dinotrk_pack_features(_lib.ptr(chw), _lib.ptr(tpc), _lib.ptr(norms), T, C, h * w,
                                                     _lib.stream_ptr()), "pack_features")
         return tpc, norms
+
+    def features_struct(self, tpc, norms):
+        """C struct for a [T][P][C] feature video (+ its cached TF32 split in tf32x3 mode)."""
+        if self.corr_precision != "tf32x3":
+            return _lib.make_features(tpc, norms)
+        key = (tpc.data_ptr(), tpc._version, tuple(tpc.shape))
+        if self._split_cache.get("key") != key:
+            hi, lo = torch.empty_like(tpc), torch.empty_like(tpc)
+            _lib.check(self._lib.dinotrk_split_tf32(_lib.ptr(tpc), _lib.ptr(hi), _lib.ptr(lo), tpc.numel(),
+                                                     _lib.stream_ptr()), "split_tf32")
+            self._split_cache = {"key": key, "hi": hi, "lo": lo}
+        return _lib.make_features(tpc, norms, self._split_cache["hi"], self._split_cache["lo"])
 
     def _set_dino(self, chw):
         self._dino_tpc, self._dino_norms = self._pack(chw)
@@ -232,10 +249,11 @@ class Tracker(nn.Module):
         out_index = order.to(device=self._dev, dtype=torch.int32).contiguous()
         out = torch.empty(B, 2, device=self._dev, dtype=torch.float32)
         n_groups = int(uniq.shape[0])
-        ws_bytes = self._lib.dinotrk_corr_track_workspace_bytes(B, n_groups, ctypes.byref(self._geom))
+        ws_bytes = self._lib.dinotrk_corr_track_workspace_bytes(B, n_groups, C, ctypes.byref(self._geom))
         ws = torch.empty(ws_bytes, device=self._dev, dtype=torch.uint8)
+        feat = self.features_struct(tpc, norms)
         _lib.check(self._lib.dinotrk_corr_track(
-            _lib.ptr(tpc), _lib.ptr(norms), T, C, ctypes.byref(self._geom), ctypes.byref(self.head_weights()),
+            ctypes.byref(feat), ctypes.byref(self._geom), ctypes.byref(self.head_weights()),
             _lib.ptr(desc), _lib.ptr(dn), _lib.ptr(grp[0]), _lib.ptr(grp[1]), _lib.ptr(grp[2]), _lib.ptr(grp[3]),
             n_groups, B, int(counts.max()), _lib.ptr(out_index), _lib.ptr(out), 2, 1,
             _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "corr_track")

@@ -51,6 +51,17 @@ typedef struct dinotrk_head_weights {
   float b2;
 } dinotrk_head_weights;
 
+/* A cached feature video.  tpc [T][P][C] and norms [T][P] are required.  hi / lo (optional, both or
+ * neither): the TF32 split of tpc produced by dinotrk_split_tf32; when present the wide correlation
+ * groups run on the tcgen05 tensor cores (3xTF32, fp32-faithful), otherwise on the exact-fp32 FFMA GEMM. */
+typedef struct dinotrk_features {
+  const float* tpc;
+  const float* norms;
+  const float* hi;
+  const float* lo;
+  int T, C;
+} dinotrk_features;
+
 int dinotrk_version(void);
 const char* dinotrk_last_error(void);
 /* Fills *g from (H, W, patch, stride, radius); returns DINOTRK_EINVAL on bad sizes. */
@@ -63,6 +74,8 @@ int dinotrk_pack_features(const float* chw, float* tpc, float* norms, int T, int
                           void* stream);
 int dinotrk_unpack_features(const float* tpc, float* chw, int T, int C, int P, void* stream);
 int dinotrk_token_norms(const float* tpc, float* norms, int T, int C, int P, void* stream);
+/* x = hi + lo with hi, lo exactly representable in TF32 (13 low mantissa bits zero); n % 4 == 0. */
+int dinotrk_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
 
 /* ---- descriptor sampling (models/tracker.py:77-111, utils.py:75-101) ------------------- */
 /* points [B][3] = (x_px, y_px, set_index) ; frames_set [N] int32 = frame of each set slot.
@@ -81,8 +94,8 @@ int dinotrk_sample_descriptors(const float* tpc, int T, int C, const dinotrk_geo
  * + {0,1}] (out_index == NULL: j).  out_mode 0: pixels (after RangeNormalizer.unnormalize,
  * models/model_inference.py:52), 1: normalised [-1,1] (Tracker.forward).
  * group arrays are device int32[n_groups]; total_maps = sum m.  Syncs: no. */
-size_t dinotrk_corr_track_workspace_bytes(int total_maps, int n_groups, const dinotrk_geom* g);
-int dinotrk_corr_track(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+size_t dinotrk_corr_track_workspace_bytes(int total_maps, int n_groups, int C, const dinotrk_geom* g);
+int dinotrk_corr_track(const dinotrk_features* feat, const dinotrk_geom* g,
                        const dinotrk_head_weights* hw, const float* desc, const float* desc_norm,
                        const int* grp_frame, const int* grp_row0, const int* grp_m,
                        const int* grp_map0, int n_groups, int total_maps, int max_group_m,
@@ -92,7 +105,8 @@ int dinotrk_corr_track(const float* tpc, const float* norms, int T, int C, const
 /* Correlation maps only (ReLU'd cosine maps, [total_maps][map_stride] fp32,
  * map_stride = dinotrk_map_stride(g)) -- the volume the fused path never keeps. */
 int dinotrk_map_stride(const dinotrk_geom* g);
-int dinotrk_corr_maps(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+size_t dinotrk_corr_maps_workspace_bytes(int total_maps, int n_groups, int C);
+int dinotrk_corr_maps(const dinotrk_features* feat, const dinotrk_geom* g,
                       const float* desc, const float* desc_norm, const int* grp_frame,
                       const int* grp_row0, const int* grp_m, const int* grp_map0, int n_groups,
                       int total_maps, int max_group_m, float* maps, void* workspace,
@@ -112,7 +126,7 @@ int dinotrk_head(const float* maps, int n_maps, const dinotrk_geom* g,
  * the outputs of earlier phases are then inputs.  SYNCS the stream once when phase 2 runs (reads
  * the per-frame anchor counts back to size the anchor work lists). */
 size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N, int chunk_maps);
-int dinotrk_infer(const float* tpc, const float* norms, int T, int C, const dinotrk_geom* g,
+int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
                   const dinotrk_head_weights* hw, const float* query_points, int N,
                   float anchor_th, float cos_th, int frame_batch, int start_phase, int stop_after,
                   int chunk_maps,

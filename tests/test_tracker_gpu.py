@@ -20,11 +20,15 @@ XY_TOL = 1e-3
 DEV = "cuda:0"
 
 
-def make_model(geo, feats, head, T=None):
+PRECISIONS = ["tf32x3", "fp32"]  # tcgen05 3xTF32 tensor-core GEMM / exact-fp32 FFMA GEMM
+
+
+def make_model(geo, feats, head, precision="tf32x3"):
     from dino_tracker_b200 import Tracker
     T = feats.shape[0]
     video = torch.zeros(T, 3, geo.H, geo.W, device=DEV)
-    m = Tracker(video=video, dino_embed_video=feats, device=DEV, delta_channels=[3, 4, 4, 4, feats.shape[1]])
+    m = Tracker(video=video, dino_embed_video=feats, device=DEV, delta_channels=[3, 4, 4, 4, feats.shape[1]],
+                corr_precision=precision)
     m.tracker_head.load_state_dict(head)
     return m
 
@@ -65,36 +69,64 @@ def test_sample_descriptors_matches_oracle(geo):
     assert (out.cpu() - ot.sample_descriptors(feats, pn2)).abs().max().item() <= 2e-6
 
 
-@pytest.mark.parametrize("m_per_frame", [3, 8, 9, 150])
-def test_corr_maps_match_oracle(m_per_frame):
-    """stream kernel (<= 8 descriptors per frame) and grouped GEMM (> 8), incl. ragged tiles."""
+def run_corr_maps(model, desc, frames, ms):
     from dino_tracker_b200 import _lib
     lib = _lib.load()
+    total = sum(ms)
+    C = desc.shape[1]
+    row0 = np.cumsum([0] + list(ms[:-1])).astype(np.int32)
+    grp = torch.tensor(np.stack([frames, row0, ms, row0]).astype(np.int32), device=DEV)
+    d_dev = desc.to(DEV).contiguous()
+    dn = d_dev.norm(dim=1).contiguous()
+    stride = lib.dinotrk_map_stride(ctypes.byref(model._geom))
+    maps = torch.zeros(total, stride, device=DEV)
+    nb = lib.dinotrk_corr_maps_workspace_bytes(total, len(ms), C)
+    ws = torch.empty(nb, device=DEV, dtype=torch.uint8)
+    feat = model.features_struct(model._dino_tpc, model._dino_norms)
+    _lib.check(lib.dinotrk_corr_maps(ctypes.byref(feat), ctypes.byref(model._geom), _lib.ptr(d_dev), _lib.ptr(dn),
+                                     _lib.ptr(grp[0]), _lib.ptr(grp[1]), _lib.ptr(grp[2]), _lib.ptr(grp[3]), len(ms),
+                                     total, max(ms), _lib.ptr(maps), _lib.ptr(ws), nb, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return maps
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("m_per_frame", [3, 8, 9, 150, 300])
+def test_corr_maps_match_oracle(m_per_frame, precision):
+    """stream kernel (<= 8 descriptors per frame) and grouped GEMM (> 8), incl. ragged tiles."""
     geo = Geometry(H=98, W=126)
     torch.manual_seed(2)
     T, C = 3, 48
     feats = torch.randn(T, C, geo.h, geo.w)
-    model = make_model(geo, feats, synth.head_weights("well"))
+    model = make_model(geo, feats, synth.head_weights("well"), precision)
     frames = [2, 0, 1]
     ms = [m_per_frame, max(1, m_per_frame - 2), m_per_frame + 1]
     total = sum(ms)
     desc = torch.randn(total, C)
     desc[0] = 0  # zero descriptor: clamp(min=1e-8) path
-    row0 = np.cumsum([0] + ms[:-1]).astype(np.int32)
-    grp = torch.tensor(np.stack([frames, row0, ms, row0]).astype(np.int32), device=DEV)
-    dn = desc.norm(dim=1).to(DEV)
-    stride = lib.dinotrk_map_stride(ctypes.byref(model._geom))
-    maps = torch.zeros(total, stride, device=DEV)
-    ws = torch.empty(4096, device=DEV, dtype=torch.uint8)
-    d_dev = desc.to(DEV)
-    _lib.check(lib.dinotrk_corr_maps(_lib.ptr(model._dino_tpc), _lib.ptr(model._refined_norms_or_dino()), T, C,
-                                     ctypes.byref(model._geom), _lib.ptr(d_dev), _lib.ptr(dn), _lib.ptr(grp[0]),
-                                     _lib.ptr(grp[1]), _lib.ptr(grp[2]), _lib.ptr(grp[3]), 3, total, max(ms),
-                                     _lib.ptr(maps), _lib.ptr(ws), 4096, _lib.stream_ptr()))
+    maps = run_corr_maps(model, desc, frames, ms)
     tgt = torch.tensor(sum([[f] * m for f, m in zip(frames, ms)], []))
     ref = torch.relu(ot.corr_maps(desc, feats, tgt))[:, 0].reshape(total, -1)
     got = maps[:, : geo.P].cpu()
     assert (got - ref).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_corr_gemm_error_vs_float64(precision):
+    """Full geometry, C=1024: error of the wide-group contraction against a float64 evaluation
+    (the fp32 reference itself sits ~1e-7 away from it)."""
+    geo = Geometry()
+    torch.manual_seed(5)
+    T, C, M = 2, 1024, 200
+    feats, _ = synth.shifted_field_features(T, C, geo.h, geo.w, seed=9, noise=0.2)
+    model = make_model(geo, feats, synth.head_weights("well"), precision)
+    desc = feats[0].reshape(C, -1).t()[torch.randint(0, geo.P, (M,))].contiguous() + 0.05 * torch.randn(M, C)
+    maps = run_corr_maps(model, desc, [1], [M])[:, : geo.P].cpu().double()
+    f = feats[1].reshape(C, -1).double()
+    ref = torch.relu((desc.double() @ f) / (desc.double().norm(dim=1)[:, None] * f.norm(dim=0)[None]).clamp_min(1e-8))
+    err = (maps - ref).abs().max().item()
+    print(f"[{precision}] max |corr - float64| = {err:.3e}")
+    assert err <= 5e-7
 
 
 @pytest.mark.parametrize("kind", ["well", "sharp", "mixed", "default"])
@@ -152,11 +184,12 @@ def test_forward_matches_reference_vectors(name):
     assert ((out2 - ref2).abs() * torch.from_numpy(scale).float()).max().item() <= XY_TOL
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("name", sorted(TRACK_CASES))
-def test_infer_matches_reference_vectors(name):
+def test_infer_matches_reference_vectors(name, precision):
     from dino_tracker_b200 import ModelInference
     cfg, geo, feats, head, g = load_track_case(name)
-    model = make_model(geo, feats, head)
+    model = make_model(geo, feats, head, precision)
     mi = ModelInference(model, model.range_normalizer, 0.7, 0.6)
     assert torch.equal(model.refined_features.cpu(), feats)  # default delta-DINO: exactly zero residual
     q = torch.from_numpy(g["query_points"]).to(DEV)
@@ -182,7 +215,8 @@ def test_infer_matches_reference_vectors(name):
     assert all(a2[n].shape == (int(g["n_anchors"][n]), cfg["T"], 2) for n in range(q.shape[0]))
 
 
-def test_infer_medium_against_oracle():
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_infer_medium_against_oracle(precision):
     """Full token geometry, wider batch (GEMM path, several chunks) against the oracle run here."""
     from dino_tracker_b200 import ModelInference
     geo = Geometry()
@@ -190,7 +224,7 @@ def test_infer_medium_against_oracle():
     feats, _ = synth.shifted_field_features(T, C, geo.h, geo.w, seed=40, noise=0.2, max_shift=2)
     head = synth.head_weights("sharp", seed=40)
     q = synth.lattice_query_points(5, 4, geo.H, geo.W, t_q=[i % T for i in range(20)], margin=30.0, jitter_seed=40)
-    model = make_model(geo, feats, head)
+    model = make_model(geo, feats, head, precision)
     mi = ModelInference(model, model.range_normalizer, 0.7, 0.6)
     r = mi.infer_all(q.to(DEV))
     t_ref, o_ref, aux = oi.infer(feats, q, head, geo, 0.7, 0.6, return_all=True)
