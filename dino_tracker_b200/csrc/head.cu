@@ -45,7 +45,19 @@ __device__ __forceinline__ float opadd(float a, float b) { return a + b; }
 // Values are >= 0 (ReLU'd), so the float bit pattern orders like the value.
 __device__ __forceinline__ unsigned long long opkey(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
 
-template <int MAXT>
+// online-softmax pair (max, sum of exp relative to max)
+struct MS { float m, s; };
+__device__ __forceinline__ MS ms_merge(MS a, MS b) {
+  float m = fmaxf(a.m, b.m);
+  float sa = a.m == -INFINITY ? 0.f : a.s * __expf(a.m - m);
+  float sb = b.m == -INFINITY ? 0.f : b.s * __expf(b.m - m);
+  return MS{m, sa + sb};
+}
+struct F3 { float a, b, c; };
+
+// kWrap: the band's last lane (tile 31) lies completely outside the map (w <= 124), so the side halo can be
+// taken with rotating shuffles (lane 0 reads the all-zero tile 31) -- no edge selects in the hot loop.
+template <int MAXT, bool kWrap>
 __global__ void __launch_bounds__(MAXT, 1)
 head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_head_weights wts,
             const int* __restrict__ out_index, float* __restrict__ out, int* __restrict__ aux) {
@@ -55,11 +67,18 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
   const int lin_elems = (hp.map_stride + 3) & ~3;
   float* sm_lin[2] = {smem, smem + lin_elems};
   float* sm_hid = smem + 2 * lin_elems;                   // [2 buffers][nwarps][2 rows][128]
-  float* sm_red = sm_hid + 2 * nwarps * 2 * 128;          // [nwarps] floats
-  unsigned long long* sm_red64 = reinterpret_cast<unsigned long long*>(sm_red + 32);  // [nwarps]
+  float* sm_red = sm_hid + 2 * nwarps * 2 * 128;          // [3 * 32] floats
+  unsigned long long* sm_red64 = reinterpret_cast<unsigned long long*>(sm_red + 96);  // [32]
 
   const int r0 = warp * 4, c0 = lane * 4;  // this lane's tile
   const int nchunks = hp.map_stride / 4;
+  constexpr float kNeg = -1e30f;
+  // additive masks: hidden activations of pixels outside the map must be exactly 0 (zero padding of the
+  // second convolution); bias + kNeg makes the ReLU do that without per-pixel selects.
+  float rmask[4], cmask[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { rmask[i] = (r0 + i < h) ? 0.f : kNeg; cmask[i] = (c0 + i < w) ? 0.f : kNeg; }
+  const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
 
   int map = blockIdx.x;
   if (map < n_maps) {
@@ -89,9 +108,9 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
       unsigned long long k = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(0x7fffffff - i);
       key = k > key ? k : key;
     }
-    key = block_bcast_reduce<unsigned long long>(key, sm_red64, warp, lane, nwarps, opkey);
-    const int amax = 0x7fffffff - (int)(key & 0xffffffffu);
-    const int arow = amax / w, acol = amax - arow * w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
+    if (lane == 0) sm_red64[warp] = key;
 
     // ---- 6x6 input window (zero outside the map = conv zero padding) -------------------------
     float m[6][6];
@@ -104,11 +123,6 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
         m[i][j] = (r >= 0 && r < h && c >= 0 && c < w) ? lin[r * w + c] : 0.f;
       }
     }
-    bool valid[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) valid[i][j] = (r0 + i < h) && (c0 + j < w);
 
     float acc[4][4];
 #pragma unroll
@@ -116,41 +130,54 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = wts.b2;
 
-#pragma unroll 1
-    for (int o = 0; o < 16; ++o) {
-      float w1[9], w2[9];
+    float hid[6][6];  // [1..4][1..4] own values, ring = halo
+    auto conv1 = [&](int o) {
+      float w1[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) { w1[k] = wts.w1[o][k]; w2[k] = wts.w2[o][k]; }
+      for (int k = 0; k < 9; ++k) w1[k] = wts.w1[o][k];
       const float b1 = wts.b1[o];
-      // hidden window: hid[1..4][1..4] own, ring = halo
-      float hid[6][6];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) {
+        const float br = b1 + rmask[i];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float a = b1;
+          float a = br + cmask[j];
 #pragma unroll
           for (int ki = 0; ki < 3; ++ki)
 #pragma unroll
             for (int kj = 0; kj < 3; ++kj) a = fmaf(w1[ki * 3 + kj], m[i + ki][j + kj], a);
-          hid[i + 1][j + 1] = valid[i][j] ? fmaxf(a, 0.f) : 0.f;  // hidden is zero-padded outside the map
+          hid[i + 1][j + 1] = fmaxf(a, 0.f);
         }
+      }
       float* hb = sm_hid + ((o & 1) * nwarps + warp) * 2 * 128;
       *reinterpret_cast<float4*>(hb + c0) = make_float4(hid[1][1], hid[1][2], hid[1][3], hid[1][4]);
       *reinterpret_cast<float4*>(hb + 128 + c0) = make_float4(hid[4][1], hid[4][2], hid[4][3], hid[4][4]);
-      __syncthreads();
+    };
+
+    conv1(0);
+    __syncthreads();  // also publishes sm_red64 (arg-max partials)
+#pragma unroll 1
+    for (int o = 0; o < 16; ++o) {
+      float w2[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w2[k] = wts.w2[o][k];
+      // halo rows of channel o were published before the previous barrier
       float4 top = make_float4(0.f, 0.f, 0.f, 0.f), bot = top;
       if (warp > 0) top = *reinterpret_cast<const float4*>(sm_hid + ((o & 1) * nwarps + warp - 1) * 2 * 128 + 128 + c0);
       if (warp + 1 < nwarps) bot = *reinterpret_cast<const float4*>(sm_hid + ((o & 1) * nwarps + warp + 1) * 2 * 128 + c0);
       hid[0][1] = top.x; hid[0][2] = top.y; hid[0][3] = top.z; hid[0][4] = top.w;
       hid[5][1] = bot.x; hid[5][2] = bot.y; hid[5][3] = bot.z; hid[5][4] = bot.w;
-      // side + corner halo from lane neighbours (lane 0 / 31: outside the band -> zero padding)
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        float l = __shfl_up_sync(0xffffffffu, hid[i][4], 1);
-        float r = __shfl_down_sync(0xffffffffu, hid[i][1], 1);
-        hid[i][0] = lane > 0 ? l : 0.f;
-        hid[i][5] = lane < 31 ? r : 0.f;
+        if (kWrap) {
+          hid[i][0] = __shfl_sync(0xffffffffu, hid[i][4], lane_l);
+          hid[i][5] = __shfl_sync(0xffffffffu, hid[i][1], lane_r);
+        } else {
+          float l = __shfl_up_sync(0xffffffffu, hid[i][4], 1);
+          float r = __shfl_down_sync(0xffffffffu, hid[i][1], 1);
+          hid[i][0] = lane > 0 ? l : 0.f;
+          hid[i][5] = lane < 31 ? r : 0.f;
+        }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -163,53 +190,84 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
             for (int kj = 0; kj < 3; ++kj) a = fmaf(w2[ki * 3 + kj], hid[i + ki][j + kj], a);
           acc[i][j] = a;
         }
+      if (o + 1 < 16) conv1(o + 1);   // next channel's hidden layer; published by the barrier below
+      __syncthreads();
     }
 
-    // ---- softmax statistics over the whole map -----------------------------------------------
+    // ---- arg-max result (partials were published before the first barrier) ---------------------
+    unsigned long long kbest = sm_red64[0];
+    for (int k = 1; k < nwarps; ++k) { unsigned long long t = sm_red64[k]; kbest = t > kbest ? t : kbest; }
+    const int amax = 0x7fffffff - (int)(kbest & 0xffffffffu);
+    const int arow = amax / w, acol = amax - arow * w;
+
+    // ---- softmax statistics over the whole map: one online (max, sum) reduction --------------------
+    MS ms{-INFINITY, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (r0 + i < h && c0 + j < w) ms.m = fmaxf(ms.m, acc[i][j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (r0 + i < h && c0 + j < w) ms.s += __expf(acc[i][j] - ms.m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      MS t{__shfl_xor_sync(0xffffffffu, ms.m, o), __shfl_xor_sync(0xffffffffu, ms.s, o)};
+      ms = ms_merge(ms, t);
+    }
+    if (lane == 0) { sm_red[warp] = ms.m; sm_red[32 + warp] = ms.s; }
+    __syncthreads();
     float zmax = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (valid[i][j]) zmax = fmaxf(zmax, acc[i][j]);
-    zmax = block_bcast_reduce<float>(zmax, sm_red, warp, lane, nwarps, opmax);
-    float e[4][4];
-    float ssum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        e[i][j] = valid[i][j] ? expf(acc[i][j] - zmax) : 0.f;
-        ssum += e[i][j];
-      }
-    ssum = block_bcast_reduce<float>(ssum, sm_red, warp, lane, nwarps, opadd);
+    for (int k = 0; k < nwarps; ++k) zmax = fmaxf(zmax, sm_red[k]);
 
     // ---- disc-masked soft-argmax (mask: |token centre - argmax centre| <= radius px) ----------
-    float s = 0.f, sx = 0.f, sy = 0.f, gx = 0.f, gy = 0.f, cnt = 0.f;
+    // Only the few threads whose tile meets the disc do any work; exact expf / division here.
+    float s = 0.f, sx = 0.f, sy = 0.f, gx = 0.f, gy = 0.f, cnt = 0.f, ssum_part = 0.f;
+    {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int dr = (r0 + i - arow) * hp.stride_px, dc = (c0 + j - acol) * hp.stride_px;
-        if (valid[i][j] && dr * dr + dc * dc <= hp.radius2) {
-          float p = __fdiv_rn(e[i][j], ssum);
-          float x = (float)(hp.half_patch + (c0 + j) * hp.stride_px), y = (float)(hp.half_patch + (r0 + i) * hp.stride_px);
-          s += p; sx = fmaf(x, p, sx); sy = fmaf(y, p, sy);
-          gx += x; gy += y; cnt += 1.f;
+        for (int j = 0; j < 4; ++j) {
+          int dr = (r0 + i - arow) * hp.stride_px, dc = (c0 + j - acol) * hp.stride_px;
+          if (r0 + i < h && c0 + j < w && dr * dr + dc * dc <= hp.radius2) {
+            float e = expf(acc[i][j] - zmax);
+            float x = (float)(hp.half_patch + (c0 + j) * hp.stride_px), y = (float)(hp.half_patch + (r0 + i) * hp.stride_px);
+            s += e; sx = fmaf(x, e, sx); sy = fmaf(y, e, sy);
+            gx += x; gy += y; cnt += 1.f;
+          }
         }
-      }
-    s = block_bcast_reduce<float>(s, sm_red, warp, lane, nwarps, opadd);
-    sx = block_bcast_reduce<float>(sx, sm_red, warp, lane, nwarps, opadd);
-    sy = block_bcast_reduce<float>(sy, sm_red, warp, lane, nwarps, opadd);
-    const bool fallback = s < 1e-8f;
-    if (fallback) {  // heatmap <- (heatmap + 1/|mask|) * mask  (tracker_head.py:87-94), block-uniform branch
-      gx = block_bcast_reduce<float>(gx, sm_red, warp, lane, nwarps, opadd);
-      gy = block_bcast_reduce<float>(gy, sm_red, warp, lane, nwarps, opadd);
-      cnt = block_bcast_reduce<float>(cnt, sm_red, warp, lane, nwarps, opadd);
-      float u = __fdiv_rn(1.f, cnt);
-      s = fmaf(cnt, u, s); sx = fmaf(gx, u, sx); sy = fmaf(gy, u, sy);
     }
+    // global sum of exp(z - zmax) from the per-warp (max, sum) pairs
+    for (int k = 0; k < nwarps; ++k) {
+      float mk = sm_red[k];
+      if (mk != -INFINITY) ssum_part += sm_red[32 + k] * expf(mk - zmax);
+    }
+    const float ssum = ssum_part;
+    // reduce (s, sx, sy, gx, gy, cnt) in one pass
+    float vals[6] = {s, sx, sy, gx, gy, cnt};
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vals[q] += __shfl_xor_sync(0xffffffffu, vals[q], o);
+    __syncthreads();  // everyone has read sm_red (max/sum pairs) -> reuse it
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) sm_red[q * 32 + warp] = vals[q];
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-      float px = __fdiv_rn(sx, s), py = __fdiv_rn(sy, s);
+      float tot[6];
+      for (int q = 0; q < 6; ++q) { float t = 0.f; for (int k = 0; k < nwarps; ++k) t += sm_red[q * 32 + k]; tot[q] = t; }
+      // p_i = e_i / S_all; s = sum p_i over the disc   (softmax then mask, tracker_head.py:84-86)
+      float sp = __fdiv_rn(tot[0], ssum), spx = __fdiv_rn(tot[1], ssum), spy = __fdiv_rn(tot[2], ssum);
+      const bool fallback = sp < 1e-8f;
+      if (fallback) {  // heatmap <- (heatmap + 1/|mask|) * mask  (tracker_head.py:87-94)
+        float u = __fdiv_rn(1.f, tot[5]);
+        sp = fmaf(tot[5], u, sp); spx = fmaf(tot[3], u, spx); spy = fmaf(tot[4], u, spy);
+      }
+      float px = __fdiv_rn(spx, sp), py = __fdiv_rn(spy, sp);
       // RangeNormalizer((W, H)) dst=(-1,1): x / (W-1); * 2; + (-1)      (data/dataset.py:33-35)
       float nx = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(px, hp.normW)), -1.f);
       float ny = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(py, hp.normH)), -1.f);
@@ -221,7 +279,7 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
       out[oi] = nx; out[oi + 1] = ny;
       if (aux) { aux[2 * map] = amax; aux[2 * map + 1] = fallback ? 1 : 0; }
     }
-    __syncthreads();  // lin / sm_hid are reused by the next iteration
+    __syncthreads();  // lin / sm_hid / sm_red are reused by the next iteration
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
 }
@@ -240,12 +298,14 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
   const int nwarps = cdiv(g.h, 4);
   const int threads = nwarps * 32;
   const int lin_elems = (map_stride + 3) & ~3;
-  size_t smem = (size_t)(2 * lin_elems + 2 * nwarps * 2 * 128 + 32) * sizeof(float) + 32 * sizeof(unsigned long long);
-  static size_t attr_smem[2] = {0, 0};
-  const int variant = threads <= 576 ? 0 : 1;  // <= 576 threads: 112 registers/thread; else 64
+  size_t smem = (size_t)(2 * lin_elems + 2 * nwarps * 2 * 128 + 6 * 32) * sizeof(float) + 32 * sizeof(unsigned long long);
+  static size_t attr_smem[4] = {0, 0, 0, 0};
+  const bool wrap = g.w <= 124;                 // tile 31 of every band lies outside the map
+  const int variant = (threads <= 576 ? 0 : 2) + (wrap ? 0 : 1);  // <= 576 threads: 112 registers/thread; else 64
+  auto kern = variant == 0 ? head_kernel<576, true> : variant == 1 ? head_kernel<576, false>
+            : variant == 2 ? head_kernel<1024, true> : head_kernel<1024, false>;
   if (smem > attr_smem[variant]) {
-    if (variant == 0) DTK_CUDA(cudaFuncSetAttribute(head_kernel<576>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else DTK_CUDA(cudaFuncSetAttribute(head_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem[variant] = smem;
   }
   int dev = 0, sms = 148;
@@ -253,8 +313,7 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = n_maps < sms ? n_maps : sms;
   ProfRange pr(PROF_HEAD, st);
-  if (variant == 0) head_kernel<576><<<grid, threads, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux);
-  else head_kernel<1024><<<grid, threads, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux);
+  kern<<<grid, threads, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }
