@@ -66,18 +66,19 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
   const int h = hp.h, w = hp.w, P = hp.P;
   const int lin_elems = (hp.map_stride + 3) & ~3;
   float* sm_lin[2] = {smem, smem + lin_elems};
-  float* sm_hid = smem + 2 * lin_elems;                   // [2 buffers][nwarps][2 rows][128]
-  float* sm_red = sm_hid + 2 * nwarps * 2 * 128;          // [3 * 32] floats
-  unsigned long long* sm_red64 = reinterpret_cast<unsigned long long*>(sm_red + 96);  // [32]
+  float* sm_red = smem + 2 * lin_elems;                   // [6 * 32] floats
+  unsigned long long* sm_red64 = reinterpret_cast<unsigned long long*>(sm_red + 192);  // [32]
 
   const int r0 = warp * 4, c0 = lane * 4;  // this lane's tile
   const int nchunks = hp.map_stride / 4;
   constexpr float kNeg = -1e30f;
   // additive masks: hidden activations of pixels outside the map must be exactly 0 (zero padding of the
   // second convolution); bias + kNeg makes the ReLU do that without per-pixel selects.
-  float rmask[4], cmask[4];
+  float rmask6[6], cmask[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { rmask[i] = (r0 + i < h) ? 0.f : kNeg; cmask[i] = (c0 + i < w) ? 0.f : kNeg; }
+  for (int i = 0; i < 6; ++i) rmask6[i] = (r0 - 1 + i >= 0 && r0 - 1 + i < h) ? 0.f : kNeg;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cmask[i] = (c0 + i < w) ? 0.f : kNeg;
   const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
 
   int map = blockIdx.x;
@@ -112,11 +113,11 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
     for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
     if (lane == 0) sm_red64[warp] = key;
 
-    // ---- 6x6 input window (zero outside the map = conv zero padding) -------------------------
-    float m[6][6];
+    // ---- 8x6 input window: rows r0-2..r0+5, cols c0-1..c0+4 (zero outside the map = conv zero padding) --
+    float m[8][6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      int r = r0 - 1 + i;
+    for (int i = 0; i < 8; ++i) {
+      int r = r0 - 2 + i;
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         int c = c0 - 1 + j;
@@ -130,68 +131,52 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = wts.b2;
 
-    float hid[6][6];  // [1..4][1..4] own values, ring = halo
-    auto conv1 = [&](int o) {
-      float w1[9];
+    __syncthreads();  // publishes sm_red64 (arg-max partials); no block-wide sync inside the channel loop
+    // Each lane computes the hidden layer for its 4 columns on 6 rows (own 4 + the row above and below:
+    // 1.5x recompute instead of a shared-memory exchange + barrier per channel), takes the two side columns
+    // from its lane neighbours, and folds each hidden row into the (up to 3) output rows it touches.
+#pragma unroll 1
+    for (int o = 0; o < 16; ++o) {
+      float w1[9], w2[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) w1[k] = wts.w1[o][k];
+      for (int k = 0; k < 9; ++k) { w1[k] = wts.w1[o][k]; w2[k] = wts.w2[o][k]; }
       const float b1 = wts.b1[o];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float br = b1 + rmask[i];
+      for (int hr = 0; hr < 6; ++hr) {
+        float hrow[6];
+        const float br = b1 + rmask6[hr];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float a = br + cmask[j];
 #pragma unroll
           for (int ki = 0; ki < 3; ++ki)
 #pragma unroll
-            for (int kj = 0; kj < 3; ++kj) a = fmaf(w1[ki * 3 + kj], m[i + ki][j + kj], a);
-          hid[i + 1][j + 1] = fmaxf(a, 0.f);
+            for (int kj = 0; kj < 3; ++kj) a = fmaf(w1[ki * 3 + kj], m[hr + ki][j + kj], a);
+          hrow[j + 1] = fmaxf(a, 0.f);
         }
-      }
-      float* hb = sm_hid + ((o & 1) * nwarps + warp) * 2 * 128;
-      *reinterpret_cast<float4*>(hb + c0) = make_float4(hid[1][1], hid[1][2], hid[1][3], hid[1][4]);
-      *reinterpret_cast<float4*>(hb + 128 + c0) = make_float4(hid[4][1], hid[4][2], hid[4][3], hid[4][4]);
-    };
-
-    conv1(0);
-    __syncthreads();  // also publishes sm_red64 (arg-max partials)
-#pragma unroll 1
-    for (int o = 0; o < 16; ++o) {
-      float w2[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) w2[k] = wts.w2[o][k];
-      // halo rows of channel o were published before the previous barrier
-      float4 top = make_float4(0.f, 0.f, 0.f, 0.f), bot = top;
-      if (warp > 0) top = *reinterpret_cast<const float4*>(sm_hid + ((o & 1) * nwarps + warp - 1) * 2 * 128 + 128 + c0);
-      if (warp + 1 < nwarps) bot = *reinterpret_cast<const float4*>(sm_hid + ((o & 1) * nwarps + warp + 1) * 2 * 128 + c0);
-      hid[0][1] = top.x; hid[0][2] = top.y; hid[0][3] = top.z; hid[0][4] = top.w;
-      hid[5][1] = bot.x; hid[5][2] = bot.y; hid[5][3] = bot.z; hid[5][4] = bot.w;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
         if (kWrap) {
-          hid[i][0] = __shfl_sync(0xffffffffu, hid[i][4], lane_l);
-          hid[i][5] = __shfl_sync(0xffffffffu, hid[i][1], lane_r);
+          hrow[0] = __shfl_sync(0xffffffffu, hrow[4], lane_l);
+          hrow[5] = __shfl_sync(0xffffffffu, hrow[1], lane_r);
         } else {
-          float l = __shfl_up_sync(0xffffffffu, hid[i][4], 1);
-          float r = __shfl_down_sync(0xffffffffu, hid[i][1], 1);
-          hid[i][0] = lane > 0 ? l : 0.f;
-          hid[i][5] = lane < 31 ? r : 0.f;
+          float l = __shfl_up_sync(0xffffffffu, hrow[4], 1);
+          float r = __shfl_down_sync(0xffffffffu, hrow[1], 1);
+          hrow[0] = lane > 0 ? l : 0.f;
+          hrow[5] = lane < 31 ? r : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ki = hr - i;  // hidden row hr is row (i - 1 + ki) of output row i's 3x3 window
+          if (ki >= 0 && ki < 3) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a = acc[i][j];
+#pragma unroll
+              for (int kj = 0; kj < 3; ++kj) a = fmaf(w2[ki * 3 + kj], hrow[j + kj], a);
+              acc[i][j] = a;
+            }
+          }
         }
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float a = acc[i][j];
-#pragma unroll
-          for (int ki = 0; ki < 3; ++ki)
-#pragma unroll
-            for (int kj = 0; kj < 3; ++kj) a = fmaf(w2[ki * 3 + kj], hid[i + ki][j + kj], a);
-          acc[i][j] = a;
-        }
-      if (o + 1 < 16) conv1(o + 1);   // next channel's hidden layer; published by the barrier below
-      __syncthreads();
     }
 
     // ---- arg-max result (partials were published before the first barrier) ---------------------
@@ -298,11 +283,11 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
   const int nwarps = cdiv(g.h, 4);
   const int threads = nwarps * 32;
   const int lin_elems = (map_stride + 3) & ~3;
-  size_t smem = (size_t)(2 * lin_elems + 2 * nwarps * 2 * 128 + 6 * 32) * sizeof(float) + 32 * sizeof(unsigned long long);
+  size_t smem = (size_t)(2 * lin_elems + 6 * 32) * sizeof(float) + 32 * sizeof(unsigned long long);
   static size_t attr_smem[4] = {0, 0, 0, 0};
   const bool wrap = g.w <= 124;                 // tile 31 of every band lies outside the map
-  const int variant = (threads <= 576 ? 0 : 2) + (wrap ? 0 : 1);  // <= 576 threads: 112 registers/thread; else 64
-  auto kern = variant == 0 ? head_kernel<576, true> : variant == 1 ? head_kernel<576, false>
+  const int variant = (threads <= 544 ? 0 : 2) + (wrap ? 0 : 1);  // <= 544 threads: 120 registers/thread; else 64
+  auto kern = variant == 0 ? head_kernel<544, true> : variant == 1 ? head_kernel<544, false>
             : variant == 2 ? head_kernel<1024, true> : head_kernel<1024, false>;
   if (smem > attr_smem[variant]) {
     DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
