@@ -47,7 +47,7 @@ SIGNATURES = {
     "dinotrk_map_stride": (c_int, [POINTER(Geom)]),
     "dinotrk_corr_maps": (c_int, [POINTER(Features), POINTER(Geom), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int,
                                   _P, _P, c_size_t, _P]),
-    "dinotrk_head": (c_int, [_P, c_int, POINTER(Geom), POINTER(HeadWeights), _P, _P, c_int, c_int, _P, _P]),
+    "dinotrk_head": (c_int, [_P, c_int, POINTER(Geom), POINTER(HeadWeights), _P, _P, c_int, c_int, _P, _P, _P]),
     "dinotrk_infer_workspace_bytes": (c_size_t, [c_int, c_int, POINTER(Geom), c_int, c_int]),
     "dinotrk_infer": (c_int, [POINTER(Features), POINTER(Geom), POINTER(HeadWeights), _P, c_int, c_float, c_float,
                               c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),

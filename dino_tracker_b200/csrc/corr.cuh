@@ -31,6 +31,6 @@ int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream
 
 int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geom& g,
                 const dinotrk_head_weights& hw, const int* out_index, float* out, int out_stride, int out_mode,
-                int* aux, cudaStream_t st);
+                int* aux, int* scratch /* n_maps + 1 ints, or NULL: full-map kernel for every map */, cudaStream_t st);
 
 }  // namespace dtk

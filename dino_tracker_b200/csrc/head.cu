@@ -2,7 +2,16 @@
 // with the numerical-stability fallback (models/networks/tracker_head.py:107-121, :68-98, :100-105;
 // conv_norm.py:34-46; data/dataset.py:21-53).
 //
-// One persistent CTA per SM; one warp per 4-row band of the map, one lane per 4x4-pixel tile
+// Two kernels:
+//  * head_window_kernel (fast path, every map): arg-max, then the EXACT refiner only on the 11x11 box around
+//    the arg-max (hidden layer on 13x13, input window 15x15).  The soft-argmax needs nothing else as long as
+//    the numerical-stability branch (disc mass < 1e-8 of the whole softmax) does not fire; that is certified
+//    with a rigorous, monotone upper bound on every logit outside the box (from the largest map value outside
+//    the 7x7 core and the positive parts of the normalised weights).  Maps that cannot be certified are
+//    queued for
+//  * head_kernel (full map): the complete refiner + softmax, exactly as the reference evaluates it.
+//
+// head_kernel: one persistent CTA per SM; one warp per 4-row band of the map, one lane per 4x4-pixel tile
 // (band = 32 tiles = 128 columns >= w).  Per hidden channel a lane computes its 16 hidden values from
 // the 6x6 input window it keeps in registers, publishes its top/bottom rows to shared memory (the only
 // cross-warp traffic), takes the side/corner halo from its lane neighbours by shuffle and
@@ -20,6 +29,7 @@ struct HeadParams {
   int stride_px, half_patch, radius2;  // pixel geometry: centre = half_patch + stride * index
   float normW, normH;                  // W - 1, H - 1
   int out_stride, out_mode;
+  float P1[16], P2[16];                // sums of the positive parts of the normalised 3x3 kernels (logit bound)
 };
 
 __device__ __forceinline__ void cp_async16_head(void* smem, const void* gmem) {
@@ -59,41 +69,45 @@ struct F3 { float a, b, c; };
 // taken with rotating shuffles (lane 0 reads the all-zero tile 31) -- no edge selects in the hot loop.
 template <int MAXT, bool kWrap>
 __global__ void __launch_bounds__(MAXT, 1)
-head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_head_weights wts,
+head_kernel(const float* __restrict__ maps, int n_maps_arg, const int* __restrict__ map_list,
+            const int* __restrict__ list_count, HeadParams hp, dinotrk_head_weights wts,
             const int* __restrict__ out_index, float* __restrict__ out, int* __restrict__ aux) {
   extern __shared__ __align__(16) float smem[];
+  // with a list: process map_list[0 .. *list_count) (maps the window kernel could not certify)
+  const int n_maps = map_list ? *list_count : n_maps_arg;
+  auto map_of = [&](int k) { return map_list ? map_list[k] : k; };
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int h = hp.h, w = hp.w, P = hp.P;
   const int lin_elems = (hp.map_stride + 3) & ~3;
   float* sm_lin[2] = {smem, smem + lin_elems};
-  float* sm_red = smem + 2 * lin_elems;                   // [6 * 32] floats
-  unsigned long long* sm_red64 = reinterpret_cast<unsigned long long*>(sm_red + 192);  // [32]
+  float* sm_hid = smem + 2 * lin_elems;                   // [2 buffers][nwarps][2 rows][128]
+  float* sm_red = sm_hid + 2 * nwarps * 2 * 128;          // [3 * 32] floats
+  unsigned long long* sm_red64 = reinterpret_cast<unsigned long long*>(sm_red + 96);  // [32]
 
   const int r0 = warp * 4, c0 = lane * 4;  // this lane's tile
   const int nchunks = hp.map_stride / 4;
   constexpr float kNeg = -1e30f;
   // additive masks: hidden activations of pixels outside the map must be exactly 0 (zero padding of the
   // second convolution); bias + kNeg makes the ReLU do that without per-pixel selects.
-  float rmask6[6], cmask[4];
+  float rmask[4], cmask[4];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) rmask6[i] = (r0 - 1 + i >= 0 && r0 - 1 + i < h) ? 0.f : kNeg;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) cmask[i] = (c0 + i < w) ? 0.f : kNeg;
+  for (int i = 0; i < 4; ++i) { rmask[i] = (r0 + i < h) ? 0.f : kNeg; cmask[i] = (c0 + i < w) ? 0.f : kNeg; }
   const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
 
-  int map = blockIdx.x;
-  if (map < n_maps) {
-    const float4* src = reinterpret_cast<const float4*>(maps + (size_t)map * hp.map_stride);
+  int mk = blockIdx.x;
+  if (mk < n_maps) {
+    const float4* src = reinterpret_cast<const float4*>(maps + (size_t)map_of(mk) * hp.map_stride);
     for (int i = threadIdx.x; i < nchunks; i += blockDim.x) cp_async16_head(sm_lin[0] + 4 * i, src + i);
   }
   asm volatile("cp.async.commit_group;\n" ::);
 
-  for (int it = 0; map < n_maps; map += gridDim.x, ++it) {
+  for (int it = 0; mk < n_maps; mk += gridDim.x, ++it) {
+    const int map = map_of(mk);
     const float* lin = sm_lin[it & 1];
     {  // prefetch the next map into the other buffer
-      int nmap = map + gridDim.x;
-      if (nmap < n_maps) {
-        const float4* src = reinterpret_cast<const float4*>(maps + (size_t)nmap * hp.map_stride);
+      int nmk = mk + gridDim.x;
+      if (nmk < n_maps) {
+        const float4* src = reinterpret_cast<const float4*>(maps + (size_t)map_of(nmk) * hp.map_stride);
         float* dst = sm_lin[(it + 1) & 1];
         for (int i = threadIdx.x; i < nchunks; i += blockDim.x) cp_async16_head(dst + 4 * i, src + i);
       }
@@ -113,11 +127,11 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
     for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
     if (lane == 0) sm_red64[warp] = key;
 
-    // ---- 8x6 input window: rows r0-2..r0+5, cols c0-1..c0+4 (zero outside the map = conv zero padding) --
-    float m[8][6];
+    // ---- 6x6 input window (zero outside the map = conv zero padding) -------------------------
+    float m[6][6];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int r = r0 - 2 + i;
+    for (int i = 0; i < 6; ++i) {
+      int r = r0 - 1 + i;
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         int c = c0 - 1 + j;
@@ -131,52 +145,68 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = wts.b2;
 
-    __syncthreads();  // publishes sm_red64 (arg-max partials); no block-wide sync inside the channel loop
-    // Each lane computes the hidden layer for its 4 columns on 6 rows (own 4 + the row above and below:
-    // 1.5x recompute instead of a shared-memory exchange + barrier per channel), takes the two side columns
-    // from its lane neighbours, and folds each hidden row into the (up to 3) output rows it touches.
-#pragma unroll 1
-    for (int o = 0; o < 16; ++o) {
-      float w1[9], w2[9];
+    float hid[6][6];  // [1..4][1..4] own values, ring = halo
+    auto conv1 = [&](int o) {
+      float w1[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) { w1[k] = wts.w1[o][k]; w2[k] = wts.w2[o][k]; }
+      for (int k = 0; k < 9; ++k) w1[k] = wts.w1[o][k];
       const float b1 = wts.b1[o];
 #pragma unroll
-      for (int hr = 0; hr < 6; ++hr) {
-        float hrow[6];
-        const float br = b1 + rmask6[hr];
+      for (int i = 0; i < 4; ++i) {
+        const float br = b1 + rmask[i];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float a = br + cmask[j];
 #pragma unroll
           for (int ki = 0; ki < 3; ++ki)
 #pragma unroll
-            for (int kj = 0; kj < 3; ++kj) a = fmaf(w1[ki * 3 + kj], m[hr + ki][j + kj], a);
-          hrow[j + 1] = fmaxf(a, 0.f);
-        }
-        if (kWrap) {
-          hrow[0] = __shfl_sync(0xffffffffu, hrow[4], lane_l);
-          hrow[5] = __shfl_sync(0xffffffffu, hrow[1], lane_r);
-        } else {
-          float l = __shfl_up_sync(0xffffffffu, hrow[4], 1);
-          float r = __shfl_down_sync(0xffffffffu, hrow[1], 1);
-          hrow[0] = lane > 0 ? l : 0.f;
-          hrow[5] = lane < 31 ? r : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ki = hr - i;  // hidden row hr is row (i - 1 + ki) of output row i's 3x3 window
-          if (ki >= 0 && ki < 3) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float a = acc[i][j];
-#pragma unroll
-              for (int kj = 0; kj < 3; ++kj) a = fmaf(w2[ki * 3 + kj], hrow[j + kj], a);
-              acc[i][j] = a;
-            }
-          }
+            for (int kj = 0; kj < 3; ++kj) a = fmaf(w1[ki * 3 + kj], m[i + ki][j + kj], a);
+          hid[i + 1][j + 1] = fmaxf(a, 0.f);
         }
       }
+      float* hb = sm_hid + ((o & 1) * nwarps + warp) * 2 * 128;
+      *reinterpret_cast<float4*>(hb + c0) = make_float4(hid[1][1], hid[1][2], hid[1][3], hid[1][4]);
+      *reinterpret_cast<float4*>(hb + 128 + c0) = make_float4(hid[4][1], hid[4][2], hid[4][3], hid[4][4]);
+    };
+
+    conv1(0);
+    __syncthreads();  // also publishes sm_red64 (arg-max partials)
+#pragma unroll 1
+    for (int o = 0; o < 16; ++o) {
+      float w2[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w2[k] = wts.w2[o][k];
+      // halo rows of channel o were published before the previous barrier
+      float4 top = make_float4(0.f, 0.f, 0.f, 0.f), bot = top;
+      if (warp > 0) top = *reinterpret_cast<const float4*>(sm_hid + ((o & 1) * nwarps + warp - 1) * 2 * 128 + 128 + c0);
+      if (warp + 1 < nwarps) bot = *reinterpret_cast<const float4*>(sm_hid + ((o & 1) * nwarps + warp + 1) * 2 * 128 + c0);
+      hid[0][1] = top.x; hid[0][2] = top.y; hid[0][3] = top.z; hid[0][4] = top.w;
+      hid[5][1] = bot.x; hid[5][2] = bot.y; hid[5][3] = bot.z; hid[5][4] = bot.w;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (kWrap) {
+          hid[i][0] = __shfl_sync(0xffffffffu, hid[i][4], lane_l);
+          hid[i][5] = __shfl_sync(0xffffffffu, hid[i][1], lane_r);
+        } else {
+          float l = __shfl_up_sync(0xffffffffu, hid[i][4], 1);
+          float r = __shfl_down_sync(0xffffffffu, hid[i][1], 1);
+          hid[i][0] = lane > 0 ? l : 0.f;
+          hid[i][5] = lane < 31 ? r : 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = acc[i][j];
+#pragma unroll
+          for (int ki = 0; ki < 3; ++ki)
+#pragma unroll
+            for (int kj = 0; kj < 3; ++kj) a = fmaf(w2[ki * 3 + kj], hid[i + ki][j + kj], a);
+          acc[i][j] = a;
+        }
+      if (o + 1 < 16) conv1(o + 1);   // next channel's hidden layer; published by the barrier below
+      __syncthreads();
     }
 
     // ---- arg-max result (partials were published before the first barrier) ---------------------
@@ -269,9 +299,180 @@ head_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_h
   asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Fast path: exact refiner on the 11x11 box around the arg-max + certified absence of the fallback branch.
+constexpr int WIN_THREADS = 128;
+constexpr int WB = 11, WH = 13, WM = 15;  // box, hidden window, input window (side lengths); disc radius <= 5 tokens
+
+__global__ void __launch_bounds__(WIN_THREADS)
+head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_head_weights wts,
+                   const int* __restrict__ out_index, float* __restrict__ out, int* __restrict__ aux,
+                   int* __restrict__ slow_list, int* __restrict__ slow_count) {
+  extern __shared__ __align__(16) float smem[];
+  const int lin_elems = (hp.map_stride + 3) & ~3;
+  float* sm_lin[2] = {smem, smem + lin_elems};
+  float* sm_m = smem + 2 * lin_elems;          // [WM][WM] input window, zero outside the map
+  float* sm_h = sm_m + WM * WM + 3;            // [16][WH][WH] hidden window, zero outside the map
+  float* sm_red = sm_h + 16 * WH * WH;         // [8][4] partials
+  unsigned long long* sm_key = reinterpret_cast<unsigned long long*>(sm_red + 32);  // [4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = hp.h, w = hp.w, P = hp.P;
+  const int nchunks = hp.map_stride / 4;
+
+  int map = blockIdx.x;
+  if (map < n_maps) {
+    const float4* src = reinterpret_cast<const float4*>(maps + (size_t)map * hp.map_stride);
+    for (int i = tid; i < nchunks; i += WIN_THREADS) cp_async16_head(sm_lin[0] + 4 * i, src + i);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+
+  for (int it = 0; map < n_maps; map += gridDim.x, ++it) {
+    const float* lin = sm_lin[it & 1];
+    {
+      int nmap = map + gridDim.x;
+      if (nmap < n_maps) {
+        const float4* src = reinterpret_cast<const float4*>(maps + (size_t)nmap * hp.map_stride);
+        float* dst = sm_lin[(it + 1) & 1];
+        for (int i = tid; i < nchunks; i += WIN_THREADS) cp_async16_head(dst + 4 * i, src + i);
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    }
+    __syncthreads();
+
+    // ---- arg-max (first maximal index) ---------------------------------------------------------
+    unsigned long long key = 0ull;
+    for (int i = tid; i < P; i += WIN_THREADS) {
+      float v = lin[i] + 0.f;
+      unsigned long long k = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(0x7fffffff - i);
+      key = k > key ? k : key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
+    if (lane == 0) sm_key[warp] = key;
+    __syncthreads();
+    unsigned long long kb = sm_key[0];
+#pragma unroll
+    for (int k = 1; k < WIN_THREADS / 32; ++k) { unsigned long long t = sm_key[k]; kb = t > kb ? t : kb; }
+    const int amax = 0x7fffffff - (int)(kb & 0xffffffffu);
+    const int arow = amax / w, acol = amax - arow * w;
+
+    // ---- largest map value outside the 7x7 core (bounds every hidden / logit outside the box) -----
+    float mout = 0.f;
+    for (int r = warp; r < h; r += WIN_THREADS / 32) {
+      const bool row_core = (r >= arow - 3) && (r <= arow + 3);
+      for (int c = lane; c < w; c += 32) {
+        float v = lin[r * w + c];
+        if (!(row_core && c >= acol - 3 && c <= acol + 3)) mout = fmaxf(mout, v);
+      }
+    }
+    mout = warp_max(mout);
+    // ---- input window (15 x 15, zero outside the map) ---------------------------------------------
+    for (int i = tid; i < WM * WM; i += WIN_THREADS) {
+      int y = i / WM, x = i - y * WM;
+      int r = arow - 7 + y, c = acol - 7 + x;
+      sm_m[i] = (r >= 0 && r < h && c >= 0 && c < w) ? lin[r * w + c] : 0.f;
+    }
+    if (lane == 0) sm_red[warp] = mout;
+    __syncthreads();
+    mout = fmaxf(fmaxf(sm_red[0], sm_red[1]), fmaxf(sm_red[2], sm_red[3]));
+
+    // ---- hidden layer on the 13 x 13 window (zero outside the map: padding of the second conv) -----
+    for (int i = tid; i < WH * WH; i += WIN_THREADS) {
+      int y = i / WH, x = i - y * WH;
+      int r = arow - 6 + y, c = acol - 6 + x;
+      const bool inside = r >= 0 && r < h && c >= 0 && c < w;
+      float mw[9];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) mw[ky * 3 + kx] = sm_m[(y + ky) * WM + x + kx];
+#pragma unroll 4
+      for (int o = 0; o < 16; ++o) {
+        float a = wts.b1[o];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a = fmaf(wts.w1[o][k], mw[k], a);
+        sm_h[o * WH * WH + i] = inside ? fmaxf(a, 0.f) : 0.f;
+      }
+    }
+    __syncthreads();
+
+    // ---- logits on the 11 x 11 box; thread = box pixel ----------------------------------------------
+    float z = -INFINITY;
+    bool valid = false, indisc = false;
+    float px = 0.f, py = 0.f;
+    if (tid < WB * WB) {
+      int y = tid / WB, x = tid - y * WB;
+      int r = arow - 5 + y, c = acol - 5 + x;
+      valid = r >= 0 && r < h && c >= 0 && c < w;
+      if (valid) {
+        float a = wts.b2;
+#pragma unroll 4
+        for (int o = 0; o < 16; ++o) {
+          const float* hb = sm_h + o * WH * WH + y * WH + x;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) a = fmaf(wts.w2[o][ky * 3 + kx], hb[ky * WH + kx], a);
+        }
+        z = a;
+        int dr = (r - arow) * hp.stride_px, dc = (c - acol) * hp.stride_px;
+        indisc = dr * dr + dc * dc <= hp.radius2;
+        px = (float)(hp.half_patch + c * hp.stride_px);
+        py = (float)(hp.half_patch + r * hp.stride_px);
+      }
+    }
+    float zmax = warp_max(z);
+    if (lane == 0) sm_red[8 + warp] = zmax;
+    __syncthreads();
+    zmax = fmaxf(fmaxf(sm_red[8], sm_red[9]), fmaxf(sm_red[10], sm_red[11]));
+    const float e = valid ? expf(z - zmax) : 0.f;
+    float v5[5] = {e, indisc ? e : 0.f, indisc ? px * e : 0.f, indisc ? py * e : 0.f, valid ? 1.f : 0.f};
+#pragma unroll
+    for (int q = 0; q < 5; ++q) v5[q] = warp_sum(v5[q]);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) sm_red[12 + q * 4 + warp] = v5[q];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float tot[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) tot[q] = sm_red[12 + q * 4] + sm_red[13 + q * 4] + sm_red[14 + q * 4] + sm_red[15 + q * 4];
+      // every logit outside the box:  z <= b2 + sum_o P2_o * relu(b1_o + P1_o * mout)   (all terms monotone in m >= 0)
+      float F = wts.b2;
+#pragma unroll
+      for (int o = 0; o < 16; ++o) F = fmaf(hp.P2[o], fmaxf(fmaf(hp.P1[o], mout, wts.b1[o]), 0.f), F);
+      const float rest = ((float)P - tot[4]) * expf(fminf(F - zmax, 80.f));
+      // certified: disc mass >= 2e-8 of (an upper bound of) the whole softmax  ->  the reference does not take the
+      // stability branch and its result is sum(x e) / sum(e) over the disc (the normaliser cancels)
+      const bool certified = tot[1] >= 2e-8f * (tot[0] + rest) && tot[1] > 0.f && isfinite(rest);
+      if (certified) {
+        float px_ = __fdiv_rn(tot[2], tot[1]), py_ = __fdiv_rn(tot[3], tot[1]);
+        float nx = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(px_, hp.normW)), -1.f);
+        float ny = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(py_, hp.normH)), -1.f);
+        if (hp.out_mode == 0) {
+          nx = __fmul_rn(__fdiv_rn(__fadd_rn(nx, 1.f), 2.f), hp.normW);
+          ny = __fmul_rn(__fdiv_rn(__fadd_rn(ny, 1.f), 2.f), hp.normH);
+        }
+        size_t oi = (size_t)(out_index ? out_index[map] : map) * hp.out_stride;
+        out[oi] = nx; out[oi + 1] = ny;
+        if (aux) { aux[2 * map] = amax; aux[2 * map + 1] = 0; }
+      } else {
+        slow_list[atomicAdd(slow_count, 1)] = map;
+      }
+    }
+    __syncthreads();  // lin / windows are reused by the next iteration
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
+__global__ void zero_int_kernel(int* p) { *p = 0; }
+
 int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geom& g,
                 const dinotrk_head_weights& hw, const int* out_index, float* out, int out_stride, int out_mode,
-                int* aux, cudaStream_t st) {
+                int* aux, int* scratch, cudaStream_t st) {
   if (n_maps <= 0) return DINOTRK_OK;
   DTK_CHECK_ARG(g.w <= HEAD_MAX_W && g.h <= HEAD_MAX_H, "head: token grid %dx%d exceeds the supported %dx%d",
                 g.h, g.w, HEAD_MAX_H, HEAD_MAX_W);
@@ -280,25 +481,56 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
   hp.stride_px = g.stride; hp.half_patch = g.patch / 2; hp.radius2 = g.radius * g.radius;
   hp.normW = (float)(g.W - 1); hp.normH = (float)(g.H - 1);
   hp.out_stride = out_stride; hp.out_mode = out_mode;
+  for (int o = 0; o < 16; ++o) {
+    float p1 = 0.f, p2 = 0.f;
+    for (int k = 0; k < 9; ++k) { p1 += hw.w1[o][k] > 0.f ? hw.w1[o][k] : 0.f; p2 += hw.w2[o][k] > 0.f ? hw.w2[o][k] : 0.f; }
+    hp.P1[o] = p1 * (1.f + 1e-6f); hp.P2[o] = p2 * (1.f + 1e-6f);   // rounded up: the bound must stay a bound
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int lin_elems = (map_stride + 3) & ~3;
+  // the window fast path needs the disc inside the 11 x 11 box and a scratch list for the uncertified maps
+  const bool window_ok = scratch != nullptr && g.radius <= 5 * g.stride && g.w <= HEAD_MAX_W;
+  int* slow_count = scratch;
+  int* slow_list = scratch ? scratch + 1 : nullptr;
+  if (window_ok) {
+    size_t smem = (size_t)(2 * lin_elems + WM * WM + 3 + 16 * WH * WH + 32) * sizeof(float) + 4 * sizeof(unsigned long long);
+    static size_t attr_w = 0;
+    if (smem > attr_w) {
+      DTK_CUDA(cudaFuncSetAttribute(head_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_w = smem;
+    }
+    {
+      ProfRange pr(PROF_MISC, st);
+      zero_int_kernel<<<1, 1, 0, st>>>(slow_count);
+      DTK_LAUNCHED();
+    }
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int grid = n_maps < sms * per_sm ? n_maps : sms * per_sm;
+    ProfRange pr(PROF_HEAD, st);
+    head_window_kernel<<<grid, WIN_THREADS, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux, slow_list, slow_count);
+    DTK_LAUNCHED();
+  }
+  // full-map kernel: every map (no scratch) or only the maps the window kernel could not certify
   const int nwarps = cdiv(g.h, 4);
   const int threads = nwarps * 32;
-  const int lin_elems = (map_stride + 3) & ~3;
-  size_t smem = (size_t)(2 * lin_elems + 6 * 32) * sizeof(float) + 32 * sizeof(unsigned long long);
+  size_t smem = (size_t)(2 * lin_elems + 2 * nwarps * 2 * 128 + 6 * 32) * sizeof(float) + 32 * sizeof(unsigned long long);
   static size_t attr_smem[4] = {0, 0, 0, 0};
   const bool wrap = g.w <= 124;                 // tile 31 of every band lies outside the map
-  const int variant = (threads <= 544 ? 0 : 2) + (wrap ? 0 : 1);  // <= 544 threads: 120 registers/thread; else 64
-  auto kern = variant == 0 ? head_kernel<544, true> : variant == 1 ? head_kernel<544, false>
+  const int variant = (threads <= 576 ? 0 : 2) + (wrap ? 0 : 1);  // <= 576 threads: 112 registers/thread; else 64
+  auto kern = variant == 0 ? head_kernel<576, true> : variant == 1 ? head_kernel<576, false>
             : variant == 2 ? head_kernel<1024, true> : head_kernel<1024, false>;
   if (smem > attr_smem[variant]) {
     DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem[variant] = smem;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = n_maps < sms ? n_maps : sms;
-  ProfRange pr(PROF_HEAD, st);
-  kern<<<grid, threads, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux);
+  ProfRange pr(PROF_HEAD_FULL, st);
+  kern<<<grid, threads, smem, st>>>(maps, n_maps, window_ok ? slow_list : nullptr, window_ok ? slow_count : nullptr, hp,
+                                    hw, out_index, out, aux);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }
@@ -308,9 +540,10 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
 using namespace dtk;
 
 extern "C" int dinotrk_head(const float* maps, int n_maps, const dinotrk_geom* g, const dinotrk_head_weights* hw,
-                            const int* out_index, float* out, int out_stride, int out_mode, int* aux, void* stream) {
+                            const int* out_index, float* out, int out_stride, int out_mode, int* aux, int* scratch,
+                            void* stream) {
   DTK_CHECK_ARG(maps && g && hw && out, "head: null pointer");
   DTK_CHECK_ARG(out_stride >= 2 && (out_mode == 0 || out_mode == 1), "head: bad out_stride/out_mode");
-  return launch_head(maps, n_maps, dinotrk_map_stride(g), *g, *hw, out_index, out, out_stride, out_mode, aux,
+  return launch_head(maps, n_maps, dinotrk_map_stride(g), *g, *hw, out_index, out, out_stride, out_mode, aux, scratch,
                      (cudaStream_t)stream);
 }

@@ -222,7 +222,7 @@ extern "C" {
 size_t dinotrk_corr_track_workspace_bytes(int total_maps, int n_groups, int C, const dinotrk_geom* g) {
   if (!g) return 0;
   return align_up((size_t)total_maps * dinotrk_map_stride(g) * sizeof(float), 256) + corr_plan_bytes(n_groups) +
-         corr_tc_workspace_bytes(total_maps, C) + 1024;
+         corr_tc_workspace_bytes(total_maps, C) + align_up((size_t)(total_maps + 1) * 4, 256) + 1024;
 }
 
 int dinotrk_corr_track(const dinotrk_features* feat, const dinotrk_geom* g,
@@ -243,11 +243,12 @@ int dinotrk_corr_track(const dinotrk_features* feat, const dinotrk_geom* g,
   float* maps = ar.take<float>((size_t)total_maps * ms);
   int* plan = ar.take<int>(n_groups + 1);
   float* split = ar.take<float>(corr_tc_workspace_bytes(total_maps, C) / 4);
+  int* hscratch = ar.take<int>(total_maps + 1);
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_corr_maps(make_view(*feat, *g), desc, total_maps, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
                             n_groups, total_maps, max_group_m, maps, ms, plan, split, st);
   if (rc) return rc;
-  return launch_head(maps, total_maps, ms, *g, *hw, out_index, out, out_stride, out_mode, nullptr, st);
+  return launch_head(maps, total_maps, ms, *g, *hw, out_index, out, out_stride, out_mode, nullptr, hscratch, st);
 }
 
 static int infer_chunk_maps(int chunk_maps) { return chunk_maps > 0 ? chunk_maps : 4096; }
@@ -264,6 +265,7 @@ size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N,
   b += align_up((size_t)5 * gcap * 4, 256) + align_up((size_t)(gcap + 1) * 4, 256);  // groups, plan
   b += align_up((size_t)T * 4, 256) + align_up((size_t)T * N * 4, 256);    // cnt, qlist
   b += corr_tc_workspace_bytes((int)(ch > (size_t)N ? ch : (size_t)N), C) + 256;  // TF32 split of the descriptors
+  b += align_up((ch + 1) * 4, 256);                                        // head: list of uncertified maps
   return b + 4096;
 }
 
@@ -342,6 +344,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   int* d_cnt = ar.take<int>(T);
   int* d_qlist = ar.take<int>((size_t)T * N);
   float* split = ar.take<float>(corr_tc_workspace_bytes(ch > N ? ch : N, C) / 4);
+  int* hscratch = ar.take<int>(ch + 1);
   DTK_CHECK_ARG(ar.ok(), "infer: workspace arena overflow");
 
   GroupBuf gb(gcap);
@@ -380,7 +383,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
       }
       rc = launch_corr_maps(fv, descA, N, normA, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, split, st);
       if (rc) return rc;
-      rc = launch_head(maps, used, ms, *g, *hw, out_index, traj, 3, 0, nullptr, st);
+      rc = launch_head(maps, used, ms, *g, *hw, out_index, traj, 3, 0, nullptr, hscratch, st);
       if (rc) return rc;
     }
   }
@@ -432,7 +435,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
       }
       rc = launch_corr_maps(fv, descC, used, normC, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, split, st);
       if (rc) return rc;
-      rc = launch_head(maps, used, ms, *g, *hw, out_index, anchors, 2, 0, nullptr, st);
+      rc = launch_head(maps, used, ms, *g, *hw, out_index, anchors, 2, 0, nullptr, hscratch, st);
       if (rc) return rc;
     }
   }

@@ -112,10 +112,12 @@ int dinotrk_corr_maps(const dinotrk_features* feat, const dinotrk_geom* g,
                       int total_maps, int max_group_m, float* maps, void* workspace,
                       size_t workspace_bytes, void* stream);
 /* Head only: maps -> (x, y) (tracker_head.py:107-121).  aux (may be NULL) receives per map
- * {argmax index, fallback flag} as int32[2]. */
+ * {argmax index, fallback flag} as int32[2].  scratch: device int32[n_maps + 1] enabling the windowed
+ * fast path (exact refiner on the 11x11 box around the arg-max + certified absence of the stability
+ * branch; uncertified maps go to the full-map kernel); NULL: full-map kernel for every map. */
 int dinotrk_head(const float* maps, int n_maps, const dinotrk_geom* g,
                  const dinotrk_head_weights* hw, const int* out_index, float* out,
-                 int out_stride, int out_mode, int* aux, void* stream);
+                 int out_stride, int out_mode, int* aux, int* scratch, void* stream);
 
 /* ---- inference driver (models/model_inference.py:97-216) ------------------------------- */
 /* query_points [N][3] (x, y, t) px; frame_batch = the reference's --batch-size (0 = whole

@@ -131,9 +131,12 @@ def test_corr_gemm_error_vs_float64(precision):
     assert err <= (3e-6 if precision == "fp32" else 4e-5)
 
 
+@pytest.mark.parametrize("fast", [True, False])
 @pytest.mark.parametrize("kind", ["well", "sharp", "mixed", "default"])
 @pytest.mark.parametrize("geo", [Geometry(H=98, W=126), Geometry(H=476, W=854)])
-def test_head_matches_oracle(kind, geo):
+def test_head_matches_oracle(kind, geo, fast):
+    """fast=True: windowed kernel + certified bound, uncertified maps re-done by the full-map kernel;
+    fast=False: full-map kernel for every map."""
     from dino_tracker_b200 import _lib
     lib = _lib.load()
     rs = np.random.RandomState(3)
@@ -153,8 +156,14 @@ def test_head_matches_oracle(kind, geo):
     buf[:, : geo.P] = torch.from_numpy(maps.reshape(n, -1)).to(DEV)
     out = torch.empty(n, 2, device=DEV)
     aux = torch.empty(n, 2, device=DEV, dtype=torch.int32)
+    scratch = torch.zeros(n + 1, device=DEV, dtype=torch.int32) if fast else None
     _lib.check(lib.dinotrk_head(_lib.ptr(buf), n, ctypes.byref(model._geom), ctypes.byref(model.head_weights()), None,
-                                _lib.ptr(out), 2, 1, _lib.ptr(aux), _lib.stream_ptr()))
+                                _lib.ptr(out), 2, 1, _lib.ptr(aux), _lib.ptr(scratch), _lib.stream_ptr()))
+    if fast:
+        n_slow = int(scratch[0])
+        print(f"[{kind} {geo.h}x{geo.w}] maps sent to the full-map kernel: {n_slow}/{n}")
+        if kind in ("well", "sharp"):
+            assert n_slow <= 2  # (the all-zero map may not certify)
     ref, raux = ot.head_forward(torch.from_numpy(maps)[:, None], head, geo, return_aux=True)
     assert torch.equal(aux[:, 0].cpu().long(), raux["argmax"])
     assert torch.equal(aux[:, 1].cpu().bool(), raux["fallback"])
