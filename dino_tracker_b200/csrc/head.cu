@@ -311,43 +311,37 @@ head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, di
                    int* __restrict__ slow_list, int* __restrict__ slow_count) {
   extern __shared__ __align__(16) float smem[];
   const int lin_elems = (hp.map_stride + 3) & ~3;
-  float* sm_lin[2] = {smem, smem + lin_elems};
-  float* sm_m = smem + 2 * lin_elems;          // [WM][WM] input window, zero outside the map
+  float* lin = smem;                           // one map (several CTAs per SM hide the load latency)
+  float* sm_m = smem + lin_elems;              // [WM][WM] input window, zero outside the map
   float* sm_h = sm_m + WM * WM + 3;            // [16][WH][WH] hidden window, zero outside the map
-  float* sm_red = sm_h + 16 * WH * WH;         // [8][4] partials
+  float* sm_red = sm_h + 16 * WH * WH;         // partials
   unsigned long long* sm_key = reinterpret_cast<unsigned long long*>(sm_red + 32);  // [4]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = hp.h, w = hp.w, P = hp.P;
-  const int nchunks = hp.map_stride / 4;
+  const int nchunks = hp.map_stride / 4;       // float4 chunks; the tail of the last chunk (>= P) is masked below
 
-  int map = blockIdx.x;
-  if (map < n_maps) {
-    const float4* src = reinterpret_cast<const float4*>(maps + (size_t)map * hp.map_stride);
-    for (int i = tid; i < nchunks; i += WIN_THREADS) cp_async16_head(sm_lin[0] + 4 * i, src + i);
-  }
-  asm volatile("cp.async.commit_group;\n" ::);
-
-  for (int it = 0; map < n_maps; map += gridDim.x, ++it) {
-    const float* lin = sm_lin[it & 1];
+  for (int map = blockIdx.x; map < n_maps; map += gridDim.x) {
     {
-      int nmap = map + gridDim.x;
-      if (nmap < n_maps) {
-        const float4* src = reinterpret_cast<const float4*>(maps + (size_t)nmap * hp.map_stride);
-        float* dst = sm_lin[(it + 1) & 1];
-        for (int i = tid; i < nchunks; i += WIN_THREADS) cp_async16_head(dst + 4 * i, src + i);
-      }
+      const float4* src = reinterpret_cast<const float4*>(maps + (size_t)map * hp.map_stride);
+      for (int i = tid; i < nchunks; i += WIN_THREADS) cp_async16_head(lin + 4 * i, src + i);
       asm volatile("cp.async.commit_group;\n" ::);
-      asm volatile("cp.async.wait_group 1;\n" ::);
+      asm volatile("cp.async.wait_group 0;\n" ::);
     }
     __syncthreads();
 
-    // ---- arg-max (first maximal index) ---------------------------------------------------------
-    unsigned long long key = 0ull;
-    for (int i = tid; i < P; i += WIN_THREADS) {
-      float v = lin[i] + 0.f;
-      unsigned long long k = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(0x7fffffff - i);
-      key = k > key ? k : key;
+    // ---- arg-max (first maximal index): chunk-wise maxima, then the first chunk / element holding the max ----
+    float best = -1.f;
+    int bchunk = 0;
+    for (int i = tid; i < nchunks; i += WIN_THREADS) {
+      float4 v = *reinterpret_cast<const float4*>(lin + 4 * i);
+      const int base = 4 * i;
+      float m4 = v.x;                                          // element base always < P
+      if (base + 1 < P) m4 = fmaxf(m4, v.y);
+      if (base + 2 < P) m4 = fmaxf(m4, v.z);
+      if (base + 3 < P) m4 = fmaxf(m4, v.w);
+      if (m4 > best) { best = m4; bchunk = i; }                // strict: keeps the first chunk of this thread
     }
+    unsigned long long key = ((unsigned long long)__float_as_uint(best + 0.f) << 32) | (unsigned)(0x7fffffff - bchunk);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
     if (lane == 0) sm_key[warp] = key;
@@ -355,29 +349,27 @@ head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, di
     unsigned long long kb = sm_key[0];
 #pragma unroll
     for (int k = 1; k < WIN_THREADS / 32; ++k) { unsigned long long t = sm_key[k]; kb = t > kb ? t : kb; }
-    const int amax = 0x7fffffff - (int)(kb & 0xffffffffu);
+    const int wchunk = 0x7fffffff - (int)(kb & 0xffffffffu);
+    const float vmax = __uint_as_float((unsigned)(kb >> 32));
+    int amax = 4 * wchunk;
+    {
+      const float* q = lin + 4 * wchunk;
+      amax += (q[0] + 0.f == vmax) ? 0 : (q[1] + 0.f == vmax) ? 1 : (q[2] + 0.f == vmax) ? 2 : 3;
+    }
     const int arow = amax / w, acol = amax - arow * w;
 
-    // ---- largest map value outside the 7x7 core (bounds every hidden / logit outside the box) -----
-    float mout = 0.f;
-    for (int r = warp; r < h; r += WIN_THREADS / 32) {
-      const bool row_core = (r >= arow - 3) && (r <= arow + 3);
-      for (int c = lane; c < w; c += 32) {
-        float v = lin[r * w + c];
-        if (!(row_core && c >= acol - 3 && c <= acol + 3)) mout = fmaxf(mout, v);
-      }
-    }
-    mout = warp_max(mout);
     // ---- input window (15 x 15, zero outside the map) ---------------------------------------------
     for (int i = tid; i < WM * WM; i += WIN_THREADS) {
       int y = i / WM, x = i - y * WM;
       int r = arow - 7 + y, c = acol - 7 + x;
       sm_m[i] = (r >= 0 && r < h && c >= 0 && c < w) ? lin[r * w + c] : 0.f;
     }
-    if (lane == 0) sm_red[warp] = mout;
     __syncthreads();
-    mout = fmaxf(fmaxf(sm_red[0], sm_red[1]), fmaxf(sm_red[2], sm_red[3]));
-
+    // ---- largest map value outside the 7x7 core: blank the core in the private copy, then a plain max ----
+    if (tid < 49) {
+      int r = arow - 3 + tid / 7, c = acol - 3 + tid % 7;
+      if (r >= 0 && r < h && c >= 0 && c < w) lin[r * w + c] = 0.f;
+    }
     // ---- hidden layer on the 13 x 13 window (zero outside the map: padding of the second conv) -----
     for (int i = tid; i < WH * WH; i += WIN_THREADS) {
       int y = i / WH, x = i - y * WH;
@@ -397,6 +389,17 @@ head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, di
       }
     }
     __syncthreads();
+    float mout = 0.f;
+    for (int i = tid; i < nchunks; i += WIN_THREADS) {
+      float4 v = *reinterpret_cast<const float4*>(lin + 4 * i);
+      const int base = 4 * i;
+      float m4 = v.x;
+      if (base + 1 < P) m4 = fmaxf(m4, v.y);
+      if (base + 2 < P) m4 = fmaxf(m4, v.z);
+      if (base + 3 < P) m4 = fmaxf(m4, v.w);
+      mout = fmaxf(mout, m4);
+    }
+    mout = warp_max(mout);
 
     // ---- logits on the 11 x 11 box; thread = box pixel ----------------------------------------------
     float z = -INFINITY;
@@ -424,8 +427,9 @@ head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, di
       }
     }
     float zmax = warp_max(z);
-    if (lane == 0) sm_red[8 + warp] = zmax;
+    if (lane == 0) { sm_red[warp] = mout; sm_red[8 + warp] = zmax; }
     __syncthreads();
+    mout = fmaxf(fmaxf(sm_red[0], sm_red[1]), fmaxf(sm_red[2], sm_red[3]));
     zmax = fmaxf(fmaxf(sm_red[8], sm_red[9]), fmaxf(sm_red[10], sm_red[11]));
     const float e = valid ? expf(z - zmax) : 0.f;
     float v5[5] = {e, indisc ? e : 0.f, indisc ? px * e : 0.f, indisc ? py * e : 0.f, valid ? 1.f : 0.f};
@@ -465,7 +469,6 @@ head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, di
     }
     __syncthreads();  // lin / windows are reused by the next iteration
   }
-  asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
 __global__ void zero_int_kernel(int* p) { *p = 0; }
@@ -495,7 +498,7 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
   int* slow_count = scratch;
   int* slow_list = scratch ? scratch + 1 : nullptr;
   if (window_ok) {
-    size_t smem = (size_t)(2 * lin_elems + WM * WM + 3 + 16 * WH * WH + 32) * sizeof(float) + 4 * sizeof(unsigned long long);
+    size_t smem = (size_t)(lin_elems + WM * WM + 3 + 16 * WH * WH + 32) * sizeof(float) + 4 * sizeof(unsigned long long);
     static size_t attr_w = 0;
     if (smem > attr_w) {
       DTK_CUDA(cudaFuncSetAttribute(head_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
