@@ -341,7 +341,9 @@ head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, di
       if (base + 3 < P) m4 = fmaxf(m4, v.w);
       if (m4 > best) { best = m4; bchunk = i; }                // strict: keeps the first chunk of this thread
     }
-    unsigned long long key = ((unsigned long long)__float_as_uint(best + 0.f) << 32) | (unsigned)(0x7fffffff - bchunk);
+    // threads without a chunk (tiny maps) must not win: key 0 (values are >= 0, so real keys order like floats)
+    unsigned long long key = best < 0.f ? 0ull
+        : (((unsigned long long)__float_as_uint(best + 0.f) << 32) | (unsigned)(0x7fffffff - bchunk));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
     if (lane == 0) sm_key[warp] = key;
