@@ -55,6 +55,9 @@ SIGNATURES = {
     "dinotrk_delta_workspace_bytes": (c_size_t, [c_int, c_int, c_int, POINTER(c_int)]),
     "dinotrk_delta_refine": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), POINTER(c_void_p), POINTER(c_void_p), _P,
                                      _P, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "dinotrk_best_buddies_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dinotrk_best_buddies_pairs": (c_int, [POINTER(Features), POINTER(Geom), _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
+    "dinotrk_bb_mutual": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "dinotrk_profile_classes": (c_int, []),
     "dinotrk_profile_class_name": (c_char_p, [c_int]),
     "dinotrk_profile_enable": (None, [c_int]),

@@ -90,7 +90,10 @@ struct CorrEpi {
   const int* grp_map0;
   float* maps;
   int map_stride, P;
-  __device__ __forceinline__ void operator()(int g, int r, int col0, const float (&f)[32], int ncols) const {
+  struct State {};
+  __device__ __forceinline__ void tile_begin(State&) const {}
+  __device__ __forceinline__ void tile_end(State&, int, int, int) const {}
+  __device__ __forceinline__ void operator()(State&, int g, int r, int col0, const float (&f)[32], int ncols) const {
     const float dn = desc_norm[grp_row0[g] + r];
     const float* fn = norms + (size_t)grp_frame[g] * P + col0;
     float* out = maps + (size_t)(grp_map0[g] + r) * map_stride + col0;

@@ -48,8 +48,11 @@ struct TcProblem {
   int N, K;                // B rows per batch item, reduction length
 };
 
-// Epi must provide:  __device__ void operator()(int g, int r_in_group, int col0, const float (&v)[32], int ncols_valid)
-// for one row (r_in_group) and 32 consecutive columns starting at col0.
+// Epi must provide a per-thread `State` plus
+//   tile_begin(State&)                                                      once per (row, tile)
+//   operator()(State&, int g, int r_in_group, int col0, const float (&v)[32], int ncols_valid)
+//                                                                           per 32 consecutive columns
+//   tile_end(State&, int g, int r_in_group, int n_tile)                     once per (row, tile)
 template <TcMode MODE, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -166,6 +169,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       decode(tile, g, m0, n0);
       const int r = m0 + quad * 32 + lane;       // row inside the group
       const bool row_ok = r < pb.grp_m[g];
+      typename Epi::State est;
+      epi.tile_begin(est);
       tc::mbar_wait(&tfull[buf], aphase);
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN;
@@ -179,9 +184,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          epi(g, r, n0 + c, f, ncols);
+          epi(est, g, r, n0 + c, f, ncols);
         }
       }
+      if (row_ok) epi.tile_end(est, g, r, n0 / TC_BN);
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[buf]);

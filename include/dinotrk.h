@@ -154,6 +154,18 @@ int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* ch
                          const float* ixs, const float* iys, int h, int w, float* refined_tpc,
                          float* norms, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- best buddies (preprocessing_dino_bb/extract_dino_best_buddies.py:12-54) ------------------------ */
+/* For every ordered pair k (source frame pair_src[k], target frame pair_tgt[k]; device int32[n_pairs]):
+ * nn_idx[k][n] = argmax_m cos(F_src[n], F_tgt[m]) (first maximum), nn_cos[k][n] = that cosine (exact fp32,
+ * clamp 1e-8 on the norm product).  The affinity matrix runs through the tcgen05 3xTF32 GEMM and never
+ * leaves TMEM; candidates are re-evaluated in exact fp32.  feat->hi / lo are required. */
+size_t dinotrk_best_buddies_workspace_bytes(int n_pairs, int P);
+int dinotrk_best_buddies_pairs(const dinotrk_features* feat, const dinotrk_geom* g, const int* pair_src,
+                               const int* pair_tgt, int n_pairs, int* nn_idx, float* nn_cos,
+                               void* workspace, size_t workspace_bytes, void* stream);
+/* mutual[k][n] = (nn_ts[k][nn_st[k][n]] == n): source token n of pair k is a best buddy. */
+int dinotrk_bb_mutual(const int* nn_st, const int* nn_ts, int n_pairs, int P, uint8_t* mutual, void* stream);
+
 /* ---- per-kernel-class device timing (CUDA events on the launching stream; bench.py roofline) ------ */
 int dinotrk_profile_classes(void);
 const char* dinotrk_profile_class_name(int cls);
