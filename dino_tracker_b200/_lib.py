@@ -24,6 +24,15 @@ class Features(Structure):
     _fields_ = [("tpc", c_void_p), ("norms", c_void_p), ("hi", c_void_p), ("lo", c_void_p), ("T", c_int), ("C", c_int)]
 
 
+class VitConfig(Structure):
+    _fields_ = [("depth", c_int), ("dim", c_int), ("heads", c_int), ("tap_layer", c_int), ("patch", c_int), ("stride", c_int)]
+
+
+class VitWeights(Structure):
+    _fields_ = [("patch_w", c_void_p), ("patch_b", c_void_p), ("cls_pos", c_void_p), ("pos", c_void_p),
+                ("blocks", POINTER(c_void_p))]
+
+
 class DinotrkError(RuntimeError):
     pass
 
@@ -55,6 +64,8 @@ SIGNATURES = {
     "dinotrk_delta_workspace_bytes": (c_size_t, [c_int, c_int, c_int, POINTER(c_int)]),
     "dinotrk_delta_refine": (c_int, [_P, c_int, c_int, c_int, POINTER(c_int), POINTER(c_void_p), POINTER(c_void_p), _P,
                                      _P, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "dinotrk_vit_workspace_bytes": (c_size_t, [POINTER(VitConfig), POINTER(Geom), c_int]),
+    "dinotrk_vit_forward": (c_int, [_P, c_int, POINTER(Geom), POINTER(VitConfig), POINTER(VitWeights), _P, _P, c_size_t, _P]),
     "dinotrk_best_buddies_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dinotrk_best_buddies_pairs": (c_int, [POINTER(Features), POINTER(Geom), _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "dinotrk_bb_mutual": (c_int, [_P, _P, c_int, c_int, _P, _P]),

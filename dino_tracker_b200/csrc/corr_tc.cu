@@ -40,16 +40,18 @@ static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t
 }
 
 int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
-                 int elem_bytes) {
+                 int elem_bytes, uint64_t ld) {
+  if (ld == 0) ld = cols;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   return encode(map, base, 2, dims, strides, box, elem_bytes);
 }
 int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                 uint32_t box_cols, int elem_bytes) {
+                 uint32_t box_cols, int elem_bytes, uint64_t ld) {
+  if (ld == 0) ld = cols;
   cuuint64_t dims[3] = {cols, rows, batch};
-  cuuint64_t strides[2] = {cols * (uint64_t)elem_bytes, rows * cols * (uint64_t)elem_bytes};
+  cuuint64_t strides[2] = {ld * (uint64_t)elem_bytes, rows * ld * (uint64_t)elem_bytes};
   cuuint32_t box[3] = {box_cols, box_rows, 1};
   return encode(map, base, 3, dims, strides, box, elem_bytes);
 }

@@ -128,9 +128,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
 }  // namespace tc
 
 // host: tensor-map encoding through the driver entry point (no libcuda link dependency)
+// ld = row pitch in elements (0: dense, = cols)
 int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
-                 int elem_bytes);
+                 int elem_bytes, uint64_t ld = 0);
 int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                 uint32_t box_cols, int elem_bytes);
+                 uint32_t box_cols, int elem_bytes, uint64_t ld = 0);
 
 }  // namespace dtk

@@ -22,21 +22,23 @@ namespace dtk {
 
 enum class TcMode { TF32X3 = 0, TF32 = 1, BF16 = 2 };
 
-constexpr int TC_BM = 128, TC_BN = 256;
+constexpr int TC_BM = 128, TC_BN = 256;   // TC_BN: default N tile (template parameter BN overrides it)
 constexpr int TC_THREADS = 192;
 
-template <TcMode MODE>
+template <TcMode MODE, int BN = TC_BN>
 struct TcCfg {
+  static_assert(BN == 64 || BN == 128 || BN == 256, "N tile must be 64, 128 or 256");
   static constexpr int kElem = (MODE == TcMode::BF16) ? 2 : 4;
   static constexpr int kBK = 128 / kElem;                         // elements per 128-byte swizzle row
   static constexpr int kOps = (MODE == TcMode::TF32X3) ? 2 : 1;   // hi (+ lo) tiles per operand
   static constexpr int kUmmaK = 32 / kElem;                       // K per tcgen05.mma
-  static constexpr int kABytes = TC_BM * 128, kBBytes = TC_BN * 128;
+  static constexpr int kABytes = TC_BM * 128, kBBytes = BN * 128;
   static constexpr int kStageBytes = kOps * (kABytes + kBBytes);
   static constexpr int kStages = (MODE == TcMode::TF32X3) ? 2 : 4;
   static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr bool kTF32 = MODE != TcMode::BF16;
-  static constexpr uint32_t kIdesc = tc::make_idesc(kTF32 ? 2 : 1, TC_BM, TC_BN);
+  static constexpr uint32_t kIdesc = tc::make_idesc(kTF32 ? 2 : 1, TC_BM, BN);
+  static constexpr uint32_t kTmemCols = 2 * BN;   // two accumulator buffers (power of two >= 32)
 };
 
 struct TcProblem {
@@ -53,12 +55,12 @@ struct TcProblem {
 //   operator()(State&, int g, int r_in_group, int col0, const float (&v)[32], int ncols_valid)
 //                                                                           per 32 consecutive columns
 //   tile_end(State&, int g, int r_in_group, int n_tile)                     once per (row, tile)
-template <TcMode MODE, class Epi>
+template <TcMode MODE, class Epi, int BN = TC_BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcProblem pb,
                Epi epi) {
-  using Cfg = TcCfg<MODE>;
+  using Cfg = TcCfg<MODE, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -69,7 +71,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles_n = (pb.N + TC_BN - 1) / TC_BN;
+  const int n_tiles_n = (pb.N + BN - 1) / BN;
   const int total_tiles = pb.tile_start[pb.n_groups] * n_tiles_n;
   const int KB = (pb.K + Cfg::kBK - 1) / Cfg::kBK;
 
@@ -80,7 +82,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], 4); }
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -90,7 +92,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // the same B rows (frame) in L2
   auto decode = [&](int tile, int& g, int& m0, int& n0) {
     int mt = tile / n_tiles_n;
-    n0 = (tile - mt * n_tiles_n) * TC_BN;
+    n0 = (tile - mt * n_tiles_n) * BN;
     int lo = 0, hi = pb.n_groups - 1;
     while (lo < hi) {
       int mid = (lo + hi + 1) >> 1;
@@ -129,7 +131,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int buf = it & 1, aphase = (it >> 1) & 1;
       tc::mbar_wait(&tempty[buf], aphase ^ 1);
       tc::fence_after_sync();
-      const uint32_t tmem_d = tmem_base + buf * TC_BN;
+      const uint32_t tmem_d = tmem_base + buf * BN;
       for (int kb = 0; kb < KB; ++kb) {
         tc::mbar_wait(&full[stage], phase);
         tc::fence_after_sync();
@@ -173,9 +175,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       epi.tile_begin(est);
       tc::mbar_wait(&tfull[buf], aphase);
       tc::fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
 #pragma unroll 1
-      for (int c = 0; c < TC_BN; c += 32) {
+      for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
         tc::tmem_ld32(taddr + c, v);
         tc::tmem_ld_wait();
@@ -187,7 +189,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           epi(est, g, r, n0 + c, f, ncols);
         }
       }
-      if (row_ok) epi.tile_end(est, g, r, n0 / TC_BN);
+      if (row_ok) epi.tile_end(est, g, r, n0 / BN);
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tempty[buf]);
@@ -198,7 +200,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, 512);
+    tc::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 

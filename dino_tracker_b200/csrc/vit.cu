@@ -1,0 +1,375 @@
+// DINOv2 ViT feature extractor: ImageNet normalisation, 14x14 / stride-7 patch embedding,
+// cls + interpolated position embedding, pre-LN blocks (LayerNorm eps 1e-6, MHA scale 1/8, LayerScale, MLP 4x with
+// exact GELU), tap = output of block `layer` before the final norm, cls dropped, written straight into the
+// token-major feature video [T][P][C]   (models/extractor.py:41-85,137-150; utils.py:32-72; the block arithmetic is
+// facebookresearch/dinov2's -- parity unpinned).
+//
+// Every contraction (patch embedding, qkv, q.k^T, p.v, proj, fc1, fc2) runs on the tcgen05 GEMM of tcgemm.cuh in
+// TF32 with fp32 accumulation in TMEM; bias / position embedding / GELU / LayerScale + residual / head scatter are
+// epilogues on the accumulator.  Round 1 materialises the attention scores per (frame, row chunk) in a workspace
+// (tensor-core GEMM -> row softmax -> tensor-core GEMM); the fused flash-style kernel is the next step.
+#include "common.cuh"
+#include "corr.cuh"
+#include "tcgemm.cuh"
+
+namespace dtk {
+
+constexpr int HD = 64;  // head dim of every DINOv2 ViT
+
+// ---------------------------------------------------------------------------------------------- small kernels
+// patches of ImageNet-normalised frames: out[(b*P + p)][c*196 + ky*14 + kx], row length Kp (zero padded)
+__global__ void vit_im2col_kernel(const float* __restrict__ frames, float* __restrict__ out, int B, int H, int W, int h,
+                                  int w, int patch, int stride, int Kp) {
+  const size_t row = blockIdx.x;  // b*P + p
+  const int P = h * w;
+  const int b = (int)(row / P), p = (int)(row - (size_t)b * P);
+  const int py = (p / w) * stride, px = (p % w) * stride;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  const int K = 3 * patch * patch;
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    float v = 0.f;
+    if (k < K) {
+      int c = k / (patch * patch), r = k - c * patch * patch;
+      int ky = r / patch, kx = r - ky * patch;
+      float x = frames[(((size_t)b * 3 + c) * H + py + ky) * W + px + kx];
+      v = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);  // torchvision Normalize: (x - mean) / std
+    }
+    out[row * Kp + k] = v;
+  }
+}
+
+__global__ void vit_cls_kernel(float* __restrict__ x, const float* __restrict__ cls_pos, int N1, int D) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) x[(size_t)b * N1 * D + i] = cls_pos[i];
+}
+
+// warp per row, D <= 2048
+__global__ void vit_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gw, const float* __restrict__ gb,
+                                     float* __restrict__ y, size_t rows, int D) {
+  const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  float4 v[16];
+  const int n4 = D >> 2;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    int idx = lane + 32 * i;
+    if (idx < n4) { v[i] = xr[idx]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+  }
+  const float mu = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    int idx = lane + 32 * i;
+    if (idx < n4) {
+      float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-6f);
+  float4* yr = reinterpret_cast<float4*>(y + row * D);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    int idx = lane + 32 * i;
+    if (idx < n4) {
+      float4 w4 = __ldg(reinterpret_cast<const float4*>(gw) + idx), b4 = __ldg(reinterpret_cast<const float4*>(gb) + idx);
+      float4 o;
+      o.x = (v[i].x - mu) * rstd * w4.x + b4.x; o.y = (v[i].y - mu) * rstd * w4.y + b4.y;
+      o.z = (v[i].z - mu) * rstd * w4.z + b4.z; o.w = (v[i].w - mu) * rstd * w4.w + b4.w;
+      yr[idx] = o;
+    }
+  }
+}
+
+// in-place row softmax over n columns (row stride ld); block per row
+__global__ void vit_softmax_kernel(float* __restrict__ s, int n, int ld, size_t group_stride) {
+  extern __shared__ float row[];
+  __shared__ float red[32];
+  float* p = s + (size_t)blockIdx.y * group_stride + (size_t)blockIdx.x * ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { float v = p[i]; row[i] = v; m = fmaxf(m, v); }
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int k = 1; k < nw; ++k) m = fmaxf(m, red[k]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { float e = expf(row[i] - m); row[i] = e; sum += e; }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int k = 0; k < nw; ++k) sum += red[k];
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = row[i] * inv;
+}
+
+// x[b][1 + p][:] -> tpc[b][p][:]
+__global__ void vit_tap_kernel(const float* __restrict__ x, float* __restrict__ tpc, int B, int P, int D) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+  const int n4 = D >> 2;
+  size_t total = (size_t)B * P * n4;
+  if (i >= total) return;
+  size_t row = i / n4;
+  int c = (int)(i - row * n4);
+  size_t b = row / P, p = row - b * P;
+  reinterpret_cast<float4*>(tpc)[i] = reinterpret_cast<const float4*>(x)[((b * (P + 1) + 1 + p)) * n4 + c];
+}
+
+// group tables for the GEMMs: kind 0: one group of m rows; kind 1: `heads` groups (attention)
+__global__ void vit_plan_kernel(int* batch, int* row0, int* m, int* tile_start, int n_groups, int rows, int row_stride,
+                                int row_base, int batch_base) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int g = 0; g < n_groups; ++g) {
+      batch[g] = batch_base + g; row0[g] = row_base + g * row_stride; m[g] = rows; tile_start[g] = acc;
+      acc += (rows + TC_BM - 1) / TC_BM;
+    }
+    tile_start[n_groups] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- epilogues
+struct EpiBase {
+  struct State {};
+  __device__ __forceinline__ void tile_begin(State&) const {}
+  __device__ __forceinline__ void tile_end(State&, int, int, int) const {}
+};
+
+// tokens: x[b][1 + p][col] = acc + bias[col] + pos[p][col]   (row r = b*P + p)
+struct EpiPatch : EpiBase {
+  float* x; const float* bias; const float* pos; int P, D;
+  __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
+    const int b = r / P, p = r - b * P;
+    float* o = x + ((size_t)b * (P + 1) + 1 + p) * D + col0;
+    const float* ps = pos + (size_t)p * D + col0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = f[i] + __ldg(bias + col0 + i) + __ldg(ps + i);
+  }
+};
+
+// qkv: scatter to q [b][hd][n][64] (scaled 1/8), k [b][hd][n][64], vT [b][hd][64][n]
+struct EpiQKV : EpiBase {
+  float* q; float* k; float* vT; const float* bias; int N1, D, heads, N1p;
+  __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
+    const int b = r / N1, n = r - b * N1;
+    const int which = col0 / D, c = col0 - which * D, hd = c / HD, e0 = c - hd * HD;
+    const size_t bh = (size_t)b * heads + hd;
+    if (which < 2) {
+      float* o = (which == 0 ? q : k) + (bh * N1 + n) * HD + e0;
+      const float sc = which == 0 ? 0.125f : 1.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = (f[i] + __ldg(bias + col0 + i)) * sc;
+    } else {
+      float* o = vT + (bh * HD + e0) * N1p + n;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (i < ncols) o[(size_t)i * N1p] = f[i] + __ldg(bias + col0 + i);
+    }
+  }
+};
+
+// plain store: out[(g * rows_per_group + r)][col] (attention scores)
+struct EpiStore : EpiBase {
+  float* out; int ld, rows_per_group;
+  __device__ __forceinline__ void operator()(State&, int g, int r, int col0, const float (&f)[32], int ncols) const {
+    float* o = out + ((size_t)g * rows_per_group + r) * ld + col0;
+    if (ncols == 32) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = f[i];
+    }
+  }
+};
+
+// p.v: group g = head; out[(frame_row0 + r)][g*64 + col]
+struct EpiPV : EpiBase {
+  float* out; size_t frame_row0; int D;
+  __device__ __forceinline__ void operator()(State&, int g, int r, int col0, const float (&f)[32], int ncols) const {
+    float* o = out + (frame_row0 + r) * D + g * HD + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)
+      if (i < ncols) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+  }
+};
+
+// x[r][col] += ls[col] * (acc + bias[col])
+struct EpiResidual : EpiBase {
+  float* x; const float* bias; const float* ls; int D;
+  __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
+    float* o = x + (size_t)r * D + col0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols) o[i] = o[i] + (f[i] + __ldg(bias + col0 + i)) * __ldg(ls + col0 + i);
+  }
+};
+
+// h[r][col] = gelu(acc + bias[col])   (exact: 0.5 x (1 + erf(x / sqrt 2)))
+struct EpiGelu : EpiBase {
+  float* h; const float* bias; int ld;
+  __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
+    float* o = h + (size_t)r * ld + col0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols) { float v = f[i] + __ldg(bias + col0 + i); o[i] = 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+  }
+};
+
+struct Plan { int* batch; int* row0; int* m; int* tile_start; };
+
+template <class Epi, int BN>
+static int run_gemm(const float* A, uint64_t a_rows, const float* Bm, uint64_t b_batch, uint64_t b_rows, int K,
+                    const Plan& pl, int n_groups, int max_tiles, const Epi& epi, int prof_cls, cudaStream_t st,
+                    uint64_t ld = 0) {
+  using Cfg = TcCfg<TcMode::TF32, BN>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_2d(&tmA, A, a_rows, K, TC_BM, Cfg::kBK, 4, ld))) return rc;
+  if ((rc = make_tmap_3d(&tmB, Bm, b_batch, b_rows, K, BN, Cfg::kBK, 4, ld))) return rc;
+  auto kern = tc_gemm_kernel<TcMode::TF32, Epi, BN>;
+  static bool attr = false;  // one static per template instantiation
+  if (!attr) {
+    DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr = true;
+  }
+  TcProblem pb{pl.batch, pl.row0, pl.m, pl.tile_start, n_groups, (int)b_rows, K};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int tiles = max_tiles * cdiv((int)b_rows, BN);
+  int grid = tiles < sms ? tiles : sms;
+  ProfRange pr(prof_cls, st);
+  kern<<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmA, tmB, tmB, pb, epi);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+static int plan(const Plan& pl, int n_groups, int rows, int row_stride, int row_base, int batch_base, cudaStream_t st) {
+  ProfRange pr(PROF_VIT_MISC, st);
+  vit_plan_kernel<<<1, 32, 0, st>>>(pl.batch, pl.row0, pl.m, pl.tile_start, n_groups, rows, row_stride, row_base, batch_base);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+constexpr int VIT_ROW_CHUNK = 1024;  // query rows per attention-score chunk
+
+}  // namespace dtk
+
+using namespace dtk;
+
+extern "C" {
+
+static int vit_kp(const dinotrk_vit_config* c) { return (int)align_up((size_t)3 * c->patch * c->patch, 4); }
+
+size_t dinotrk_vit_workspace_bytes(const dinotrk_vit_config* c, const dinotrk_geom* g, int B) {
+  if (!c || !g) return 0;
+  const size_t P = (size_t)g->h * g->w, N1 = P + 1, D = c->dim;
+  size_t b = 0;
+  const size_t N1p = align_up(N1, 4);
+  b += align_up(B * N1 * D * 4, 256) * 2;                                  // x, y
+  b += align_up(B * N1 * D * 4, 256) * 2 + align_up(B * N1p * D * 4, 256); // q, k, vT
+  size_t hid = B * N1 * 4 * D * 4, col = B * P * (size_t)vit_kp(c) * 4;
+  b += align_up(hid > col ? hid : col, 256);                               // MLP hidden / im2col (aliased)
+  b += align_up((size_t)c->heads * VIT_ROW_CHUNK * N1p * 4, 256);          // attention scores of one row chunk
+  b += 4 * align_up((size_t)(c->heads + 2) * 4, 256) + 4096;               // plan tables
+  return b;
+}
+
+int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const dinotrk_vit_config* c,
+                        const dinotrk_vit_weights* wt, float* out_tpc, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  DTK_CHECK_ARG(frames && g && c && wt && out_tpc && wt->blocks, "vit_forward: null pointer");
+  const int D = c->dim, heads = c->heads, P = g->h * g->w, N1 = P + 1, Kp = vit_kp(c);
+  DTK_CHECK_ARG(D == heads * HD && D % 64 == 0 && D <= 2048, "vit_forward: dim must be heads x 64 (<= 2048)");
+  DTK_CHECK_ARG(c->tap_layer >= 0 && c->tap_layer < c->depth, "vit_forward: tap layer out of range");
+  const int N1p = (int)align_up((size_t)N1, 4);   // row pitch of the score / v^T arrays (TMA strides are 16-byte multiples)
+  DTK_CHECK_ARG(workspace && workspace_bytes >= dinotrk_vit_workspace_bytes(c, g, B), "vit_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ar(workspace, workspace_bytes);
+  const size_t rows = (size_t)B * N1;
+  float* x = ar.take<float>(rows * D);
+  float* y = ar.take<float>(rows * D);
+  float* q = ar.take<float>(rows * D);
+  float* k = ar.take<float>(rows * D);
+  float* vT = ar.take<float>((size_t)B * N1p * D);
+  size_t hid = rows * 4 * D, col = (size_t)B * P * Kp;
+  float* hbuf = ar.take<float>(hid > col ? hid : col);
+  float* S = ar.take<float>((size_t)heads * VIT_ROW_CHUNK * N1p);
+  Plan pl{ar.take<int>(heads + 2), ar.take<int>(heads + 2), ar.take<int>(heads + 2), ar.take<int>(heads + 2)};
+  DTK_CHECK_ARG(ar.ok(), "vit_forward: workspace arena overflow");
+  int rc;
+
+  // ---- patch embedding + cls + position embedding
+  {
+    ProfRange pr(PROF_VIT_MISC, st);
+    vit_im2col_kernel<<<B * P, 128, 0, st>>>(frames, hbuf, B, g->H, g->W, g->h, g->w, c->patch, c->stride, Kp);
+    DTK_LAUNCHED();
+  }
+  if ((rc = plan(pl, 1, B * P, 0, 0, 0, st))) return rc;
+  if ((rc = run_gemm<EpiPatch, 256>(hbuf, (uint64_t)B * P, wt->patch_w, 1, D, Kp, pl, 1, cdiv(B * P, TC_BM),
+                                    EpiPatch{{}, x, wt->patch_b, wt->pos, P, D}, PROF_VIT_GEMM, st))) return rc;
+  {
+    ProfRange pr(PROF_VIT_MISC, st);
+    vit_cls_kernel<<<B, 256, 0, st>>>(x, wt->cls_pos, N1, D);
+    DTK_LAUNCHED();
+  }
+
+  const int all_tiles = cdiv((int)rows, TC_BM);
+  for (int l = 0; l <= c->tap_layer; ++l) {
+    const float* const* w = wt->blocks + (size_t)l * 14;
+    // w: 0 norm1.w 1 norm1.b 2 qkv.w 3 qkv.b 4 proj.w 5 proj.b 6 ls1 7 norm2.w 8 norm2.b 9 fc1.w 10 fc1.b 11 fc2.w 12 fc2.b 13 ls2
+    {
+      ProfRange pr(PROF_VIT_MISC, st);
+      vit_layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w[0], w[1], y, rows, D);
+      DTK_LAUNCHED();
+    }
+    if ((rc = plan(pl, 1, (int)rows, 0, 0, 0, st))) return rc;
+    if ((rc = run_gemm<EpiQKV, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, EpiQKV{{}, q, k, vT, w[3], N1, D, heads, N1p},
+                                    PROF_VIT_GEMM, st))) return rc;
+    // attention, per frame and chunk of query rows: S = q k^T (all heads) -> softmax -> y = S v
+    for (int b = 0; b < B; ++b) {
+      for (int c0 = 0; c0 < N1; c0 += VIT_ROW_CHUNK) {
+        const int rc_rows = N1 - c0 < VIT_ROW_CHUNK ? N1 - c0 : VIT_ROW_CHUNK;
+        if ((rc = plan(pl, heads, rc_rows, N1, (b * heads) * N1 + c0, b * heads, st))) return rc;
+        if ((rc = run_gemm<EpiStore, 256>(q, rows * heads, k, (uint64_t)B * heads, N1, HD, pl, heads,
+                                          heads * cdiv(rc_rows, TC_BM), EpiStore{{}, S, N1p, VIT_ROW_CHUNK},
+                                          PROF_VIT_ATTN, st))) return rc;
+        {
+          ProfRange pr(PROF_VIT_ATTN, st);  // rows of S live at (head * VIT_ROW_CHUNK + r)
+          vit_softmax_kernel<<<dim3(rc_rows, heads), 256, (size_t)N1 * 4, st>>>(S, N1, N1p, (size_t)VIT_ROW_CHUNK * N1p);
+          DTK_LAUNCHED();
+        }
+        if ((rc = plan(pl, heads, rc_rows, VIT_ROW_CHUNK, 0, b * heads, st))) return rc;
+        if ((rc = run_gemm<EpiPV, 64>(S, (uint64_t)heads * VIT_ROW_CHUNK, vT, (uint64_t)B * heads, HD, N1, pl, heads,
+                                      heads * cdiv(rc_rows, TC_BM), EpiPV{{}, y, (size_t)b * N1 + c0, D},
+                                      PROF_VIT_ATTN, st, (uint64_t)N1p))) return rc;
+      }
+    }
+    if ((rc = plan(pl, 1, (int)rows, 0, 0, 0, st))) return rc;
+    if ((rc = run_gemm<EpiResidual, 256>(y, rows, w[4], 1, D, D, pl, 1, all_tiles, EpiResidual{{}, x, w[5], w[6], D},
+                                         PROF_VIT_GEMM, st))) return rc;
+    {
+      ProfRange pr(PROF_VIT_MISC, st);
+      vit_layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w[7], w[8], y, rows, D);
+      DTK_LAUNCHED();
+    }
+    if ((rc = run_gemm<EpiGelu, 256>(y, rows, w[9], 1, 4 * D, D, pl, 1, all_tiles, EpiGelu{{}, hbuf, w[10], 4 * D},
+                                     PROF_VIT_GEMM, st))) return rc;
+    if ((rc = run_gemm<EpiResidual, 256>(hbuf, rows, w[11], 1, D, 4 * D, pl, 1, all_tiles,
+                                         EpiResidual{{}, x, w[12], w[13], D}, PROF_VIT_GEMM, st))) return rc;
+  }
+  {
+    ProfRange pr(PROF_VIT_MISC, st);
+    size_t tot = (size_t)B * P * (D / 4);
+    vit_tap_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, out_tpc, B, P, D);
+    DTK_LAUNCHED();
+  }
+  return DINOTRK_OK;
+}
+
+}  // extern "C"

@@ -154,6 +154,26 @@ int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* ch
                          const float* ixs, const float* iys, int h, int w, float* refined_tpc,
                          float* norms, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- DINOv2 ViT feature extractor (utils.py:32-72, models/extractor.py:41-85,137-150) -------------- */
+typedef struct dinotrk_vit_config {
+  int depth, dim, heads;   /* ViT-L/14: 24, 1024, 16; ViT-B/14: 12, 768, 12 (head dim 64) */
+  int tap_layer;           /* 0-based block whose output (before the final norm) is returned; 15 in the shipped config */
+  int patch, stride;       /* 14, 7 */
+} dinotrk_vit_config;
+/* All device fp32.  patch_w: patch-embedding conv weight flattened K-major [dim][3*patch*patch]; cls_pos [dim] =
+ * cls_token + pos_embed[0]; pos [h*w][dim] = bicubic-interpolated patch position embedding (extractor.py:57-85);
+ * blocks: HOST array of depth x 14 device pointers in the order norm1.w, norm1.b, qkv.w [3D][D], qkv.b, proj.w,
+ * proj.b, ls1.gamma, norm2.w, norm2.b, fc1.w [4D][D], fc1.b, fc2.w [D][4D], fc2.b, ls2.gamma. */
+typedef struct dinotrk_vit_weights {
+  const float* patch_w; const float* patch_b; const float* cls_pos; const float* pos;
+  const float* const* blocks;
+} dinotrk_vit_weights;
+size_t dinotrk_vit_workspace_bytes(const dinotrk_vit_config* c, const dinotrk_geom* g, int B);
+/* frames [B][3][H][W] RGB in [0,1] -> out_tpc [B][h*w][dim] (token-major features of block tap_layer). */
+int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const dinotrk_vit_config* c,
+                        const dinotrk_vit_weights* wt, float* out_tpc, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* ---- best buddies (preprocessing_dino_bb/extract_dino_best_buddies.py:12-54) ------------------------ */
 /* For every ordered pair k (source frame pair_src[k], target frame pair_tgt[k]; device int32[n_pairs]):
  * nn_idx[k][n] = argmax_m cos(F_src[n], F_tgt[m]) (first maximum), nn_cos[k][n] = that cosine (exact fp32,
