@@ -52,6 +52,7 @@ def parse():
                     help="wide correlation groups: tcgen05 3xTF32 tensor cores, or the exact-fp32 FFMA GEMM")
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the cpu_baseline leg")
     ap.add_argument("--stream-probe", type=int, default=1, help="0: skip the dedicated corr_stream HBM probe")
+    ap.add_argument("--stages", type=int, default=1, help="0: skip the ViT / delta-DINO / best-buddies stage timings")
     return ap.parse_args()
 
 
@@ -329,6 +330,8 @@ def run_b200(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": extra,
             "kernels": kernels, "peaks": peaks}
+    if args.stages and world == 1:
+        line["stages"] = stage_timings(args, dev, _lib, peaks)
     if args.cpu_baseline and world == 1:
         v, cores, desc, _ = cpu_reference_sample(T, C, nq, args.noise, seed=0, max_anchor_calls=3)
         line["cpu_baseline"] = {"value": v, "unit": "query-points/s", "cores": cores, "kind": "port", "sample": desc}
@@ -347,9 +350,10 @@ def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks):
         ach = flops / avg_s / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sustained"], "traffic": None,
-                "note": "algorithmic FLOPs = 2*maps*P*C per launch; peak = sustained cuBLAS bf16 (%s); this kernel is "
-                        "exact-fp32 FFMA (CUDA cores), so its own ceiling is the fp32 pipe, see fp32_frac" % peaks["which"],
-                "fp32_frac": ach / fp32_peak_tflops(clocks)}
+                "note": ("algorithmic FLOPs = 2*maps*P*C per launch; peak = sustained cuBLAS bf16 (%s). precision=%s: "
+                         "tf32x3 executes 3 TF32 MMA passes per algorithmic FLOP (TF32 peak = bf16/2), so the tensor pipe "
+                         "is busy ~6x this fraction; fp32 = exact FFMA GEMM on the CUDA cores") % (peaks["which"], args.precision),
+                "executed_mma_tflops": ach * 3 if args.precision == "tf32x3" else None}
     if name == "head":
         flops = 4.67e6 * maps_per_launch  # 2 x (144 + 144) FMA per token, SURVEY.md 8a row a7
         ach = flops / avg_s / 1e12
@@ -361,6 +365,70 @@ def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks):
     nbytes = maps_per_launch * 0  # filled by the dedicated probe
     return {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
             "traffic": None, "note": "see roofline_other.corr_stream_probe"}
+
+
+def stage_timings(args, dev, _lib, peaks):
+    """Per-video preprocessing stages on real shapes (854x476): ViT feature extraction (a1), delta-DINO refinement
+    (a2) and best-buddies (a13), device-timed.  Random-init weights of the named architectures."""
+    from dino_tracker_b200.vit import DinoV2Features, CONFIGS
+    from dino_tracker_b200.networks import DeltaDINO
+    from dino_tracker_b200.best_buddies import nearest_neighbours
+    out = {}
+    name = "dinov2_vitl14" if args.C == 1024 else "dinov2_vitb14"
+    depth, dim, heads = CONFIGS[name]
+    layer = 15 if args.C == 1024 else depth - 1
+    g = torch.Generator(device=dev).manual_seed(7)
+
+    def rn(*shape, std=0.02):
+        return torch.randn(*shape, device=dev, generator=g) * std
+    sd = {"cls_token": rn(1, 1, dim), "pos_embed": rn(1, 1 + 37 * 37, dim), "patch_embed.proj.weight": rn(dim, 3, 14, 14),
+          "patch_embed.proj.bias": rn(dim)}
+    for i in range(layer + 1):
+        p = f"blocks.{i}."
+        sd.update({p + "norm1.weight": 1 + rn(dim), p + "norm1.bias": rn(dim), p + "attn.qkv.weight": rn(3 * dim, dim),
+                   p + "attn.qkv.bias": rn(3 * dim), p + "attn.proj.weight": rn(dim, dim), p + "attn.proj.bias": rn(dim),
+                   p + "ls1.gamma": 1 + rn(dim), p + "norm2.weight": 1 + rn(dim), p + "norm2.bias": rn(dim),
+                   p + "mlp.fc1.weight": rn(4 * dim, dim), p + "mlp.fc1.bias": rn(4 * dim),
+                   p + "mlp.fc2.weight": rn(dim, 4 * dim), p + "mlp.fc2.bias": rn(dim), p + "ls2.gamma": 1 + rn(dim)})
+    ex = DinoV2Features(sd, heads=heads, layer=layer, device=dev, frames_per_call=2)
+    frames = torch.rand(2, 3, H, W, device=dev, generator=g)
+
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.profile_enable(True); _lib.profile_collect()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        prof = _lib.profile_collect(); _lib.profile_enable(False)
+        return e0.elapsed_time(e1) / reps, {k: round(v[0] / reps, 3) for k, v in prof.items()}
+
+    ms, prof = timed(lambda: ex(frames), 2)
+    flops = 2.0 * (12 * dim * dim * (P + 1) + 2 * (P + 1) ** 2 * dim) * (layer + 1) * frames.shape[0]
+    out["vit"] = {"model": f"{name}@block{layer}", "frames_per_s": frames.shape[0] / (ms / 1000), "ms_per_frame": ms / frames.shape[0],
+                  "tflops": flops / (ms / 1000) / 1e12, "frac_of_bf16_peak": flops / (ms / 1000) / 1e12 / peaks["tf_sustained"],
+                  "kernel_ms_per_call": prof, "math": "TF32 tcgen05 GEMMs, fp32 accumulate; attention scores materialised per row chunk"}
+    del ex, sd
+    # delta-DINO with the shipped channel widths
+    dd = DeltaDINO(channels=[3, 64, 128, 256, args.C]).to(dev)
+    torch.nn.init.normal_(dd.layers[12].weight, std=0.01)
+    geom = _lib.make_geom(H, W)
+    dino = torch.randn(4, P, args.C, device=dev, generator=g)
+    fr4 = torch.rand(4, 3, H, W, device=dev, generator=g)
+    ms, prof = timed(lambda: dd.refine_tpc(fr4, dino, geom), 2)
+    out["delta_dino"] = {"frames_per_s": 4 / (ms / 1000), "ms_per_frame": ms / 4, "tflops": 171.4e9 * 4 / (ms / 1000) / 1e12,
+                         "kernel_ms_per_call": prof, "math": "exact fp32 implicit-GEMM convs (CUDA cores)"}
+    del dd
+    # best buddies: 4 frames -> 12 ordered pairs
+    feats = dino
+    norms = feats.norm(dim=2).contiguous()
+    pairs = [(s, t) for s in range(4) for t in range(4) if s != t]
+    ms, prof = timed(lambda: nearest_neighbours(feats, norms, geom, pairs), 2)
+    out["best_buddies"] = {"ordered_pairs_per_s": len(pairs) / (ms / 1000), "ms_per_ordered_pair": ms / len(pairs),
+                           "tflops": 2.0 * P * P * args.C * len(pairs) / (ms / 1000) / 1e12, "kernel_ms_per_call": prof,
+                           "math": "tcgen05 3xTF32 GEMM + top-2 epilogue + exact fp32 resolve"}
+    return out
 
 
 def fp32_peak_tflops(clocks):
