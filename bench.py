@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--nq", type=int, default=256)
     ap.add_argument("--noise", type=float, default=0.25)
     ap.add_argument("--chunk-maps", type=int, default=4096)
-    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "fp32"],
+    ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp32"],
                     help="wide correlation groups: tcgen05 3xTF32 tensor cores, or the exact-fp32 FFMA GEMM")
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the cpu_baseline leg")
     ap.add_argument("--stream-probe", type=int, default=1, help="0: skip the dedicated corr_stream HBM probe")
@@ -351,9 +351,9 @@ def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks):
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sustained"], "traffic": None,
                 "note": ("algorithmic FLOPs = 2*maps*P*C per launch; peak = sustained cuBLAS bf16 (%s). precision=%s: "
-                         "tf32x3 executes 3 TF32 MMA passes per algorithmic FLOP (TF32 peak = bf16/2), so the tensor pipe "
-                         "is busy ~6x this fraction; fp32 = exact FFMA GEMM on the CUDA cores") % (peaks["which"], args.precision),
-                "executed_mma_tflops": ach * 3 if args.precision == "tf32x3" else None}
+                         "fp16x3 executes 3 kind::f16 MMA passes (lo*hi, hi*lo, hi*hi) per algorithmic FLOP, so the tensor "
+                         "pipe is busy ~3x this fraction; fp32 = exact FFMA GEMM on the CUDA cores") % (peaks["which"], args.precision),
+                "executed_mma_tflops": ach * 3 if args.precision == "fp16x3" else None}
     if name == "head":
         flops = 4.67e6 * maps_per_launch  # 2 x (144 + 144) FMA per token, SURVEY.md 8a row a7
         ach = flops / avg_s / 1e12

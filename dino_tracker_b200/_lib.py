@@ -48,7 +48,7 @@ SIGNATURES = {
     "dinotrk_unpack_features": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "dinotrk_token_norms": (c_int, [_P, _P, c_int, c_int, c_int, _P]),
     "dinotrk_sample_descriptors": (c_int, [_P, c_int, c_int, POINTER(Geom), _P, c_int, _P, c_int, c_int, _P, _P, _P]),
-    "dinotrk_split_tf32": (c_int, [_P, _P, _P, c_size_t, _P]),
+    "dinotrk_split_fp16": (c_int, [_P, _P, _P, c_size_t, _P]),
     "dinotrk_corr_track_workspace_bytes": (c_size_t, [c_int, c_int, c_int, POINTER(Geom)]),
     "dinotrk_corr_track": (c_int, [POINTER(Features), POINTER(Geom), POINTER(HeadWeights), _P, _P, _P, _P, _P, _P,
                                    c_int, c_int, c_int, _P, _P, c_int, c_int, _P, c_size_t, _P]),

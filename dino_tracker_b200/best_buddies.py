@@ -2,7 +2,7 @@
 
 ``run(args)`` keeps the reference script's contract (``--dino-emb-path --h --w --stride --out-path``;
 output ``dict['s_t'] -> {source_coords, target_coords, cos_sims}``, rows in ascending source-token
-order).  The affinity matrices never reach HBM: every ordered pair runs through the tcgen05 3xTF32
+order).  The affinity matrices never reach HBM: every ordered pair runs through the tcgen05 split-fp16
 GEMM with a fused top-2 epilogue, candidates are re-evaluated in exact fp32, and the mutual check
 works on index vectors (``dinotrk_best_buddies_pairs`` / ``dinotrk_bb_mutual``).
 
@@ -32,8 +32,9 @@ def nearest_neighbours(tpc, norms, geom, pairs, hi=None, lo=None, pairs_per_laun
     dev = tpc.device
     T, P, C = tpc.shape
     if hi is None:
-        hi, lo = torch.empty_like(tpc), torch.empty_like(tpc)
-        _lib.check(lib.dinotrk_split_tf32(_lib.ptr(tpc), _lib.ptr(hi), _lib.ptr(lo), tpc.numel(), _lib.stream_ptr()))
+        hi = torch.empty(tpc.shape, device=dev, dtype=torch.float16)
+        lo = torch.empty(tpc.shape, device=dev, dtype=torch.float16)
+        _lib.check(lib.dinotrk_split_fp16(_lib.ptr(tpc), _lib.ptr(hi), _lib.ptr(lo), tpc.numel(), _lib.stream_ptr()))
     feat = _lib.make_features(tpc, norms, hi, lo)
     n = len(pairs)
     nn_idx = torch.empty(n, P, device=dev, dtype=torch.int32)

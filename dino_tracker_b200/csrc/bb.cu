@@ -3,7 +3,7 @@
 //
 // The reference materialises the 8107 x 8107 cosine-affinity matrix per ordered pair (263 MB), divides it,
 // and runs two arg-max passes over it.  Here, per ordered pair (s, t):
-//   1. tcgen05 3xTF32 GEMM  Fs x Ft^T  with a fused epilogue that keeps, per source token and 256-token
+//   1. tcgen05 split-fp16 (hi/lo, 3-pass) GEMM  Fs x Ft^T  with a fused epilogue that keeps, per source token and 256-token
 //      column tile, the best and second-best cosine (value + index) -- the matrix never leaves TMEM;
 //   2. a warp per source token merges the 32 tile partials, and re-evaluates its (one or two) candidates in
 //      exact fp32 so that the arg-max and the reported cosine do not depend on tensor-core rounding;
@@ -146,10 +146,10 @@ int dinotrk_best_buddies_pairs(const dinotrk_features* feat, const dinotrk_geom*
   DTK_CHECK_ARG(feat && feat->tpc && feat->norms && feat->hi && feat->lo && g && pair_src && pair_tgt && nn_idx && nn_cos,
                 "best_buddies: null pointer (the TF32 split of the features is required)");
   const int P = g->h * g->w, C = feat->C, T = feat->T;
-  DTK_CHECK_ARG(C % 4 == 0 && n_pairs >= 0, "best_buddies: bad sizes");
+  DTK_CHECK_ARG(C % 8 == 0 && n_pairs >= 0, "best_buddies: C must be a multiple of 8");
   DTK_CHECK_ARG(workspace && workspace_bytes >= dinotrk_best_buddies_workspace_bytes(n_pairs, P), "best_buddies: workspace too small");
   if (n_pairs == 0) return DINOTRK_OK;
-  using Cfg = TcCfg<TcMode::TF32X3>;
+  using Cfg = TcCfg<TcMode::F16X3>;
   cudaStream_t st = (cudaStream_t)stream;
   const int n_tiles = cdiv(P, TC_BN);
   Arena ar(workspace, workspace_bytes);
@@ -164,13 +164,13 @@ int dinotrk_best_buddies_pairs(const dinotrk_features* feat, const dinotrk_geom*
   }
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   int rc;
-  if ((rc = make_tmap_2d(&tmA_hi, feat->hi, (uint64_t)T * P, C, TC_BM, Cfg::kBK, 4))) return rc;
-  if ((rc = make_tmap_2d(&tmA_lo, feat->lo, (uint64_t)T * P, C, TC_BM, Cfg::kBK, 4))) return rc;
-  if ((rc = make_tmap_3d(&tmB_hi, feat->hi, T, P, C, TC_BN, Cfg::kBK, 4))) return rc;
-  if ((rc = make_tmap_3d(&tmB_lo, feat->lo, T, P, C, TC_BN, Cfg::kBK, 4))) return rc;
+  if ((rc = make_tmap_2d(&tmA_hi, feat->hi, (uint64_t)T * P, C, TC_BM, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_2d(&tmA_lo, feat->lo, (uint64_t)T * P, C, TC_BM, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tmB_hi, feat->hi, T, P, C, TC_BN, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tmB_lo, feat->lo, T, P, C, TC_BN, Cfg::kBK, TMAP_F16))) return rc;
   static bool attr = false;
   if (!attr) {
-    DTK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TcMode::TF32X3, BBEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    DTK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TcMode::F16X3, BBEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr = true;
   }
   TcProblem pb{pair_tgt, row0, m, tile_start, n_pairs, P, C};
@@ -180,7 +180,7 @@ int dinotrk_best_buddies_pairs(const dinotrk_features* feat, const dinotrk_geom*
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   {
     ProfRange pr(PROF_BB, st);
-    tc_gemm_kernel<TcMode::TF32X3, BBEpi><<<sms, TC_THREADS, Cfg::kSmem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, pb, epi);
+    tc_gemm_kernel<TcMode::F16X3, BBEpi><<<sms, TC_THREADS, Cfg::kSmem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, pb, epi);
     DTK_LAUNCHED();
   }
   {

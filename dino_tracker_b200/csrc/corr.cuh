@@ -7,7 +7,7 @@ namespace dtk {
 constexpr int STREAM_MAX_M = 8;  // groups with at most this many descriptors use the streaming kernel
 
 struct FeatView {
-  const float* tpc; const float* norms; const float* hi; const float* lo;
+  const float* tpc; const float* norms; const void* hi; const void* lo;
   int T, C, P;
   bool tensor() const { return hi != nullptr && lo != nullptr; }
 };
@@ -23,11 +23,11 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
                      const int* grp_frame, const int* grp_row0, const int* grp_m, const int* grp_map0, int n_groups,
                      int total_maps, int max_group_m, float* maps, int map_stride, int* tile_start, float* split_ws,
                      cudaStream_t st);
-int launch_corr_gemm_tc(const float* tpc_hi, const float* tpc_lo, const float* norms, int T, int C, int P,
+int launch_corr_gemm_tc(const void* tpc_hi, const void* tpc_lo, const float* norms, int T, int C, int P,
                         const float* desc, int desc_rows, const float* desc_norm, const int* grp_frame,
                         const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
                         int max_tiles, float* maps, int map_stride, float* desc_split_ws, cudaStream_t st);
-int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
+int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st);
 
 int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geom& g,
                 const dinotrk_head_weights& hw, const int* out_index, float* out, int out_stride, int out_mode,

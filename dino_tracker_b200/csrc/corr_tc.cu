@@ -1,10 +1,12 @@
-// Tensor-core correlation GEMM (tcgen05, 3xTF32) + TF32 operand splitting + TMA tensor-map helpers.
+// Tensor-core correlation GEMM (tcgen05, split-precision fp16 hi/lo) + operand splitting + TMA tensor-map helpers.
 //
 //   corr[j][p] = relu( <d_j, F[frame][p]> / max(|d_j| |F[frame][p]|, 1e-8) )     (models/tracker.py:158-173)
 //
-// The contraction runs as hi*hi + hi*lo + lo*hi on TF32 tensor cores with fp32 accumulation in TMEM
-// (operands pre-split into exactly-representable TF32 parts), which keeps the products faithful to
-// ~2^-21; the cosine normalisation and ReLU are the epilogue on the accumulator as it leaves TMEM.
+// The contraction runs as lo*hi + hi*lo + hi*hi on the kind::f16 tensor pipe with fp32 accumulation in TMEM
+// (operands pre-split into fp16 hi + fp16 lo, x = hi + lo up to 2^-22 |x|), which keeps the products
+// faithful to ~2^-21; the cosine normalisation and ReLU are the epilogue on the accumulator as it leaves TMEM.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "corr.cuh"
 #include "tcgemm.cuh"
@@ -28,11 +30,12 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box, int elem_bytes) {
+                  const cuuint32_t* box, int elem) {
   EncodeTiledFn fn = get_encode();
   if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return DINOTRK_ECUDA; }
   cuuint32_t estr[3] = {1, 1, 1};
-  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMapDataType dt = elem == TMAP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                         : elem == TMAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = fn(map, dt, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DINOTRK_ECUDA; }
@@ -40,46 +43,48 @@ static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t
 }
 
 int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
-                 int elem_bytes, uint64_t ld) {
+                 int elem, uint64_t ld) {
+  const int elem_bytes = elem == TMAP_F32 ? 4 : 2;
   if (ld == 0) ld = cols;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
-  return encode(map, base, 2, dims, strides, box, elem_bytes);
+  return encode(map, base, 2, dims, strides, box, elem);
 }
 int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                 uint32_t box_cols, int elem_bytes, uint64_t ld) {
+                 uint32_t box_cols, int elem, uint64_t ld) {
+  const int elem_bytes = elem == TMAP_F32 ? 4 : 2;
   if (ld == 0) ld = cols;
   cuuint64_t dims[3] = {cols, rows, batch};
   cuuint64_t strides[2] = {ld * (uint64_t)elem_bytes, rows * ld * (uint64_t)elem_bytes};
   cuuint32_t box[3] = {box_cols, box_rows, 1};
-  return encode(map, base, 3, dims, strides, box, elem_bytes);
+  return encode(map, base, 3, dims, strides, box, elem);
 }
 
-// x = hi + lo (+ residual < 2^-22 |x|): hi = x with the 13 low mantissa bits cleared, lo = (x - hi) likewise
-__global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, size_t n4) {
+// x = hi + lo (+ residual <= 2^-22 |x| in the fp16 normal range): hi = rn_fp16(x), lo = rn_fp16(x - hi)
+__global__ void split_f16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, size_t n4) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
-    float4 v = __ldg(x + i), h, l;
-    auto sp = [](float a, float& ah, float& al) {
-      ah = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
-      al = __uint_as_float(__float_as_uint(__fsub_rn(a, ah)) & 0xffffe000u);
-    };
-    sp(v.x, h.x, l.x); sp(v.y, h.y, l.y); sp(v.z, h.z, l.z); sp(v.w, h.w, l.w);
-    hi[i] = h; lo[i] = l;
+    float4 v = __ldg(x + i);
+    __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+    __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
+    __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
+    __half2 a = __halves2half2(h0, h1), b2 = __halves2half2(h2, h3), c = __halves2half2(l0, l1), d = __halves2half2(l2, l3);
+    hi[i] = make_uint2(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&b2));
+    lo[i] = make_uint2(*reinterpret_cast<unsigned*>(&c), *reinterpret_cast<unsigned*>(&d));
   }
 }
 
-int launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
+int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st) {
   if (n == 0) return DINOTRK_OK;
-  DTK_CHECK_ARG(n % 4 == 0, "split_tf32: length must be a multiple of 4");
+  DTK_CHECK_ARG(n % 4 == 0, "split_fp16: length must be a multiple of 4");
   size_t n4 = n / 4;
   unsigned grid = (unsigned)((n4 + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
   ProfRange pr(PROF_MISC, st);
-  split_tf32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi),
-                                          reinterpret_cast<float4*>(lo), n4);
+  split_f16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(hi),
+                                         reinterpret_cast<uint2*>(lo), n4);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }
@@ -119,27 +124,27 @@ struct CorrEpi {
   }
 };
 
-size_t corr_tc_workspace_bytes(int total_rows, int C) { return 2 * align_up((size_t)total_rows * C * 4, 256); }
+size_t corr_tc_workspace_bytes(int total_rows, int C) { return 2 * align_up((size_t)total_rows * C * 2, 256); }
 
 // wide groups on tensor cores; tile_start must already hold the plan (corr_plan_kernel).
-int launch_corr_gemm_tc(const float* tpc_hi, const float* tpc_lo, const float* norms, int T, int C, int P,
+int launch_corr_gemm_tc(const void* tpc_hi, const void* tpc_lo, const float* norms, int T, int C, int P,
                         const float* desc, int desc_rows, const float* desc_norm, const int* grp_frame,
                         const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
                         int max_tiles, float* maps, int map_stride, float* desc_split_ws, cudaStream_t st) {
-  using Cfg = TcCfg<TcMode::TF32X3>;
-  DTK_CHECK_ARG(((size_t)P * C * 4) % 16 == 0 && C % 4 == 0, "corr_tc: C must be a multiple of 4");
-  float* d_hi = desc_split_ws;
-  float* d_lo = desc_split_ws + align_up((size_t)desc_rows * C * 4, 256) / 4;
-  int rc = launch_split_tf32(desc, d_hi, d_lo, (size_t)desc_rows * C, st);
+  using Cfg = TcCfg<TcMode::F16X3>;
+  DTK_CHECK_ARG(C % 8 == 0, "corr (tensor path): C must be a multiple of 8");
+  char* d_hi = reinterpret_cast<char*>(desc_split_ws);
+  char* d_lo = d_hi + align_up((size_t)desc_rows * C * 2, 256);
+  int rc = launch_split_f16(desc, d_hi, d_lo, (size_t)desc_rows * C, st);
   if (rc) return rc;
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
-  if ((rc = make_tmap_2d(&tmA_hi, d_hi, desc_rows, C, TC_BM, Cfg::kBK, 4))) return rc;
-  if ((rc = make_tmap_2d(&tmA_lo, d_lo, desc_rows, C, TC_BM, Cfg::kBK, 4))) return rc;
-  if ((rc = make_tmap_3d(&tmB_hi, tpc_hi, T, P, C, TC_BN, Cfg::kBK, 4))) return rc;
-  if ((rc = make_tmap_3d(&tmB_lo, tpc_lo, T, P, C, TC_BN, Cfg::kBK, 4))) return rc;
+  if ((rc = make_tmap_2d(&tmA_hi, d_hi, desc_rows, C, TC_BM, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_2d(&tmA_lo, d_lo, desc_rows, C, TC_BM, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tmB_hi, tpc_hi, T, P, C, TC_BN, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tmB_lo, tpc_lo, T, P, C, TC_BN, Cfg::kBK, TMAP_F16))) return rc;
   static bool attr = false;
   if (!attr) {
-    DTK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TcMode::TF32X3, CorrEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DTK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TcMode::F16X3, CorrEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmem));
     attr = true;
   }
@@ -152,7 +157,7 @@ int launch_corr_gemm_tc(const float* tpc_hi, const float* tpc_lo, const float* n
   int grid = tiles_bound < sms ? tiles_bound : sms;
   if (grid < 1) grid = 1;
   ProfRange pr(PROF_CORR_GEMM, st);
-  tc_gemm_kernel<TcMode::TF32X3, CorrEpi><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, pb, epi);
+  tc_gemm_kernel<TcMode::F16X3, CorrEpi><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, pb, epi);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }
@@ -161,7 +166,7 @@ int launch_corr_gemm_tc(const float* tpc_hi, const float* tpc_lo, const float* n
 
 using namespace dtk;
 
-extern "C" int dinotrk_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
-  DTK_CHECK_ARG(x && hi && lo, "split_tf32: null pointer");
-  return launch_split_tf32(x, hi, lo, n, (cudaStream_t)stream);
+extern "C" int dinotrk_split_fp16(const float* x, void* hi, void* lo, size_t n, void* stream) {
+  DTK_CHECK_ARG(x && hi && lo, "split_fp16: null pointer");
+  return launch_split_f16(x, hi, lo, n, (cudaStream_t)stream);
 }

@@ -128,10 +128,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
 }  // namespace tc
 
 // host: tensor-map encoding through the driver entry point (no libcuda link dependency)
-// ld = row pitch in elements (0: dense, = cols)
+// elem: TMAP_F32 / TMAP_BF16 / TMAP_F16; ld = row pitch in elements (0: dense, = cols)
+enum { TMAP_F32 = 4, TMAP_BF16 = 2, TMAP_F16 = 102 };
 int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
-                 int elem_bytes, uint64_t ld = 0);
+                 int elem, uint64_t ld = 0);
 int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                 uint32_t box_cols, int elem_bytes, uint64_t ld = 0);
+                 uint32_t box_cols, int elem, uint64_t ld = 0);
 
 }  // namespace dtk

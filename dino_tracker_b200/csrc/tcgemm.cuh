@@ -8,8 +8,9 @@
 //   warps 2..5  : epilogue (tcgen05.ld of the warp's 32-lane quadrant -> Epi functor -> global)
 //
 // Modes:
-//   TF32X3 : fp32-faithful "3xTF32": operands pre-split into exactly-representable TF32 hi / lo parts,
-//            hi*hi + hi*lo + lo*hi accumulated in fp32 (error ~2^-21 per product before accumulation)
+//   F16X3  : fp32-faithful split-precision: operands pre-split into fp16 hi + fp16 lo (x = hi + lo up to 2^-22),
+//            lo*hi + hi*lo + hi*hi on the kind::f16 pipe (K = 16 per MMA: twice the TF32 rate), fp32 accumulation
+//   TF32X3 : the same scheme with TF32 parts (fp32 storage, K = 8 per MMA)
 //   TF32   : single pass on fp32 data (the tensor core reads the top 19 bits)
 //   BF16   : single pass on bf16 data
 // Work = grouped tiles: group g covers A rows [row0[g], row0[g] + m[g]) against B batch item batch[g];
@@ -20,7 +21,7 @@
 
 namespace dtk {
 
-enum class TcMode { TF32X3 = 0, TF32 = 1, BF16 = 2 };
+enum class TcMode { TF32X3 = 0, TF32 = 1, BF16 = 2, F16X3 = 3 };
 
 constexpr int TC_BM = 128, TC_BN = 256;   // TC_BN: default N tile (template parameter BN overrides it)
 constexpr int TC_THREADS = 192;
@@ -28,16 +29,17 @@ constexpr int TC_THREADS = 192;
 template <TcMode MODE, int BN = TC_BN>
 struct TcCfg {
   static_assert(BN == 64 || BN == 128 || BN == 256, "N tile must be 64, 128 or 256");
-  static constexpr int kElem = (MODE == TcMode::BF16) ? 2 : 4;
+  static constexpr int kElem = (MODE == TcMode::BF16 || MODE == TcMode::F16X3) ? 2 : 4;
   static constexpr int kBK = 128 / kElem;                         // elements per 128-byte swizzle row
-  static constexpr int kOps = (MODE == TcMode::TF32X3) ? 2 : 1;   // hi (+ lo) tiles per operand
+  static constexpr int kOps = (MODE == TcMode::TF32X3 || MODE == TcMode::F16X3) ? 2 : 1;   // hi (+ lo) tiles per operand
   static constexpr int kUmmaK = 32 / kElem;                       // K per tcgen05.mma
   static constexpr int kABytes = TC_BM * 128, kBBytes = BN * 128;
   static constexpr int kStageBytes = kOps * (kABytes + kBBytes);
-  static constexpr int kStages = (MODE == TcMode::TF32X3) ? 2 : 4;
+  static constexpr int kStages = (kOps == 2) ? 2 : 4;
   static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr bool kTF32 = MODE != TcMode::BF16;
-  static constexpr uint32_t kIdesc = tc::make_idesc(kTF32 ? 2 : 1, TC_BM, BN);
+  static constexpr bool kTF32 = (MODE == TcMode::TF32X3 || MODE == TcMode::TF32);
+  static constexpr int kFmt = kTF32 ? 2 : (MODE == TcMode::BF16 ? 1 : 0);   // 0 f16, 1 bf16, 2 tf32
+  static constexpr uint32_t kIdesc = tc::make_idesc(kFmt, TC_BM, BN);
   static constexpr uint32_t kTmemCols = 2 * BN;   // two accumulator buffers (power of two >= 32)
 };
 
@@ -147,9 +149,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const uint64_t a_lo = tc::smem_desc_sw128(sa + Cfg::kABytes + koff);
               const uint64_t b_lo = tc::smem_desc_sw128(sb + Cfg::kBBytes + koff);
               // small terms first, then the dominant hi*hi
-              tc::mma_ss<true>(tmem_d, a_lo, b_hi, Cfg::kIdesc, first);
-              tc::mma_ss<true>(tmem_d, a_hi, b_lo, Cfg::kIdesc, 1u);
-              tc::mma_ss<true>(tmem_d, a_hi, b_hi, Cfg::kIdesc, 1u);
+              tc::mma_ss<Cfg::kTF32>(tmem_d, a_lo, b_hi, Cfg::kIdesc, first);
+              tc::mma_ss<Cfg::kTF32>(tmem_d, a_hi, b_lo, Cfg::kIdesc, 1u);
+              tc::mma_ss<Cfg::kTF32>(tmem_d, a_hi, b_hi, Cfg::kIdesc, 1u);
             } else {
               tc::mma_ss<Cfg::kTF32>(tmem_d, a_hi, b_hi, Cfg::kIdesc, first);
             }

@@ -229,8 +229,8 @@ static int run_gemm(const float* A, uint64_t a_rows, const float* Bm, uint64_t b
   using Cfg = TcCfg<TcMode::TF32, BN>;
   CUtensorMap tmA, tmB;
   int rc;
-  if ((rc = make_tmap_2d(&tmA, A, a_rows, K, TC_BM, Cfg::kBK, 4, ld))) return rc;
-  if ((rc = make_tmap_3d(&tmB, Bm, b_batch, b_rows, K, BN, Cfg::kBK, 4, ld))) return rc;
+  if ((rc = make_tmap_2d(&tmA, A, a_rows, K, TC_BM, Cfg::kBK, TMAP_F32, ld))) return rc;
+  if ((rc = make_tmap_3d(&tmB, Bm, b_batch, b_rows, K, BN, Cfg::kBK, TMAP_F32, ld))) return rc;
   auto kern = tc_gemm_kernel<TcMode::TF32, Epi, BN>;
   static bool attr = false;  // one static per template instantiation
   if (!attr) {

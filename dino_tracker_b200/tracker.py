@@ -31,7 +31,7 @@ def _as_f32(t, device):
 class Tracker(nn.Module):
     def __init__(self, video=None, ckpt_path="", dino_embed_path="", dino_patch_size=14, stride=7,
                  device="cuda:0", cyc_n_frames=4, cyc_batch_size_per_frame=256, cyc_fg_points_ratio=0.7,
-                 cyc_thresh=4, dino_embed_video=None, delta_channels=None, corr_precision="tf32x3"):
+                 cyc_thresh=4, dino_embed_video=None, delta_channels=None, corr_precision="fp16x3"):
         super().__init__()
         self.device = device
         self._dev = _lib.require_cuda(device)
@@ -47,8 +47,8 @@ class Tracker(nn.Module):
         self.video = video
         t, c, h, w = video.shape
         self._geom = _lib.make_geom(h, w, dino_patch_size, stride, 35)
-        assert corr_precision in ("tf32x3", "fp32")
-        # "tf32x3": wide correlation groups on tcgen05 tensor cores (3xTF32, fp32-faithful);
+        assert corr_precision in ("fp16x3", "fp32")
+        # "fp16x3": wide correlation groups on tcgen05 tensor cores (fp16 hi/lo split, 3 passes, fp32-faithful);
         # "fp32"  : exact-fp32 FFMA GEMM on the CUDA cores (validation path)
         self.corr_precision = corr_precision
         self._refined_tpc = None
@@ -87,14 +87,15 @@ class Tracker(nn.Module):
         return tpc, norms
 
     def features_struct(self, tpc, norms):
-        """C struct for a [T][P][C] feature video (+ its cached TF32 split in tf32x3 mode)."""
-        if self.corr_precision != "tf32x3":
+        """C struct for a [T][P][C] feature video (+ its cached fp16 hi/lo split in fp16x3 mode)."""
+        if self.corr_precision != "fp16x3" or tpc.shape[-1] % 8:
             return _lib.make_features(tpc, norms)
         key = (tpc.data_ptr(), tpc._version, tuple(tpc.shape))
         if self._split_cache.get("key") != key:
-            hi, lo = torch.empty_like(tpc), torch.empty_like(tpc)
-            _lib.check(self._lib.dinotrk_split_tf32(_lib.ptr(tpc), _lib.ptr(hi), _lib.ptr(lo), tpc.numel(),
-                                                     _lib.stream_ptr()), "split_tf32")
+            hi = torch.empty(tpc.shape, device=tpc.device, dtype=torch.float16)
+            lo = torch.empty(tpc.shape, device=tpc.device, dtype=torch.float16)
+            _lib.check(self._lib.dinotrk_split_fp16(_lib.ptr(tpc), _lib.ptr(hi), _lib.ptr(lo), tpc.numel(),
+                                                     _lib.stream_ptr()), "split_fp16")
             self._split_cache = {"key": key, "hi": hi, "lo": lo}
         return _lib.make_features(tpc, norms, self._split_cache["hi"], self._split_cache["lo"])
 

@@ -52,13 +52,14 @@ typedef struct dinotrk_head_weights {
 } dinotrk_head_weights;
 
 /* A cached feature video.  tpc [T][P][C] and norms [T][P] are required.  hi / lo (optional, both or
- * neither): the TF32 split of tpc produced by dinotrk_split_tf32; when present the wide correlation
- * groups run on the tcgen05 tensor cores (3xTF32, fp32-faithful), otherwise on the exact-fp32 FFMA GEMM. */
+ * neither): the fp16 split of tpc ([T][P][C] halves each, x = hi + lo) produced by dinotrk_split_fp16; when
+ * present the wide correlation groups run on the tcgen05 tensor cores (3-pass split precision,
+ * fp32-faithful), otherwise on the exact-fp32 FFMA GEMM.  C must then be a multiple of 8. */
 typedef struct dinotrk_features {
   const float* tpc;
   const float* norms;
-  const float* hi;
-  const float* lo;
+  const void* hi;
+  const void* lo;
   int T, C;
 } dinotrk_features;
 
@@ -74,8 +75,8 @@ int dinotrk_pack_features(const float* chw, float* tpc, float* norms, int T, int
                           void* stream);
 int dinotrk_unpack_features(const float* tpc, float* chw, int T, int C, int P, void* stream);
 int dinotrk_token_norms(const float* tpc, float* norms, int T, int C, int P, void* stream);
-/* x = hi + lo with hi, lo exactly representable in TF32 (13 low mantissa bits zero); n % 4 == 0. */
-int dinotrk_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
+/* x = hi + lo with hi = rn_fp16(x), lo = rn_fp16(x - hi) (fp16 arrays of n elements); n % 4 == 0. */
+int dinotrk_split_fp16(const float* x, void* hi, void* lo, size_t n, void* stream);
 
 /* ---- descriptor sampling (models/tracker.py:77-111, utils.py:75-101) ------------------- */
 /* points [B][3] = (x_px, y_px, set_index) ; frames_set [N] int32 = frame of each set slot.
@@ -177,7 +178,7 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
 /* ---- best buddies (preprocessing_dino_bb/extract_dino_best_buddies.py:12-54) ------------------------ */
 /* For every ordered pair k (source frame pair_src[k], target frame pair_tgt[k]; device int32[n_pairs]):
  * nn_idx[k][n] = argmax_m cos(F_src[n], F_tgt[m]) (first maximum), nn_cos[k][n] = that cosine (exact fp32,
- * clamp 1e-8 on the norm product).  The affinity matrix runs through the tcgen05 3xTF32 GEMM and never
+ * clamp 1e-8 on the norm product).  The affinity matrix runs through the tcgen05 split-fp16 GEMM and never
  * leaves TMEM; candidates are re-evaluated in exact fp32.  feat->hi / lo are required. */
 size_t dinotrk_best_buddies_workspace_bytes(int n_pairs, int P);
 int dinotrk_best_buddies_pairs(const dinotrk_features* feat, const dinotrk_geom* g, const int* pair_src,

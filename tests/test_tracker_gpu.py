@@ -20,10 +20,10 @@ XY_TOL = 1e-3
 DEV = "cuda:0"
 
 
-PRECISIONS = ["tf32x3", "fp32"]  # tcgen05 3xTF32 tensor-core GEMM / exact-fp32 FFMA GEMM
+PRECISIONS = ["fp16x3", "fp32"]  # tcgen05 3xTF32 tensor-core GEMM / exact-fp32 FFMA GEMM
 
 
-def make_model(geo, feats, head, precision="tf32x3"):
+def make_model(geo, feats, head, precision="fp16x3"):
     from dino_tracker_b200 import Tracker
     T = feats.shape[0]
     video = torch.zeros(T, 3, geo.H, geo.W, device=DEV)

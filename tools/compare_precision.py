@@ -26,7 +26,7 @@ def main():
     video = torch.zeros(a.T, 3, bench.H, bench.W, device=dev)
     q = bench.query_lattice(a.nq, 0).to(dev)
     res = {}
-    for prec in ("fp32", "tf32x3"):
+    for prec in ("fp32", "fp16x3"):
         m = Tracker(video=video, dino_embed_video=feats, device=dev, delta_channels=[3, 4, 4, 4, a.C], corr_precision=prec)
         m.tracker_head.load_state_dict(sharp_head(0))
         mi = ModelInference(m, m.range_normalizer, 0.7, 0.6)
@@ -37,7 +37,7 @@ def main():
         res[prec] = r
         print(f"{prec}: {dt * 1000:.1f} ms per infer ({a.nq / dt:.0f} qp/s)")
         del m, mi
-    A, B = res["fp32"], res["tf32x3"]
+    A, B = res["fp32"], res["fp16x3"]
     dtraj = (A["traj"] - B["traj"]).abs()
     print("max |traj diff| px:", dtraj.max().item(), " #points > 1e-3:", int((dtraj[..., :2].max(-1).values > 1e-3).sum()))
     print("occlusion mismatches:", int((A["occ"] != B["occ"]).sum()), "of", A["occ"].numel())
