@@ -25,7 +25,8 @@ class Features(Structure):
 
 
 class VitConfig(Structure):
-    _fields_ = [("depth", c_int), ("dim", c_int), ("heads", c_int), ("tap_layer", c_int), ("patch", c_int), ("stride", c_int)]
+    _fields_ = [("depth", c_int), ("dim", c_int), ("heads", c_int), ("tap_layer", c_int), ("patch", c_int), ("stride", c_int),
+                ("attn_materialized", c_int)]
 
 
 class VitWeights(Structure):

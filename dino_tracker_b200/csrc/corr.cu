@@ -146,8 +146,19 @@ corr_gemm_kernel(const float* __restrict__ tpc, const float* __restrict__ norms,
 }
 
 // ---- thin groups: stream every token row once --------------------------------------------------
+// HBM-bound: a warp owns 4 token rows at a time; per 16-byte column chunk it issues the 4 row loads
+// back to back (x2 unrolled: 8 x LDG.128 in flight per lane, L1 bypassed), reads each descriptor chunk once from
+// shared memory and reuses it for the 4 rows.  Grid = token tiles x groups.
 constexpr int STREAM_THREADS = 256;
-constexpr int STREAM_TOK = 64;  // tokens per CTA (8 per warp)
+constexpr int STREAM_TOK = 64;   // tokens per CTA: 8 warps x 2 passes x 4 rows
+constexpr int STREAM_RB = 4;     // rows per warp pass
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
 
 template <int MAXM>
 __global__ void __launch_bounds__(STREAM_THREADS)
@@ -169,31 +180,52 @@ corr_stream_kernel(const float* __restrict__ tpc, const float* __restrict__ norm
     for (int i = threadIdx.x; i < mc * C4; i += STREAM_THREADS)
       reinterpret_cast<float4*>(sdesc)[i] = __ldg(reinterpret_cast<const float4*>(desc + (size_t)(row0 + mb) * C) + i);
     __syncthreads();
-    for (int t = warp; t < STREAM_TOK; t += STREAM_THREADS / 32) {
-      const int p = blockIdx.x * STREAM_TOK + t;
-      if (p >= P) break;
-      const float4* row = reinterpret_cast<const float4*>(tpc + ((size_t)frame * P + p) * C);
-      float acc[MAXM];
+    for (int t0 = warp * STREAM_RB; t0 < STREAM_TOK; t0 += (STREAM_THREADS / 32) * STREAM_RB) {
+      const int p0 = blockIdx.x * STREAM_TOK + t0;
+      if (p0 >= P) break;
+      const float4* rows[STREAM_RB];
 #pragma unroll
-      for (int q = 0; q < MAXM; ++q) acc[q] = 0.f;
-      for (int i = lane; i < C4; i += 32) {
-        float4 f = __ldg(row + i);
+      for (int r = 0; r < STREAM_RB; ++r)   // rows past the end re-read the last valid row (result discarded)
+        rows[r] = reinterpret_cast<const float4*>(tpc + ((size_t)frame * P + min(p0 + r, P - 1)) * C);
+      float acc[MAXM][STREAM_RB];
+#pragma unroll
+      for (int q = 0; q < MAXM; ++q)
+#pragma unroll
+        for (int r = 0; r < STREAM_RB; ++r) acc[q][r] = 0.f;
+      for (int i = lane; i < C4; i += 64) {
+        const int i2 = i + 32;
+        const bool two = i2 < C4;
+        float4 f0[STREAM_RB], f1[STREAM_RB];
+#pragma unroll
+        for (int r = 0; r < STREAM_RB; ++r) f0[r] = ldg_stream(rows[r] + i);
+#pragma unroll
+        for (int r = 0; r < STREAM_RB; ++r) f1[r] = two ? ldg_stream(rows[r] + i2) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < MAXM; ++q) {
           if (q < mc) {
-            float4 d = reinterpret_cast<const float4*>(sdesc + q * C)[i];
-            acc[q] = fmaf(f.x, d.x, acc[q]); acc[q] = fmaf(f.y, d.y, acc[q]);
-            acc[q] = fmaf(f.z, d.z, acc[q]); acc[q] = fmaf(f.w, d.w, acc[q]);
+            const float4 d0 = reinterpret_cast<const float4*>(sdesc + q * C)[i];
+            const float4 d1 = two ? reinterpret_cast<const float4*>(sdesc + q * C)[i2] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < STREAM_RB; ++r) {
+              float a = acc[q][r];
+              a = fmaf(f0[r].x, d0.x, a); a = fmaf(f0[r].y, d0.y, a); a = fmaf(f0[r].z, d0.z, a); a = fmaf(f0[r].w, d0.w, a);
+              a = fmaf(f1[r].x, d1.x, a); a = fmaf(f1[r].y, d1.y, a); a = fmaf(f1[r].z, d1.z, a); a = fmaf(f1[r].w, d1.w, a);
+              acc[q][r] = a;
+            }
           }
         }
       }
-      const float fn = norms[(size_t)frame * P + p];
 #pragma unroll
-      for (int q = 0; q < MAXM; ++q) {
-        float s = warp_sum(acc[q]);
-        if (lane == 0 && q < mc) {
-          float v = __fdiv_rn(s, fmaxf(__fmul_rn(desc_norm[row0 + mb + q], fn), 1e-8f));
-          maps[(size_t)(map0 + mb + q) * map_stride + p] = fmaxf(v, 0.f);
+      for (int r = 0; r < STREAM_RB; ++r) {
+        const int p = p0 + r;
+        const float fn = p < P ? norms[(size_t)frame * P + p] : 1.f;
+#pragma unroll
+        for (int q = 0; q < MAXM; ++q) {
+          float s = warp_sum(acc[q][r]);
+          if (lane == 0 && q < mc && p < P) {
+            float v = __fdiv_rn(s, fmaxf(__fmul_rn(desc_norm[row0 + mb + q], fn), 1e-8f));
+            maps[(size_t)(map0 + mb + q) * map_stride + p] = fmaxf(v, 0.f);
+          }
         }
       }
     }

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "corr.cuh"
 #include "tcgemm.cuh"
+#include "flash.cuh"
 
 namespace dtk {
 
@@ -172,6 +173,28 @@ struct EpiQKV : EpiBase {
   }
 };
 
+// qkv for the fused attention: fp16 q [b][hd][n][64] (scaled 1/8), k [b][hd][n][64], vT [b][hd][64][n] (pitch N1p)
+struct EpiQKV16 : EpiBase {
+  __half* q; __half* k; __half* vT; const float* bias; int N1, D, heads, N1p;
+  __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
+    const int b = r / N1, n = r - b * N1;
+    const int which = col0 / D, c = col0 - which * D, hd = c / HD, e0 = c - hd * HD;
+    const size_t bh = (size_t)b * heads + hd;
+    if (which < 2) {
+      __half* o = (which == 0 ? q : k) + (bh * N1 + n) * HD + e0;
+      const float sc = which == 0 ? 0.125f : 1.f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2)
+        if (i < ncols) *reinterpret_cast<__half2*>(o + i) =
+            __floats2half2_rn((f[i] + __ldg(bias + col0 + i)) * sc, (f[i + 1] + __ldg(bias + col0 + i + 1)) * sc);
+    } else {
+      __half* o = vT + (bh * HD + e0) * N1p + n;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (i < ncols) o[(size_t)i * N1p] = __float2half_rn(f[i] + __ldg(bias + col0 + i));
+    }
+  }
+};
+
 // plain store: out[(g * rows_per_group + r)][col] (attention scores)
 struct EpiStore : EpiBase {
   float* out; int ld, rows_per_group;
@@ -329,6 +352,28 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
       DTK_LAUNCHED();
     }
     if ((rc = plan(pl, 1, (int)rows, 0, 0, 0, st))) return rc;
+    if (c->attn_materialized == 0) {
+      // fused attention: fp16 q / k / v^T, scores stay in TMEM / shared memory
+      __half* q16 = reinterpret_cast<__half*>(q);
+      __half* k16 = reinterpret_cast<__half*>(k);
+      __half* v16 = reinterpret_cast<__half*>(vT);
+      const int N1p8 = (int)align_up((size_t)N1, 8);
+      if ((rc = run_gemm<EpiQKV16, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles,
+                                        EpiQKV16{{}, q16, k16, v16, w[3], N1, D, heads, N1p8}, PROF_VIT_GEMM, st))) return rc;
+      CUtensorMap tmQ, tmK, tmV;
+      if ((rc = make_tmap_2d(&tmQ, q16, (uint64_t)B * heads * N1, HD, FA_BQ, HD, TMAP_F16))) return rc;
+      if ((rc = make_tmap_3d(&tmK, k16, (uint64_t)B * heads, N1, HD, FA_BKV, HD, TMAP_F16))) return rc;
+      if ((rc = make_tmap_3d(&tmV, v16, (uint64_t)B * heads, HD, N1, HD, 64, TMAP_F16, (uint64_t)N1p8))) return rc;
+      static bool fattr = false;
+      if (!fattr) {
+        DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        fattr = true;
+      }
+      FlashParams fpar{N1, D, heads, y};
+      ProfRange pr(PROF_VIT_ATTN, st);
+      flash_attn_kernel<<<dim3(cdiv(N1, FA_BQ), B * heads), FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
+      DTK_LAUNCHED();
+    } else {
     if ((rc = run_gemm<EpiQKV, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, EpiQKV{{}, q, k, vT, w[3], N1, D, heads, N1p},
                                     PROF_VIT_GEMM, st))) return rc;
     // attention, per frame and chunk of query rows: S = q k^T (all heads) -> softmax -> y = S v
@@ -349,6 +394,7 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
                                       heads * cdiv(rc_rows, TC_BM), EpiPV{{}, y, (size_t)b * N1 + c0, D},
                                       PROF_VIT_ATTN, st, (uint64_t)N1p))) return rc;
       }
+    }
     }
     if ((rc = plan(pl, 1, (int)rows, 0, 0, 0, st))) return rc;
     if ((rc = run_gemm<EpiResidual, 256>(y, rows, w[4], 1, D, D, pl, 1, all_tiles, EpiResidual{{}, x, w[5], w[6], D},

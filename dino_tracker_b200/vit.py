@@ -49,7 +49,8 @@ def interpolate_pos_embed(pos_embed, n_h, n_w):
 class DinoV2Features(torch.nn.Module):
     """``VitExtractor`` replacement: ``forward(video01)`` -> token-major features [T][P][C] on the GPU."""
 
-    def __init__(self, state_dict, heads, layer=None, stride=7, patch=14, device="cuda:0", frames_per_call=2):
+    def __init__(self, state_dict, heads, layer=None, stride=7, patch=14, device="cuda:0", frames_per_call=2,
+                 attention="fused"):
         super().__init__()
         self._dev = _lib.require_cuda(device)
         self._lib = _lib.load()
@@ -60,6 +61,8 @@ class DinoV2Features(torch.nn.Module):
         self.layer = self.depth - 1 if layer is None else layer
         self.stride, self.patch = stride, patch
         self.frames_per_call = frames_per_call
+        assert attention in ("fused", "materialized")
+        self.attention = attention
         self._sd = sd
         self._patch_w = sd["patch_embed.proj.weight"].reshape(self.dim, -1).contiguous()
         assert self._patch_w.shape[1] % 4 == 0
@@ -87,7 +90,8 @@ class DinoV2Features(torch.nn.Module):
         T, _, H, W = video01.shape
         geom = _lib.make_geom(H, W, self.patch, self.stride, 35)
         P = geom.h * geom.w
-        cfg = _lib.VitConfig(self.depth, self.dim, self.heads, self.layer, self.patch, self.stride)
+        cfg = _lib.VitConfig(self.depth, self.dim, self.heads, self.layer, self.patch, self.stride,
+                             0 if self.attention == "fused" else 1)
         cls_pos, pos = self._pos(geom.h, geom.w)
         wt = _lib.VitWeights()
         wt.patch_w, wt.patch_b = self._patch_w.data_ptr(), self._sd["patch_embed.proj.bias"].data_ptr()

@@ -160,6 +160,8 @@ typedef struct dinotrk_vit_config {
   int depth, dim, heads;   /* ViT-L/14: 24, 1024, 16; ViT-B/14: 12, 768, 12 (head dim 64) */
   int tap_layer;           /* 0-based block whose output (before the final norm) is returned; 15 in the shipped config */
   int patch, stride;       /* 14, 7 */
+  int attn_materialized;   /* 0: fused tcgen05 attention (fp16 q/k/v/p, scores stay on the SM); 1: TF32 scores through a
+                              workspace (tensor-core GEMM -> softmax -> tensor-core GEMM), validation path */
 } dinotrk_vit_config;
 /* All device fp32.  patch_w: patch-embedding conv weight flattened K-major [dim][3*patch*patch]; cls_pos [dim] =
  * cls_token + pos_embed[0]; pos [h*w][dim] = bicubic-interpolated patch position embedding (extractor.py:57-85);

@@ -10,20 +10,22 @@ from oracle import synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("attention", ["fused", "materialized"])
 @pytest.mark.parametrize("cfg", [dict(H=98, W=126, depth=2, dim=128, heads=2, layer=1, T=3),
-                                 dict(H=112, W=140, depth=3, dim=192, heads=3, layer=1, T=2)])
-def test_vit_features_match_oracle(cfg):
+                                 dict(H=112, W=140, depth=3, dim=192, heads=3, layer=1, T=2),
+                                 dict(H=182, W=238, depth=1, dim=64, heads=1, layer=0, T=1)])
+def test_vit_features_match_oracle(cfg, attention):
     from dino_tracker_b200.vit import DinoV2Features
     g = torch.Generator().manual_seed(3)
     sd = ovit.random_state_dict(cfg["depth"], cfg["dim"], g, n_pos=4, std=0.05)
     video = synth.random_video(cfg["T"], cfg["H"], cfg["W"], seed=4)
     ref = ovit.dino_features_video(video, sd, cfg["heads"], cfg["layer"])          # T x C x h x w
-    ex = DinoV2Features(sd, heads=cfg["heads"], layer=cfg["layer"], device="cuda:0")
+    ex = DinoV2Features(sd, heads=cfg["heads"], layer=cfg["layer"], device="cuda:0", attention=attention)
     got = ex.features_chw(video).cpu()
     assert got.shape == ref.shape
     scale = ref.abs().max().item()
     err = (got - ref).abs().max().item()
-    print(f"ViT max |diff| = {err:.3e} (max |ref| = {scale:.3f})")
+    print(f"ViT[{attention}] max |diff| = {err:.3e} (max |ref| = {scale:.3f})")
     assert err <= 5e-3 * scale   # TF32 single-pass contractions (10-bit mantissa inputs), fp32 accumulation
     # cosine between corresponding tokens
     cos = torch.nn.functional.cosine_similarity(got.flatten(2), ref.flatten(2), dim=1)
