@@ -150,8 +150,7 @@ corr_gemm_kernel(const float* __restrict__ tpc, const float* __restrict__ norms,
 // back to back (x2 unrolled: 8 x LDG.128 in flight per lane, L1 bypassed), reads each descriptor chunk once from
 // shared memory and reuses it for the 4 rows.  Grid = token tiles x groups.
 constexpr int STREAM_THREADS = 256;
-constexpr int STREAM_TOK = 64;   // tokens per CTA: 8 warps x 2 passes x 4 rows
-constexpr int STREAM_RB = 4;     // rows per warp pass
+constexpr int STREAM_TOK = 64;   // tokens per CTA: 8 warps x (64 / (8 * RB)) passes x RB rows
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 r;
@@ -160,7 +159,7 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return r;
 }
 
-template <int MAXM>
+template <int MAXM, int STREAM_RB>
 __global__ void __launch_bounds__(STREAM_THREADS)
 corr_stream_kernel(const float* __restrict__ tpc, const float* __restrict__ norms, int C, int P,
                    const float* __restrict__ desc, const float* __restrict__ desc_norm,
@@ -177,8 +176,9 @@ corr_stream_kernel(const float* __restrict__ tpc, const float* __restrict__ norm
   for (int mb = 0; mb < m; mb += MAXM) {
     const int mc = min(MAXM, m - mb);
     __syncthreads();
-    for (int i = threadIdx.x; i < mc * C4; i += STREAM_THREADS)
-      reinterpret_cast<float4*>(sdesc)[i] = __ldg(reinterpret_cast<const float4*>(desc + (size_t)(row0 + mb) * C) + i);
+    for (int i = threadIdx.x; i < MAXM * C4; i += STREAM_THREADS)   // unused descriptor slots are zero: no predicates below
+      reinterpret_cast<float4*>(sdesc)[i] = i < mc * C4
+          ? __ldg(reinterpret_cast<const float4*>(desc + (size_t)(row0 + mb) * C) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     for (int t0 = warp * STREAM_RB; t0 < STREAM_TOK; t0 += (STREAM_THREADS / 32) * STREAM_RB) {
       const int p0 = blockIdx.x * STREAM_TOK + t0;
@@ -202,16 +202,14 @@ corr_stream_kernel(const float* __restrict__ tpc, const float* __restrict__ norm
         for (int r = 0; r < STREAM_RB; ++r) f1[r] = two ? ldg_stream(rows[r] + i2) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < MAXM; ++q) {
-          if (q < mc) {
-            const float4 d0 = reinterpret_cast<const float4*>(sdesc + q * C)[i];
-            const float4 d1 = two ? reinterpret_cast<const float4*>(sdesc + q * C)[i2] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 d0 = reinterpret_cast<const float4*>(sdesc + q * C)[i];
+          const float4 d1 = two ? reinterpret_cast<const float4*>(sdesc + q * C)[i2] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int r = 0; r < STREAM_RB; ++r) {
-              float a = acc[q][r];
-              a = fmaf(f0[r].x, d0.x, a); a = fmaf(f0[r].y, d0.y, a); a = fmaf(f0[r].z, d0.z, a); a = fmaf(f0[r].w, d0.w, a);
-              a = fmaf(f1[r].x, d1.x, a); a = fmaf(f1[r].y, d1.y, a); a = fmaf(f1[r].z, d1.z, a); a = fmaf(f1[r].w, d1.w, a);
-              acc[q][r] = a;
-            }
+          for (int r = 0; r < STREAM_RB; ++r) {
+            float a = acc[q][r];
+            a = fmaf(f0[r].x, d0.x, a); a = fmaf(f0[r].y, d0.y, a); a = fmaf(f0[r].z, d0.z, a); a = fmaf(f0[r].w, d0.w, a);
+            a = fmaf(f1[r].x, d1.x, a); a = fmaf(f1[r].y, d1.y, a); a = fmaf(f1[r].z, d1.z, a); a = fmaf(f1[r].w, d1.w, a);
+            acc[q][r] = a;
           }
         }
       }
@@ -270,19 +268,25 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
     }
   }
   {
-    // thin groups (there may be none; CTAs of wide groups exit at once)
-    constexpr int MAXM = 8;
-    size_t smem = (size_t)MAXM * C * sizeof(float);
-    static size_t attr_smem = 0;
-    if (smem > 48 * 1024 && smem > attr_smem) {
-      DTK_CUDA(cudaFuncSetAttribute(corr_stream_kernel<MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_smem = smem;
+    // thin groups (there may be none; CTAs of wide groups exit at once).  Two instantiations: up to 2 descriptors per
+    // pass with 8 rows in flight per warp (pure streaming), up to 8 descriptors with 4 rows.
+    const bool tiny = max_group_m <= 2;
+    const int maxm = tiny ? 2 : 8;
+    size_t smem = (size_t)maxm * C * sizeof(float);
+    static size_t attr_smem[2] = {0, 0};
+    auto k2 = corr_stream_kernel<2, 8>;
+    auto k8 = corr_stream_kernel<8, 4>;
+    if (smem > 48 * 1024 && smem > attr_smem[tiny ? 0 : 1]) {
+      if (tiny) DTK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else DTK_CUDA(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem[tiny ? 0 : 1] = smem;
     }
     dim3 grid(cdiv(P, STREAM_TOK), n_groups);
     ProfRange pr(PROF_CORR_STREAM, st);
-    corr_stream_kernel<MAXM><<<grid, STREAM_THREADS, smem, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame,
-                                                                grp_row0, grp_m, grp_map0, stream_max, maps,
-                                                                map_stride);
+    if (tiny) k2<<<grid, STREAM_THREADS, smem, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
+                                                     stream_max, maps, map_stride);
+    else k8<<<grid, STREAM_THREADS, smem, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
+                                                stream_max, maps, map_stride);
     DTK_LAUNCHED();
   }
   return DINOTRK_OK;
