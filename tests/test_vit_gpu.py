@@ -36,3 +36,17 @@ def test_pos_embed_interpolation_matches_oracle():
     from dino_tracker_b200.vit import interpolate_pos_embed
     pe = torch.randn(1, 1 + 37 * 37, 32)
     assert torch.equal(interpolate_pos_embed(pe, 67, 121), ovit.interpolate_pos_embed(pe, 67, 121))
+
+
+def test_vit_is_deterministic_and_batch_invariant():
+    """Frame features must not depend on which other frames share the call (frame sharding relies on it)."""
+    from dino_tracker_b200.vit import DinoV2Features
+    g = torch.Generator().manual_seed(5)
+    sd = ovit.random_state_dict(2, 128, g, n_pos=4, std=0.05)
+    video = synth.random_video(5, 98, 126, seed=6)
+    ex = DinoV2Features(sd, heads=2, layer=1, device="cuda:0")
+    a = ex(video).clone()
+    b = ex(video).clone()
+    assert torch.equal(a, b), f"non-deterministic: {(a - b).abs().max().item()}"
+    c = ex(video[1:4]).clone()
+    assert torch.equal(a[1:4], c), f"batch-dependent: {(a[1:4] - c).abs().max().item()}"

@@ -63,8 +63,8 @@ def run():
     q[:, 2] = torch.arange(N, device=dev) % T
 
     def build_tracker(feats_tpc_chw):
+        torch.manual_seed(5)   # identical delta-DINO weights (incl. default-initialised biases) on every rank / build
         m = Tracker(video=video.to(dev), dino_embed_video=feats_tpc_chw, device=dev, delta_channels=[3, 16, 16, 16, C])
-        torch.manual_seed(5)
         for p_ in m.delta_dino.parameters():
             torch.nn.init.normal_(p_, std=0.05) if p_.dim() > 1 else None
         m.tracker_head.load_state_dict(sharp_head(0))
