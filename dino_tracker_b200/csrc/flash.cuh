@@ -1,8 +1,9 @@
 // Fused attention for the ViT (sm_100a, tcgen05):  O = softmax(Q K^T) V  per (frame, head), scale pre-folded into Q.
 //
 // One CTA per (frame*head, 128-query tile); 192 threads:
-//   warp 0     : TMA producer (Q once; K_j [128 keys][64] and V^T_j [64][128 keys] through a 2-stage ring)
-//   warp 1     : TMEM alloc + MMA issue:  S = Q K_j^T (kind::f16, M128 N128 K64) -> TMEM;  O_j = P_j V_j (M128 N64 K128)
+//   warp 0     : TMA producer (Q once; K_j [BKV keys][64] and V^T_j [64][BKV keys] through a 2-stage ring)
+//   warp 1     : TMEM alloc + MMA issue:  S = Q K_j^T (kind::f16, M128 N=BKV K64) -> TMEM;  O_j = P_j V_j (M128 N64 K=BKV)
+//                (BKV = 64: 66 KB of shared memory and 128 TMEM columns per CTA -> 3 CTAs per SM overlap each other)
 //   warps 2..5 : online softmax, thread = query row: running max / sum in registers, P_j written as fp16 into a
 //                128B-swizzled shared-memory tile (the A operand of the second MMA), O accumulated in registers
 //                (O_j is read back from TMEM and added after the rescale), final normalise + fp32 store.
@@ -15,11 +16,16 @@
 
 namespace dtk {
 
-constexpr int FA_BQ = 128, FA_BKV = 128, FA_D = 64, FA_THREADS = 192;
+#ifndef DTK_FA_BKV
+#define DTK_FA_BKV 64
+#endif
+constexpr int FA_BQ = 128, FA_BKV = DTK_FA_BKV, FA_D = 64, FA_THREADS = 192;
+constexpr int FA_NSUB = FA_BKV / 64;               // 64-key sub-tiles (one 128-byte swizzle row of fp16 each)
 constexpr int FA_SQ = FA_BQ * 128;                 // Q tile bytes (128 rows x 64 fp16)
 constexpr int FA_SK = FA_BKV * 128;                // K tile bytes
-constexpr int FA_SV = 2 * FA_D * 128;              // V^T tile: two sub-tiles [64 d][64 keys]
-constexpr int FA_SP = 2 * FA_BQ * 128;             // P tile: two sub-tiles [128 rows][64 keys]
+constexpr int FA_SV = FA_NSUB * FA_D * 128;        // V^T tile: sub-tiles [64 d][64 keys]
+constexpr int FA_SP = FA_NSUB * FA_BQ * 128;       // P tile: sub-tiles [128 rows][64 keys]
+constexpr int FA_TMEM = FA_BKV + 64 <= 128 ? 128 : 256;
 constexpr int FA_STAGE = FA_SK + FA_SV;
 constexpr int FA_SMEM = FA_SQ + 2 * FA_STAGE + FA_SP + 256;   // extern smem is declared 1024-byte aligned
 
@@ -27,10 +33,11 @@ struct FlashParams {
   int N1;          // tokens per frame (keys = queries)
   int D;           // model dim (output row pitch)
   int heads;
-  float* out;      // [B*N1][D] fp32; head h writes columns [h*64, h*64+64)
+  void* out;       // [B*N1][D] fp32 or fp16; head h writes columns [h*64, h*64+64)
+  int out_f16;
 };
 
-__global__ void __launch_bounds__(FA_THREADS, 2)
+__global__ void __launch_bounds__(FA_THREADS, FA_BKV == 64 ? 2 : 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, FlashParams fp) {
   extern __shared__ __align__(1024) uint8_t fa_smem[];
@@ -58,13 +65,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc::mbar_init(s_full, 1); tc::mbar_init(p_ready, 4); tc::mbar_init(o_full, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tc::tmem_alloc(tmem_slot, FA_TMEM);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
-  constexpr uint32_t kIdescS = tc::make_idesc(0, 128, 128);   // f16 inputs, fp32 accumulate
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + FA_BKV;
+  constexpr uint32_t kIdescS = tc::make_idesc(0, 128, FA_BKV);   // f16 inputs, fp32 accumulate
   constexpr uint32_t kIdescO = tc::make_idesc(0, 128, 64);
 
   if (warp == 0) {
@@ -77,8 +84,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc::mbar_expect_tx(&kv_full[s], FA_STAGE);
         uint8_t* st = sKV + s * FA_STAGE;
         tc::tma_load_3d(&tmK, &kv_full[s], st, 0, j * FA_BKV, bh);
-        tc::tma_load_3d(&tmV, &kv_full[s], st + FA_SK, j * FA_BKV, 0, bh);
-        tc::tma_load_3d(&tmV, &kv_full[s], st + FA_SK + FA_D * 128, j * FA_BKV + 64, 0, bh);
+#pragma unroll
+        for (int kb = 0; kb < FA_NSUB; ++kb)
+          tc::tma_load_3d(&tmV, &kv_full[s], st + FA_SK + kb * FA_D * 128, j * FA_BKV + kb * 64, 0, bh);
       }
     }
   } else if (warp == 1) {
@@ -91,7 +99,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     auto mma_O = [&](int s) {   // O_j = P V : 2 sub-tiles x 4 k-steps over 128 keys
       const uint32_t a = tc::smem_u32(sP), b = tc::smem_u32(sKV + s * FA_STAGE + FA_SK);
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb)
+      for (int kb = 0; kb < FA_NSUB; ++kb)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
           tc::mma_ss<false>(tmem_O, tc::smem_desc_sw128(a + kb * (FA_BQ * 128) + ks * 32),
@@ -203,10 +211,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (qrow < N1) {
       const float inv = 1.f / l_run;
       const int b = bh / fp.heads, hd = bh - b * fp.heads;
-      float* dst = fp.out + ((size_t)b * N1 + qrow) * fp.D + hd * FA_D;
+      const size_t off = ((size_t)b * N1 + qrow) * fp.D + hd * FA_D;
+      if (fp.out_f16) {
+        __half* dst = reinterpret_cast<__half*>(fp.out) + off;
 #pragma unroll
-      for (int i = 0; i < FA_D; i += 4)
-        *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+        for (int i = 0; i < FA_D; i += 8) {
+          __half2 h0 = __floats2half2_rn(o[i] * inv, o[i + 1] * inv), h1 = __floats2half2_rn(o[i + 2] * inv, o[i + 3] * inv);
+          __half2 h2 = __floats2half2_rn(o[i + 4] * inv, o[i + 5] * inv), h3 = __floats2half2_rn(o[i + 6] * inv, o[i + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + i) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                          *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        }
+      } else {
+        float* dst = reinterpret_cast<float*>(fp.out) + off;
+#pragma unroll
+        for (int i = 0; i < FA_D; i += 4)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+      }
     }
   }
 
@@ -214,7 +234,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc::fence_after_sync();
-    tc::tmem_dealloc(tmem_base, 256);
+    tc::tmem_dealloc(tmem_base, FA_TMEM);
   }
 }
 

@@ -13,6 +13,7 @@
 //   TF32X3 : the same scheme with TF32 parts (fp32 storage, K = 8 per MMA)
 //   TF32   : single pass on fp32 data (the tensor core reads the top 19 bits)
 //   BF16   : single pass on bf16 data
+//   F16    : single pass on fp16 data (11-bit significand like TF32, twice its rate)
 // Work = grouped tiles: group g covers A rows [row0[g], row0[g] + m[g]) against B batch item batch[g];
 // m-tiles are numbered through the prefix array tile_start[] (device), n-tiles cover N.
 #pragma once
@@ -21,7 +22,7 @@
 
 namespace dtk {
 
-enum class TcMode { TF32X3 = 0, TF32 = 1, BF16 = 2, F16X3 = 3 };
+enum class TcMode { TF32X3 = 0, TF32 = 1, BF16 = 2, F16X3 = 3, F16 = 4 };
 
 constexpr int TC_BM = 128, TC_BN = 256;   // TC_BN: default N tile (template parameter BN overrides it)
 constexpr int TC_THREADS = 192;
@@ -29,7 +30,7 @@ constexpr int TC_THREADS = 192;
 template <TcMode MODE, int BN = TC_BN>
 struct TcCfg {
   static_assert(BN == 64 || BN == 128 || BN == 256, "N tile must be 64, 128 or 256");
-  static constexpr int kElem = (MODE == TcMode::BF16 || MODE == TcMode::F16X3) ? 2 : 4;
+  static constexpr int kElem = (MODE == TcMode::BF16 || MODE == TcMode::F16X3 || MODE == TcMode::F16) ? 2 : 4;
   static constexpr int kBK = 128 / kElem;                         // elements per 128-byte swizzle row
   static constexpr int kOps = (MODE == TcMode::TF32X3 || MODE == TcMode::F16X3) ? 2 : 1;   // hi (+ lo) tiles per operand
   static constexpr int kUmmaK = 32 / kElem;                       // K per tcgen05.mma

@@ -19,7 +19,12 @@ constexpr int HD = 64;  // head dim of every DINOv2 ViT
 
 // ---------------------------------------------------------------------------------------------- small kernels
 // patches of ImageNet-normalised frames: out[(b*P + p)][c*196 + ky*14 + kx], row length Kp (zero padded)
-__global__ void vit_im2col_kernel(const float* __restrict__ frames, float* __restrict__ out, int B, int H, int W, int h,
+template <typename T> __device__ __forceinline__ T cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
+
+template <typename OutT>
+__global__ void vit_im2col_kernel(const float* __restrict__ frames, OutT* __restrict__ out, int B, int H, int W, int h,
                                   int w, int patch, int stride, int Kp) {
   const size_t row = blockIdx.x;  // b*P + p
   const int P = h * w;
@@ -35,7 +40,7 @@ __global__ void vit_im2col_kernel(const float* __restrict__ frames, float* __res
       float x = frames[(((size_t)b * 3 + c) * H + py + ky) * W + px + kx];
       v = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);  // torchvision Normalize: (x - mean) / std
     }
-    out[row * Kp + k] = v;
+    out[row * Kp + k] = cvt_out<OutT>(v);
   }
 }
 
@@ -45,8 +50,9 @@ __global__ void vit_cls_kernel(float* __restrict__ x, const float* __restrict__ 
 }
 
 // warp per row, D <= 2048
+template <typename OutT>
 __global__ void vit_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gw, const float* __restrict__ gb,
-                                     float* __restrict__ y, size_t rows, int D) {
+                                     OutT* __restrict__ y, size_t rows, int D) {
   const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -70,7 +76,7 @@ __global__ void vit_layernorm_kernel(const float* __restrict__ x, const float* _
     }
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-6f);
-  float4* yr = reinterpret_cast<float4*>(y + row * D);
+  OutT* yr = y + row * D;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     int idx = lane + 32 * i;
@@ -79,7 +85,12 @@ __global__ void vit_layernorm_kernel(const float* __restrict__ x, const float* _
       float4 o;
       o.x = (v[i].x - mu) * rstd * w4.x + b4.x; o.y = (v[i].y - mu) * rstd * w4.y + b4.y;
       o.z = (v[i].z - mu) * rstd * w4.z + b4.z; o.w = (v[i].w - mu) * rstd * w4.w + b4.w;
-      yr[idx] = o;
+      if constexpr (sizeof(OutT) == 4) {
+        reinterpret_cast<float4*>(yr)[idx] = o;
+      } else {
+        __half2 a = __floats2half2_rn(o.x, o.y), b = __floats2half2_rn(o.z, o.w);
+        reinterpret_cast<uint2*>(yr)[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      }
     }
   }
 }
@@ -233,28 +244,33 @@ struct EpiResidual : EpiBase {
 };
 
 // h[r][col] = gelu(acc + bias[col])   (exact: 0.5 x (1 + erf(x / sqrt 2)))
+template <typename OutT>
 struct EpiGelu : EpiBase {
-  float* h; const float* bias; int ld;
+  OutT* h; const float* bias; int ld;
   __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
-    float* o = h + (size_t)r * ld + col0;
+    OutT* o = h + (size_t)r * ld + col0;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      if (i < ncols) { float v = f[i] + __ldg(bias + col0 + i); o[i] = 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+      if (i < ncols) {
+        float v = f[i] + __ldg(bias + col0 + i);
+        o[i] = cvt_out<OutT>(0.5f * v * (1.f + erff(v * 0.70710678118654752f)));
+      }
   }
 };
 
 struct Plan { int* batch; int* row0; int* m; int* tile_start; };
 
-template <class Epi, int BN>
-static int run_gemm(const float* A, uint64_t a_rows, const float* Bm, uint64_t b_batch, uint64_t b_rows, int K,
+template <class Epi, int BN, TcMode MODE = TcMode::TF32>
+static int run_gemm(const void* A, uint64_t a_rows, const void* Bm, uint64_t b_batch, uint64_t b_rows, int K,
                     const Plan& pl, int n_groups, int max_tiles, const Epi& epi, int prof_cls, cudaStream_t st,
                     uint64_t ld = 0) {
-  using Cfg = TcCfg<TcMode::TF32, BN>;
+  using Cfg = TcCfg<MODE, BN>;
+  constexpr int kT = MODE == TcMode::F16 ? TMAP_F16 : TMAP_F32;
   CUtensorMap tmA, tmB;
   int rc;
-  if ((rc = make_tmap_2d(&tmA, A, a_rows, K, TC_BM, Cfg::kBK, TMAP_F32, ld))) return rc;
-  if ((rc = make_tmap_3d(&tmB, Bm, b_batch, b_rows, K, BN, Cfg::kBK, TMAP_F32, ld))) return rc;
-  auto kern = tc_gemm_kernel<TcMode::TF32, Epi, BN>;
+  if ((rc = make_tmap_2d(&tmA, A, a_rows, K, TC_BM, Cfg::kBK, kT, ld))) return rc;
+  if ((rc = make_tmap_3d(&tmB, Bm, b_batch, b_rows, K, BN, Cfg::kBK, kT, ld))) return rc;
+  auto kern = tc_gemm_kernel<MODE, Epi, BN>;
   static bool attr = false;  // one static per template instantiation
   if (!attr) {
     DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
@@ -287,7 +303,11 @@ using namespace dtk;
 
 extern "C" {
 
-static int vit_kp(const dinotrk_vit_config* c) { return (int)align_up((size_t)3 * c->patch * c->patch, 4); }
+// row length of the im2col matrix / patch weight: 16-byte multiple of the operand type
+static int vit_kp(const dinotrk_vit_config* c) {
+  const bool f16 = c->gemm_f16 != 0 && c->attn_materialized == 0;
+  return (int)align_up((size_t)3 * c->patch * c->patch, f16 ? 8 : 4);
+}
 
 size_t dinotrk_vit_workspace_bytes(const dinotrk_vit_config* c, const dinotrk_geom* g, int B) {
   if (!c || !g) return 0;
@@ -327,15 +347,27 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
   DTK_CHECK_ARG(ar.ok(), "vit_forward: workspace arena overflow");
   int rc;
 
+  // fp16 operand mode (default): LayerNorm / GELU / attention write fp16 activations, weights are fp16 (11-bit
+  // significand like TF32, twice the tensor rate, half the operand traffic).  The validation path
+  // (attn_materialized) keeps every operand fp32 / TF32.
+  const bool f16 = c->gemm_f16 != 0 && c->attn_materialized == 0;
+  __half* y16 = reinterpret_cast<__half*>(y);
+  __half* h16 = reinterpret_cast<__half*>(hbuf);
+
   // ---- patch embedding + cls + position embedding
   {
     ProfRange pr(PROF_VIT_MISC, st);
-    vit_im2col_kernel<<<B * P, 128, 0, st>>>(frames, hbuf, B, g->H, g->W, g->h, g->w, c->patch, c->stride, Kp);
+    if (f16) vit_im2col_kernel<__half><<<B * P, 128, 0, st>>>(frames, h16, B, g->H, g->W, g->h, g->w, c->patch, c->stride, Kp);
+    else vit_im2col_kernel<float><<<B * P, 128, 0, st>>>(frames, hbuf, B, g->H, g->W, g->h, g->w, c->patch, c->stride, Kp);
     DTK_LAUNCHED();
   }
   if ((rc = plan(pl, 1, B * P, 0, 0, 0, st))) return rc;
-  if ((rc = run_gemm<EpiPatch, 256>(hbuf, (uint64_t)B * P, wt->patch_w, 1, D, Kp, pl, 1, cdiv(B * P, TC_BM),
-                                    EpiPatch{{}, x, wt->patch_b, wt->pos, P, D}, PROF_VIT_GEMM, st))) return rc;
+  {
+    EpiPatch ep{{}, x, wt->patch_b, wt->pos, P, D};
+    rc = f16 ? run_gemm<EpiPatch, 256, TcMode::F16>(h16, (uint64_t)B * P, wt->patch_w, 1, D, Kp, pl, 1, cdiv(B * P, TC_BM), ep, PROF_VIT_GEMM, st)
+             : run_gemm<EpiPatch, 256>(hbuf, (uint64_t)B * P, wt->patch_w, 1, D, Kp, pl, 1, cdiv(B * P, TC_BM), ep, PROF_VIT_GEMM, st);
+    if (rc) return rc;
+  }
   {
     ProfRange pr(PROF_VIT_MISC, st);
     vit_cls_kernel<<<B, 256, 0, st>>>(x, wt->cls_pos, N1, D);
@@ -343,14 +375,18 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
   }
 
   const int all_tiles = cdiv((int)rows, TC_BM);
+  auto layernorm = [&](const float* gw, const float* gb) -> int {
+    ProfRange pr(PROF_VIT_MISC, st);
+    if (f16) vit_layernorm_kernel<__half><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, gw, gb, y16, rows, D);
+    else vit_layernorm_kernel<float><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, gw, gb, y, rows, D);
+    DTK_LAUNCHED();
+    return DINOTRK_OK;
+  };
   for (int l = 0; l <= c->tap_layer; ++l) {
     const float* const* w = wt->blocks + (size_t)l * 14;
     // w: 0 norm1.w 1 norm1.b 2 qkv.w 3 qkv.b 4 proj.w 5 proj.b 6 ls1 7 norm2.w 8 norm2.b 9 fc1.w 10 fc1.b 11 fc2.w 12 fc2.b 13 ls2
-    {
-      ProfRange pr(PROF_VIT_MISC, st);
-      vit_layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w[0], w[1], y, rows, D);
-      DTK_LAUNCHED();
-    }
+    // (the four weight matrices are fp16 arrays in fp16 operand mode)
+    if ((rc = layernorm(w[0], w[1]))) return rc;
     if ((rc = plan(pl, 1, (int)rows, 0, 0, 0, st))) return rc;
     if (c->attn_materialized == 0) {
       // fused attention: fp16 q / k / v^T, scores stay in TMEM / shared memory
@@ -358,8 +394,10 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
       __half* k16 = reinterpret_cast<__half*>(k);
       __half* v16 = reinterpret_cast<__half*>(vT);
       const int N1p8 = (int)align_up((size_t)N1, 8);
-      if ((rc = run_gemm<EpiQKV16, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles,
-                                        EpiQKV16{{}, q16, k16, v16, w[3], N1, D, heads, N1p8}, PROF_VIT_GEMM, st))) return rc;
+      EpiQKV16 eq{{}, q16, k16, v16, w[3], N1, D, heads, N1p8};
+      rc = f16 ? run_gemm<EpiQKV16, 256, TcMode::F16>(y16, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st)
+               : run_gemm<EpiQKV16, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st);
+      if (rc) return rc;
       CUtensorMap tmQ, tmK, tmV;
       if ((rc = make_tmap_2d(&tmQ, q16, (uint64_t)B * heads * N1, HD, FA_BQ, HD, TMAP_F16))) return rc;
       if ((rc = make_tmap_3d(&tmK, k16, (uint64_t)B * heads, N1, HD, FA_BKV, HD, TMAP_F16))) return rc;
@@ -369,45 +407,52 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
         DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         fattr = true;
       }
-      FlashParams fpar{N1, D, heads, y};
+      FlashParams fpar{N1, D, heads, f16 ? (void*)y16 : (void*)y, f16 ? 1 : 0};
       ProfRange pr(PROF_VIT_ATTN, st);
       flash_attn_kernel<<<dim3(cdiv(N1, FA_BQ), B * heads), FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
       DTK_LAUNCHED();
     } else {
-    if ((rc = run_gemm<EpiQKV, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, EpiQKV{{}, q, k, vT, w[3], N1, D, heads, N1p},
-                                    PROF_VIT_GEMM, st))) return rc;
-    // attention, per frame and chunk of query rows: S = q k^T (all heads) -> softmax -> y = S v
-    for (int b = 0; b < B; ++b) {
-      for (int c0 = 0; c0 < N1; c0 += VIT_ROW_CHUNK) {
-        const int rc_rows = N1 - c0 < VIT_ROW_CHUNK ? N1 - c0 : VIT_ROW_CHUNK;
-        if ((rc = plan(pl, heads, rc_rows, N1, (b * heads) * N1 + c0, b * heads, st))) return rc;
-        if ((rc = run_gemm<EpiStore, 256>(q, rows * heads, k, (uint64_t)B * heads, N1, HD, pl, heads,
-                                          heads * cdiv(rc_rows, TC_BM), EpiStore{{}, S, N1p, VIT_ROW_CHUNK},
-                                          PROF_VIT_ATTN, st))) return rc;
-        {
-          ProfRange pr(PROF_VIT_ATTN, st);  // rows of S live at (head * VIT_ROW_CHUNK + r)
-          vit_softmax_kernel<<<dim3(rc_rows, heads), 256, (size_t)N1 * 4, st>>>(S, N1, N1p, (size_t)VIT_ROW_CHUNK * N1p);
-          DTK_LAUNCHED();
+      if ((rc = run_gemm<EpiQKV, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, EpiQKV{{}, q, k, vT, w[3], N1, D, heads, N1p},
+                                      PROF_VIT_GEMM, st))) return rc;
+      // attention, per frame and chunk of query rows: S = q k^T (all heads) -> softmax -> y = S v
+      for (int b = 0; b < B; ++b) {
+        for (int c0 = 0; c0 < N1; c0 += VIT_ROW_CHUNK) {
+          const int rc_rows = N1 - c0 < VIT_ROW_CHUNK ? N1 - c0 : VIT_ROW_CHUNK;
+          if ((rc = plan(pl, heads, rc_rows, N1, (b * heads) * N1 + c0, b * heads, st))) return rc;
+          if ((rc = run_gemm<EpiStore, 256>(q, rows * heads, k, (uint64_t)B * heads, N1, HD, pl, heads,
+                                            heads * cdiv(rc_rows, TC_BM), EpiStore{{}, S, N1p, VIT_ROW_CHUNK},
+                                            PROF_VIT_ATTN, st))) return rc;
+          {
+            ProfRange pr(PROF_VIT_ATTN, st);  // rows of S live at (head * VIT_ROW_CHUNK + r)
+            vit_softmax_kernel<<<dim3(rc_rows, heads), 256, (size_t)N1 * 4, st>>>(S, N1, N1p, (size_t)VIT_ROW_CHUNK * N1p);
+            DTK_LAUNCHED();
+          }
+          if ((rc = plan(pl, heads, rc_rows, VIT_ROW_CHUNK, 0, b * heads, st))) return rc;
+          if ((rc = run_gemm<EpiPV, 64>(S, (uint64_t)heads * VIT_ROW_CHUNK, vT, (uint64_t)B * heads, HD, N1, pl, heads,
+                                        heads * cdiv(rc_rows, TC_BM), EpiPV{{}, y, (size_t)b * N1 + c0, D},
+                                        PROF_VIT_ATTN, st, (uint64_t)N1p))) return rc;
         }
-        if ((rc = plan(pl, heads, rc_rows, VIT_ROW_CHUNK, 0, b * heads, st))) return rc;
-        if ((rc = run_gemm<EpiPV, 64>(S, (uint64_t)heads * VIT_ROW_CHUNK, vT, (uint64_t)B * heads, HD, N1, pl, heads,
-                                      heads * cdiv(rc_rows, TC_BM), EpiPV{{}, y, (size_t)b * N1 + c0, D},
-                                      PROF_VIT_ATTN, st, (uint64_t)N1p))) return rc;
       }
     }
-    }
     if ((rc = plan(pl, 1, (int)rows, 0, 0, 0, st))) return rc;
-    if ((rc = run_gemm<EpiResidual, 256>(y, rows, w[4], 1, D, D, pl, 1, all_tiles, EpiResidual{{}, x, w[5], w[6], D},
-                                         PROF_VIT_GEMM, st))) return rc;
     {
-      ProfRange pr(PROF_VIT_MISC, st);
-      vit_layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, w[7], w[8], y, rows, D);
-      DTK_LAUNCHED();
+      EpiResidual er{{}, x, w[5], w[6], D};
+      rc = f16 ? run_gemm<EpiResidual, 256, TcMode::F16>(y16, rows, w[4], 1, D, D, pl, 1, all_tiles, er, PROF_VIT_GEMM, st)
+               : run_gemm<EpiResidual, 256>(y, rows, w[4], 1, D, D, pl, 1, all_tiles, er, PROF_VIT_GEMM, st);
+      if (rc) return rc;
     }
-    if ((rc = run_gemm<EpiGelu, 256>(y, rows, w[9], 1, 4 * D, D, pl, 1, all_tiles, EpiGelu{{}, hbuf, w[10], 4 * D},
-                                     PROF_VIT_GEMM, st))) return rc;
-    if ((rc = run_gemm<EpiResidual, 256>(hbuf, rows, w[11], 1, D, 4 * D, pl, 1, all_tiles,
-                                         EpiResidual{{}, x, w[12], w[13], D}, PROF_VIT_GEMM, st))) return rc;
+    if ((rc = layernorm(w[7], w[8]))) return rc;
+    if (f16) {
+      if ((rc = run_gemm<EpiGelu<__half>, 256, TcMode::F16>(y16, rows, w[9], 1, 4 * D, D, pl, 1, all_tiles,
+                                                            EpiGelu<__half>{{}, h16, w[10], 4 * D}, PROF_VIT_GEMM, st))) return rc;
+      if ((rc = run_gemm<EpiResidual, 256, TcMode::F16>(h16, rows, w[11], 1, D, 4 * D, pl, 1, all_tiles,
+                                                        EpiResidual{{}, x, w[12], w[13], D}, PROF_VIT_GEMM, st))) return rc;
+    } else {
+      if ((rc = run_gemm<EpiGelu<float>, 256>(y, rows, w[9], 1, 4 * D, D, pl, 1, all_tiles,
+                                              EpiGelu<float>{{}, hbuf, w[10], 4 * D}, PROF_VIT_GEMM, st))) return rc;
+      if ((rc = run_gemm<EpiResidual, 256>(hbuf, rows, w[11], 1, D, 4 * D, pl, 1, all_tiles,
+                                           EpiResidual{{}, x, w[12], w[13], D}, PROF_VIT_GEMM, st))) return rc;
+    }
   }
   {
     ProfRange pr(PROF_VIT_MISC, st);

@@ -64,9 +64,17 @@ class DinoV2Features(torch.nn.Module):
         assert attention in ("fused", "materialized")
         self.attention = attention
         self._sd = sd
-        self._patch_w = sd["patch_embed.proj.weight"].reshape(self.dim, -1).contiguous()
-        assert self._patch_w.shape[1] % 4 == 0
-        self._blocks = [sd[f"blocks.{i}.{k}"] for i in range(self.depth) for k in _BLOCK_KEYS]
+        # fused mode: weight matrices in fp16 (kind::f16 MMAs); materialized (validation) mode: fp32 / TF32
+        self._f16 = attention == "fused"
+        wdt = torch.float16 if self._f16 else torch.float32
+        mats = ("attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight")
+        pw = sd["patch_embed.proj.weight"].reshape(self.dim, -1)
+        mult = 8 if self._f16 else 4
+        if pw.shape[1] % mult:
+            pw = F.pad(pw, (0, mult - pw.shape[1] % mult))
+        self._patch_w = pw.to(wdt).contiguous()
+        self._blocks = [sd[f"blocks.{i}.{k}"].to(wdt).contiguous() if k in mats else sd[f"blocks.{i}.{k}"]
+                        for i in range(self.depth) for k in _BLOCK_KEYS]
         self._block_ptrs = (ctypes.c_void_p * len(self._blocks))(*[t.data_ptr() for t in self._blocks])
         self._pos_cache = {}
 
@@ -91,7 +99,7 @@ class DinoV2Features(torch.nn.Module):
         geom = _lib.make_geom(H, W, self.patch, self.stride, 35)
         P = geom.h * geom.w
         cfg = _lib.VitConfig(self.depth, self.dim, self.heads, self.layer, self.patch, self.stride,
-                             0 if self.attention == "fused" else 1)
+                             0 if self.attention == "fused" else 1, 1 if self._f16 else 0)
         cls_pos, pos = self._pos(geom.h, geom.w)
         wt = _lib.VitWeights()
         wt.patch_w, wt.patch_b = self._patch_w.data_ptr(), self._sd["patch_embed.proj.bias"].data_ptr()

@@ -162,13 +162,17 @@ typedef struct dinotrk_vit_config {
   int patch, stride;       /* 14, 7 */
   int attn_materialized;   /* 0: fused tcgen05 attention (fp16 q/k/v/p, scores stay on the SM); 1: TF32 scores through a
                               workspace (tensor-core GEMM -> softmax -> tensor-core GEMM), validation path */
+  int gemm_f16;            /* 1: linear layers on the kind::f16 pipe -- patch_w and the qkv / proj / fc1 / fc2 weight matrices
+                              are passed as fp16 arrays, activations are written in fp16 by the producing epilogue;
+                              0 (or attn_materialized): fp32 arrays, TF32 MMAs */
 } dinotrk_vit_config;
-/* All device fp32.  patch_w: patch-embedding conv weight flattened K-major [dim][3*patch*patch]; cls_pos [dim] =
+/* Device fp32 (weight matrices fp16 when gemm_f16).  patch_w: patch-embedding conv weight flattened K-major
+ * [dim][Kp], Kp = 3*patch*patch zero-padded to a multiple of 4 (fp32) / 8 (fp16) elements; cls_pos [dim] =
  * cls_token + pos_embed[0]; pos [h*w][dim] = bicubic-interpolated patch position embedding (extractor.py:57-85);
  * blocks: HOST array of depth x 14 device pointers in the order norm1.w, norm1.b, qkv.w [3D][D], qkv.b, proj.w,
  * proj.b, ls1.gamma, norm2.w, norm2.b, fc1.w [4D][D], fc1.b, fc2.w [D][4D], fc2.b, ls2.gamma. */
 typedef struct dinotrk_vit_weights {
-  const float* patch_w; const float* patch_b; const float* cls_pos; const float* pos;
+  const void* patch_w; const float* patch_b; const float* cls_pos; const float* pos;
   const float* const* blocks;
 } dinotrk_vit_weights;
 size_t dinotrk_vit_workspace_bytes(const dinotrk_vit_config* c, const dinotrk_geom* g, int B);
