@@ -269,13 +269,13 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
   }
   {
     // thin groups (there may be none; CTAs of wide groups exit at once).  Two instantiations: up to 2 descriptors per
-    // pass with 8 rows in flight per warp (pure streaming), up to 8 descriptors with 4 rows.
+    // pass with 8 rows in flight per warp (pure streaming), otherwise 4 descriptors per pass, again 8 rows in flight.
     const bool tiny = max_group_m <= 2;
-    const int maxm = tiny ? 2 : 8;
+    const int maxm = tiny ? 2 : 4;   // groups of 5..8 descriptors take two passes (the second one hits L2)
     size_t smem = (size_t)maxm * C * sizeof(float);
     static size_t attr_smem[2] = {0, 0};
     auto k2 = corr_stream_kernel<2, 8>;
-    auto k8 = corr_stream_kernel<8, 4>;
+    auto k8 = corr_stream_kernel<4, 8>;
     if (smem > 48 * 1024 && smem > attr_smem[tiny ? 0 : 1]) {
       if (tiny) DTK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       else DTK_CUDA(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
