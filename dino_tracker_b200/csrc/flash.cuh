@@ -1,4 +1,5 @@
-// Fused attention for the ViT (sm_100a, tcgen05):  O = softmax(Q K^T) V  per (frame, head), scale pre-folded into Q.
+// Fused attention for the ViT (sm_100a, tcgen05):  O = softmax(Q K^T) V  per (frame, head).  Q arrives pre-scaled by
+// head_dim^-1/2 * log2(e), so the softmax is exp2(s - max) (one FADD + one MUFU.EX2 per score).
 //
 // One CTA per (frame*head, 128-query tile); 192 threads:
 //   warp 0     : TMA producer (Q once; K_j [BKV keys][64] and V^T_j [64][BKV keys] through a 2-stage ring)
@@ -28,6 +29,12 @@ constexpr int FA_SP = FA_NSUB * FA_BQ * 128;       // P tile: sub-tiles [128 row
 constexpr int FA_TMEM = FA_BKV + 64 <= 128 ? 128 : 256;
 constexpr int FA_STAGE = FA_SK + FA_SV;
 constexpr int FA_SMEM = FA_SQ + 2 * FA_STAGE + FA_SP + 256;   // extern smem is declared 1024-byte aligned
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct FlashParams {
   int N1;          // tokens per frame (keys = queries)
@@ -136,16 +143,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int kbase = j * FA_BKV;
       tc::mbar_wait(s_full, j & 1);
       tc::fence_after_sync();
+      const bool tail = kbase + FA_BKV > N1;          // only the last key tile needs masking
       // pass 1: row maximum over the valid keys of this tile
       float mx = -INFINITY;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < FA_BKV; c += 32) {
         uint32_t v[32];
         tc::tmem_ld32(tmem_S + lane_addr + c, v);
         tc::tmem_ld_wait();
+        if (!tail) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + c + i < N1) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c + i < N1) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
       // fold in the previous tile's P V (computed relative to the current running max)
       if (j > 0) {
@@ -161,27 +174,29 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
       }
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = __expf(m_run - m_new);     // m_run = -inf on the first tile -> 0
+      const float alpha = fast_exp2(m_run - m_new);      // m_run = -inf on the first tile -> 0
       l_run *= alpha;
 #pragma unroll
       for (int i = 0; i < FA_D; ++i) o[i] *= alpha;
       m_run = m_new;
       // pass 2: p = exp(s - m), row sum, fp16 P tile in the 128B-swizzled K-major layout of the MMA A operand
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < FA_BKV; c += 32) {
         uint32_t v[32];
         tc::tmem_ld32(tmem_S + lane_addr + c, v);
         tc::tmem_ld_wait();
         uint32_t packed[16];
+        float lpart = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = (kbase + c + i < N1) ? __expf(__uint_as_float(v[i]) - m_new) : 0.f;
-          float p1 = (kbase + c + i + 1 < N1) ? __expf(__uint_as_float(v[i + 1]) - m_new) : 0.f;
+          float p0 = fast_exp2(__uint_as_float(v[i]) - m_new), p1 = fast_exp2(__uint_as_float(v[i + 1]) - m_new);
+          if (tail) { if (kbase + c + i >= N1) p0 = 0.f; if (kbase + c + i + 1 >= N1) p1 = 0.f; }
           __half2 h = __floats2half2_rn(p0, p1);
-          // accumulate the sum from the ROUNDED values so that numerator (P V) and denominator match
-          l_run += __low2float(h) + __high2float(h);
+          float2 hf = __half22float2(h);
+          lpart += hf.x + hf.y;
           packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
+        l_run += lpart;
         // 32 keys = 4 chunks of 16 bytes; key (c + 8*cc .. ) -> sub-tile kb = c / 64, chunk ((c % 64) / 8 + cc)
         uint8_t* base = sP + (c >> 6) * (FA_BQ * 128) + row * 128;
 #pragma unroll

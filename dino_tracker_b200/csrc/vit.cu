@@ -160,7 +160,11 @@ struct EpiPatch : EpiBase {
     float* o = x + ((size_t)b * (P + 1) + 1 + p) * D + col0;
     const float* ps = pos + (size_t)p * D + col0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) if (i < ncols) o[i] = f[i] + __ldg(bias + col0 + i) + __ldg(ps + i);
+    for (int i = 0; i < 32; i += 4)
+      if (i < ncols) {   // ncols is a multiple of 4 (D % 64 == 0)
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + i)), pp = __ldg(reinterpret_cast<const float4*>(ps + i));
+        *reinterpret_cast<float4*>(o + i) = make_float4(f[i] + bb.x + pp.x, f[i + 1] + bb.y + pp.y, f[i + 2] + bb.z + pp.z, f[i + 3] + bb.w + pp.w);
+      }
   }
 };
 
@@ -186,18 +190,23 @@ struct EpiQKV : EpiBase {
 
 // qkv for the fused attention: fp16 q [b][hd][n][64] (scaled 1/8), k [b][hd][n][64], vT [b][hd][64][n] (pitch N1p)
 struct EpiQKV16 : EpiBase {
-  __half* q; __half* k; __half* vT; const float* bias; int N1, D, heads, N1p;
+  __half* q; __half* k; __half* vT; const float* bias; int N1, D, heads, N1p; float qscale;
   __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
     const int b = r / N1, n = r - b * N1;
     const int which = col0 / D, c = col0 - which * D, hd = c / HD, e0 = c - hd * HD;
     const size_t bh = (size_t)b * heads + hd;
     if (which < 2) {
       __half* o = (which == 0 ? q : k) + (bh * N1 + n) * HD + e0;
-      const float sc = which == 0 ? 0.125f : 1.f;
+      const float sc = which == 0 ? qscale : 1.f;
 #pragma unroll
-      for (int i = 0; i < 32; i += 2)
-        if (i < ncols) *reinterpret_cast<__half2*>(o + i) =
-            __floats2half2_rn((f[i] + __ldg(bias + col0 + i)) * sc, (f[i + 1] + __ldg(bias + col0 + i + 1)) * sc);
+      for (int i = 0; i < 32; i += 8)
+        if (i < ncols) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + i + 4));
+          __half2 h0 = __floats2half2_rn((f[i] + b0.x) * sc, (f[i + 1] + b0.y) * sc), h1 = __floats2half2_rn((f[i + 2] + b0.z) * sc, (f[i + 3] + b0.w) * sc);
+          __half2 h2 = __floats2half2_rn((f[i + 4] + b1.x) * sc, (f[i + 5] + b1.y) * sc), h3 = __floats2half2_rn((f[i + 6] + b1.z) * sc, (f[i + 7] + b1.w) * sc);
+          *reinterpret_cast<uint4*>(o + i) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                        *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        }
     } else {
       __half* o = vT + (bh * HD + e0) * N1p + n;
 #pragma unroll
@@ -238,8 +247,13 @@ struct EpiResidual : EpiBase {
   __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
     float* o = x + (size_t)r * D + col0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols) o[i] = o[i] + (f[i] + __ldg(bias + col0 + i)) * __ldg(ls + col0 + i);
+    for (int i = 0; i < 32; i += 4)
+      if (i < ncols) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + i)), ll = __ldg(reinterpret_cast<const float4*>(ls + col0 + i));
+        float4 xv = *reinterpret_cast<const float4*>(o + i);
+        xv.x += (f[i] + bb.x) * ll.x; xv.y += (f[i + 1] + bb.y) * ll.y; xv.z += (f[i + 2] + bb.z) * ll.z; xv.w += (f[i + 3] + bb.w) * ll.w;
+        *reinterpret_cast<float4*>(o + i) = xv;
+      }
   }
 };
 
@@ -249,12 +263,28 @@ struct EpiGelu : EpiBase {
   OutT* h; const float* bias; int ld;
   __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
     OutT* o = h + (size_t)r * ld + col0;
+    float gl[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols) {
-        float v = f[i] + __ldg(bias + col0 + i);
-        o[i] = cvt_out<OutT>(0.5f * v * (1.f + erff(v * 0.70710678118654752f)));
-      }
+    for (int i = 0; i < 32; i += 4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + (i < ncols ? i : 0)));
+      const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float v = f[i + j] + bv[j]; gl[i + j] = 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+    }
+    if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        if (i < ncols) *reinterpret_cast<float4*>(o + i) = make_float4(gl[i], gl[i + 1], gl[i + 2], gl[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8)
+        if (i < ncols) {
+          __half2 h0 = __floats2half2_rn(gl[i], gl[i + 1]), h1 = __floats2half2_rn(gl[i + 2], gl[i + 3]);
+          __half2 h2 = __floats2half2_rn(gl[i + 4], gl[i + 5]), h3 = __floats2half2_rn(gl[i + 6], gl[i + 7]);
+          *reinterpret_cast<uint4*>(o + i) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                        *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        }
+    }
   }
 };
 
@@ -394,7 +424,7 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
       __half* k16 = reinterpret_cast<__half*>(k);
       __half* v16 = reinterpret_cast<__half*>(vT);
       const int N1p8 = (int)align_up((size_t)N1, 8);
-      EpiQKV16 eq{{}, q16, k16, v16, w[3], N1, D, heads, N1p8};
+      EpiQKV16 eq{{}, q16, k16, v16, w[3], N1, D, heads, N1p8, 0.125f * 1.4426950408889634f};  // 1/sqrt(64) * log2(e)
       rc = f16 ? run_gemm<EpiQKV16, 256, TcMode::F16>(y16, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st)
                : run_gemm<EpiQKV16, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st);
       if (rc) return rc;

@@ -1,0 +1,35 @@
+"""Summarise .ncu-rep files (gpurun_out/) into small CSVs under profiles/ (read with `ncu -i ... --page raw --csv`)."""
+import csv
+import io
+import subprocess
+import sys
+
+KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__cycles_active.avg", "sm__cycles_elapsed.avg"]
+
+
+def main():
+    src, dst = sys.argv[1], sys.argv[2]
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = rows[0]
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full --clock-control none, source {src}\n")
+        f.write("metric,unit," + ",".join(f"launch{i}" for i in range(len(rows) - 2)) + "\n")
+        for k in KEEP:
+            if k in hdr:
+                i = hdr.index(k)
+                f.write(k + "," + rows[1][i] + "," + ",".join('"%s"' % r[i] if "," in r[i] else r[i] for r in rows[2:]) + "\n")
+
+
+if __name__ == "__main__":
+    main()
