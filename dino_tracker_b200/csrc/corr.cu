@@ -268,25 +268,21 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
     }
   }
   {
-    // thin groups (there may be none; CTAs of wide groups exit at once).  Two instantiations: up to 2 descriptors per
-    // pass with 8 rows in flight per warp (pure streaming), otherwise 4 descriptors per pass, again 8 rows in flight.
-    const bool tiny = max_group_m <= 2;
-    const int maxm = tiny ? 2 : 4;   // groups of 5..8 descriptors take two passes (the second one hits L2)
+    // thin groups (there may be none; CTAs of wide groups exit at once).  Three instantiations: <= 2 or <= 4 descriptors
+    // with 8 rows in flight per warp (pure streaming), <= 8 descriptors with 4 rows.
+    const int variant = max_group_m <= 2 ? 0 : (max_group_m <= 4 ? 1 : 2);
+    const int maxm = variant == 0 ? 2 : (variant == 1 ? 4 : 8);
     size_t smem = (size_t)maxm * C * sizeof(float);
-    static size_t attr_smem[2] = {0, 0};
-    auto k2 = corr_stream_kernel<2, 8>;
-    auto k8 = corr_stream_kernel<4, 8>;
-    if (smem > 48 * 1024 && smem > attr_smem[tiny ? 0 : 1]) {
-      if (tiny) DTK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      else DTK_CUDA(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_smem[tiny ? 0 : 1] = smem;
+    static size_t attr_smem[3] = {0, 0, 0};
+    auto kern = variant == 0 ? corr_stream_kernel<2, 8> : (variant == 1 ? corr_stream_kernel<4, 8> : corr_stream_kernel<8, 4>);
+    if (smem > 48 * 1024 && smem > attr_smem[variant]) {
+      DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem[variant] = smem;
     }
     dim3 grid(cdiv(P, STREAM_TOK), n_groups);
     ProfRange pr(PROF_CORR_STREAM, st);
-    if (tiny) k2<<<grid, STREAM_THREADS, smem, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
-                                                     stream_max, maps, map_stride);
-    else k8<<<grid, STREAM_THREADS, smem, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
-                                                stream_max, maps, map_stride);
+    kern<<<grid, STREAM_THREADS, smem, st>>>(tpc, norms, C, P, desc, desc_norm, grp_frame, grp_row0, grp_m, grp_map0,
+                                             stream_max, maps, map_stride);
     DTK_LAUNCHED();
   }
   return DINOTRK_OK;
