@@ -12,5 +12,8 @@ from .tracker import Tracker  # noqa: F401
 from .model_inference import (ModelInference, generate_trajectory_input, generate_trajectory,  # noqa: F401
                               generate_trajectories)
 
-__all__ = ["Tracker", "ModelInference", "RangeNormalizer", "generate_trajectory_input", "generate_trajectory",
+from .vit import DinoV2Features, get_dino_features_video  # noqa: F401
+from .pipeline import build_tracker_from_video, track_video, save_dino_embed_video  # noqa: F401
+
+__all__ = ["DinoV2Features", "get_dino_features_video", "build_tracker_from_video", "track_video", "save_dino_embed_video","Tracker", "ModelInference", "RangeNormalizer", "generate_trajectory_input", "generate_trajectory",
            "generate_trajectories"]

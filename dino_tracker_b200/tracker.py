@@ -31,7 +31,7 @@ def _as_f32(t, device):
 class Tracker(nn.Module):
     def __init__(self, video=None, ckpt_path="", dino_embed_path="", dino_patch_size=14, stride=7,
                  device="cuda:0", cyc_n_frames=4, cyc_batch_size_per_frame=256, cyc_fg_points_ratio=0.7,
-                 cyc_thresh=4, dino_embed_video=None, delta_channels=None, corr_precision="fp16x3"):
+                 cyc_thresh=4, dino_embed_video=None, delta_channels=None, corr_precision="fp16x3", _adopt_tpc=None):
         super().__init__()
         self.device = device
         self._dev = _lib.require_cuda(device)
@@ -56,7 +56,12 @@ class Tracker(nn.Module):
         self._split_cache = {}
         self._head_cache = (None, None)
 
-        if dino_embed_video is not None:      # in-process features (ViT stage of this package)
+        if _adopt_tpc is not None:            # token-major features straight from the in-process ViT stage (no copy)
+            self._dino_tpc = _adopt_tpc
+            self._dino_norms = torch.empty(_adopt_tpc.shape[:2], device=self._dev, dtype=torch.float32)
+            _lib.check(self._lib.dinotrk_token_norms(_lib.ptr(_adopt_tpc), _lib.ptr(self._dino_norms), _adopt_tpc.shape[0],
+                                                      _adopt_tpc.shape[2], _adopt_tpc.shape[1], _lib.stream_ptr()), "token_norms")
+        elif dino_embed_video is not None:    # in-process features given as T x C x h x w
             self._set_dino(dino_embed_video)
         else:
             self.load_dino_embed_video()

@@ -1,0 +1,56 @@
+"""GPU: the in-process pipeline (ViT -> delta-DINO -> tracker) against the chained oracles."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import delta_dino as od
+from oracle import inference as oi
+from oracle import synth
+from oracle import vit as ovit
+from oracle.tracker import Geometry
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pixels_to_tracks_pipeline():
+    from dino_tracker_b200 import DinoV2Features, ModelInference, build_tracker_from_video, save_dino_embed_video
+    H, W, T, D, heads = 98, 126, 4, 64, 1
+    geo = Geometry(H=H, W=W)
+    g = torch.Generator().manual_seed(8)
+    sd = ovit.random_state_dict(2, D, g, n_pos=4, std=0.08)
+    video = synth.random_video(T, H, W, seed=9)
+    vit = DinoV2Features(sd, heads=heads, layer=1, device="cuda:0")
+    model = build_tracker_from_video(video, vit, delta_channels=[3, 8, 8, 8, D])
+    dsd = od.random_state_dict([3, 8, 8, 8, D], torch.Generator().manual_seed(10), last_std=0.05)
+    model.delta_dino.load_state_dict(dsd)
+    head = synth.head_weights("sharp", seed=3)
+    model.tracker_head.load_state_dict(head)
+    mi = ModelInference(model, model.range_normalizer, 0.7, 0.6)
+    # stage parity: ViT (fp16 operands, TF32-level) then delta-DINO (exact fp32 on top of the ViT output)
+    ref_dino = ovit.dino_features_video(video, sd, heads, 1)
+    got_dino = model.dino_embed_video.cpu()
+    scale = ref_dino.abs().max().item()
+    assert (got_dino - ref_dino).abs().max().item() <= 5e-3 * scale
+    ref_refined = od.refined_features(video, got_dino.contiguous(), dsd)        # delta stage checked on OUR dino features
+    assert (model.refined_features.cpu() - ref_refined).abs().max().item() <= 1e-4
+    # tracker stage on our refined features: exact parity bar
+    q = synth.lattice_query_points(2, 2, H, W, t_q=[0, 1, 2, 3], margin=14.0, jitter_seed=1)
+    traj, occ = mi.infer(q.to("cuda:0"))
+    t_ref, o_ref = oi.infer(model.refined_features.cpu().contiguous(), q, head, geo, 0.7, 0.6)
+    assert (traj.cpu() - t_ref).abs().max().item() <= 1e-3
+    assert torch.equal(occ.cpu(), o_ref)
+
+
+def test_dino_embed_file_round_trip(tmp_path):
+    """the ViT stage can still write the reference's dino_embed_video.pt, and Tracker loads it."""
+    from dino_tracker_b200 import DinoV2Features, Tracker, save_dino_embed_video
+    H, W, T, D = 98, 126, 2, 64
+    sd = ovit.random_state_dict(1, D, torch.Generator().manual_seed(1), n_pos=4)
+    video = synth.random_video(T, H, W, seed=2)
+    vit = DinoV2Features(sd, heads=1, layer=0, device="cuda:0")
+    path = str(tmp_path / "dino_embeddings" / "dino_embed_video.pt")
+    save_dino_embed_video(video, vit, path)
+    saved = torch.load(path)
+    assert saved.shape == (T, D, 13, 17) and saved.dtype == torch.float32 and saved.device.type == "cpu"
+    m = Tracker(video=video.to("cuda:0"), dino_embed_path=path, device="cuda:0", delta_channels=[3, 4, 4, 4, D])
+    assert torch.equal(m.dino_embed_video.cpu(), saved)
