@@ -180,9 +180,18 @@ __global__ void blurpool_kernel(const float* __restrict__ in, float* __restrict_
 // refined[t][p][:] = dino[t][p][:] + bilinear(cnn[t], iy[r], ix[c])   (grid_sample border, align_corners=True)
 // ix/iy: un-normalised, clipped source coordinates per token column / row (computed on the host with the
 // reference's fp32 arithmetic, models/utils.py:31-43).
+// When `peers` is set (frame-sharded multi-GPU run), every refined row is also stored into the same slot of each
+// peer GPU's feature video through its NVLink-mapped pointer: the all-gather of the refined features is fused into
+// this epilogue (stores to mapped peer memory; no separate collective, no staging copy).
+struct PeerOut {
+  float* base[8];       // peers' [T][P][C] buffers (device pointers mapped with cudaIpcOpenMemHandle)
+  int n;                // number of peers (0: single GPU)
+  size_t row_offset;    // row (t*P + p) of this call's first output row inside the peers' buffers
+};
+
 __global__ void align_add_kernel(const float* __restrict__ cnn, const float* __restrict__ dino,
                                  float* __restrict__ refined, const float* __restrict__ ixs,
-                                 const float* __restrict__ iys, int Hc, int Wc, int C, int h, int w) {
+                                 const float* __restrict__ iys, int Hc, int Wc, int C, int h, int w, PeerOut peers) {
   const int p = blockIdx.x, b = blockIdx.y;
   const int r = p / w, c = p - r * w;
   const float ix = ixs[c], iy = iys[r];
@@ -208,7 +217,10 @@ __global__ void align_add_kernel(const float* __restrict__ cnn, const float* __r
     if (oky1) { v = __ldg(psw + i); acc.x = fmaf(v.x, wsw, acc.x); acc.y = fmaf(v.y, wsw, acc.y); acc.z = fmaf(v.z, wsw, acc.z); acc.w = fmaf(v.w, wsw, acc.w); }
     if (okx1 && oky1) { v = __ldg(pse + i); acc.x = fmaf(v.x, wse, acc.x); acc.y = fmaf(v.y, wse, acc.y); acc.z = fmaf(v.z, wse, acc.z); acc.w = fmaf(v.w, wse, acc.w); }
     float4 dv = __ldg(d + i);
-    o[i] = make_float4(dv.x + acc.x, dv.y + acc.y, dv.z + acc.z, dv.w + acc.w);
+    const float4 val = make_float4(dv.x + acc.x, dv.y + acc.y, dv.z + acc.z, dv.w + acc.w);
+    o[i] = val;
+    for (int k = 0; k < peers.n; ++k)
+      reinterpret_cast<float4*>(peers.base[k] + (peers.row_offset + (size_t)b * h * w + p) * C)[i] = val;
   }
 }
 
@@ -247,10 +259,10 @@ size_t dinotrk_delta_workspace_bytes(int B, int H, int W, const int* channels) {
   return 2 * align_up(delta_max_activation(B, H, W, channels) * sizeof(float), 256) + 4096;
 }
 
-int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* channels, const float* const* wgt,
-                         const float* const* bias, const float* dino_tpc, const float* ixs, const float* iys,
-                         int h, int w, float* refined_tpc, float* norms, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+static int delta_refine_impl(const float* frames, int B, int H, int W, const int* channels, const float* const* wgt,
+                             const float* const* bias, const float* dino_tpc, const float* ixs, const float* iys,
+                             int h, int w, float* refined_tpc, float* norms, void* workspace, size_t workspace_bytes,
+                             const PeerOut& peers, void* stream) {
   DTK_CHECK_ARG(frames && channels && wgt && bias && dino_tpc && ixs && iys && refined_tpc, "delta_refine: null pointer");
   DTK_CHECK_ARG(channels[0] == 3, "delta_refine: input must be RGB");
   for (int l = 1; l <= 4; ++l) DTK_CHECK_ARG(channels[l] % 4 == 0, "delta_refine: channel counts must be multiples of 4");
@@ -292,11 +304,54 @@ int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* ch
   }
   {
     ProfRange pr(PROF_ALIGN, st);
-    align_add_kernel<<<dim3(h * w, B), 128, 0, st>>>(cur, dino_tpc, refined_tpc, ixs, iys, ch, cw, cin, h, w);
+    align_add_kernel<<<dim3(h * w, B), 128, 0, st>>>(cur, dino_tpc, refined_tpc, ixs, iys, ch, cw, cin, h, w, peers);
     DTK_LAUNCHED();
   }
   if (norms) return dinotrk_token_norms(refined_tpc, norms, B, cin, h * w, stream);
   return DINOTRK_OK;
 }
+
+int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* channels, const float* const* wgt,
+                         const float* const* bias, const float* dino_tpc, const float* ixs, const float* iys,
+                         int h, int w, float* refined_tpc, float* norms, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  PeerOut none{};
+  return delta_refine_impl(frames, B, H, W, channels, wgt, bias, dino_tpc, ixs, iys, h, w, refined_tpc, norms, workspace,
+                           workspace_bytes, none, stream);
+}
+
+int dinotrk_delta_refine_allgather(const float* frames, int B, int H, int W, const int* channels, const float* const* wgt,
+                                   const float* const* bias, const float* dino_tpc, const float* ixs, const float* iys,
+                                   int h, int w, float* refined_tpc, float* norms, void* workspace,
+                                   size_t workspace_bytes, float* const* peer_bases, int n_peers, size_t first_frame,
+                                   void* stream) {
+  DTK_CHECK_ARG(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_bases), "delta_refine_allgather: bad peer list");
+  PeerOut po{};
+  po.n = n_peers;
+  for (int k = 0; k < n_peers; ++k) po.base[k] = peer_bases[k];
+  po.row_offset = first_frame * (size_t)h * w;
+  return delta_refine_impl(frames, B, H, W, channels, wgt, bias, dino_tpc, ixs, iys, h, w, refined_tpc, norms, workspace,
+                           workspace_bytes, po, stream);
+}
+
+// ---- peer-mapped buffers (one process per GPU on one node): cudaMalloc + CUDA IPC --------------------------------
+int dinotrk_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  DTK_CHECK_ARG(ptr && handle64 && bytes > 0, "peer_alloc: bad args");
+  DTK_CUDA(cudaMalloc(ptr, bytes));
+  cudaIpcMemHandle_t hdl;
+  DTK_CUDA(cudaIpcGetMemHandle(&hdl, *ptr));
+  static_assert(sizeof(hdl) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &hdl, 64);
+  return DINOTRK_OK;
+}
+int dinotrk_peer_open(const unsigned char* handle64, void** ptr) {
+  DTK_CHECK_ARG(ptr && handle64, "peer_open: bad args");
+  cudaIpcMemHandle_t hdl;
+  memcpy(&hdl, handle64, 64);
+  DTK_CUDA(cudaIpcOpenMemHandle(ptr, hdl, cudaIpcMemLazyEnablePeerAccess));
+  return DINOTRK_OK;
+}
+int dinotrk_peer_close(void* ptr) { DTK_CUDA(cudaIpcCloseMemHandle(ptr)); return DINOTRK_OK; }
+int dinotrk_peer_free(void* ptr) { DTK_CUDA(cudaFree(ptr)); return DINOTRK_OK; }
 
 }  // extern "C"

@@ -137,9 +137,11 @@ class DeltaDINO(nn.Module):
         return out  # ixs [w], iys [h]
 
     @torch.no_grad()
-    def refine_tpc(self, frames, dino_tpc, geom, batch=8):
+    def refine_tpc(self, frames, dino_tpc, geom, batch=8, out=None, peer_ptrs=None, first_frame=0):
         """frames B x 3 x H x W, dino_tpc [B][P][C] -> (refined_tpc, norms) via dinotrk_delta_refine,
-        in batches of 8 frames like models/tracker.py:118-123."""
+        in batches of 8 frames like models/tracker.py:118-123.  ``out``: write the refined rows there ([B][P][C]
+        view, e.g. this rank's slice of a full feature video); ``peer_ptrs`` (+ ``first_frame``): also store every
+        row into the peers' full buffers from inside the producing kernel (fused all-gather over NVLink)."""
         lib = _lib.load()
         dev = dino_tpc.device
         ws, bs = self._fold()
@@ -153,18 +155,28 @@ class DeltaDINO(nn.Module):
         chan = (ctypes.c_int * 5)(*self.channels)
         wp = (ctypes.c_void_p * 4)(*[w.data_ptr() for w in ws])
         bp = (ctypes.c_void_p * 4)(*[b.data_ptr() for b in bs])
-        refined = torch.empty_like(dino_tpc)
+        refined = torch.empty_like(dino_tpc) if out is None else out
+        assert refined.is_contiguous() and refined.shape == dino_tpc.shape
         norms = torch.empty(dino_tpc.shape[:2], device=dev, dtype=torch.float32)
+        peers = None
+        if peer_ptrs:
+            peers = (ctypes.c_void_p * len(peer_ptrs))(*peer_ptrs)
         nb = min(batch, B)
         ws_bytes = lib.dinotrk_delta_workspace_bytes(nb, H, W, chan)
         work = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         for i in range(0, B, batch):
             e = min(i + batch, B)
             fr = frames[i:e].contiguous()
-            _lib.check(lib.dinotrk_delta_refine(
-                _lib.ptr(fr), e - i, H, W, chan, wp, bp, _lib.ptr(dino_tpc[i:e]), _lib.ptr(ixs), _lib.ptr(iys),
-                geom.h, geom.w, _lib.ptr(refined[i:e]), _lib.ptr(norms[i:e]), _lib.ptr(work), ws_bytes,
-                _lib.stream_ptr()), "delta_refine")
+            if peers is None:
+                _lib.check(lib.dinotrk_delta_refine(
+                    _lib.ptr(fr), e - i, H, W, chan, wp, bp, _lib.ptr(dino_tpc[i:e]), _lib.ptr(ixs), _lib.ptr(iys),
+                    geom.h, geom.w, _lib.ptr(refined[i:e]), _lib.ptr(norms[i:e]), _lib.ptr(work), ws_bytes,
+                    _lib.stream_ptr()), "delta_refine")
+            else:
+                _lib.check(lib.dinotrk_delta_refine_allgather(
+                    _lib.ptr(fr), e - i, H, W, chan, wp, bp, _lib.ptr(dino_tpc[i:e]), _lib.ptr(ixs), _lib.ptr(iys),
+                    geom.h, geom.w, _lib.ptr(refined[i:e]), _lib.ptr(norms[i:e]), _lib.ptr(work), ws_bytes,
+                    peers, len(peer_ptrs), first_frame + i, _lib.stream_ptr()), "delta_refine_allgather")
         return refined, norms
 
     def forward(self, x, vit_features):

@@ -94,3 +94,54 @@ def sharded_long_video_infer(T: int, N: int, world: int, rank: int, refine_block
     traj = gather_rows(traj, N, world, rank, group)
     occ = gather_rows(occ.to(torch.uint8), N, world, rank, group).bool()
     return traj, occ
+
+
+class _DevPtr:
+    """Minimal __cuda_array_interface__ carrier so that torch can view a raw device allocation."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+
+class PeerFeatureBuffer:
+    """A full ``[T][P][C]`` fp32 feature video on every rank of one node whose allocation is mapped into all peers
+    (cudaMalloc + CUDA IPC), so that a producing kernel can store rows straight into every GPU's copy over NVLink.
+    ``tensor`` views this rank's copy; ``peer_ptrs`` are the peers' mapped base pointers (own rank excluded)."""
+
+    def __init__(self, T, P, C, rank, world, group=None):
+        import ctypes
+        from . import _lib
+        self._lib = _lib.load()
+        self.rank, self.world = rank, world
+        nbytes = T * P * C * 4
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(self._lib.dinotrk_peer_alloc(nbytes, ctypes.byref(ptr), handle), "peer_alloc")
+        self._own = ptr
+        self.tensor = torch.as_tensor(_DevPtr(ptr.value, (T, P, C)), device=f"cuda:{torch.cuda.current_device()}")
+        self.peer_ptrs, self._opened = [], []
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            for r, hraw in enumerate(handles):
+                if r == rank:
+                    continue
+                p = ctypes.c_void_p()
+                _lib.check(self._lib.dinotrk_peer_open(hraw, ctypes.byref(p)), "peer_open")
+                self.peer_ptrs.append(p.value)
+                self._opened.append(p)
+
+    def sync(self, group=None):
+        """Make every rank's peer stores visible: drain the local stream, then a rank barrier."""
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def close(self):
+        for p in self._opened:
+            self._lib.dinotrk_peer_close(p)
+        self._opened = []
+        if self._own is not None:
+            self.tensor = None
+            self._lib.dinotrk_peer_free(self._own)
+            self._own = None

@@ -155,6 +155,22 @@ int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* ch
                          const float* ixs, const float* iys, int h, int w, float* refined_tpc,
                          float* norms, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Frame-sharded multi-GPU variant: as dinotrk_delta_refine, and every refined row is ALSO
+ * stored into the same slot of each peer GPU's full feature video -- peer_bases[k] (HOST array of n_peers <= 8 device
+ * pointers mapped with dinotrk_peer_open) + (first_frame * h*w + row) * C -- by the producing kernel itself
+ * (stores over NVLink to mapped peer memory): the all-gather is fused into the delta-DINO epilogue.  The caller
+ * synchronises the ranks afterwards (stream sync + barrier) before reading remote frames. */
+int dinotrk_delta_refine_allgather(const float* frames, int B, int H, int W, const int* channels,
+                                   const float* const* wgt, const float* const* bias, const float* dino_tpc,
+                                   const float* ixs, const float* iys, int h, int w, float* refined_tpc,
+                                   float* norms, void* workspace, size_t workspace_bytes,
+                                   float* const* peer_bases, int n_peers, size_t first_frame, void* stream);
+/* Peer-mapped buffers for the above (one process per GPU, one node): cudaMalloc + CUDA IPC handle (64 bytes). */
+int dinotrk_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int dinotrk_peer_open(const unsigned char* handle64, void** ptr);
+int dinotrk_peer_close(void* ptr);
+int dinotrk_peer_free(void* ptr);
+
 /* ---- DINOv2 ViT feature extractor (utils.py:32-72, models/extractor.py:41-85,137-150) -------------- */
 typedef struct dinotrk_vit_config {
   int depth, dim, heads;   /* ViT-L/14: 24, 1024, 16; ViT-B/14: 12, 768, 12 (head dim 64) */

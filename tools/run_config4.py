@@ -45,6 +45,7 @@ def run():
     ap.add_argument("--dim", type=int, default=256)
     ap.add_argument("--depth", type=int, default=2)
     ap.add_argument("--check", type=int, default=1)
+    ap.add_argument("--fused", type=int, default=0, help="1: all-gather fused into the delta-DINO epilogue (peer stores)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -71,7 +72,10 @@ def run():
         return m
 
     P = 67 * 121
-    full = torch.zeros(T, P, C, device=dev)
+    pbuf = par.PeerFeatureBuffer(T, P, C, rank, world) if a.fused else None
+    full = pbuf.tensor if a.fused else torch.zeros(T, P, C, device=dev)
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     s, e = par.frame_shard(T, world, rank)
@@ -79,11 +83,19 @@ def run():
     dino_local = vit(video[s:e])                                             # [e-s][P][C]
     m_local = build_tracker(dino_local.view(e - s, 67, 121, C).permute(0, 3, 1, 2))
     m_local.video = video[s:e].to(dev)
-    m_local.cache_refined_embeddings()
-    full[s:e] = m_local._refined_tpc
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    par.allgather_frames(full, T, world, rank)
+    if a.fused:
+        # refined rows go to this rank's slice AND, from inside the producing kernel, to every peer's buffer
+        m_local.delta_dino.refine_tpc(video[s:e].to(dev), m_local._dino_tpc, m_local._geom, out=full[s:e],
+                                      peer_ptrs=pbuf.peer_ptrs, first_frame=s)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        pbuf.sync()
+    else:
+        m_local.cache_refined_embeddings()
+        full[s:e] = m_local._refined_tpc
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        par.allgather_frames(full, T, world, rank)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     # tracker over all frames, this rank's query rows
@@ -100,7 +112,7 @@ def run():
     occ = par.gather_rows(occ.to(torch.uint8), N, world, rank).bool()
     torch.cuda.synchronize()
     t3 = time.perf_counter()
-    res = {"world": world, "T": T, "nq": N, "C": C, "features_s": t1 - t0, "allgather_s": t2 - t1,
+    res = {"world": world, "T": T, "nq": N, "C": C, "fused_allgather": bool(a.fused), "features_s": t1 - t0, "allgather_s": t2 - t1,
            "allgather_GB": full.numel() * 4 / 1e9, "track_s": t3 - t2}
     if a.check and rank == 0:
         dino_all = vit(video)
