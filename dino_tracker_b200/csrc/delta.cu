@@ -6,9 +6,13 @@
 // K = 25 taps x C_in, K-major weights with the BatchNorm folded in on the host) on the same
 // 128 x 128 x 16 cp.async pipeline as the correlation GEMM; the im2col gather (reflection, dilation)
 // happens in the cp.async address computation, nothing is materialised.
+#include <cuda_fp16.h>
+
 #include <utility>
 
 #include "common.cuh"
+#include "corr.cuh"
+#include "tcgemm.cuh"
 
 namespace dtk {
 
@@ -224,6 +228,110 @@ __global__ void align_add_kernel(const float* __restrict__ cnn, const float* __r
   }
 }
 
+
+// ---- tensor-core path: explicit im2col (fp16 hi/lo split on the fly) + tcgen05 split-precision GEMM ------------------
+// A[m][k] = in[b][reflect(y + (ky-2) d)][reflect(x + (kx-2) d)][ci],  k = (ky*5 + kx)*Cin + ci, zero padded to Kp
+__global__ void im2col_split_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo,
+                                    int H, int W, int Cin, int dil, int Kp, size_t m0, size_t m_count) {
+  const size_t m = m0 + blockIdx.x;          // pixel index within the batch (b*H*W + y*W + x)
+  if (blockIdx.x >= m_count) return;
+  const int HW = H * W;
+  const int b = (int)(m / HW), rem = (int)(m - (size_t)b * HW);
+  const int y = rem / W, x = rem - y * W;
+  const int K = 25 * Cin;
+  __half* oh = hi + (size_t)blockIdx.x * Kp;
+  __half* ol = lo + (size_t)blockIdx.x * Kp;
+  for (int k4 = threadIdx.x * 4; k4 < Kp; k4 += blockDim.x * 4) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k4 < K) {
+      const int tap = k4 / Cin, ci = k4 - tap * Cin;   // Cin % 4 == 0: the 4 elements share the tap
+      const int ky = tap / 5, kx = tap - ky * 5;
+      const int sy = reflect(y + (ky - 2) * dil, H), sx = reflect(x + (kx - 2) * dil, W);
+      v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + sy) * W + sx) * Cin + ci));
+    }
+    __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+    __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
+    __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
+    __half2 a = __halves2half2(h0, h1), c = __halves2half2(h2, h3), d = __halves2half2(l0, l1), e = __halves2half2(l2, l3);
+    *reinterpret_cast<uint2*>(oh + k4) = make_uint2(*reinterpret_cast<unsigned*>(&a), *reinterpret_cast<unsigned*>(&c));
+    *reinterpret_cast<uint2*>(ol + k4) = make_uint2(*reinterpret_cast<unsigned*>(&d), *reinterpret_cast<unsigned*>(&e));
+  }
+}
+
+// out[m0 + r][col] = relu?(acc + bias[col])   (NHWC fp32)
+struct EpiConv {
+  float* out; const float* bias; int Cout, relu; size_t m0;
+  struct State {};
+  __device__ __forceinline__ void tile_begin(State&) const {}
+  __device__ __forceinline__ void tile_end(State&, int, int, int) const {}
+  __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
+    float* o = out + (m0 + r) * Cout + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)
+      if (i < ncols) {   // Cout % 8 == 0 -> ncols % 4 == 0
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+        float4 v = make_float4(f[i] + bb.x, f[i + 1] + bb.y, f[i + 2] + bb.z, f[i + 3] + bb.w);
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        *reinterpret_cast<float4*>(o + i) = v;
+      }
+  }
+};
+
+__global__ void conv_plan_kernel(int* batch, int* row0, int* m, int* tile_start, int rows) {
+  if (threadIdx.x == 0) { batch[0] = 0; row0[0] = 0; m[0] = rows; tile_start[0] = 0; tile_start[1] = (rows + TC_BM - 1) / TC_BM; }
+}
+
+template <int BN>
+static int conv_gemm(const __half* a_hi, const __half* a_lo, int rows, int Kp, const __half* w_hi, const __half* w_lo,
+                     int Cout, int* plan, const EpiConv& epi, cudaStream_t st) {
+  using Cfg = TcCfg<TcMode::F16X3, BN>;
+  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  int rc;
+  if ((rc = make_tmap_2d(&tA_hi, a_hi, rows, Kp, TC_BM, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_2d(&tA_lo, a_lo, rows, Kp, TC_BM, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tB_hi, w_hi, 1, Cout, Kp, BN, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tB_lo, w_lo, 1, Cout, Kp, BN, Cfg::kBK, TMAP_F16))) return rc;
+  auto kern = tc_gemm_kernel<TcMode::F16X3, EpiConv, BN>;
+  static bool attr = false;
+  if (!attr) {
+    DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr = true;
+  }
+  TcProblem pb{plan, plan + 4, plan + 8, plan + 12, 1, Cout, Kp};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int tiles = cdiv(rows, TC_BM) * cdiv(Cout, BN);
+  ProfRange pr(PROF_CONV, st);
+  kern<<<tiles < sms ? tiles : sms, TC_THREADS, Cfg::kSmem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, pb, epi);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+constexpr size_t CONV_TC_ROWS = 32768;   // im2col rows per GEMM pass (bounds the fp16 scratch)
+
+// one conv layer on tensor cores, row chunks of CONV_TC_ROWS output pixels
+static int launch_conv_tc(const float* in, const __half* w_hi, const __half* w_lo, const float* bias, float* out,
+                          ConvShape cs, int Kp, __half* col_hi, __half* col_lo, int* plan, cudaStream_t st) {
+  const size_t M = (size_t)cs.B * cs.H * cs.W;
+  for (size_t m0 = 0; m0 < M; m0 += CONV_TC_ROWS) {
+    const size_t rows = M - m0 < CONV_TC_ROWS ? M - m0 : CONV_TC_ROWS;
+    {
+      ProfRange pr(PROF_CONV, st);
+      im2col_split_kernel<<<(unsigned)rows, 128, 0, st>>>(in, col_hi, col_lo, cs.H, cs.W, cs.Cin, cs.dil, Kp, m0, rows);
+      DTK_LAUNCHED();
+      conv_plan_kernel<<<1, 32, 0, st>>>(plan, plan + 4, plan + 8, plan + 12, (int)rows);
+      DTK_LAUNCHED();
+    }
+    EpiConv epi{out, bias, cs.Cout, cs.relu, m0};
+    int rc = cs.Cout <= 64 ? conv_gemm<64>(col_hi, col_lo, (int)rows, Kp, w_hi, w_lo, cs.Cout, plan, epi, st)
+           : cs.Cout <= 128 ? conv_gemm<128>(col_hi, col_lo, (int)rows, Kp, w_hi, w_lo, cs.Cout, plan, epi, st)
+                            : conv_gemm<256>(col_hi, col_lo, (int)rows, Kp, w_hi, w_lo, cs.Cout, plan, epi, st);
+    if (rc) return rc;
+  }
+  return DINOTRK_OK;
+}
+
 static int launch_conv(const float* in, const float* wgt, const float* bias, float* out, ConvShape cs, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
@@ -256,14 +364,21 @@ static size_t delta_max_activation(int B, int H, int W, const int* channels) {
 }
 
 size_t dinotrk_delta_workspace_bytes(int B, int H, int W, const int* channels) {
-  return 2 * align_up(delta_max_activation(B, H, W, channels) * sizeof(float), 256) + 4096;
+  size_t kmax = 0;
+  for (int l = 0; l < 4; ++l) { size_t k = align_up((size_t)25 * (l == 0 ? 4 : channels[l]), 8); if (k > kmax) kmax = k; }
+  return 2 * align_up(delta_max_activation(B, H, W, channels) * sizeof(float), 256) +
+         2 * align_up(CONV_TC_ROWS * kmax * 2, 256) + 8192;   // + fp16 im2col scratch of the tensor-core path
 }
 
 static int delta_refine_impl(const float* frames, int B, int H, int W, const int* channels, const float* const* wgt,
                              const float* const* bias, const float* dino_tpc, const float* ixs, const float* iys,
                              int h, int w, float* refined_tpc, float* norms, void* workspace, size_t workspace_bytes,
-                             const PeerOut& peers, void* stream) {
-  DTK_CHECK_ARG(frames && channels && wgt && bias && dino_tpc && ixs && iys && refined_tpc, "delta_refine: null pointer");
+                             const PeerOut& peers, void* stream, const void* const* wgt_hi = nullptr,
+                             const void* const* wgt_lo = nullptr) {
+  DTK_CHECK_ARG(frames && channels && (wgt || (wgt_hi && wgt_lo)) && bias && dino_tpc && ixs && iys && refined_tpc,
+                "delta_refine: null pointer");
+  if (wgt_hi && wgt_lo)
+    for (int l = 1; l <= 4; ++l) DTK_CHECK_ARG(channels[l] % 8 == 0, "delta_refine (tensor path): channel counts must be multiples of 8");
   DTK_CHECK_ARG(channels[0] == 3, "delta_refine: input must be RGB");
   for (int l = 1; l <= 4; ++l) DTK_CHECK_ARG(channels[l] % 4 == 0, "delta_refine: channel counts must be multiples of 4");
   DTK_CHECK_ARG(workspace && workspace_bytes >= dinotrk_delta_workspace_bytes(B, H, W, channels),
@@ -273,6 +388,16 @@ static int delta_refine_impl(const float* frames, int B, int H, int W, const int
   size_t half = delta_max_activation(B, H, W, channels);
   float* buf0 = ar.take<float>(half);
   float* buf1 = ar.take<float>(half);
+  const bool tensor = wgt_hi != nullptr && wgt_lo != nullptr;
+  __half* col_hi = nullptr; __half* col_lo = nullptr; int* cplan = nullptr;
+  if (tensor) {
+    size_t kmax = 0;
+    for (int l = 0; l < 4; ++l) { size_t k = align_up((size_t)25 * (l == 0 ? 4 : channels[l]), 8); if (k > kmax) kmax = k; }
+    col_hi = ar.take<__half>(CONV_TC_ROWS * kmax);
+    col_lo = ar.take<__half>(CONV_TC_ROWS * kmax);
+    cplan = ar.take<int>(16);
+    DTK_CHECK_ARG(ar.ok(), "delta_refine: workspace too small for the tensor-core path");
+  }
 
   {
     size_t n = (size_t)B * H * W;
@@ -286,7 +411,9 @@ static int delta_refine_impl(const float* frames, int B, int H, int W, const int
   const int dil[4] = {1, 1, 1, 2};
   for (int l = 0; l < 4; ++l) {
     ConvShape cs{B, ch, cw, cin, channels[l + 1], dil[l], l < 3 ? 1 : 0};
-    int rc = launch_conv(cur, wgt[l], bias[l], oth, cs, st);
+    int rc = tensor ? launch_conv_tc(cur, (const __half*)wgt_hi[l], (const __half*)wgt_lo[l], bias[l], oth, cs,
+                                     (int)align_up((size_t)25 * cin, 8), col_hi, col_lo, cplan, st)
+                    : launch_conv(cur, wgt[l], bias[l], oth, cs, st);
     if (rc) return rc;
     std::swap(cur, oth);
     cin = channels[l + 1];
@@ -318,6 +445,20 @@ int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* ch
   PeerOut none{};
   return delta_refine_impl(frames, B, H, W, channels, wgt, bias, dino_tpc, ixs, iys, h, w, refined_tpc, norms, workspace,
                            workspace_bytes, none, stream);
+}
+
+int dinotrk_delta_refine_tc(const float* frames, int B, int H, int W, const int* channels, const void* const* wgt_hi,
+                            const void* const* wgt_lo, const float* const* bias, const float* dino_tpc, const float* ixs,
+                            const float* iys, int h, int w, float* refined_tpc, float* norms, void* workspace,
+                            size_t workspace_bytes, float* const* peer_bases, int n_peers, size_t first_frame,
+                            void* stream) {
+  DTK_CHECK_ARG(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_bases), "delta_refine_tc: bad peer list");
+  PeerOut po{};
+  po.n = n_peers;
+  for (int k = 0; k < n_peers; ++k) po.base[k] = peer_bases[k];
+  po.row_offset = first_frame * (size_t)h * w;
+  return delta_refine_impl(frames, B, H, W, channels, nullptr, bias, dino_tpc, ixs, iys, h, w, refined_tpc, norms, workspace,
+                           workspace_bytes, po, stream, wgt_hi, wgt_lo);
 }
 
 int dinotrk_delta_refine_allgather(const float* frames, int B, int H, int W, const int* channels, const float* const* wgt,

@@ -76,7 +76,8 @@ class _BlurPoolParams(nn.Module):
 
 class DeltaDINO(nn.Module):
     def __init__(self, channels=(3, 64, 128, 256, 1024), dilations=(1, 1, 1, 2), kernel_size=5, down_stride=2,
-                 padding_mode="reflect", downsample_layers=(True, True, True, False), vit_stride=7):
+                 padding_mode="reflect", downsample_layers=(True, True, True, False), vit_stride=7,
+                 conv_precision=None):
         super().__init__()
         channels = list(channels)
         assert len(channels) == 5 and kernel_size == 5 and tuple(dilations) == (1, 1, 1, 2)
@@ -100,6 +101,11 @@ class DeltaDINO(nn.Module):
                 layers.append(_BlurPoolParams(channels[i + 1]))
         self.layers = nn.ModuleList(layers)
         self._folded = (None, None)
+        # "fp16x3": convolutions as im2col + tcgen05 split-precision GEMMs (needs channel counts % 8 == 0);
+        # "fp32": exact-fp32 implicit GEMM on the CUDA cores
+        ok8 = all(c % 8 == 0 for c in channels[1:])
+        self.conv_precision = conv_precision or ("fp16x3" if ok8 else "fp32")
+        assert self.conv_precision in ("fp16x3", "fp32") and (ok8 or self.conv_precision == "fp32")
 
     def get_total_stride(self):
         return self.down_stride ** 3
@@ -120,8 +126,21 @@ class DeltaDINO(nn.Module):
                 w = torch.nn.functional.pad(w, (0, 4 - w.shape[-1] % 4))
             ws.append(w.contiguous().float())
             bs.append(b.contiguous().float())
-        self._folded = (key, (ws, bs))
-        return ws, bs
+        # fp16 hi / lo split of the K-major weights, K padded to a multiple of 8 (tensor-core path)
+        his, los = [], []
+        if self.conv_precision == "fp16x3":
+            lib = _lib.load()
+            for w in ws:
+                w2 = w.reshape(w.shape[0], -1)
+                if w2.shape[1] % 8:
+                    w2 = torch.nn.functional.pad(w2, (0, 8 - w2.shape[1] % 8))
+                w2 = w2.contiguous()
+                hi = torch.empty(w2.shape, device=w2.device, dtype=torch.float16)
+                lo = torch.empty(w2.shape, device=w2.device, dtype=torch.float16)
+                _lib.check(lib.dinotrk_split_fp16(_lib.ptr(w2), _lib.ptr(hi), _lib.ptr(lo), w2.numel(), _lib.stream_ptr()))
+                his.append(hi); los.append(lo)
+        self._folded = (key, (ws, bs, his, los))
+        return ws, bs, his, los
 
     @staticmethod
     def align_tables(cnn_hw, vit_hw, device, vit_patch_size=14, vit_stride=7, cnn_stride=8):
@@ -144,7 +163,8 @@ class DeltaDINO(nn.Module):
         row into the peers' full buffers from inside the producing kernel (fused all-gather over NVLink)."""
         lib = _lib.load()
         dev = dino_tpc.device
-        ws, bs = self._fold()
+        ws, bs, his, los = self._fold()
+        tensor = self.conv_precision == "fp16x3"
         B, _, H, W = frames.shape
         C = self.channels[-1]
         assert dino_tpc.shape[-1] == C, f"DeltaDINO emits {C} channels, features have {dino_tpc.shape[-1]}"
@@ -155,6 +175,9 @@ class DeltaDINO(nn.Module):
         chan = (ctypes.c_int * 5)(*self.channels)
         wp = (ctypes.c_void_p * 4)(*[w.data_ptr() for w in ws])
         bp = (ctypes.c_void_p * 4)(*[b.data_ptr() for b in bs])
+        if tensor:
+            whp = (ctypes.c_void_p * 4)(*[w.data_ptr() for w in his])
+            wlp = (ctypes.c_void_p * 4)(*[w.data_ptr() for w in los])
         refined = torch.empty_like(dino_tpc) if out is None else out
         assert refined.is_contiguous() and refined.shape == dino_tpc.shape
         norms = torch.empty(dino_tpc.shape[:2], device=dev, dtype=torch.float32)
@@ -167,7 +190,12 @@ class DeltaDINO(nn.Module):
         for i in range(0, B, batch):
             e = min(i + batch, B)
             fr = frames[i:e].contiguous()
-            if peers is None:
+            if tensor:
+                _lib.check(lib.dinotrk_delta_refine_tc(
+                    _lib.ptr(fr), e - i, H, W, chan, whp, wlp, bp, _lib.ptr(dino_tpc[i:e]), _lib.ptr(ixs), _lib.ptr(iys),
+                    geom.h, geom.w, _lib.ptr(refined[i:e]), _lib.ptr(norms[i:e]), _lib.ptr(work), ws_bytes,
+                    peers, len(peer_ptrs) if peer_ptrs else 0, first_frame + i, _lib.stream_ptr()), "delta_refine_tc")
+            elif peers is None:
                 _lib.check(lib.dinotrk_delta_refine(
                     _lib.ptr(fr), e - i, H, W, chan, wp, bp, _lib.ptr(dino_tpc[i:e]), _lib.ptr(ixs), _lib.ptr(iys),
                     geom.h, geom.w, _lib.ptr(refined[i:e]), _lib.ptr(norms[i:e]), _lib.ptr(work), ws_bytes,

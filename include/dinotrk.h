@@ -165,6 +165,15 @@ int dinotrk_delta_refine_allgather(const float* frames, int B, int H, int W, con
                                    const float* ixs, const float* iys, int h, int w, float* refined_tpc,
                                    float* norms, void* workspace, size_t workspace_bytes,
                                    float* const* peer_bases, int n_peers, size_t first_frame, void* stream);
+/* Tensor-core variant: the four convolutions run as explicit-im2col (fp16 hi/lo split on the fly) + tcgen05
+ * split-precision GEMMs (fp32-faithful).  wgt_hi[l] / wgt_lo[l]: fp16 split (dinotrk_split_fp16) of the folded K-major
+ * weights [C_out][Kp], Kp = 25 * C_in_pad rounded up to 8; channel counts multiples of 8.  peer_bases / n_peers /
+ * first_frame as in dinotrk_delta_refine_allgather (n_peers = 0: single GPU). */
+int dinotrk_delta_refine_tc(const float* frames, int B, int H, int W, const int* channels,
+                            const void* const* wgt_hi, const void* const* wgt_lo, const float* const* bias,
+                            const float* dino_tpc, const float* ixs, const float* iys, int h, int w,
+                            float* refined_tpc, float* norms, void* workspace, size_t workspace_bytes,
+                            float* const* peer_bases, int n_peers, size_t first_frame, void* stream);
 /* Peer-mapped buffers for the above (one process per GPU, one node): cudaMalloc + CUDA IPC handle (64 bytes). */
 int dinotrk_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
 int dinotrk_peer_open(const unsigned char* handle64, void** ptr);

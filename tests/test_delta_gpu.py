@@ -58,3 +58,28 @@ def test_state_dict_keys_match_reference_checkpoint_format():
     assert keys == want
     assert set(TrackerHead().state_dict().keys()) == {"cnn_refiner.0.weight", "cnn_refiner.0.bias",
                                                        "cnn_refiner.2.weight", "cnn_refiner.2.bias"}
+
+
+@gpu
+def test_tensor_core_convs_match_exact_path_and_oracle():
+    """delta-DINO with the convolutions on tcgen05 (im2col + split-fp16 GEMM) vs the exact-fp32 CUDA-core path and
+    the oracle, at a shape with ragged tiles (channels 16/24/40/72)."""
+    from dino_tracker_b200 import Tracker
+    channels = [3, 16, 24, 40, 72]
+    H, W, T = 126, 154, 2
+    geo = Geometry(H=H, W=W)
+    sd = od.random_state_dict(channels, torch.Generator().manual_seed(33), last_std=0.05)
+    video = synth.random_video(T, H, W, seed=34)
+    dino = synth.random_features(T, channels[-1], geo.h, geo.w, seed=35)
+    out = {}
+    for prec in ("fp16x3", "fp32"):
+        m = Tracker(video=video.to(DEV), dino_embed_video=dino, device=DEV, delta_channels=channels)
+        m.delta_dino.conv_precision = prec
+        m.delta_dino.load_state_dict(sd)
+        m.cache_refined_embeddings()
+        out[prec] = m.refined_features.cpu()
+    ref = od.refined_features(video, dino, sd)
+    e_tc = (out["fp16x3"] - ref).abs().max().item()
+    e_ff = (out["fp32"] - ref).abs().max().item()
+    print(f"delta-DINO max |diff| vs oracle: tensor {e_tc:.2e}, fp32 {e_ff:.2e}")
+    assert e_ff <= 5e-5 and e_tc <= 5e-5
