@@ -410,7 +410,7 @@ def stage_timings(args, dev, _lib, peaks):
     flops = 2.0 * (12 * dim * dim * (P + 1) + 2 * (P + 1) ** 2 * dim) * (layer + 1) * frames.shape[0]
     out["vit"] = {"model": f"{name}@block{layer}", "frames_per_s": frames.shape[0] / (ms / 1000), "ms_per_frame": ms / frames.shape[0],
                   "tflops": flops / (ms / 1000) / 1e12, "frac_of_bf16_peak": flops / (ms / 1000) / 1e12 / peaks["tf_sustained"],
-                  "kernel_ms_per_call": prof, "math": "TF32 tcgen05 GEMMs, fp32 accumulate; attention scores materialised per row chunk"}
+                  "kernel_ms_per_call": prof, "math": "kind::f16 tcgen05 GEMMs (fp16 operands, fp32 accumulate, fp32 residual stream) + fused tcgen05 attention"}
     del ex, sd
     # delta-DINO with the shipped channel widths
     dd = DeltaDINO(channels=[3, 64, 128, 256, args.C]).to(dev)
@@ -420,7 +420,8 @@ def stage_timings(args, dev, _lib, peaks):
     fr4 = torch.rand(4, 3, H, W, device=dev, generator=g)
     ms, prof = timed(lambda: dd.refine_tpc(fr4, dino, geom), 2)
     out["delta_dino"] = {"frames_per_s": 4 / (ms / 1000), "ms_per_frame": ms / 4, "tflops": 171.4e9 * 4 / (ms / 1000) / 1e12,
-                         "kernel_ms_per_call": prof, "math": "exact fp32 implicit-GEMM convs (CUDA cores)"}
+                         "kernel_ms_per_call": prof,
+                         "math": "convs = im2col (fp16 hi/lo split) + tcgen05 split-precision GEMMs, fp32-faithful"}
     del dd
     # pixels -> tracks for one video of the bench shape: ViT + delta-DINO once per video, then the tracker step
     per_video_s = (out["vit"]["ms_per_frame"] + out["delta_dino"]["ms_per_frame"]) * args.T / 1000.0
