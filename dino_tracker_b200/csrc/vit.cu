@@ -12,6 +12,7 @@
 #include "corr.cuh"
 #include "tcgemm.cuh"
 #include "flash.cuh"
+#include "tcgemm2.cuh"
 
 namespace dtk {
 
@@ -134,12 +135,12 @@ __global__ void vit_tap_kernel(const float* __restrict__ x, float* __restrict__ 
 
 // group tables for the GEMMs: kind 0: one group of m rows; kind 1: `heads` groups (attention)
 __global__ void vit_plan_kernel(int* batch, int* row0, int* m, int* tile_start, int n_groups, int rows, int row_stride,
-                                int row_base, int batch_base) {
+                                int row_base, int batch_base, int tile_rows) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int acc = 0;
     for (int g = 0; g < n_groups; ++g) {
       batch[g] = batch_base + g; row0[g] = row_base + g * row_stride; m[g] = rows; tile_start[g] = acc;
-      acc += (rows + TC_BM - 1) / TC_BM;
+      acc += (rows + tile_rows - 1) / tile_rows;
     }
     tile_start[n_groups] = acc;
   }
@@ -318,9 +319,40 @@ static int run_gemm(const void* A, uint64_t a_rows, const void* Bm, uint64_t b_b
   return DINOTRK_OK;
 }
 
-static int plan(const Plan& pl, int n_groups, int rows, int row_stride, int row_base, int batch_base, cudaStream_t st) {
+static int plan(const Plan& pl, int n_groups, int rows, int row_stride, int row_base, int batch_base, cudaStream_t st,
+                int tile_rows = TC_BM) {
   ProfRange pr(PROF_VIT_MISC, st);
-  vit_plan_kernel<<<1, 32, 0, st>>>(pl.batch, pl.row0, pl.m, pl.tile_start, n_groups, rows, row_stride, row_base, batch_base);
+  vit_plan_kernel<<<1, 32, 0, st>>>(pl.batch, pl.row0, pl.m, pl.tile_start, n_groups, rows, row_stride, row_base, batch_base,
+                                    tile_rows);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+// CTA-pair variant (cta_group::2, 256 x 256 tiles) for the single-pass fp16 linear layers; the plan must be in
+// 256-row tiles.
+template <class Epi>
+static int run_gemm_pair(const void* A, uint64_t a_rows, const void* Bm, uint64_t b_rows, int K, const Plan& pl,
+                         int max_tiles, const Epi& epi, int prof_cls, cudaStream_t st) {
+  using Base = TcCfg<TcMode::F16, TC2_BN>;
+  using Cfg = Tc2Cfg<TcMode::F16>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_2d(&tmA, A, a_rows, K, 128, Base::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tmB, Bm, 1, b_rows, K, TC2_BN / 2, Base::kBK, TMAP_F16))) return rc;
+  auto kern = tc_gemm2_kernel<TcMode::F16, Epi>;
+  static bool attr = false;
+  if (!attr) {
+    DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr = true;
+  }
+  TcProblem pb{pl.batch, pl.row0, pl.m, pl.tile_start, 1, (int)b_rows, K};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int pairs = max_tiles * cdiv((int)b_rows, TC2_BN);
+  int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
+  ProfRange pr(prof_cls, st);
+  kern<<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmA, tmB, tmB, pb, epi);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }
@@ -381,6 +413,8 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
   // significand like TF32, twice the tensor rate, half the operand traffic).  The validation path
   // (attn_materialized) keeps every operand fp32 / TF32.
   const bool f16 = c->gemm_f16 != 0 && c->attn_materialized == 0;
+  const bool pairs = f16 && c->gemm_pair != 0;   // linear layers on CTA pairs (cta_group::2)
+  const int pair_tiles = cdiv((int)((size_t)B * (g->h * g->w + 1)), TC2_BM);
   __half* y16 = reinterpret_cast<__half*>(y);
   __half* h16 = reinterpret_cast<__half*>(hbuf);
 
@@ -417,7 +451,7 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
     // w: 0 norm1.w 1 norm1.b 2 qkv.w 3 qkv.b 4 proj.w 5 proj.b 6 ls1 7 norm2.w 8 norm2.b 9 fc1.w 10 fc1.b 11 fc2.w 12 fc2.b 13 ls2
     // (the four weight matrices are fp16 arrays in fp16 operand mode)
     if ((rc = layernorm(w[0], w[1]))) return rc;
-    if ((rc = plan(pl, 1, (int)rows, 0, 0, 0, st))) return rc;
+    if ((rc = plan(pl, 1, (int)rows, 0, 0, 0, st, pairs ? TC2_BM : TC_BM))) return rc;
     if (c->attn_materialized == 0) {
       // fused attention: fp16 q / k / v^T, scores stay in TMEM / shared memory
       __half* q16 = reinterpret_cast<__half*>(q);
@@ -425,7 +459,8 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
       __half* v16 = reinterpret_cast<__half*>(vT);
       const int N1p8 = (int)align_up((size_t)N1, 8);
       EpiQKV16 eq{{}, q16, k16, v16, w[3], N1, D, heads, N1p8, 0.125f * 1.4426950408889634f};  // 1/sqrt(64) * log2(e)
-      rc = f16 ? run_gemm<EpiQKV16, 256, TcMode::F16>(y16, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st)
+      rc = pairs ? run_gemm_pair<EpiQKV16>(y16, rows, w[2], 3 * D, D, pl, pair_tiles, eq, PROF_VIT_GEMM, st)
+         : f16 ? run_gemm<EpiQKV16, 256, TcMode::F16>(y16, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st)
                : run_gemm<EpiQKV16, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st);
       if (rc) return rc;
       CUtensorMap tmQ, tmK, tmV;
@@ -464,15 +499,21 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
         }
       }
     }
-    if ((rc = plan(pl, 1, (int)rows, 0, 0, 0, st))) return rc;
+    if ((rc = plan(pl, 1, (int)rows, 0, 0, 0, st, pairs ? TC2_BM : TC_BM))) return rc;
     {
       EpiResidual er{{}, x, w[5], w[6], D};
-      rc = f16 ? run_gemm<EpiResidual, 256, TcMode::F16>(y16, rows, w[4], 1, D, D, pl, 1, all_tiles, er, PROF_VIT_GEMM, st)
+      rc = pairs ? run_gemm_pair<EpiResidual>(y16, rows, w[4], D, D, pl, pair_tiles, er, PROF_VIT_GEMM, st)
+         : f16 ? run_gemm<EpiResidual, 256, TcMode::F16>(y16, rows, w[4], 1, D, D, pl, 1, all_tiles, er, PROF_VIT_GEMM, st)
                : run_gemm<EpiResidual, 256>(y, rows, w[4], 1, D, D, pl, 1, all_tiles, er, PROF_VIT_GEMM, st);
       if (rc) return rc;
     }
     if ((rc = layernorm(w[7], w[8]))) return rc;
-    if (f16) {
+    if (pairs) {
+      if ((rc = run_gemm_pair<EpiGelu<__half>>(y16, rows, w[9], 4 * D, D, pl, pair_tiles, EpiGelu<__half>{{}, h16, w[10], 4 * D},
+                                               PROF_VIT_GEMM, st))) return rc;
+      if ((rc = run_gemm_pair<EpiResidual>(h16, rows, w[11], D, 4 * D, pl, pair_tiles, EpiResidual{{}, x, w[12], w[13], D},
+                                           PROF_VIT_GEMM, st))) return rc;
+    } else if (f16) {
       if ((rc = run_gemm<EpiGelu<__half>, 256, TcMode::F16>(y16, rows, w[9], 1, 4 * D, D, pl, 1, all_tiles,
                                                             EpiGelu<__half>{{}, h16, w[10], 4 * D}, PROF_VIT_GEMM, st))) return rc;
       if ((rc = run_gemm<EpiResidual, 256, TcMode::F16>(h16, rows, w[11], 1, D, 4 * D, pl, 1, all_tiles,

@@ -50,7 +50,7 @@ class DinoV2Features(torch.nn.Module):
     """``VitExtractor`` replacement: ``forward(video01)`` -> token-major features [T][P][C] on the GPU."""
 
     def __init__(self, state_dict, heads, layer=None, stride=7, patch=14, device="cuda:0", frames_per_call=2,
-                 attention="fused"):
+                 attention="fused", cta_pairs=True):
         super().__init__()
         self._dev = _lib.require_cuda(device)
         self._lib = _lib.load()
@@ -63,6 +63,7 @@ class DinoV2Features(torch.nn.Module):
         self.frames_per_call = frames_per_call
         assert attention in ("fused", "materialized")
         self.attention = attention
+        self.cta_pairs = cta_pairs
         self._sd = sd
         # fused mode: weight matrices in fp16 (kind::f16 MMAs); materialized (validation) mode: fp32 / TF32
         self._f16 = attention == "fused"
@@ -99,7 +100,7 @@ class DinoV2Features(torch.nn.Module):
         geom = _lib.make_geom(H, W, self.patch, self.stride, 35)
         P = geom.h * geom.w
         cfg = _lib.VitConfig(self.depth, self.dim, self.heads, self.layer, self.patch, self.stride,
-                             0 if self.attention == "fused" else 1, 1 if self._f16 else 0)
+                             0 if self.attention == "fused" else 1, 1 if self._f16 else 0, 1 if self.cta_pairs else 0)
         cls_pos, pos = self._pos(geom.h, geom.w)
         wt = _lib.VitWeights()
         wt.patch_w, wt.patch_b = self._patch_w.data_ptr(), self._sd["patch_embed.proj.bias"].data_ptr()

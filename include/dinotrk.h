@@ -190,6 +190,8 @@ typedef struct dinotrk_vit_config {
   int gemm_f16;            /* 1: linear layers on the kind::f16 pipe -- patch_w and the qkv / proj / fc1 / fc2 weight matrices
                               are passed as fp16 arrays, activations are written in fp16 by the producing epilogue;
                               0 (or attn_materialized): fp32 arrays, TF32 MMAs */
+  int gemm_pair;           /* with gemm_f16: 1 = linear layers on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, each SM
+                              stages half of the weight tile), 0 = single-CTA 128 x 256 tiles */
 } dinotrk_vit_config;
 /* Device fp32 (weight matrices fp16 when gemm_f16).  patch_w: patch-embedding conv weight flattened K-major
  * [dim][Kp], Kp = 3*patch*patch zero-padded to a multiple of 4 (fp32) / 8 (fp16) elements; cls_pos [dim] =

@@ -10,7 +10,7 @@ from oracle import synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("attention", ["fused", "materialized"])
+@pytest.mark.parametrize("attention", ["fused", "fused-single-cta", "materialized"])
 @pytest.mark.parametrize("cfg", [dict(H=98, W=126, depth=2, dim=128, heads=2, layer=1, T=3),
                                  dict(H=112, W=140, depth=3, dim=192, heads=3, layer=1, T=2),
                                  dict(H=182, W=238, depth=1, dim=64, heads=1, layer=0, T=1)])
@@ -20,7 +20,9 @@ def test_vit_features_match_oracle(cfg, attention):
     sd = ovit.random_state_dict(cfg["depth"], cfg["dim"], g, n_pos=4, std=0.05)
     video = synth.random_video(cfg["T"], cfg["H"], cfg["W"], seed=4)
     ref = ovit.dino_features_video(video, sd, cfg["heads"], cfg["layer"])          # T x C x h x w
-    ex = DinoV2Features(sd, heads=cfg["heads"], layer=cfg["layer"], device="cuda:0", attention=attention)
+    ex = DinoV2Features(sd, heads=cfg["heads"], layer=cfg["layer"], device="cuda:0",
+                        attention="fused" if attention.startswith("fused") else attention,
+                        cta_pairs=attention == "fused")
     got = ex.features_chw(video).cpu()
     assert got.shape == ref.shape
     scale = ref.abs().max().item()
