@@ -1,13 +1,21 @@
 // Fused attention for the ViT (sm_100a, tcgen05):  O = softmax(Q K^T) V  per (frame, head).  Q arrives pre-scaled by
-// head_dim^-1/2 * log2(e), so the softmax is exp2(s - max) (one FADD + one MUFU.EX2 per score).
+// head_dim^-1/2 * log2(e), so the softmax is exp2(s - max).
 //
-// One CTA per (frame*head, 128-query tile); 192 threads:
-//   warp 0     : TMA producer (Q once; K_j [BKV keys][64] and V^T_j [64][BKV keys] through a 2-stage ring)
-//   warp 1     : TMEM alloc + MMA issue:  S = Q K_j^T (kind::f16, M128 N=BKV K64) -> TMEM;  O_j = P_j V_j (M128 N64 K=BKV)
-//                (BKV = 64: 66 KB of shared memory and 128 TMEM columns per CTA -> 3 CTAs per SM overlap each other)
-//   warps 2..5 : online softmax, thread = query row: running max / sum in registers, P_j written as fp16 into a
-//                128B-swizzled shared-memory tile (the A operand of the second MMA), O accumulated in registers
-//                (O_j is read back from TMEM and added after the rescale), final normalise + fp32 store.
+// One CTA per (frame*head, 128-query tile), two CTAs per SM; 192 threads:
+//   warp 0     : TMA producer (Q once; K_j [64 keys][64] and V^T_j [64][64 keys] through a 3-stage ring)
+//   warp 1     : TMEM alloc + MMA issue.  S_j = Q K_j^T (kind::f16, M128 N64 K64) goes to one of TWO TMEM score buffers,
+//                so S_{j+1} is computed while the softmax warps work on S_j;  O += P_j V_j (M128 N80 K64) accumulates IN
+//                TMEM across all key tiles.  The V^T stage carries a 65th row of ones (written once, never touched by
+//                the TMA), so accumulator column 64 is the softmax denominator sum_j P_j 1 - computed by the tensor
+//                core from the same fp16 P that multiplies V, at no issue-slot cost.
+//   warps 2..5 : softmax, thread = query row = TMEM lane.  Per key tile: one TMEM read of the 64 scores, row max
+//                (FMNMX3), p = exp2(s - m), fp16 P into one of two 128B-swizzled shared-memory tiles (A operand of the
+//                second MMA).  The running max m is LAZY: it only moves (and the TMEM accumulator is only rescaled,
+//                tcgen05.ld -> multiply -> tcgen05.st) when some row of the warp would exceed it by 2^8, so after the
+//                first few tiles there is no per-tile accumulator traffic at all; p <= 256 keeps fp16 P in range, and
+//                the final O / l is independent of which m was used.  The exponentials are MUFU-bound (16/clk/SM
+//                against 4 x 128 x 64-wide MMAs), so every FA_POLY_EVERY-th one is evaluated on the FMA pipe instead
+//                (Cody-Waite split + cubic, relative error 1.1e-4 < fp16 rounding of P).
 // The score matrix (8108 x 8108 per head) never leaves the SM.
 #pragma once
 #include <cuda_fp16.h>
@@ -17,23 +25,41 @@
 
 namespace dtk {
 
-#ifndef DTK_FA_BKV
-#define DTK_FA_BKV 64
+#ifndef DTK_FA_POLY_EVERY
+#define DTK_FA_POLY_EVERY 4   // 0: all exponentials on the MUFU
 #endif
-constexpr int FA_BQ = 128, FA_BKV = DTK_FA_BKV, FA_D = 64, FA_THREADS = 192;
-constexpr int FA_NSUB = FA_BKV / 64;               // 64-key sub-tiles (one 128-byte swizzle row of fp16 each)
+constexpr int FA_BQ = 128, FA_BKV = 64, FA_D = 64, FA_THREADS = 192;
+constexpr int FA_NV = 80;                          // V^T tile rows = MMA N: 64 head dims, one row of ones, 15 rows of zeros
+constexpr int FA_KV_STAGES = 3;
 constexpr int FA_SQ = FA_BQ * 128;                 // Q tile bytes (128 rows x 64 fp16)
 constexpr int FA_SK = FA_BKV * 128;                // K tile bytes
-constexpr int FA_SV = FA_NSUB * FA_D * 128;        // V^T tile: sub-tiles [64 d][64 keys]
-constexpr int FA_SP = FA_NSUB * FA_BQ * 128;       // P tile: sub-tiles [128 rows][64 keys]
-constexpr int FA_TMEM = FA_BKV + 64 <= 128 ? 128 : 256;
+constexpr int FA_SVT = FA_D * 128;                 // TMA-written part of the V^T tile
+constexpr int FA_SV = FA_NV * 128;                 // whole V^T tile
+constexpr int FA_SP = FA_BQ * 128;                 // P tile: [128 rows][64 keys] fp16
 constexpr int FA_STAGE = FA_SK + FA_SV;
-constexpr int FA_SMEM = FA_SQ + 2 * FA_STAGE + FA_SP + 256;   // extern smem is declared 1024-byte aligned
+constexpr int FA_TMEM = 256;                       // S0 [0,64) S1 [64,128) O [128,208)
+constexpr int FA_SMEM = FA_SQ + FA_KV_STAGES * FA_STAGE + 2 * FA_SP + 256;   // extern smem is declared 1024-byte aligned
+constexpr float FA_RESCALE_STEP = 8.f;             // log2 units
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// exp2 on the FMA pipe for x <= 0: n = round(x), 2^(x-n) by a cubic on [-0.5, 0.5], exponent patched in by integer add
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                  // 1.5 * 2^23: low mantissa bits of t hold n
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.055268917f, f, 0.24221092f);
+  p = fmaf(p, f, 0.6932298f);
+  p = fmaf(p, f, 1.f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 
 struct FlashParams {
@@ -44,21 +70,21 @@ struct FlashParams {
   int out_f16;
 };
 
-__global__ void __launch_bounds__(FA_THREADS, FA_BKV == 64 ? 2 : 1)
+__global__ void __launch_bounds__(FA_THREADS, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, FlashParams fp) {
   extern __shared__ __align__(1024) uint8_t fa_smem[];
   uint8_t* sQ = fa_smem;
-  uint8_t* sKV = sQ + FA_SQ;                 // stage s: K at sKV + s*FA_STAGE, V at + FA_SK
-  uint8_t* sP = sKV + 2 * FA_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_SP);
-  uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;      // 1
-  uint64_t* p_ready = bars + 6;     // 1 (4 arrivals)
-  uint64_t* o_full = bars + 7;      // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint8_t* sKV = sQ + FA_SQ;                 // stage s: K at sKV + s*FA_STAGE, V^T at + FA_SK
+  uint8_t* sP = sKV + FA_KV_STAGES * FA_STAGE;   // two P tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_SP);
+  uint64_t* q_full = bars;           // 1
+  uint64_t* kv_full = bars + 1;      // [3]
+  uint64_t* kv_empty = bars + 4;     // [3]
+  uint64_t* s_full = bars + 7;       // [2]
+  uint64_t* p_ready = bars + 9;      // [2] (4 arrivals: one per softmax warp)
+  uint64_t* pv_done = bars + 11;     // [2] P V_j retired: P tile j&1 reusable, accumulator quiescent until p_ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, q0 = blockIdx.x * FA_BQ;
@@ -68,179 +94,194 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV);
     tc::mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
-    tc::mbar_init(s_full, 1); tc::mbar_init(p_ready, 4); tc::mbar_init(o_full, 1);
+    for (int s = 0; s < FA_KV_STAGES; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_ready[s], 4); tc::mbar_init(&pv_done[s], 1); }
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, FA_TMEM);
+  if (warp >= 2) {
+    // rows 64..79 of every V^T stage: ones (fp16 0x3C00) in row 64, zeros below; a constant row is swizzle-invariant
+    const int t = threadIdx.x - 64;   // 0..127: 3 stages x 16 rows x 8 chunks of 16 B = 384 chunks
+    for (int i = t; i < FA_KV_STAGES * 16 * 8; i += 128) {
+      const int s = i / 128, r = (i >> 3) & 15, ch = i & 7;
+      const uint32_t val = r == 0 ? 0x3C003C00u : 0u;
+      *reinterpret_cast<uint4*>(sKV + s * FA_STAGE + FA_SK + FA_SVT + r * 128 + ch * 16) = make_uint4(val, val, val, val);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + FA_BKV;
+  const uint32_t tmem_O = tmem_base + 2 * FA_BKV;
   constexpr uint32_t kIdescS = tc::make_idesc(0, 128, FA_BKV);   // f16 inputs, fp32 accumulate
-  constexpr uint32_t kIdescO = tc::make_idesc(0, 128, 64);
+  constexpr uint32_t kIdescO = tc::make_idesc(0, 128, FA_NV);
 
   if (warp == 0) {
     if (tc::elect_one()) {
       tc::mbar_expect_tx(q_full, FA_SQ);
       tc::tma_load_2d(&tmQ, q_full, sQ, 0, bh * N1 + q0);
+      int s = 0, ph = 0;
       for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        tc::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        tc::mbar_expect_tx(&kv_full[s], FA_STAGE);
+        tc::mbar_wait(&kv_empty[s], ph ^ 1);
+        tc::mbar_expect_tx(&kv_full[s], FA_SK + FA_SVT);
         uint8_t* st = sKV + s * FA_STAGE;
         tc::tma_load_3d(&tmK, &kv_full[s], st, 0, j * FA_BKV, bh);
-#pragma unroll
-        for (int kb = 0; kb < FA_NSUB; ++kb)
-          tc::tma_load_3d(&tmV, &kv_full[s], st + FA_SK + kb * FA_D * 128, j * FA_BKV + kb * 64, 0, bh);
+        tc::tma_load_3d(&tmV, &kv_full[s], st + FA_SK, j * FA_BKV, 0, bh);
+        if (++s == FA_KV_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    auto mma_S = [&](int s) {   // S = Q K^T : 4 k-steps of 16 over d = 64
+    auto mma_S = [&](int s, int buf) {   // S = Q K^T : 4 k-steps of 16 over d = 64
       const uint32_t a = tc::smem_u32(sQ), b = tc::smem_u32(sKV + s * FA_STAGE);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        tc::mma_ss<false>(tmem_S, tc::smem_desc_sw128(a + ks * 32), tc::smem_desc_sw128(b + ks * 32), kIdescS, ks ? 1u : 0u);
+        tc::mma_ss<false>(tmem_base + buf * FA_BKV, tc::smem_desc_sw128(a + ks * 32), tc::smem_desc_sw128(b + ks * 32), kIdescS,
+                          ks ? 1u : 0u);
     };
-    auto mma_O = [&](int s) {   // O_j = P V : 2 sub-tiles x 4 k-steps over 128 keys
-      const uint32_t a = tc::smem_u32(sP), b = tc::smem_u32(sKV + s * FA_STAGE + FA_SK);
+    auto mma_O = [&](int s, int buf, bool acc) {   // O (+)= P [V | 1] : 4 k-steps over 64 keys
+      const uint32_t a = tc::smem_u32(sP + buf * FA_SP), b = tc::smem_u32(sKV + s * FA_STAGE + FA_SK);
 #pragma unroll
-      for (int kb = 0; kb < FA_NSUB; ++kb)
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          tc::mma_ss<false>(tmem_O, tc::smem_desc_sw128(a + kb * (FA_BQ * 128) + ks * 32),
-                            tc::smem_desc_sw128(b + kb * (FA_D * 128) + ks * 32), kIdescO, (kb | ks) ? 1u : 0u);
+      for (int ks = 0; ks < 4; ++ks)
+        tc::mma_ss<false>(tmem_O, tc::smem_desc_sw128(a + ks * 32), tc::smem_desc_sw128(b + ks * 32), kIdescO,
+                          (acc || ks) ? 1u : 0u);
     };
     tc::mbar_wait(q_full, 0);
     tc::mbar_wait(&kv_full[0], 0);
     tc::fence_after_sync();
-    if (tc::elect_one()) { mma_S(0); tc::mma_commit(s_full); }
+    if (tc::elect_one()) { mma_S(0, 0); tc::mma_commit(&s_full[0]); }
     __syncwarp();
+    int s = 0, s1 = 1, ph1 = 0;   // s: stage of tile j; s1 / ph1: stage and phase of tile j + 1
     for (int j = 0; j < n_kv; ++j) {
-      const int s = j & 1;
-      if (j + 1 < n_kv) tc::mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-      tc::mbar_wait(p_ready, j & 1);
+      if (j + 1 < n_kv) {
+        // score buffer (j+1)&1 was last read by the softmax of tile j-1, which arrived on p_ready before PV_{j-1} was issued
+        tc::mbar_wait(&kv_full[s1], ph1);
+        tc::fence_after_sync();
+        if (tc::elect_one()) { mma_S(s1, (j + 1) & 1); tc::mma_commit(&s_full[(j + 1) & 1]); }
+        __syncwarp();
+      }
+      tc::mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        mma_O(s);
-        tc::mma_commit(o_full);
+        mma_O(s, j & 1, j > 0);
+        tc::mma_commit(&pv_done[j & 1]);
         tc::mma_commit(&kv_empty[s]);
-        if (j + 1 < n_kv) { mma_S((j + 1) & 1); tc::mma_commit(s_full); }
       }
       __syncwarp();
+      s = s1;
+      if (++s1 == FA_KV_STAGES) { s1 = 0; ph1 ^= 1; }
     }
   } else {
-    // ---------------- online softmax: thread = query row ----------------
+    // ---------------- softmax: thread = query row ----------------
     const int quad = warp & 3;
     const int row = quad * 32 + lane;                 // row inside the Q tile = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[FA_D];
-#pragma unroll
-    for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
+    float m_run = -INFINITY;
     for (int j = 0; j < n_kv; ++j) {
-      const int kbase = j * FA_BKV;
-      tc::mbar_wait(s_full, j & 1);
+      const int buf = j & 1, kbase = j * FA_BKV;
+      tc::mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc::fence_after_sync();
-      const bool tail = kbase + FA_BKV > N1;          // only the last key tile needs masking
-      // pass 1: row maximum over the valid keys of this tile
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < FA_BKV; c += 32) {
-        uint32_t v[32];
-        tc::tmem_ld32(tmem_S + lane_addr + c, v);
+      uint32_t v[FA_BKV];
+      {
+        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+        tc::tmem_ld32(tmem_base + lane_addr + buf * FA_BKV, v0);
+        tc::tmem_ld32(tmem_base + lane_addr + buf * FA_BKV + 32, v1);
         tc::tmem_ld_wait();
-        if (!tail) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kbase + c + i < N1) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
       }
-      // fold in the previous tile's P V (computed relative to the current running max)
-      if (j > 0) {
-        tc::mbar_wait(o_full, (j - 1) & 1);
-        tc::fence_after_sync();
+      if (kbase + FA_BKV > N1) {                      // only the last key tile needs masking
 #pragma unroll
-        for (int c = 0; c < FA_D; c += 32) {
-          uint32_t v[32];
-          tc::tmem_ld32(tmem_O + lane_addr + c, v);
+        for (int i = 0; i < FA_BKV; ++i)
+          if (kbase + i >= N1) v[i] = 0xff800000u;    // -inf: ignored by the max, exp2 -> 0
+      }
+      float mx = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+#pragma unroll
+      for (int i = 3; i + 1 < FA_BKV; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+      mx = fmaxf(mx, __uint_as_float(v[FA_BKV - 1]));
+      // lazy running max: move it (and rescale the TMEM accumulator, row sums included) only on a 2^8 overshoot
+      if (__any_sync(0xffffffffu, mx > m_run + FA_RESCALE_STEP)) {
+        const float m_new = fmaxf(m_run, mx);
+        if (j > 0) {
+          tc::mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // accumulator quiescent: PV_j waits for our p_ready
+          tc::fence_after_sync();
+          const float alpha = fast_exp2(m_run - m_new);
+#pragma unroll
+          for (int c = 0; c < FA_D; c += 32) {
+            uint32_t o[32];
+            tc::tmem_ld32(tmem_O + lane_addr + c, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc::tmem_st32(tmem_O + lane_addr + c, o);
+          }
+          uint32_t l16[16];
+          tc::tmem_ld16(tmem_O + lane_addr + FA_D, l16);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
+          for (int i = 0; i < 16; ++i) l16[i] = __float_as_uint(__uint_as_float(l16[i]) * alpha);
+          tc::tmem_st16(tmem_O + lane_addr + FA_D, l16);
+          tc::tmem_st_wait();
         }
+        m_run = m_new;
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = fast_exp2(m_run - m_new);      // m_run = -inf on the first tile -> 0
-      l_run *= alpha;
+      // p = exp2(s - m) as fp16 pairs
+      uint32_t packed[FA_BKV / 2];
 #pragma unroll
-      for (int i = 0; i < FA_D; ++i) o[i] *= alpha;
-      m_run = m_new;
-      // pass 2: p = exp(s - m), row sum, fp16 P tile in the 128B-swizzled K-major layout of the MMA A operand
-#pragma unroll
-      for (int c = 0; c < FA_BKV; c += 32) {
-        uint32_t v[32];
-        tc::tmem_ld32(tmem_S + lane_addr + c, v);
-        tc::tmem_ld_wait();
-        uint32_t packed[16];
-        float lpart = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(__uint_as_float(v[i]) - m_new), p1 = fast_exp2(__uint_as_float(v[i + 1]) - m_new);
-          if (tail) { if (kbase + c + i >= N1) p0 = 0.f; if (kbase + c + i + 1 >= N1) p1 = 0.f; }
-          __half2 h = __floats2half2_rn(p0, p1);
-          float2 hf = __half22float2(h);
-          lpart += hf.x + hf.y;
-          packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        l_run += lpart;
-        // 32 keys = 4 chunks of 16 bytes; key (c + 8*cc .. ) -> sub-tile kb = c / 64, chunk ((c % 64) / 8 + cc)
-        uint8_t* base = sP + (c >> 6) * (FA_BQ * 128) + row * 128;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int chunk = ((c & 63) >> 3) + cc;
-          *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) =
-              make_uint4(packed[cc * 4], packed[cc * 4 + 1], packed[cc * 4 + 2], packed[cc * 4 + 3]);
-        }
+      for (int i = 0; i < FA_BKV; i += 2) {
+        const float x0 = __uint_as_float(v[i]) - m_run, x1 = __uint_as_float(v[i + 1]) - m_run;
+        float p0, p1;
+        if (DTK_FA_POLY_EVERY > 0 && (i / 2) % DTK_FA_POLY_EVERY == DTK_FA_POLY_EVERY - 1) { p0 = poly_exp2(x0); p1 = poly_exp2(x1); }
+        else { p0 = fast_exp2(x0); p1 = fast_exp2(x1); }
+        __half2 h = __floats2half2_rn(p0, p1);
+        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
       }
+      if (j >= 2) tc::mbar_wait(&pv_done[buf], ((j - 2) >> 1) & 1);   // P tile `buf` was the A operand of PV_{j-2}
+      // fp16 P tile in the 128B-swizzled K-major layout: 64 keys = 8 chunks of 16 bytes per row
+      uint8_t* base = sP + buf * FA_SP + row * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        *reinterpret_cast<uint4*>(base + ((ch ^ (row & 7)) << 4)) =
+            make_uint4(packed[ch * 4], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the MMA
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(p_ready);
+      if (lane == 0) tc::mbar_arrive(&p_ready[buf]);
     }
-    // last tile's P V, normalise, store
-    tc::mbar_wait(o_full, (n_kv - 1) & 1);
+    // accumulator complete: normalise by the tensor-core row sum (column 64) and store
+    tc::mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc::fence_after_sync();
+    uint32_t l16[16];
+    tc::tmem_ld16(tmem_O + lane_addr + FA_D, l16);
+    tc::tmem_ld_wait();
+    const float inv = 1.f / __uint_as_float(l16[0]);
+    const int qrow = q0 + row;
+    const int b = bh / fp.heads, hd = bh - b * fp.heads;
+    const size_t off = ((size_t)b * N1 + qrow) * fp.D + hd * FA_D;
 #pragma unroll
     for (int c = 0; c < FA_D; c += 32) {
       uint32_t v[32];
       tc::tmem_ld32(tmem_O + lane_addr + c, v);
       tc::tmem_ld_wait();
+      if (qrow < N1) {
+        if (fp.out_f16) {
+          __half* dst = reinterpret_cast<__half*>(fp.out) + off + c;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
-    }
-    const int qrow = q0 + row;
-    if (qrow < N1) {
-      const float inv = 1.f / l_run;
-      const int b = bh / fp.heads, hd = bh - b * fp.heads;
-      const size_t off = ((size_t)b * N1 + qrow) * fp.D + hd * FA_D;
-      if (fp.out_f16) {
-        __half* dst = reinterpret_cast<__half*>(fp.out) + off;
+          for (int i = 0; i < 32; i += 8) {
+            uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < FA_D; i += 8) {
-          __half2 h0 = __floats2half2_rn(o[i] * inv, o[i + 1] * inv), h1 = __floats2half2_rn(o[i + 2] * inv, o[i + 3] * inv);
-          __half2 h2 = __floats2half2_rn(o[i + 4] * inv, o[i + 5] * inv), h3 = __floats2half2_rn(o[i + 6] * inv, o[i + 7] * inv);
-          *reinterpret_cast<uint4*>(dst + i) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                                          *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            for (int k = 0; k < 4; ++k) {
+              __half2 h = __floats2half2_rn(__uint_as_float(v[i + 2 * k]) * inv, __uint_as_float(v[i + 2 * k + 1]) * inv);
+              w[k] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(fp.out) + off + c;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv,
+                                                              __uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
         }
-      } else {
-        float* dst = reinterpret_cast<float*>(fp.out) + off;
-#pragma unroll
-        for (int i = 0; i < FA_D; i += 4)
-          *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
       }
     }
   }

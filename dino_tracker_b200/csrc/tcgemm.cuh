@@ -17,10 +17,14 @@
 // Work = grouped tiles: group g covers A rows [row0[g], row0[g] + m[g]) against B batch item batch[g];
 // m-tiles are numbered through the prefix array tile_start[] (device), n-tiles cover N.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
 namespace dtk {
+
+constexpr int TC_EPI_SCRATCH = 4 * 32 * 36 * 4;   // bytes: one 32 x 36 fp32 block per epilogue warp
 
 enum class TcMode { TF32X3 = 0, TF32 = 1, BF16 = 2, F16X3 = 3, F16 = 4 };
 
@@ -37,12 +41,19 @@ struct TcCfg {
   static constexpr int kABytes = TC_BM * 128, kBBytes = BN * 128;
   static constexpr int kStageBytes = kOps * (kABytes + kBBytes);
   static constexpr int kStages = (kOps == 2) ? 2 : 4;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+                               (kOps == 1 ? TC_EPI_SCRATCH : 0) /*epilogue transpose (single-pass modes)*/;
   static constexpr bool kTF32 = (MODE == TcMode::TF32X3 || MODE == TcMode::TF32);
   static constexpr int kFmt = kTF32 ? 2 : (MODE == TcMode::BF16 ? 1 : 0);   // 0 f16, 1 bf16, 2 tf32
   static constexpr uint32_t kIdesc = tc::make_idesc(kFmt, TC_BM, BN);
   static constexpr uint32_t kTmemCols = 2 * BN;   // two accumulator buffers (power of two >= 32)
 };
+
+// Epilogues that declare `static constexpr bool kCoalesced = true` get their accumulator block transposed through shared
+// memory (see the epilogue loop) and are called as vec4(g, row, col, float4) with lanes running along a row; they also
+// provide `bool direct(int col0)` to keep the thread-per-row call for selected column ranges.
+template <class E, class = void> struct EpiCoalesced { static constexpr bool value = false; };
+template <class E> struct EpiCoalesced<E, std::enable_if_t<E::kCoalesced>> { static constexpr bool value = true; };
 
 struct TcProblem {
   const int* grp_batch;    // [n_groups] B batch item (frame) of each group
@@ -72,6 +83,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tempty = tfull + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_scratch = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
+  static_assert(!EpiCoalesced<Epi>::value || Cfg::kOps == 1, "coalesced epilogues need the scratch of the single-pass modes");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles_n = (pb.N + BN - 1) / BN;
@@ -185,6 +198,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc::tmem_ld32(taddr + c, v);
         tc::tmem_ld_wait();
         const int ncols = min(32, pb.N - (n0 + c));
+        if constexpr (EpiCoalesced<Epi>::value) {
+          if (!epi.direct(n0 + c)) {
+            // transpose the warp's 32 x 32 block through shared memory so that global accesses run along rows:
+            // lane (r4, c4) then owns 4 consecutive columns of rows it*4 + r4 -> 8 lanes cover 128 contiguous bytes
+            float* sw = epi_scratch + (warp - 2) * (32 * 36);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(sw + lane * 36 + i) =
+                  make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            __syncwarp();
+            const int c4 = (lane & 7) * 4, r4 = lane >> 3;
+            const int row_base = m0 + quad * 32;
+            if (c4 < ncols) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + r4;
+                if (row_base + rr < pb.grp_m[g])
+                  epi.vec4(g, row_base + rr, n0 + c + c4, *reinterpret_cast<const float4*>(sw + rr * 36 + c4));
+              }
+            }
+            __syncwarp();
+            continue;
+          }
+        }
         if (row_ok && ncols > 0) {
           float f[32];
 #pragma unroll

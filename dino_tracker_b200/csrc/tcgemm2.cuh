@@ -96,7 +96,7 @@ struct Tc2Cfg {
   static constexpr int kABytes = 128 * 128, kBBytes = (TC2_BN / 2) * 128;
   static constexpr int kStageBytes = Base::kOps * (kABytes + kBBytes);
   static constexpr int kStages = (Base::kOps == 2) ? 3 : 6;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 + 256 + (Base::kOps == 1 ? TC_EPI_SCRATCH : 0);
   static constexpr uint32_t kIdesc = tc::make_idesc(Base::kFmt, TC2_BM, TC2_BN);
 };
 
@@ -117,6 +117,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]        per CTA (multicast commit)
   uint64_t* tempty = tfull + 2;                // [2]        leader's copy, 8 arrivals (4 epilogue warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* epi_scratch = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
+  static_assert(!EpiCoalesced<Epi>::value || Base::kOps == 1, "coalesced epilogues need the scratch of the single-pass modes");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc::cluster_ctarank();
@@ -233,6 +235,30 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         tc::tmem_ld32(taddr + c, v);
         tc::tmem_ld_wait();
         const int ncols = min(32, pb.N - (n0 + c));
+        if constexpr (EpiCoalesced<Epi>::value) {
+          if (!epi.direct(n0 + c)) {
+            // transpose the warp's 32 x 32 block through shared memory so that global accesses run along rows:
+            // lane (r4, c4) then owns 4 consecutive columns of rows it*4 + r4 -> 8 lanes cover 128 contiguous bytes
+            float* sw = epi_scratch + (warp - 2) * (32 * 36);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(sw + lane * 36 + i) =
+                  make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            __syncwarp();
+            const int c4 = (lane & 7) * 4, r4 = lane >> 3;
+            const int row_base = m0 + (int)rank * 128 + quad * 32;
+            if (c4 < ncols) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + r4;
+                if (row_base + rr < pb.grp_m[g])
+                  epi.vec4(g, row_base + rr, n0 + c + c4, *reinterpret_cast<const float4*>(sw + rr * 36 + c4));
+              }
+            }
+            __syncwarp();
+            continue;
+          }
+        }
         if (row_ok && ncols > 0) {
           float f[32];
 #pragma unroll

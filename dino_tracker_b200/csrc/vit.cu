@@ -151,11 +151,23 @@ struct EpiBase {
   struct State {};
   __device__ __forceinline__ void tile_begin(State&) const {}
   __device__ __forceinline__ void tile_end(State&, int, int, int) const {}
+  __device__ __forceinline__ bool direct(int) const { return false; }
 };
+__device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) {
+  __half2 x = __floats2half2_rn(a, b), y = __floats2half2_rn(c, d);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&x), *reinterpret_cast<uint32_t*>(&y));
+}
 
 // tokens: x[b][1 + p][col] = acc + bias[col] + pos[p][col]   (row r = b*P + p)
 struct EpiPatch : EpiBase {
+  static constexpr bool kCoalesced = true;
   float* x; const float* bias; const float* pos; int P, D;
+  __device__ __forceinline__ void vec4(int, int r, int col, float4 v) const {
+    const int b = r / P, p = r - b * P;
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col)), pp = __ldg(reinterpret_cast<const float4*>(pos + (size_t)p * D + col));
+    *reinterpret_cast<float4*>(x + ((size_t)b * (P + 1) + 1 + p) * D + col) =
+        make_float4(v.x + bb.x + pp.x, v.y + bb.y + pp.y, v.z + bb.z + pp.z, v.w + bb.w + pp.w);
+  }
   __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
     const int b = r / P, p = r - b * P;
     float* o = x + ((size_t)b * (P + 1) + 1 + p) * D + col0;
@@ -191,7 +203,18 @@ struct EpiQKV : EpiBase {
 
 // qkv for the fused attention: fp16 q [b][hd][n][64] (scaled 1/8), k [b][hd][n][64], vT [b][hd][64][n] (pitch N1p)
 struct EpiQKV16 : EpiBase {
+  static constexpr bool kCoalesced = true;
   __half* q; __half* k; __half* vT; const float* bias; int N1, D, heads, N1p; float qscale;
+  // v goes out transposed ([d][n]): thread-per-row already writes consecutive n per lane -> keep the direct call there
+  __device__ __forceinline__ bool direct(int col0) const { return col0 >= 2 * D; }
+  __device__ __forceinline__ void vec4(int, int r, int col, float4 v) const {
+    const int b = r / N1, n = r - b * N1;
+    const int which = col / D, c = col - which * D, hd = c / HD, e0 = c - hd * HD;
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col));
+    const float sc = which == 0 ? qscale : 1.f;
+    __half* o = (which == 0 ? q : k) + (((size_t)b * heads + hd) * N1 + n) * HD + e0;
+    *reinterpret_cast<uint2*>(o) = pack_half4((v.x + bb.x) * sc, (v.y + bb.y) * sc, (v.z + bb.z) * sc, (v.w + bb.w) * sc);
+  }
   __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
     const int b = r / N1, n = r - b * N1;
     const int which = col0 / D, c = col0 - which * D, hd = c / HD, e0 = c - hd * HD;
@@ -244,7 +267,15 @@ struct EpiPV : EpiBase {
 
 // x[r][col] += ls[col] * (acc + bias[col])
 struct EpiResidual : EpiBase {
+  static constexpr bool kCoalesced = true;
   float* x; const float* bias; const float* ls; int D;
+  __device__ __forceinline__ void vec4(int, int r, int col, float4 v) const {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col)), ll = __ldg(reinterpret_cast<const float4*>(ls + col));
+    float4* o = reinterpret_cast<float4*>(x + (size_t)r * D + col);
+    float4 xv = *o;
+    xv.x += (v.x + bb.x) * ll.x; xv.y += (v.y + bb.y) * ll.y; xv.z += (v.z + bb.z) * ll.z; xv.w += (v.w + bb.w) * ll.w;
+    *o = xv;
+  }
   __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
     float* o = x + (size_t)r * D + col0;
 #pragma unroll
@@ -261,7 +292,16 @@ struct EpiResidual : EpiBase {
 // h[r][col] = gelu(acc + bias[col])   (exact: 0.5 x (1 + erf(x / sqrt 2)))
 template <typename OutT>
 struct EpiGelu : EpiBase {
+  static constexpr bool kCoalesced = true;
   OutT* h; const float* bias; int ld;
+  __device__ __forceinline__ void vec4(int, int r, int col, float4 v) const {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col));
+    float t[4] = {v.x + bb.x, v.y + bb.y, v.z + bb.z, v.w + bb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = 0.5f * t[j] * (1.f + erff(t[j] * 0.70710678118654752f));
+    if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(h + (size_t)r * ld + col) = make_float4(t[0], t[1], t[2], t[3]);
+    else *reinterpret_cast<uint2*>(h + (size_t)r * ld + col) = pack_half4(t[0], t[1], t[2], t[3]);
+  }
   __device__ __forceinline__ void operator()(State&, int, int r, int col0, const float (&f)[32], int ncols) const {
     OutT* o = h + (size_t)r * ld + col0;
     float gl[32];
