@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--C", type=int, default=1024, help="feature dim: 1024 = ViT-L/14@15 (shipped config), 768 = ViT-B/14")
     ap.add_argument("--nq", type=int, default=256)
     ap.add_argument("--noise", type=float, default=0.25)
-    ap.add_argument("--chunk-maps", type=int, default=4096)
+    ap.add_argument("--chunk-maps", type=int, default=16384)
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp32"],
                     help="wide correlation groups: tcgen05 3xTF32 tensor cores, or the exact-fp32 FFMA GEMM")
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the cpu_baseline leg")
@@ -236,6 +236,8 @@ def run_b200(args):
     del feats
     from bench_inputs import sharp_head
     model.tracker_head.load_state_dict(sharp_head(0))
+    from dino_tracker_b200 import model_inference as _mi_mod
+    _mi_mod.DEFAULT_CHUNK_MAPS = args.chunk_maps
     mi = ModelInference(model, model.range_normalizer, 0.7, 0.6)
     q_host = query_lattice(nq, 0).pin_memory()
     q_dev = q_host.to(dev)
@@ -369,7 +371,7 @@ def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks):
             "traffic": None, "note": "see roofline_other.corr_stream_probe"}
 
 
-def stage_timings(args, dev, _lib, peaks):
+def stage_timings(args, dev, _lib, peaks, vit_only=False):
     """Per-video preprocessing stages on real shapes (854x476): ViT feature extraction (a1), delta-DINO refinement
     (a2) and best-buddies (a13), device-timed.  Random-init weights of the named architectures."""
     from dino_tracker_b200.vit import DinoV2Features, CONFIGS
@@ -412,6 +414,8 @@ def stage_timings(args, dev, _lib, peaks):
                   "tflops": flops / (ms / 1000) / 1e12, "frac_of_bf16_peak": flops / (ms / 1000) / 1e12 / peaks["tf_sustained"],
                   "kernel_ms_per_call": prof, "math": "kind::f16 tcgen05 GEMMs (fp16 operands, fp32 accumulate, fp32 residual stream) + fused tcgen05 attention"}
     del ex, sd
+    if vit_only:
+        return out
     # delta-DINO with the shipped channel widths
     dd = DeltaDINO(channels=[3, 64, 128, 256, args.C]).to(dev)
     torch.nn.init.normal_(dd.layers[12].weight, std=0.01)

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "corr.cuh"
 #include "tcgemm.cuh"
+#include "tcgemm2.cuh"
 
 namespace dtk {
 
@@ -97,10 +98,14 @@ struct CorrEpi {
   const int* grp_map0;
   float* maps;
   int map_stride, P;
-  struct State {};
-  __device__ __forceinline__ void tile_begin(State&) const {}
-  __device__ __forceinline__ void tile_end(State&, int, int, int) const {}
-  __device__ __forceinline__ void operator()(State&, int g, int r, int col0, const float (&f)[32], int ncols) const {
+  float* tmax;             // optional [maps][n_tiles]: maximum of every (map, 256-token tile), for the head's fast path
+  int n_tiles;
+  struct State { float mx; };
+  __device__ __forceinline__ void tile_begin(State& s) const { s.mx = 0.f; }   // map values are >= 0 (ReLU)
+  __device__ __forceinline__ void tile_end(State& s, int g, int r, int nt) const {
+    if (tmax) tmax[(size_t)(grp_map0[g] + r) * n_tiles + nt] = s.mx + 0.f;   // + 0: never -0
+  }
+  __device__ __forceinline__ void operator()(State& s, int g, int r, int col0, const float (&f)[32], int ncols) const {
     const float dn = desc_norm[grp_row0[g] + r];
     const float* fn = norms + (size_t)grp_frame[g] * P + col0;
     float* out = maps + (size_t)(grp_map0[g] + r) * map_stride + col0;
@@ -115,14 +120,28 @@ struct CorrEpi {
         o.z = fmaxf(__fdiv_rn(f[i + 2], fmaxf(__fmul_rn(dn, n4.z), 1e-8f)), 0.f);
         o.w = fmaxf(__fdiv_rn(f[i + 3], fmaxf(__fmul_rn(dn, n4.w), 1e-8f)), 0.f);
         *reinterpret_cast<float4*>(out + i) = o;
+        s.mx = fmaxf(fmaxf(fmaxf(s.mx, o.x), fmaxf(o.y, o.z)), o.w);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (i < ncols) out[i] = fmaxf(__fdiv_rn(f[i], fmaxf(__fmul_rn(dn, fn[i]), 1e-8f)), 0.f);
+        if (i < ncols) {
+          const float o = fmaxf(__fdiv_rn(f[i], fmaxf(__fmul_rn(dn, fn[i]), 1e-8f)), 0.f);
+          out[i] = o;
+          s.mx = fmaxf(s.mx, o);
+        }
     }
   }
 };
+
+int corr_tc_tile_rows() {
+  static int rows = 0;
+  if (rows == 0) {
+    const char* e = getenv("DTK_CORR_PAIRS");
+    rows = (e && atoi(e) == 0) ? TC_BM : TC2_BM;
+  }
+  return rows;
+}
 
 size_t corr_tc_workspace_bytes(int total_rows, int C) { return 2 * align_up((size_t)total_rows * C * 2, 256); }
 
@@ -130,33 +149,47 @@ size_t corr_tc_workspace_bytes(int total_rows, int C) { return 2 * align_up((siz
 int launch_corr_gemm_tc(const void* tpc_hi, const void* tpc_lo, const float* norms, int T, int C, int P,
                         const float* desc, int desc_rows, const float* desc_norm, const int* grp_frame,
                         const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
-                        int max_tiles, float* maps, int map_stride, float* desc_split_ws, cudaStream_t st) {
+                        int max_tiles, float* maps, int map_stride, float* desc_split_ws, cudaStream_t st, float* tmax,
+                        bool split_ready) {
   using Cfg = TcCfg<TcMode::F16X3>;
+  static_assert(TC_BN == CORR_TILE, "the tile maxima are per GEMM N tile");
   DTK_CHECK_ARG(C % 8 == 0, "corr (tensor path): C must be a multiple of 8");
   char* d_hi = reinterpret_cast<char*>(desc_split_ws);
   char* d_lo = d_hi + align_up((size_t)desc_rows * C * 2, 256);
-  int rc = launch_split_f16(desc, d_hi, d_lo, (size_t)desc_rows * C, st);
+  int rc = split_ready ? DINOTRK_OK : launch_split_f16(desc, d_hi, d_lo, (size_t)desc_rows * C, st);
   if (rc) return rc;
+  const bool pairs = corr_tc_tile_rows() == TC2_BM;   // tile_start was planned with this M tile
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  const uint32_t b_box = pairs ? TC2_BN / 2 : TC_BN;   // a CTA of a pair stages half of the B tile
   if ((rc = make_tmap_2d(&tmA_hi, d_hi, desc_rows, C, TC_BM, Cfg::kBK, TMAP_F16))) return rc;
   if ((rc = make_tmap_2d(&tmA_lo, d_lo, desc_rows, C, TC_BM, Cfg::kBK, TMAP_F16))) return rc;
-  if ((rc = make_tmap_3d(&tmB_hi, tpc_hi, T, P, C, TC_BN, Cfg::kBK, TMAP_F16))) return rc;
-  if ((rc = make_tmap_3d(&tmB_lo, tpc_lo, T, P, C, TC_BN, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tmB_hi, tpc_hi, T, P, C, b_box, Cfg::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tmB_lo, tpc_lo, T, P, C, b_box, Cfg::kBK, TMAP_F16))) return rc;
   static bool attr = false;
   if (!attr) {
     DTK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TcMode::F16X3, CorrEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmem));
+    DTK_CUDA(cudaFuncSetAttribute(tc_gemm2_kernel<TcMode::F16X3, CorrEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Tc2Cfg<TcMode::F16X3>::kSmem));
     attr = true;
   }
   TcProblem pb{grp_frame, grp_row0, grp_m, tile_start, n_groups, P, C};
-  CorrEpi epi{norms, desc_norm, grp_frame, grp_row0, grp_map0, maps, map_stride, P};
+  CorrEpi epi{norms, desc_norm, grp_frame, grp_row0, grp_map0, maps, map_stride, P, tmax, cdiv(P, CORR_TILE)};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int tiles_bound = max_tiles * cdiv(P, TC_BN);
+  ProfRange pr(PROF_CORR_GEMM, st);
+  if (pairs) {
+    int grid = 2 * (tiles_bound < sms / 2 ? tiles_bound : sms / 2);
+    if (grid < 2) grid = 2;
+    tc_gemm2_kernel<TcMode::F16X3, CorrEpi><<<grid, TC_THREADS, Tc2Cfg<TcMode::F16X3>::kSmem, st>>>(tmA_hi, tmA_lo, tmB_hi,
+                                                                                                   tmB_lo, pb, epi);
+    DTK_LAUNCHED();
+    return DINOTRK_OK;
+  }
   int grid = tiles_bound < sms ? tiles_bound : sms;
   if (grid < 1) grid = 1;
-  ProfRange pr(PROF_CORR_GEMM, st);
   tc_gemm_kernel<TcMode::F16X3, CorrEpi><<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, pb, epi);
   DTK_LAUNCHED();
   return DINOTRK_OK;

@@ -25,9 +25,8 @@
 
 namespace dtk {
 
-#ifndef DTK_FA_POLY_EVERY
-#define DTK_FA_POLY_EVERY 4   // 0: all exponentials on the MUFU
-#endif
+// POLY (template parameter of the kernel): bit k set -> the k-th fp16 pair of every 8 pairs takes the FMA-pipe exp2
+constexpr int FA_POLY_DEFAULT = 0x88;   // 25 %
 constexpr int FA_BQ = 128, FA_BKV = 64, FA_D = 64, FA_THREADS = 192;
 constexpr int FA_NV = 80;                          // V^T tile rows = MMA N: 64 head dims, one row of ones, 15 rows of zeros
 constexpr int FA_KV_STAGES = 3;
@@ -70,6 +69,7 @@ struct FlashParams {
   int out_f16;
 };
 
+template <int POLY>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, FlashParams fp) {
@@ -194,10 +194,18 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int i = 0; i < FA_BKV; ++i)
           if (kbase + i >= N1) v[i] = 0xff800000u;    // -inf: ignored by the max, exp2 -> 0
       }
-      float mx = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+      float mx;
+      {   // four independent FMNMX3 chains (the SMSP holds only two softmax warps: latency matters)
+        float m4[4];
 #pragma unroll
-      for (int i = 3; i + 1 < FA_BKV; i += 2) mx = fmax3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-      mx = fmaxf(mx, __uint_as_float(v[FA_BKV - 1]));
+        for (int k = 0; k < 4; ++k) {
+          m4[k] = fmax3(__uint_as_float(v[16 * k]), __uint_as_float(v[16 * k + 1]), __uint_as_float(v[16 * k + 2]));
+#pragma unroll
+          for (int i = 3; i + 1 < 16; i += 2) m4[k] = fmax3(m4[k], __uint_as_float(v[16 * k + i]), __uint_as_float(v[16 * k + i + 1]));
+          m4[k] = fmaxf(m4[k], __uint_as_float(v[16 * k + 15]));
+        }
+        mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+      }
       // lazy running max: move it (and rescale the TMEM accumulator, row sums included) only on a 2^8 overshoot
       if (__any_sync(0xffffffffu, mx > m_run + FA_RESCALE_STEP)) {
         const float m_new = fmaxf(m_run, mx);
@@ -230,7 +238,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int i = 0; i < FA_BKV; i += 2) {
         const float x0 = __uint_as_float(v[i]) - m_run, x1 = __uint_as_float(v[i + 1]) - m_run;
         float p0, p1;
-        if (DTK_FA_POLY_EVERY > 0 && (i / 2) % DTK_FA_POLY_EVERY == DTK_FA_POLY_EVERY - 1) { p0 = poly_exp2(x0); p1 = poly_exp2(x1); }
+        if ((POLY >> ((i / 2) & 7)) & 1) { p0 = poly_exp2(x0); p1 = poly_exp2(x1); }
         else { p0 = fast_exp2(x0); p1 = fast_exp2(x1); }
         __half2 h = __floats2half2_rn(p0, p1);
         packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);

@@ -304,26 +304,68 @@ head_kernel(const float* __restrict__ maps, int n_maps_arg, const int* __restric
 // Fast path: exact refiner on the 11x11 box around the arg-max + certified absence of the fallback branch.
 constexpr int WIN_THREADS = 128;
 constexpr int WB = 11, WH = 13, WM = 15;  // box, hidden window, input window (side lengths); disc radius <= 5 tokens
+constexpr int WHC = 20;   // hidden window is stored [position][16 channels] with a 20-float pitch: float4 accesses of
+                          // consecutive positions fall into distinct bank groups
 
+// TM = true: the correlation GEMM already reduced every 256-token tile of the map to its maximum (tmax, corr.cuh), so the
+// arg-max and the largest value outside the 7x7 core come from ~1.3 k tokens instead of two passes over all 8107, and the
+// map is never staged in shared memory (12 KB instead of 44 KB per CTA: 16 CTAs per SM).
+template <bool TM>
 __global__ void __launch_bounds__(WIN_THREADS)
-head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_head_weights wts,
-                   const int* __restrict__ out_index, float* __restrict__ out, int* __restrict__ aux,
-                   int* __restrict__ slow_list, int* __restrict__ slow_count) {
+head_window_kernel(const float* __restrict__ maps, const float* __restrict__ tmax, int n_tiles, int n_maps, HeadParams hp,
+                   dinotrk_head_weights wts, const int* __restrict__ out_index, float* __restrict__ out,
+                   int* __restrict__ aux, int* __restrict__ slow_list, int* __restrict__ slow_count) {
   extern __shared__ __align__(16) float smem[];
-  const int lin_elems = (hp.map_stride + 3) & ~3;
-  float* lin = smem;                           // one map (several CTAs per SM hide the load latency)
+  const int lin_elems = TM ? 0 : (hp.map_stride + 3) & ~3;
+  float* lin = smem;                           // one map (several CTAs per SM hide the load latency); unused when TM
   float* sm_m = smem + lin_elems;              // [WM][WM] input window, zero outside the map
-  float* sm_h = sm_m + WM * WM + 3;            // [16][WH][WH] hidden window, zero outside the map
-  float* sm_red = sm_h + 16 * WH * WH;         // partials
+  float* sm_h = sm_m + WM * WM + 3;            // [WH * WH][WHC] hidden window (channel-innermost), zero outside the map
+  float* sm_red = sm_h + WHC * WH * WH;        // partials
   unsigned long long* sm_key = reinterpret_cast<unsigned long long*>(sm_red + 32);  // [4]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = hp.h, w = hp.w, P = hp.P;
   const int nchunks = hp.map_stride / 4;       // float4 chunks; the tail of the last chunk (>= P) is masked below
 
   for (int map = blockIdx.x; map < n_maps; map += gridDim.x) {
+    const float* src = TM ? maps + (size_t)map * hp.map_stride : lin;   // where map values are read from below
+    int amax;
+    float mout_tiles = 0.f;   // TM: largest tile maximum among the tiles that do not touch the core rows
+    int tok_lo = 0, tok_n = 0;   // TM: token range of the tiles that do
+    if constexpr (TM) {
+      const float* tm = tmax + (size_t)map * n_tiles;
+      if (__ldg(tm) < 0.f) {   // thin group (streaming kernel): no tile maxima -> full-map kernel
+        if (tid == 0) slow_list[atomicAdd(slow_count, 1)] = map;
+        continue;
+      }
+      // every warp redundantly: (max, first tile holding it), then the first token of that tile equal to the max
+      unsigned long long key = 0ull;
+      for (int t = lane; t < n_tiles; t += 32) {
+        unsigned long long k = ((unsigned long long)__float_as_uint(__ldg(tm + t) + 0.f) << 32) | (unsigned)(0x7fffffff - t);
+        key = k > key ? k : key;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
+      const int wt = 0x7fffffff - (int)(key & 0xffffffffu);
+      const float vmax = __uint_as_float((unsigned)(key >> 32));
+      int cand = 0x7fffffff;
+      for (int i = lane; i < CORR_TILE; i += 32) {
+        const int p = wt * CORR_TILE + i;
+        if (p < P && __ldg(src + p) + 0.f == vmax) cand = min(cand, p);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+      amax = cand < P ? cand : wt * CORR_TILE;   // (always found: the tile maximum is one of the stored values)
+      const int ar = amax / w, ac = amax - ar * w;
+      const int t_lo = (max(ar - 3, 0) * w + max(ac - 3, 0)) / CORR_TILE;
+      const int t_hi = (min(ar + 3, h - 1) * w + min(ac + 3, w - 1)) / CORR_TILE;
+      for (int t = lane; t < n_tiles; t += 32)
+        if (t < t_lo || t > t_hi) mout_tiles = fmaxf(mout_tiles, __ldg(tm + t));
+      tok_lo = t_lo * CORR_TILE;
+      tok_n = min((t_hi + 1) * CORR_TILE, P) - tok_lo;
+    } else {
     {
-      const float4* src = reinterpret_cast<const float4*>(maps + (size_t)map * hp.map_stride);
-      for (int i = tid; i < nchunks; i += WIN_THREADS) cp_async16_head(lin + 4 * i, src + i);
+      const float4* gsrc = reinterpret_cast<const float4*>(maps + (size_t)map * hp.map_stride);
+      for (int i = tid; i < nchunks; i += WIN_THREADS) cp_async16_head(lin + 4 * i, gsrc + i);
       asm volatile("cp.async.commit_group;\n" ::);
       asm volatile("cp.async.wait_group 0;\n" ::);
     }
@@ -353,10 +395,11 @@ head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, di
     for (int k = 1; k < WIN_THREADS / 32; ++k) { unsigned long long t = sm_key[k]; kb = t > kb ? t : kb; }
     const int wchunk = 0x7fffffff - (int)(kb & 0xffffffffu);
     const float vmax = __uint_as_float((unsigned)(kb >> 32));
-    int amax = 4 * wchunk;
+    amax = 4 * wchunk;
     {
       const float* q = lin + 4 * wchunk;
       amax += (q[0] + 0.f == vmax) ? 0 : (q[1] + 0.f == vmax) ? 1 : (q[2] + 0.f == vmax) ? 2 : 3;
+    }
     }
     const int arow = amax / w, acol = amax - arow * w;
 
@@ -364,11 +407,11 @@ head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, di
     for (int i = tid; i < WM * WM; i += WIN_THREADS) {
       int y = i / WM, x = i - y * WM;
       int r = arow - 7 + y, c = acol - 7 + x;
-      sm_m[i] = (r >= 0 && r < h && c >= 0 && c < w) ? lin[r * w + c] : 0.f;
+      sm_m[i] = (r >= 0 && r < h && c >= 0 && c < w) ? src[r * w + c] : 0.f;
     }
     __syncthreads();
     // ---- largest map value outside the 7x7 core: blank the core in the private copy, then a plain max ----
-    if (tid < 49) {
+    if (!TM && tid < 49) {
       int r = arow - 3 + tid / 7, c = acol - 3 + tid % 7;
       if (r >= 0 && r < h && c >= 0 && c < w) lin[r * w + c] = 0.f;
     }
@@ -382,24 +425,43 @@ head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, di
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) mw[ky * 3 + kx] = sm_m[(y + ky) * WM + x + kx];
-#pragma unroll 4
-      for (int o = 0; o < 16; ++o) {
-        float a = wts.b1[o];
+      float4* hrow = reinterpret_cast<float4*>(sm_h + i * WHC);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) a = fmaf(wts.w1[o][k], mw[k], a);
-        sm_h[o * WH * WH + i] = inside ? fmaxf(a, 0.f) : 0.f;
+      for (int o4 = 0; o4 < 4; ++o4) {
+        float a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = o4 * 4 + j;
+          a[j] = wts.b1[o];
+#pragma unroll
+          for (int k = 0; k < 9; ++k) a[j] = fmaf(wts.w1[o][k], mw[k], a[j]);
+          a[j] = inside ? fmaxf(a[j], 0.f) : 0.f;
+        }
+        hrow[o4] = make_float4(a[0], a[1], a[2], a[3]);
       }
     }
     __syncthreads();
-    float mout = 0.f;
-    for (int i = tid; i < nchunks; i += WIN_THREADS) {
-      float4 v = *reinterpret_cast<const float4*>(lin + 4 * i);
-      const int base = 4 * i;
-      float m4 = v.x;
-      if (base + 1 < P) m4 = fmaxf(m4, v.y);
-      if (base + 2 < P) m4 = fmaxf(m4, v.z);
-      if (base + 3 < P) m4 = fmaxf(m4, v.w);
-      mout = fmaxf(mout, m4);
+    float mout = mout_tiles;
+    if constexpr (TM) {
+      // tokens of the tiles that touch the core rows, core excluded; row by row (no division per token)
+      const int r_lo = tok_lo / w, r_hi = (tok_lo + tok_n - 1) / w;
+      for (int r = r_lo; r <= r_hi; ++r) {
+        const bool core_row = abs(r - arow) <= 3;
+        for (int c = tid; c < w; c += WIN_THREADS) {
+          const int p = r * w + c;
+          if (p >= tok_lo && p < tok_lo + tok_n && !(core_row && abs(c - acol) <= 3)) mout = fmaxf(mout, __ldg(src + p));
+        }
+      }
+    } else {
+      for (int i = tid; i < nchunks; i += WIN_THREADS) {
+        float4 v = *reinterpret_cast<const float4*>(lin + 4 * i);
+        const int base = 4 * i;
+        float m4 = v.x;
+        if (base + 1 < P) m4 = fmaxf(m4, v.y);
+        if (base + 2 < P) m4 = fmaxf(m4, v.z);
+        if (base + 3 < P) m4 = fmaxf(m4, v.w);
+        mout = fmaxf(mout, m4);
+      }
     }
     mout = warp_max(mout);
 
@@ -413,13 +475,23 @@ head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, di
       valid = r >= 0 && r < h && c >= 0 && c < w;
       if (valid) {
         float a = wts.b2;
-#pragma unroll 4
-        for (int o = 0; o < 16; ++o) {
-          const float* hb = sm_h + o * WH * WH + y * WH + x;
+        // same accumulation order as before: channel-major, then the 3 x 3 taps
+#pragma unroll
+        for (int o4 = 0; o4 < 4; ++o4) {
+          float4 hv[9];
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) a = fmaf(wts.w2[o][ky * 3 + kx], hb[ky * WH + kx], a);
+            for (int kx = 0; kx < 3; ++kx)
+              hv[ky * 3 + kx] = *reinterpret_cast<const float4*>(sm_h + ((y + ky) * WH + x + kx) * WHC + o4 * 4);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) a = fmaf(wts.w2[o4 * 4 + 0][k], hv[k].x, a);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) a = fmaf(wts.w2[o4 * 4 + 1][k], hv[k].y, a);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) a = fmaf(wts.w2[o4 * 4 + 2][k], hv[k].z, a);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) a = fmaf(wts.w2[o4 * 4 + 3][k], hv[k].w, a);
         }
         z = a;
         int dr = (r - arow) * hp.stride_px, dc = (c - acol) * hp.stride_px;
@@ -477,7 +549,7 @@ __global__ void zero_int_kernel(int* p) { *p = 0; }
 
 int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geom& g,
                 const dinotrk_head_weights& hw, const int* out_index, float* out, int out_stride, int out_mode,
-                int* aux, int* scratch, cudaStream_t st) {
+                int* aux, int* scratch, cudaStream_t st, const float* tmax, bool counter_zeroed) {
   if (n_maps <= 0) return DINOTRK_OK;
   DTK_CHECK_ARG(g.w <= HEAD_MAX_W && g.h <= HEAD_MAX_H, "head: token grid %dx%d exceeds the supported %dx%d",
                 g.h, g.w, HEAD_MAX_H, HEAD_MAX_W);
@@ -500,23 +572,29 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
   int* slow_count = scratch;
   int* slow_list = scratch ? scratch + 1 : nullptr;
   if (window_ok) {
-    size_t smem = (size_t)(lin_elems + WM * WM + 3 + 16 * WH * WH + 32) * sizeof(float) + 4 * sizeof(unsigned long long);
+    const bool tm = tmax != nullptr;
+    size_t smem = (size_t)((tm ? 0 : lin_elems) + WM * WM + 3 + WHC * WH * WH + 32) * sizeof(float) + 4 * sizeof(unsigned long long);
     static size_t attr_w = 0;
-    if (smem > attr_w) {
-      DTK_CUDA(cudaFuncSetAttribute(head_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!tm && smem > attr_w) {
+      DTK_CUDA(cudaFuncSetAttribute(head_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_w = smem;
     }
-    {
+    if (!counter_zeroed) {
       ProfRange pr(PROF_MISC, st);
       zero_int_kernel<<<1, 1, 0, st>>>(slow_count);
       DTK_LAUNCHED();
     }
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > (tm ? 16 : 8)) per_sm = tm ? 16 : 8;
     int grid = n_maps < sms * per_sm ? n_maps : sms * per_sm;
     ProfRange pr(PROF_HEAD, st);
-    head_window_kernel<<<grid, WIN_THREADS, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux, slow_list, slow_count);
+    if (tm)
+      head_window_kernel<true><<<grid, WIN_THREADS, smem, st>>>(maps, tmax, cdiv(hp.P, CORR_TILE), n_maps, hp, hw, out_index,
+                                                                out, aux, slow_list, slow_count);
+    else
+      head_window_kernel<false><<<grid, WIN_THREADS, smem, st>>>(maps, nullptr, 0, n_maps, hp, hw, out_index, out, aux,
+                                                                 slow_list, slow_count);
     DTK_LAUNCHED();
   }
   // full-map kernel: every map (no scratch) or only the maps the window kernel could not certify

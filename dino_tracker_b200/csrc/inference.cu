@@ -119,7 +119,8 @@ __global__ void sample_anchor_kernel(const float* __restrict__ tpc, int T, int C
                                      const float* __restrict__ traj, const int* __restrict__ qlist, int N,
                                      const int* __restrict__ grp_frame, const int* __restrict__ grp_map0,
                                      const int* __restrict__ grp_item0, int n_groups, int frame_batch,
-                                     float* __restrict__ desc, float* __restrict__ dnorm, int* __restrict__ out_index) {
+                                     float* __restrict__ desc, float* __restrict__ dnorm, int* __restrict__ out_index,
+                                     __half* __restrict__ desc_hi, __half* __restrict__ desc_lo) {
   const int j = blockIdx.x;
   int lo = 0, hi = n_groups - 1;
   while (lo < hi) {
@@ -138,7 +139,8 @@ __global__ void sample_anchor_kernel(const float* __restrict__ tpc, int T, int C
   TriCorners c = tri_setup(x, y, (float)(i - i0 + 1), Nset, h, w);
   int f0 = c.z0 == 0 ? a : i0 + c.z0 - 1;
   int f1 = c.z1 < 0 ? -1 : (c.z1 == 0 ? a : i0 + c.z1 - 1);
-  sample_point(tpc, C, P, c, f0, f1, desc + (size_t)j * C, dnorm + j);
+  sample_point(tpc, C, P, c, f0, f1, desc + (size_t)j * C, dnorm + j, desc_hi ? desc_hi + (size_t)j * C : nullptr,
+               desc_lo ? desc_lo + (size_t)j * C : nullptr);
   if (threadIdx.x == 0) out_index[j] = (n * T + a) * T + i;
 }
 
@@ -266,6 +268,7 @@ size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N,
   b += align_up((size_t)T * 4, 256) + align_up((size_t)T * N * 4, 256);    // cnt, qlist
   b += corr_tc_workspace_bytes((int)(ch > (size_t)N ? ch : (size_t)N), C) + 256;  // TF32 split of the descriptors
   b += align_up((ch + 1) * 4, 256);                                        // head: list of uncertified maps
+  b += align_up(ch * (size_t)cdiv(g->h * g->w, CORR_TILE) * 4, 256);       // tile maxima of the chunk's maps
   return b + 4096;
 }
 
@@ -332,6 +335,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   const int gcap = T + 2;
   const PointAffine pa = make_point_affine(*g);
 
+  GroupBuf* gb_ptr = nullptr;
   Arena ar(workspace, workspace_bytes);
   float* descA = ar.take<float>((size_t)N * C);
   float* normA = ar.take<float>(N);
@@ -345,9 +349,16 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   int* d_qlist = ar.take<int>((size_t)T * N);
   float* split = ar.take<float>(corr_tc_workspace_bytes(ch > N ? ch : N, C) / 4);
   int* hscratch = ar.take<int>(ch + 1);
+  float* tmax = ar.take<float>((size_t)ch * cdiv(P, CORR_TILE));
   DTK_CHECK_ARG(ar.ok(), "infer: workspace arena overflow");
+  const bool tensor = fv.tensor();   // tensor-core GEMM: tile maxima for the head, fp16 split fused into the samplers
+  auto thin_free = [&]() {
+    for (int k = 0; k < gb_ptr->n; ++k) if (gb_ptr->v[2 * gb_ptr->cap + k] <= STREAM_MAX_M) return false;
+    return true;
+  };
 
   GroupBuf gb(gcap);
+  gb_ptr = &gb;
   auto upload_groups = [&]() -> int {
     DTK_CUDA(cudaMemcpyAsync(d_grp, gb.v.data(), (size_t)5 * gcap * sizeof(int), cudaMemcpyHostToDevice, st));
     return DINOTRK_OK;
@@ -360,6 +371,11 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
     ProfRange pr(PROF_SAMPLE, st);
     sample_query_kernel<<<N, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, query_points, descA, normA);
     DTK_LAUNCHED();
+  }
+  if (tensor) {   // the query descriptors are reused by every chunk: split them once
+    char* a_hi = reinterpret_cast<char*>(split);
+    int rc = launch_split_f16(descA, a_hi, a_hi + align_up((size_t)N * C * 2, 256), (size_t)N * C, st);
+    if (rc) return rc;
   }
   {
     int t = 0, row = 0;  // next work item: (frame t, query row)
@@ -381,9 +397,11 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
         index_traj_kernel<<<cdiv(used, 256), 256, 0, st>>>(gf, gr, gmap, gb.n, used, T, out_index, traj);
         DTK_LAUNCHED();
       }
-      rc = launch_corr_maps(fv, descA, N, normA, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, split, st);
+      CorrAssist as;
+      as.tmax = tensor ? tmax : nullptr; as.zero_word = hscratch; as.split_ready = tensor; as.no_thin = thin_free();
+      rc = launch_corr_maps(fv, descA, N, normA, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, split, st, as);
       if (rc) return rc;
-      rc = launch_head(maps, used, ms, *g, *hw, out_index, traj, 3, 0, nullptr, hscratch, st);
+      rc = launch_head(maps, used, ms, *g, *hw, out_index, traj, 3, 0, nullptr, hscratch, st, as.tmax, true);
       if (rc) return rc;
     }
   }
@@ -429,13 +447,19 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
       if (rc) return rc;
       {
         ProfRange pr(PROF_SAMPLE, st);
+        // the split layout of launch_corr_gemm_tc for desc_rows = used: hi rows, then lo rows at the next 256-byte boundary
+        __half* c_hi = tensor ? reinterpret_cast<__half*>(split) : nullptr;
+        __half* c_lo = tensor ? reinterpret_cast<__half*>(reinterpret_cast<char*>(split) + align_up((size_t)used * C * 2, 256))
+                              : nullptr;
         sample_anchor_kernel<<<used, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, traj, d_qlist, N, gf, gmap,
-                                                             gitem, gb.n, fb, descC, normC, out_index);
+                                                             gitem, gb.n, fb, descC, normC, out_index, c_hi, c_lo);
         DTK_LAUNCHED();
       }
-      rc = launch_corr_maps(fv, descC, used, normC, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, split, st);
+      CorrAssist as;
+      as.tmax = tensor ? tmax : nullptr; as.zero_word = hscratch; as.split_ready = tensor; as.no_thin = thin_free();
+      rc = launch_corr_maps(fv, descC, used, normC, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, split, st, as);
       if (rc) return rc;
-      rc = launch_head(maps, used, ms, *g, *hw, out_index, anchors, 2, 0, nullptr, hscratch, st);
+      rc = launch_head(maps, used, ms, *g, *hw, out_index, anchors, 2, 0, nullptr, hscratch, st, as.tmax, true);
       if (rc) return rc;
     }
   }

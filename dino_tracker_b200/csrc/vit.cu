@@ -507,14 +507,23 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
       if ((rc = make_tmap_2d(&tmQ, q16, (uint64_t)B * heads * N1, HD, FA_BQ, HD, TMAP_F16))) return rc;
       if ((rc = make_tmap_3d(&tmK, k16, (uint64_t)B * heads, N1, HD, FA_BKV, HD, TMAP_F16))) return rc;
       if ((rc = make_tmap_3d(&tmV, v16, (uint64_t)B * heads, HD, N1, HD, 64, TMAP_F16, (uint64_t)N1p8))) return rc;
-      static bool fattr = false;
-      if (!fattr) {
-        DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        fattr = true;
+      // share of the exponentials evaluated on the FMA pipe (DTK_FA_POLY = 0 / 25 / 37 / 50 %, default 25)
+      static int poly = -1;
+      if (poly < 0) {
+        const char* e = getenv("DTK_FA_POLY");
+        poly = e ? atoi(e) : 25;
+        DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0xA8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0xAA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
       }
       FlashParams fpar{N1, D, heads, f16 ? (void*)y16 : (void*)y, f16 ? 1 : 0};
       ProfRange pr(PROF_VIT_ATTN, st);
-      flash_attn_kernel<<<dim3(cdiv(N1, FA_BQ), B * heads), FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
+      const dim3 fgrid(cdiv(N1, FA_BQ), B * heads);
+      if (poly <= 0) flash_attn_kernel<0><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
+      else if (poly <= 25) flash_attn_kernel<0x88><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
+      else if (poly <= 37) flash_attn_kernel<0xA8><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
+      else flash_attn_kernel<0xAA><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
       DTK_LAUNCHED();
     } else {
       if ((rc = run_gemm<EpiQKV, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, EpiQKV{{}, q, k, vT, w[3], N1, D, heads, N1p},

@@ -15,7 +15,7 @@ from . import _lib
 from .range_normalizer import RangeNormalizer
 from .tracker import Tracker
 
-DEFAULT_CHUNK_MAPS = 4096
+DEFAULT_CHUNK_MAPS = 16384   # maps per correlation/head chunk (32 KB each at 854x476); clamped to the work of the call
 
 
 # ---- module-level helpers (models/model_inference.py:8-74) -------------------------------------
@@ -53,7 +53,10 @@ def generate_trajectories(query_points, video, model, range_normalizer, dst_rang
 
 
 def _run_phases(model: Tracker, query_points, start, stop, batch_size, anchor_th=0.5, cos_th=0.5, traj=None,
-                cos_sims=None, anchors=None, use_raw_features=False, chunk_maps=DEFAULT_CHUNK_MAPS):
+                cos_sims=None, anchors=None, use_raw_features=False, chunk_maps=None):
+    if chunk_maps is None:
+        chunk_maps = DEFAULT_CHUNK_MAPS   # module attribute: read at call time (bench.py --chunk-maps sets it)
+    chunk_maps = int(min(chunk_maps, max(256, query_points.shape[0] * model.video.shape[0] ** 2)))
     lib = _lib.load()
     dev = model._dev
     if use_raw_features:
