@@ -28,13 +28,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // prefix of 128-row tiles per group; thin groups (m <= stream_max) get 0 GEMM tiles.
 __global__ void corr_plan_kernel(const int* __restrict__ grp_m, int n_groups, int stream_max, int tile_rows,
-                                 int* __restrict__ tile_start, const int* __restrict__ grp_map0, float* __restrict__ tmax,
+                                 int* __restrict__ tile_start, const int* __restrict__ grp_map0, unsigned long long* __restrict__ tkeys,
                                  int n_tiles, int* __restrict__ zero_word) {
-  if (tmax != nullptr) {   // maps of thin groups get no tile maxima from the streaming kernel: mark them
+  if (tkeys != nullptr) {   // maps of thin groups get no tile keys from the streaming kernel: mark them
     for (int k = 0; k < n_groups; ++k) {
       const int m = grp_m[k];
       if (m <= stream_max)
-        for (int r = threadIdx.x; r < m; r += blockDim.x) tmax[(size_t)(grp_map0[k] + r) * n_tiles] = -1.f;
+        for (int r = threadIdx.x; r < m; r += blockDim.x) tkeys[(size_t)(grp_map0[k] + r) * n_tiles] = ~0ull;
     }
   }
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -246,16 +246,16 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
                      int total_maps, int max_group_m, float* maps, int map_stride, int* tile_start, float* split_ws,
                      cudaStream_t st, const CorrAssist& assist) {
   if (n_groups <= 0 || total_maps <= 0) return DINOTRK_OK;
-  float* tmax = fv.tensor() ? assist.tmax : nullptr;
+  unsigned long long* tkeys = fv.tensor() ? assist.tkeys : nullptr;
   const int tile_rows = fv.tensor() ? corr_tc_tile_rows() : BM;   // rows per GEMM M tile (256 on CTA pairs)
   const int n_tiles = cdiv(fv.P, CORR_TILE);
   const float* tpc = fv.tpc;
   const float* norms = fv.norms;
   const int C = fv.C, P = fv.P;
   const int stream_max = STREAM_MAX_M;
-  if (max_group_m > stream_max || tmax != nullptr || assist.zero_word != nullptr) {
+  if (max_group_m > stream_max || tkeys != nullptr || assist.zero_word != nullptr) {
     ProfRange pr(PROF_MISC, st);
-    corr_plan_kernel<<<1, 32, 0, st>>>(grp_m, n_groups, stream_max, tile_rows, tile_start, grp_map0, tmax, n_tiles,
+    corr_plan_kernel<<<1, 32, 0, st>>>(grp_m, n_groups, stream_max, tile_rows, tile_start, grp_map0, tkeys, n_tiles,
                                        assist.zero_word);
     DTK_LAUNCHED();
   }
@@ -264,7 +264,7 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
     int max_tiles = total_maps / tile_rows + n_groups;
     if (fv.tensor()) {
       int rc = launch_corr_gemm_tc(fv.hi, fv.lo, norms, fv.T, C, P, desc, desc_rows, desc_norm, grp_frame, grp_row0,
-                                   grp_m, grp_map0, tile_start, n_groups, max_tiles, maps, map_stride, split_ws, st, tmax,
+                                   grp_m, grp_map0, tile_start, n_groups, max_tiles, maps, map_stride, split_ws, st, tkeys,
                                    assist.split_ready);
       if (rc) return rc;
     } else {

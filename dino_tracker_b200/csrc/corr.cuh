@@ -18,14 +18,15 @@ static inline FeatView make_view(const dinotrk_features& f, const dinotrk_geom& 
 constexpr int CORR_TILE = 256;   // token tile of the tensor-core correlation GEMM (= TC_BN); unit of the tile maxima
 
 // Optional by-products / shortcuts of one launch_corr_maps call (all members may stay zero):
-//   tmax        [total_maps][cdiv(P, CORR_TILE)]: per-map maxima of every 256-token tile, written by the GEMM epilogue
-//               (maps of thin groups, which the streaming kernel computes, get -1 in tile 0 = "no tile maxima");
-//               only produced on the tensor path (fv.tensor()).
+//   tkeys       [total_maps][cdiv(P, CORR_TILE)]: per map and 256-token tile, (bits of the tile maximum) << 32 |
+//               (0x7fffffff - first token holding it), written by the GEMM epilogue: the maximum over a map's keys is its
+//               first arg-max.  Maps of thin groups (streaming kernel) get ~0 in tile 0 = "no keys".  Only produced on
+//               the tensor path (fv.tensor()).
 //   zero_word   an int the plan kernel sets to 0 (the head's counter of uncertified maps: saves a launch)
 //   split_ready the fp16 hi/lo copies of `desc` are already in split_ws (written by the sampler): skip the split kernel
 //   no_thin     the caller knows that no group has <= STREAM_MAX_M descriptors: skip the streaming kernel launch
 struct CorrAssist {
-  float* tmax = nullptr;
+  unsigned long long* tkeys = nullptr;
   int* zero_word = nullptr;
   bool split_ready = false;
   bool no_thin = false;
@@ -44,12 +45,14 @@ int launch_corr_gemm_tc(const void* tpc_hi, const void* tpc_lo, const float* nor
                         const float* desc, int desc_rows, const float* desc_norm, const int* grp_frame,
                         const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
                         int max_tiles, float* maps, int map_stride, float* desc_split_ws, cudaStream_t st,
-                        float* tmax = nullptr, bool split_ready = false);
+                        unsigned long long* tkeys = nullptr, bool split_ready = false);
 int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st);
 
 int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geom& g,
                 const dinotrk_head_weights& hw, const int* out_index, float* out, int out_stride, int out_mode,
                 int* aux, int* scratch /* n_maps + 1 ints, or NULL: full-map kernel for every map */, cudaStream_t st,
-                const float* tmax = nullptr /* tile maxima of launch_corr_maps */, bool counter_zeroed = false);
+                const unsigned long long* tkeys = nullptr /* tile keys of launch_corr_maps */, bool counter_zeroed = false,
+                int ctas_per_sm = 0 /* > 0: cap of the fast-path grid (co-residency with a GEMM on another stream) */,
+                int parts = 3 /* bit 0: fast path over all maps, bit 1: full-map kernel over the uncertified ones */);
 
 }  // namespace dtk

@@ -98,12 +98,14 @@ struct CorrEpi {
   const int* grp_map0;
   float* maps;
   int map_stride, P;
-  float* tmax;             // optional [maps][n_tiles]: maximum of every (map, 256-token tile), for the head's fast path
+  unsigned long long* tkeys;   // optional [maps][n_tiles]: (tile maximum, first token holding it) keys for the head (corr.cuh)
   int n_tiles;
-  struct State { float mx; };
-  __device__ __forceinline__ void tile_begin(State& s) const { s.mx = 0.f; }   // map values are >= 0 (ReLU)
+  struct State { float mx; int tok; };
+  __device__ __forceinline__ void tile_begin(State& s) const { s.mx = -1.f; s.tok = 0; }   // map values are >= 0 (ReLU)
   __device__ __forceinline__ void tile_end(State& s, int g, int r, int nt) const {
-    if (tmax) tmax[(size_t)(grp_map0[g] + r) * n_tiles + nt] = s.mx + 0.f;   // + 0: never -0
+    if (tkeys)   // + 0.f: never the bit pattern of -0
+      tkeys[(size_t)(grp_map0[g] + r) * n_tiles + nt] =
+          ((unsigned long long)__float_as_uint(s.mx + 0.f) << 32) | (unsigned)(0x7fffffff - s.tok);
   }
   __device__ __forceinline__ void operator()(State& s, int g, int r, int col0, const float (&f)[32], int ncols) const {
     const float dn = desc_norm[grp_row0[g] + r];
@@ -120,7 +122,11 @@ struct CorrEpi {
         o.z = fmaxf(__fdiv_rn(f[i + 2], fmaxf(__fmul_rn(dn, n4.z), 1e-8f)), 0.f);
         o.w = fmaxf(__fdiv_rn(f[i + 3], fmaxf(__fmul_rn(dn, n4.w), 1e-8f)), 0.f);
         *reinterpret_cast<float4*>(out + i) = o;
-        s.mx = fmaxf(fmaxf(fmaxf(s.mx, o.x), fmaxf(o.y, o.z)), o.w);
+        // strict >: the first token of the tile holding the maximum (columns are visited in increasing order)
+        if (o.x > s.mx) { s.mx = o.x; s.tok = col0 + i; }
+        if (o.y > s.mx) { s.mx = o.y; s.tok = col0 + i + 1; }
+        if (o.z > s.mx) { s.mx = o.z; s.tok = col0 + i + 2; }
+        if (o.w > s.mx) { s.mx = o.w; s.tok = col0 + i + 3; }
       }
     } else {
 #pragma unroll
@@ -128,7 +134,7 @@ struct CorrEpi {
         if (i < ncols) {
           const float o = fmaxf(__fdiv_rn(f[i], fmaxf(__fmul_rn(dn, fn[i]), 1e-8f)), 0.f);
           out[i] = o;
-          s.mx = fmaxf(s.mx, o);
+          if (o > s.mx) { s.mx = o; s.tok = col0 + i; }
         }
     }
   }
@@ -149,8 +155,8 @@ size_t corr_tc_workspace_bytes(int total_rows, int C) { return 2 * align_up((siz
 int launch_corr_gemm_tc(const void* tpc_hi, const void* tpc_lo, const float* norms, int T, int C, int P,
                         const float* desc, int desc_rows, const float* desc_norm, const int* grp_frame,
                         const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
-                        int max_tiles, float* maps, int map_stride, float* desc_split_ws, cudaStream_t st, float* tmax,
-                        bool split_ready) {
+                        int max_tiles, float* maps, int map_stride, float* desc_split_ws, cudaStream_t st,
+                        unsigned long long* tkeys, bool split_ready) {
   using Cfg = TcCfg<TcMode::F16X3>;
   static_assert(TC_BN == CORR_TILE, "the tile maxima are per GEMM N tile");
   DTK_CHECK_ARG(C % 8 == 0, "corr (tensor path): C must be a multiple of 8");
@@ -174,7 +180,7 @@ int launch_corr_gemm_tc(const void* tpc_hi, const void* tpc_lo, const float* nor
     attr = true;
   }
   TcProblem pb{grp_frame, grp_row0, grp_m, tile_start, n_groups, P, C};
-  CorrEpi epi{norms, desc_norm, grp_frame, grp_row0, grp_map0, maps, map_stride, P, tmax, cdiv(P, CORR_TILE)};
+  CorrEpi epi{norms, desc_norm, grp_frame, grp_row0, grp_map0, maps, map_stride, P, tkeys, cdiv(P, CORR_TILE)};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

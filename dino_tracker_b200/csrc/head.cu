@@ -304,68 +304,26 @@ head_kernel(const float* __restrict__ maps, int n_maps_arg, const int* __restric
 // Fast path: exact refiner on the 11x11 box around the arg-max + certified absence of the fallback branch.
 constexpr int WIN_THREADS = 128;
 constexpr int WB = 11, WH = 13, WM = 15;  // box, hidden window, input window (side lengths); disc radius <= 5 tokens
-constexpr int WHC = 20;   // hidden window is stored [position][16 channels] with a 20-float pitch: float4 accesses of
-                          // consecutive positions fall into distinct bank groups
 
-// TM = true: the correlation GEMM already reduced every 256-token tile of the map to its maximum (tmax, corr.cuh), so the
-// arg-max and the largest value outside the 7x7 core come from ~1.3 k tokens instead of two passes over all 8107, and the
-// map is never staged in shared memory (12 KB instead of 44 KB per CTA: 16 CTAs per SM).
-template <bool TM>
 __global__ void __launch_bounds__(WIN_THREADS)
-head_window_kernel(const float* __restrict__ maps, const float* __restrict__ tmax, int n_tiles, int n_maps, HeadParams hp,
-                   dinotrk_head_weights wts, const int* __restrict__ out_index, float* __restrict__ out,
-                   int* __restrict__ aux, int* __restrict__ slow_list, int* __restrict__ slow_count) {
+head_window_kernel(const float* __restrict__ maps, int n_maps, HeadParams hp, dinotrk_head_weights wts,
+                   const int* __restrict__ out_index, float* __restrict__ out, int* __restrict__ aux,
+                   int* __restrict__ slow_list, int* __restrict__ slow_count) {
   extern __shared__ __align__(16) float smem[];
-  const int lin_elems = TM ? 0 : (hp.map_stride + 3) & ~3;
-  float* lin = smem;                           // one map (several CTAs per SM hide the load latency); unused when TM
+  const int lin_elems = (hp.map_stride + 3) & ~3;
+  float* lin = smem;                           // one map (several CTAs per SM hide the load latency)
   float* sm_m = smem + lin_elems;              // [WM][WM] input window, zero outside the map
-  float* sm_h = sm_m + WM * WM + 3;            // [WH * WH][WHC] hidden window (channel-innermost), zero outside the map
-  float* sm_red = sm_h + WHC * WH * WH;        // partials
+  float* sm_h = sm_m + WM * WM + 3;            // [16][WH][WH] hidden window, zero outside the map
+  float* sm_red = sm_h + 16 * WH * WH;         // partials
   unsigned long long* sm_key = reinterpret_cast<unsigned long long*>(sm_red + 32);  // [4]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = hp.h, w = hp.w, P = hp.P;
   const int nchunks = hp.map_stride / 4;       // float4 chunks; the tail of the last chunk (>= P) is masked below
 
   for (int map = blockIdx.x; map < n_maps; map += gridDim.x) {
-    const float* src = TM ? maps + (size_t)map * hp.map_stride : lin;   // where map values are read from below
-    int amax;
-    float mout_tiles = 0.f;   // TM: largest tile maximum among the tiles that do not touch the core rows
-    int tok_lo = 0, tok_n = 0;   // TM: token range of the tiles that do
-    if constexpr (TM) {
-      const float* tm = tmax + (size_t)map * n_tiles;
-      if (__ldg(tm) < 0.f) {   // thin group (streaming kernel): no tile maxima -> full-map kernel
-        if (tid == 0) slow_list[atomicAdd(slow_count, 1)] = map;
-        continue;
-      }
-      // every warp redundantly: (max, first tile holding it), then the first token of that tile equal to the max
-      unsigned long long key = 0ull;
-      for (int t = lane; t < n_tiles; t += 32) {
-        unsigned long long k = ((unsigned long long)__float_as_uint(__ldg(tm + t) + 0.f) << 32) | (unsigned)(0x7fffffff - t);
-        key = k > key ? k : key;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
-      const int wt = 0x7fffffff - (int)(key & 0xffffffffu);
-      const float vmax = __uint_as_float((unsigned)(key >> 32));
-      int cand = 0x7fffffff;
-      for (int i = lane; i < CORR_TILE; i += 32) {
-        const int p = wt * CORR_TILE + i;
-        if (p < P && __ldg(src + p) + 0.f == vmax) cand = min(cand, p);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
-      amax = cand < P ? cand : wt * CORR_TILE;   // (always found: the tile maximum is one of the stored values)
-      const int ar = amax / w, ac = amax - ar * w;
-      const int t_lo = (max(ar - 3, 0) * w + max(ac - 3, 0)) / CORR_TILE;
-      const int t_hi = (min(ar + 3, h - 1) * w + min(ac + 3, w - 1)) / CORR_TILE;
-      for (int t = lane; t < n_tiles; t += 32)
-        if (t < t_lo || t > t_hi) mout_tiles = fmaxf(mout_tiles, __ldg(tm + t));
-      tok_lo = t_lo * CORR_TILE;
-      tok_n = min((t_hi + 1) * CORR_TILE, P) - tok_lo;
-    } else {
     {
-      const float4* gsrc = reinterpret_cast<const float4*>(maps + (size_t)map * hp.map_stride);
-      for (int i = tid; i < nchunks; i += WIN_THREADS) cp_async16_head(lin + 4 * i, gsrc + i);
+      const float4* src = reinterpret_cast<const float4*>(maps + (size_t)map * hp.map_stride);
+      for (int i = tid; i < nchunks; i += WIN_THREADS) cp_async16_head(lin + 4 * i, src + i);
       asm volatile("cp.async.commit_group;\n" ::);
       asm volatile("cp.async.wait_group 0;\n" ::);
     }
@@ -395,11 +353,10 @@ head_window_kernel(const float* __restrict__ maps, const float* __restrict__ tma
     for (int k = 1; k < WIN_THREADS / 32; ++k) { unsigned long long t = sm_key[k]; kb = t > kb ? t : kb; }
     const int wchunk = 0x7fffffff - (int)(kb & 0xffffffffu);
     const float vmax = __uint_as_float((unsigned)(kb >> 32));
-    amax = 4 * wchunk;
+    int amax = 4 * wchunk;
     {
       const float* q = lin + 4 * wchunk;
       amax += (q[0] + 0.f == vmax) ? 0 : (q[1] + 0.f == vmax) ? 1 : (q[2] + 0.f == vmax) ? 2 : 3;
-    }
     }
     const int arow = amax / w, acol = amax - arow * w;
 
@@ -407,11 +364,11 @@ head_window_kernel(const float* __restrict__ maps, const float* __restrict__ tma
     for (int i = tid; i < WM * WM; i += WIN_THREADS) {
       int y = i / WM, x = i - y * WM;
       int r = arow - 7 + y, c = acol - 7 + x;
-      sm_m[i] = (r >= 0 && r < h && c >= 0 && c < w) ? src[r * w + c] : 0.f;
+      sm_m[i] = (r >= 0 && r < h && c >= 0 && c < w) ? lin[r * w + c] : 0.f;
     }
     __syncthreads();
     // ---- largest map value outside the 7x7 core: blank the core in the private copy, then a plain max ----
-    if (!TM && tid < 49) {
+    if (tid < 49) {
       int r = arow - 3 + tid / 7, c = acol - 3 + tid % 7;
       if (r >= 0 && r < h && c >= 0 && c < w) lin[r * w + c] = 0.f;
     }
@@ -425,43 +382,24 @@ head_window_kernel(const float* __restrict__ maps, const float* __restrict__ tma
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) mw[ky * 3 + kx] = sm_m[(y + ky) * WM + x + kx];
-      float4* hrow = reinterpret_cast<float4*>(sm_h + i * WHC);
+#pragma unroll 4
+      for (int o = 0; o < 16; ++o) {
+        float a = wts.b1[o];
 #pragma unroll
-      for (int o4 = 0; o4 < 4; ++o4) {
-        float a[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int o = o4 * 4 + j;
-          a[j] = wts.b1[o];
-#pragma unroll
-          for (int k = 0; k < 9; ++k) a[j] = fmaf(wts.w1[o][k], mw[k], a[j]);
-          a[j] = inside ? fmaxf(a[j], 0.f) : 0.f;
-        }
-        hrow[o4] = make_float4(a[0], a[1], a[2], a[3]);
+        for (int k = 0; k < 9; ++k) a = fmaf(wts.w1[o][k], mw[k], a);
+        sm_h[o * WH * WH + i] = inside ? fmaxf(a, 0.f) : 0.f;
       }
     }
     __syncthreads();
-    float mout = mout_tiles;
-    if constexpr (TM) {
-      // tokens of the tiles that touch the core rows, core excluded; row by row (no division per token)
-      const int r_lo = tok_lo / w, r_hi = (tok_lo + tok_n - 1) / w;
-      for (int r = r_lo; r <= r_hi; ++r) {
-        const bool core_row = abs(r - arow) <= 3;
-        for (int c = tid; c < w; c += WIN_THREADS) {
-          const int p = r * w + c;
-          if (p >= tok_lo && p < tok_lo + tok_n && !(core_row && abs(c - acol) <= 3)) mout = fmaxf(mout, __ldg(src + p));
-        }
-      }
-    } else {
-      for (int i = tid; i < nchunks; i += WIN_THREADS) {
-        float4 v = *reinterpret_cast<const float4*>(lin + 4 * i);
-        const int base = 4 * i;
-        float m4 = v.x;
-        if (base + 1 < P) m4 = fmaxf(m4, v.y);
-        if (base + 2 < P) m4 = fmaxf(m4, v.z);
-        if (base + 3 < P) m4 = fmaxf(m4, v.w);
-        mout = fmaxf(mout, m4);
-      }
+    float mout = 0.f;
+    for (int i = tid; i < nchunks; i += WIN_THREADS) {
+      float4 v = *reinterpret_cast<const float4*>(lin + 4 * i);
+      const int base = 4 * i;
+      float m4 = v.x;
+      if (base + 1 < P) m4 = fmaxf(m4, v.y);
+      if (base + 2 < P) m4 = fmaxf(m4, v.z);
+      if (base + 3 < P) m4 = fmaxf(m4, v.w);
+      mout = fmaxf(mout, m4);
     }
     mout = warp_max(mout);
 
@@ -475,23 +413,13 @@ head_window_kernel(const float* __restrict__ maps, const float* __restrict__ tma
       valid = r >= 0 && r < h && c >= 0 && c < w;
       if (valid) {
         float a = wts.b2;
-        // same accumulation order as before: channel-major, then the 3 x 3 taps
-#pragma unroll
-        for (int o4 = 0; o4 < 4; ++o4) {
-          float4 hv[9];
+#pragma unroll 4
+        for (int o = 0; o < 16; ++o) {
+          const float* hb = sm_h + o * WH * WH + y * WH + x;
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-              hv[ky * 3 + kx] = *reinterpret_cast<const float4*>(sm_h + ((y + ky) * WH + x + kx) * WHC + o4 * 4);
-#pragma unroll
-          for (int k = 0; k < 9; ++k) a = fmaf(wts.w2[o4 * 4 + 0][k], hv[k].x, a);
-#pragma unroll
-          for (int k = 0; k < 9; ++k) a = fmaf(wts.w2[o4 * 4 + 1][k], hv[k].y, a);
-#pragma unroll
-          for (int k = 0; k < 9; ++k) a = fmaf(wts.w2[o4 * 4 + 2][k], hv[k].z, a);
-#pragma unroll
-          for (int k = 0; k < 9; ++k) a = fmaf(wts.w2[o4 * 4 + 3][k], hv[k].w, a);
+            for (int kx = 0; kx < 3; ++kx) a = fmaf(wts.w2[o][ky * 3 + kx], hb[ky * WH + kx], a);
         }
         z = a;
         int dr = (r - arow) * hp.stride_px, dc = (c - acol) * hp.stride_px;
@@ -545,11 +473,214 @@ head_window_kernel(const float* __restrict__ maps, const float* __restrict__ tma
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Fast path on the tensor-core pipeline: the correlation GEMM epilogue leaves, per map and 256-token tile, one 64-bit key
+// (value bits << 32 | 0x7fffffff - first token holding it; corr.cuh), so the arg-max is a 32-key reduction and the largest
+// value outside the 7x7 core needs only the ~1 k tokens of the tiles that touch the core rows.  The map itself is touched
+// for the 15x15 window and those tokens only.  Same certificate and same per-value arithmetic as head_window_kernel;
+// the work is laid out so that the refiner weights sit in registers (hidden layer: thread = channel x row, weights of
+// that channel loaded once per kernel) or shared memory (output layer), not in constant-bank operands.
+constexpr int TMK_THREADS = 128;
+constexpr int WMP = 16;   // pitch of the input window rows (15 used): float4 loads
+constexpr int WHC = 20;   // hidden window [position][16 channels], 20-float pitch: float4 reads of consecutive positions
+                          // fall into distinct bank groups
+
+__global__ void __launch_bounds__(TMK_THREADS, 8)
+head_tm_kernel(const float* __restrict__ maps, const unsigned long long* __restrict__ tkeys, int n_tiles, int n_maps,
+               HeadParams hp, dinotrk_head_weights wts, const int* __restrict__ out_index, float* __restrict__ out,
+               int* __restrict__ aux, int* __restrict__ slow_list, int* __restrict__ slow_count) {
+  __shared__ __align__(16) float sm_m[WM * WMP];          // input window, zero outside the map
+  __shared__ __align__(16) float sm_h[WH * WH * WHC];     // hidden window, zero outside the map
+  __shared__ __align__(16) float sm_w2[16 * 12];          // output-layer weights [channel][9 taps + 3 pad]
+  __shared__ float sm_red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = hp.h, w = hp.w, P = hp.P;
+  const int ch = tid & 15, rg = tid >> 4;                 // hidden layer: channel, row group
+  float w1r[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w1r[k] = wts.w1[ch][k];
+  const float b1r = wts.b1[ch];
+  for (int i = tid; i < 16 * 12; i += TMK_THREADS) { const int o = i / 12, k = i - o * 12; sm_w2[i] = k < 9 ? wts.w2[o][k] : 0.f; }
+  __syncthreads();
+
+  int map = blockIdx.x;
+  unsigned long long knext = (map < n_maps && lane < n_tiles) ? __ldg(tkeys + (size_t)map * n_tiles + lane) : 0ull;
+  for (; map < n_maps; map += gridDim.x) {
+    const float* src = maps + (size_t)map * hp.map_stride;
+    const unsigned long long* tk = tkeys + (size_t)map * n_tiles;
+    // ---- arg-max from the tile keys (every warp redundantly; keys of the next map are already in flight) ----
+    unsigned long long kown = knext, key = knext;
+    {
+      const int nm = map + gridDim.x;
+      knext = (nm < n_maps && lane < n_tiles) ? __ldg(tkeys + (size_t)nm * n_tiles + lane) : 0ull;
+    }
+    for (int t = lane + 32; t < n_tiles; t += 32) { unsigned long long k = __ldg(tk + t); key = k > key ? k : key; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
+    if (key == ~0ull) {   // thin group (streaming kernel): no tile keys -> full-map kernel
+      if (tid == 0) slow_list[atomicAdd(slow_count, 1)] = map;
+      continue;
+    }
+    const int amax = 0x7fffffff - (int)(key & 0xffffffffu);
+    const int arow = amax / w, acol = amax - arow * w;
+    // ---- largest map value outside the 7x7 core: whole tiles from the keys, the tiles touching the core rows token-wise
+    const int t_lo = (max(arow - 3, 0) * w + max(acol - 3, 0)) / CORR_TILE;
+    const int t_hi = (min(arow + 3, h - 1) * w + min(acol + 3, w - 1)) / CORR_TILE;
+    float mout = 0.f;
+    if (lane < n_tiles && (lane < t_lo || lane > t_hi)) mout = __uint_as_float((unsigned)(kown >> 32));
+    for (int t = lane + 32; t < n_tiles; t += 32)
+      if (t < t_lo || t > t_hi) mout = fmaxf(mout, __uint_as_float((unsigned)(__ldg(tk + t) >> 32)));
+    if (warp != 0) mout = 0.f;   // the keys are counted once
+    // All global loads of this map (window + the tokens of the tiles touching the core rows) are issued before any is
+    // consumed: one DRAM round trip per map instead of one per row.
+    constexpr int WROUNDS = (WM * WMP + TMK_THREADS - 1) / TMK_THREADS;
+    float wv[WROUNDS];
+#pragma unroll
+    for (int q = 0; q < WROUNDS; ++q) {
+      const int i = tid + q * TMK_THREADS;
+      const int y = i >> 4, x = i & 15;
+      const int r = arow - 7 + y, c = acol - 7 + x;
+      wv[q] = (i < WM * WMP && x < WM && r >= 0 && r < h && c >= 0 && c < w) ? __ldg(src + r * w + c) : 0.f;
+    }
+    {
+      const int tok_lo = t_lo * CORR_TILE, tok_hi = min((t_hi + 1) * CORR_TILE, P);   // [tok_lo, tok_hi)
+      const int r_lo = tok_lo / w, r_hi = (tok_hi - 1) / w;
+      constexpr int RB = 12;   // rows per batch of loads (4 tiles of 256 tokens span <= 10 rows at w = 121)
+      for (int c = tid; c < w; c += TMK_THREADS)
+        for (int rb = r_lo; rb <= r_hi; rb += RB) {
+          float tv[RB];
+#pragma unroll
+          for (int j = 0; j < RB; ++j) {
+            const int r = rb + j, p = r * w + c;
+            const bool ok = r <= r_hi && p >= tok_lo && p < tok_hi && !(abs(r - arow) <= 3 && abs(c - acol) <= 3);
+            tv[j] = ok ? __ldg(src + p) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < RB; ++j) mout = fmaxf(mout, tv[j]);
+        }
+    }
+    // ---- input window (15 x 15, zero outside the map) ---------------------------------------------
+#pragma unroll
+    for (int q = 0; q < WROUNDS; ++q) {
+      const int i = tid + q * TMK_THREADS;
+      if (i < WM * WMP) sm_m[i] = wv[q];
+    }
+    __syncthreads();
+    // ---- hidden layer on the 13 x 13 window: thread = (channel, row); taps in (ky, kx) order as everywhere else ----
+    for (int y = rg; y < WH; y += TMK_THREADS / 16) {
+      const int r = arow - 6 + y;
+      const bool row_in = r >= 0 && r < h;
+      float in[3][16];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(sm_m + (y + ky) * WMP + 4 * q);
+          in[ky][4 * q] = v.x; in[ky][4 * q + 1] = v.y; in[ky][4 * q + 2] = v.z; in[ky][4 * q + 3] = v.w;
+        }
+#pragma unroll
+      for (int x = 0; x < WH; ++x) {
+        float a = b1r;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) a = fmaf(w1r[ky * 3 + kx], in[ky][x + kx], a);
+        const int c = acol - 6 + x;
+        sm_h[(y * WH + x) * WHC + ch] = (row_in && c >= 0 && c < w) ? fmaxf(a, 0.f) : 0.f;
+      }
+    }
+    __syncthreads();
+    mout = warp_max(mout);
+
+    // ---- logits on the 11 x 11 box; thread = box pixel; channel-major accumulation, then the 3 x 3 taps ----
+    float z = -INFINITY;
+    bool valid = false, indisc = false;
+    float px = 0.f, py = 0.f;
+    if (tid < WB * WB) {
+      const int y = tid / WB, x = tid - y * WB;
+      const int r = arow - 5 + y, c = acol - 5 + x;
+      valid = r >= 0 && r < h && c >= 0 && c < w;
+      if (valid) {
+        float a = wts.b2;
+#pragma unroll
+        for (int o4 = 0; o4 < 4; ++o4) {
+          float4 hv[9];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+              hv[ky * 3 + kx] = *reinterpret_cast<const float4*>(sm_h + ((y + ky) * WH + x + kx) * WHC + o4 * 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 wa = *reinterpret_cast<const float4*>(sm_w2 + (o4 * 4 + j) * 12);
+            const float4 wb = *reinterpret_cast<const float4*>(sm_w2 + (o4 * 4 + j) * 12 + 4);
+            const float w8 = sm_w2[(o4 * 4 + j) * 12 + 8];
+            const float wk[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, w8};
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+              const float hvk = j == 0 ? hv[k].x : j == 1 ? hv[k].y : j == 2 ? hv[k].z : hv[k].w;
+              a = fmaf(wk[k], hvk, a);
+            }
+          }
+        }
+        z = a;
+        const int dr = (r - arow) * hp.stride_px, dc = (c - acol) * hp.stride_px;
+        indisc = dr * dr + dc * dc <= hp.radius2;
+        px = (float)(hp.half_patch + c * hp.stride_px);
+        py = (float)(hp.half_patch + r * hp.stride_px);
+      }
+    }
+    float zmax = warp_max(z);
+    if (lane == 0) { sm_red[warp] = mout; sm_red[4 + warp] = zmax; }
+    __syncthreads();
+    mout = fmaxf(fmaxf(sm_red[0], sm_red[1]), fmaxf(sm_red[2], sm_red[3]));
+    zmax = fmaxf(fmaxf(sm_red[4], sm_red[5]), fmaxf(sm_red[6], sm_red[7]));
+    const float e = valid ? expf(z - zmax) : 0.f;
+    float v5[5] = {e, indisc ? e : 0.f, indisc ? px * e : 0.f, indisc ? py * e : 0.f, valid ? 1.f : 0.f};
+#pragma unroll
+    for (int q = 0; q < 5; ++q) v5[q] = warp_sum(v5[q]);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) sm_red[8 + q * 4 + warp] = v5[q];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float tot[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) tot[q] = sm_red[8 + q * 4] + sm_red[9 + q * 4] + sm_red[10 + q * 4] + sm_red[11 + q * 4];
+      // every logit outside the box:  z <= b2 + sum_o P2_o * relu(b1_o + P1_o * mout)   (all terms monotone in m >= 0)
+      float F = wts.b2;
+#pragma unroll
+      for (int o = 0; o < 16; ++o) F = fmaf(hp.P2[o], fmaxf(fmaf(hp.P1[o], mout, wts.b1[o]), 0.f), F);
+      const float rest = ((float)P - tot[4]) * expf(fminf(F - zmax, 80.f));
+      const bool certified = tot[1] >= 2e-8f * (tot[0] + rest) && tot[1] > 0.f && isfinite(rest);
+      if (certified) {
+        float px_ = __fdiv_rn(tot[2], tot[1]), py_ = __fdiv_rn(tot[3], tot[1]);
+        float nx = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(px_, hp.normW)), -1.f);
+        float ny = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(py_, hp.normH)), -1.f);
+        if (hp.out_mode == 0) {
+          nx = __fmul_rn(__fdiv_rn(__fadd_rn(nx, 1.f), 2.f), hp.normW);
+          ny = __fmul_rn(__fdiv_rn(__fadd_rn(ny, 1.f), 2.f), hp.normH);
+        }
+        size_t oi = (size_t)(out_index ? out_index[map] : map) * hp.out_stride;
+        out[oi] = nx; out[oi + 1] = ny;
+        if (aux) { aux[2 * map] = amax; aux[2 * map + 1] = 0; }
+      } else {
+        slow_list[atomicAdd(slow_count, 1)] = map;
+      }
+    }
+    // no barrier here: the next iteration writes sm_m before its 1st barrier (last read before this iteration's 2nd),
+    // sm_h after its 1st (last read before this iteration's 3rd), sm_red[0..7] after its 2nd (read between the 3rd and
+    // 4th) and sm_red[8..] after its 3rd -- which tid 0, the only reader after the 4th, has to reach first.
+  }
+}
+
 __global__ void zero_int_kernel(int* p) { *p = 0; }
 
 int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geom& g,
                 const dinotrk_head_weights& hw, const int* out_index, float* out, int out_stride, int out_mode,
-                int* aux, int* scratch, cudaStream_t st, const float* tmax, bool counter_zeroed) {
+                int* aux, int* scratch, cudaStream_t st, const unsigned long long* tkeys, bool counter_zeroed,
+                int ctas_per_sm, int parts) {
   if (n_maps <= 0) return DINOTRK_OK;
   DTK_CHECK_ARG(g.w <= HEAD_MAX_W && g.h <= HEAD_MAX_H, "head: token grid %dx%d exceeds the supported %dx%d",
                 g.h, g.w, HEAD_MAX_H, HEAD_MAX_W);
@@ -571,32 +702,41 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
   const bool window_ok = scratch != nullptr && g.radius <= 5 * g.stride && g.w <= HEAD_MAX_W;
   int* slow_count = scratch;
   int* slow_list = scratch ? scratch + 1 : nullptr;
-  if (window_ok) {
-    const bool tm = tmax != nullptr;
-    size_t smem = (size_t)((tm ? 0 : lin_elems) + WM * WM + 3 + WHC * WH * WH + 32) * sizeof(float) + 4 * sizeof(unsigned long long);
-    static size_t attr_w = 0;
-    if (!tm && smem > attr_w) {
-      DTK_CUDA(cudaFuncSetAttribute(head_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_w = smem;
-    }
+  if (window_ok && (parts & 1)) {
     if (!counter_zeroed) {
       ProfRange pr(PROF_MISC, st);
       zero_int_kernel<<<1, 1, 0, st>>>(slow_count);
       DTK_LAUNCHED();
     }
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > (tm ? 16 : 8)) per_sm = tm ? 16 : 8;
-    int grid = n_maps < sms * per_sm ? n_maps : sms * per_sm;
-    ProfRange pr(PROF_HEAD, st);
-    if (tm)
-      head_window_kernel<true><<<grid, WIN_THREADS, smem, st>>>(maps, tmax, cdiv(hp.P, CORR_TILE), n_maps, hp, hw, out_index,
-                                                                out, aux, slow_list, slow_count);
-    else
-      head_window_kernel<false><<<grid, WIN_THREADS, smem, st>>>(maps, nullptr, 0, n_maps, hp, hw, out_index, out, aux,
-                                                                 slow_list, slow_count);
-    DTK_LAUNCHED();
+    if (tkeys != nullptr) {
+      static int per_sm_tm = 0;
+      if (per_sm_tm == 0) {
+        DTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tm, head_tm_kernel, TMK_THREADS, 0));
+        if (per_sm_tm < 1) per_sm_tm = 1;
+      }
+      const int per_sm_use = (ctas_per_sm > 0 && ctas_per_sm < per_sm_tm) ? ctas_per_sm : per_sm_tm;
+      int grid = n_maps < sms * per_sm_use ? n_maps : sms * per_sm_use;
+      ProfRange pr(PROF_HEAD, st);
+      head_tm_kernel<<<grid, TMK_THREADS, 0, st>>>(maps, tkeys, cdiv(hp.P, CORR_TILE), n_maps, hp, hw, out_index, out, aux,
+                                                   slow_list, slow_count);
+      DTK_LAUNCHED();
+    } else {
+      size_t smem = (size_t)(lin_elems + WM * WM + 3 + 16 * WH * WH + 32) * sizeof(float) + 4 * sizeof(unsigned long long);
+      static size_t attr_w = 0;
+      if (smem > attr_w) {
+        DTK_CUDA(cudaFuncSetAttribute(head_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_w = smem;
+      }
+      int per_sm = (int)((220 * 1024) / (smem + 1024));
+      if (per_sm < 1) per_sm = 1;
+      if (per_sm > 8) per_sm = 8;
+      int grid = n_maps < sms * per_sm ? n_maps : sms * per_sm;
+      ProfRange pr(PROF_HEAD, st);
+      head_window_kernel<<<grid, WIN_THREADS, smem, st>>>(maps, n_maps, hp, hw, out_index, out, aux, slow_list, slow_count);
+      DTK_LAUNCHED();
+    }
   }
+  if (!(parts & 2)) return DINOTRK_OK;
   // full-map kernel: every map (no scratch) or only the maps the window kernel could not certify
   const int nwarps = cdiv(g.h, 4);
   const int threads = nwarps * 32;

@@ -215,6 +215,33 @@ struct GroupBuf {  // host mirror of the per-chunk group arrays: [frame | row0 |
   }
 };
 
+// auxiliary stream + events of the phase-C pipeline (one set per process; DTK_OVERLAP=0 disables the overlap)
+struct InferAsync {
+  int mode;                 // 1: sampling overlapped with the GEMMs (default); 2: sampling and the head fast path
+  cudaStream_t aux, aux2;   // head stream, sampling stream
+  cudaEvent_t fork, join, sample[2], gemm[2], head[2];
+  int head_ctas_per_sm;
+};
+static InferAsync* infer_async() {
+  static InferAsync ia;
+  static int state = 0;   // 0: not tried, 1: ready, -1: disabled / failed
+  if (state == 0) {
+    state = -1;
+    const char* e = getenv("DTK_OVERLAP");
+    if (e && atoi(e) == 0) return nullptr;
+    ia.mode = e ? atoi(e) : 1;
+    const char* hc = getenv("DTK_HEAD_OVERLAP_CTAS");
+    ia.head_ctas_per_sm = hc ? atoi(hc) : 1;
+    if (cudaStreamCreateWithFlags(&ia.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&ia.aux2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEvent_t* evs[] = {&ia.fork, &ia.join, &ia.sample[0], &ia.sample[1], &ia.gemm[0], &ia.gemm[1], &ia.head[0], &ia.head[1]};
+    for (cudaEvent_t* ev : evs)
+      if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    state = 1;
+  }
+  return state == 1 ? &ia : nullptr;
+}
+
 }  // namespace dtk
 
 using namespace dtk;
@@ -254,6 +281,8 @@ int dinotrk_corr_track(const dinotrk_features* feat, const dinotrk_geom* g,
 }
 
 static int infer_chunk_maps(int chunk_maps) { return chunk_maps > 0 ? chunk_maps : 4096; }
+// upper bound on the number of chunks of one phase (phase C has the most work items: N * T * T)
+static size_t infer_max_chunks(int T, int N, size_t ch) { return ((size_t)N * T * T + ch - 1) / ch + 2; }
 
 size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N, int chunk_maps) {
   if (!g) return 0;
@@ -261,15 +290,18 @@ size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N,
   const int gcap = T + 2;
   size_t b = 0;
   b += align_up((size_t)N * C * 4, 256) + align_up((size_t)N * 4, 256);   // descA, normA
-  b += align_up(ch * ms * 4, 256);                                         // maps chunk
-  b += align_up(ch * C * 4, 256) + align_up(ch * 4, 256);                  // descC, normC
-  b += align_up(ch * 4, 256);                                              // out_index
-  b += align_up((size_t)5 * gcap * 4, 256) + align_up((size_t)(gcap + 1) * 4, 256);  // groups, plan
+  size_t c = 0;                                                            // per chunk buffer set (two: pipelining)
+  c += align_up(ch * ms * 4, 256);                                         // maps chunk
+  c += align_up(ch * C * 4, 256) + align_up(ch * 4, 256);                  // descC, normC
+  c += align_up((size_t)(gcap + 1) * 4, 256);                              // GEMM tile plan
+  c += corr_tc_workspace_bytes((int)(ch > (size_t)N ? ch : (size_t)N), C) + 256;  // fp16 split of the descriptors
+  c += align_up((ch + 1) * 4, 256);                                        // head: list of uncertified maps
+  c += align_up(ch * (size_t)cdiv(g->h * g->w, CORR_TILE) * 8, 256);       // tile keys of the chunk's maps
+  b += 2 * c;
+  b += 4 * align_up(ch * 4, 256);                                          // out_index ring
+  b += align_up(infer_max_chunks(T, N, ch) * 5 * gcap * 4, 256);           // group arrays of every chunk of a phase
   b += align_up((size_t)T * 4, 256) + align_up((size_t)T * N * 4, 256);    // cnt, qlist
-  b += corr_tc_workspace_bytes((int)(ch > (size_t)N ? ch : (size_t)N), C) + 256;  // TF32 split of the descriptors
-  b += align_up((ch + 1) * 4, 256);                                        // head: list of uncertified maps
-  b += align_up(ch * (size_t)cdiv(g->h * g->w, CORR_TILE) * 4, 256);       // tile maxima of the chunk's maps
-  return b + 4096;
+  return b + 8192;
 }
 
 int dinotrk_traj_cos_sims(const float* tpc, int T, int C, const dinotrk_geom* g, const float* traj,
@@ -335,76 +367,104 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   const int gcap = T + 2;
   const PointAffine pa = make_point_affine(*g);
 
-  GroupBuf* gb_ptr = nullptr;
   Arena ar(workspace, workspace_bytes);
   float* descA = ar.take<float>((size_t)N * C);
   float* normA = ar.take<float>(N);
-  float* maps = ar.take<float>((size_t)ch * ms);
-  float* descC = ar.take<float>((size_t)ch * C);
-  float* normC = ar.take<float>(ch);
-  int* out_index = ar.take<int>(ch);
-  int* d_grp = ar.take<int>((size_t)5 * gcap);
-  int* plan = ar.take<int>(gcap + 1);
+  struct ChunkBufs {   // everything one chunk in flight owns
+    float* maps; float* desc; float* norm; int* plan; float* split; int* hscratch; unsigned long long* tkeys;
+  } cb[2];
+  int* out_index_ring[4];   // written by the sampler of chunk k, read by both head kernels of chunk k (the second one late)
+  for (int k = 0; k < 2; ++k) {
+    cb[k].maps = ar.take<float>((size_t)ch * ms);
+    cb[k].desc = ar.take<float>((size_t)ch * C);
+    cb[k].norm = ar.take<float>(ch);
+    cb[k].plan = ar.take<int>(gcap + 1);
+    cb[k].split = ar.take<float>(corr_tc_workspace_bytes(ch > N ? ch : N, C) / 4);
+    cb[k].hscratch = ar.take<int>(ch + 1);
+    cb[k].tkeys = ar.take<unsigned long long>((size_t)ch * cdiv(P, CORR_TILE));
+  }
+  for (int k = 0; k < 4; ++k) out_index_ring[k] = ar.take<int>(ch);
+  const size_t max_chunks = infer_max_chunks(T, N, (size_t)ch);
+  int* d_groups = ar.take<int>(max_chunks * 5 * gcap);
   int* d_cnt = ar.take<int>(T);
   int* d_qlist = ar.take<int>((size_t)T * N);
-  float* split = ar.take<float>(corr_tc_workspace_bytes(ch > N ? ch : N, C) / 4);
-  int* hscratch = ar.take<int>(ch + 1);
-  float* tmax = ar.take<float>((size_t)ch * cdiv(P, CORR_TILE));
   DTK_CHECK_ARG(ar.ok(), "infer: workspace arena overflow");
-  const bool tensor = fv.tensor();   // tensor-core GEMM: tile maxima for the head, fp16 split fused into the samplers
-  auto thin_free = [&]() {
-    for (int k = 0; k < gb_ptr->n; ++k) if (gb_ptr->v[2 * gb_ptr->cap + k] <= STREAM_MAX_M) return false;
-    return true;
-  };
+  const bool tensor = fv.tensor();   // tensor-core GEMM: tile keys for the head, fp16 split fused into the samplers
 
+  // The chunks of a phase are planned on the host in one go and their group arrays uploaded with ONE copy, so the
+  // per-chunk launches below never block the host (a pageable cudaMemcpyAsync per chunk would).
+  struct ChunkMeta { int used, maxm, n_groups; bool no_thin; };
+  std::vector<ChunkMeta> metas;
+  std::vector<int> plan_host;
   GroupBuf gb(gcap);
-  gb_ptr = &gb;
-  auto upload_groups = [&]() -> int {
-    DTK_CUDA(cudaMemcpyAsync(d_grp, gb.v.data(), (size_t)5 * gcap * sizeof(int), cudaMemcpyHostToDevice, st));
+  auto commit_chunk = [&](int used, int maxm) {
+    bool no_thin = true;
+    for (int k = 0; k < gb.n; ++k) no_thin = no_thin && gb.v[2 * gb.cap + k] > STREAM_MAX_M;
+    metas.push_back(ChunkMeta{used, maxm, gb.n, no_thin});
+    plan_host.insert(plan_host.end(), gb.v.begin(), gb.v.end());
+  };
+  auto upload_plan = [&]() -> int {
+    DTK_CHECK_ARG(metas.size() <= max_chunks, "infer: chunk plan exceeds its bound (%zu > %zu)", metas.size(), max_chunks);
+    if (!plan_host.empty())
+      DTK_CUDA(cudaMemcpyAsync(d_groups, plan_host.data(), plan_host.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     return DINOTRK_OK;
   };
-  const int *gf = d_grp, *gr = d_grp + gcap, *gm = d_grp + 2 * gcap, *gmap = d_grp + 3 * gcap, *gitem = d_grp + 4 * gcap;
+  struct Grp { const int *f, *r, *m, *map0, *item; };
+  auto grp_of = [&](size_t k) {
+    const int* b = d_groups + k * 5 * gcap;
+    return Grp{b, b + gcap, b + 2 * gcap, b + 3 * gcap, b + 4 * gcap};
+  };
 
   // ---- phase A: trajectories -------------------------------------------------------------------
   if (start_phase <= 0) {
-  {
-    ProfRange pr(PROF_SAMPLE, st);
-    sample_query_kernel<<<N, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, query_points, descA, normA);
-    DTK_LAUNCHED();
-  }
-  if (tensor) {   // the query descriptors are reused by every chunk: split them once
-    char* a_hi = reinterpret_cast<char*>(split);
-    int rc = launch_split_f16(descA, a_hi, a_hi + align_up((size_t)N * C * 2, 256), (size_t)N * C, st);
-    if (rc) return rc;
-  }
-  {
-    int t = 0, row = 0;  // next work item: (frame t, query row)
-    while (t < T) {
-      gb.clear();
-      int used = 0, maxm = 0;
-      while (t < T && used < ch && gb.n < gcap) {
-        int m = N - row;
-        if (m > ch - used) m = ch - used;
-        gb.push(t, row, m, used, 0);
-        used += m; row += m;
-        if (m > maxm) maxm = m;
-        if (row == N) { row = 0; ++t; }
+    {
+      ProfRange pr(PROF_SAMPLE, st);
+      sample_query_kernel<<<N, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, query_points, descA, normA);
+      DTK_LAUNCHED();
+    }
+    if (tensor) {   // the query descriptors are reused by every chunk: split them once (layout of desc_rows = N)
+      for (int k = 0; k < 2; ++k) {
+        char* a_hi = reinterpret_cast<char*>(cb[k].split);
+        int rc = launch_split_f16(descA, a_hi, a_hi + align_up((size_t)N * C * 2, 256), (size_t)N * C, st);
+        if (rc) return rc;
       }
-      int rc = upload_groups();
-      if (rc) return rc;
+    }
+    metas.clear(); plan_host.clear();
+    {
+      int t = 0, row = 0;  // next work item: (frame t, query row)
+      while (t < T) {
+        gb.clear();
+        int used = 0, maxm = 0;
+        while (t < T && used < ch && gb.n < gcap) {
+          int m = N - row;
+          if (m > ch - used) m = ch - used;
+          gb.push(t, row, m, used, 0);
+          used += m; row += m;
+          if (m > maxm) maxm = m;
+          if (row == N) { row = 0; ++t; }
+        }
+        commit_chunk(used, maxm);
+      }
+    }
+    int rc = upload_plan();
+    if (rc) return rc;
+    for (size_t k = 0; k < metas.size(); ++k) {
+      const ChunkMeta& cm = metas[k];
+      const ChunkBufs& b = cb[k & 1];
+      const Grp gp = grp_of(k);
       {
         ProfRange pr(PROF_MISC, st);
-        index_traj_kernel<<<cdiv(used, 256), 256, 0, st>>>(gf, gr, gmap, gb.n, used, T, out_index, traj);
+        index_traj_kernel<<<cdiv(cm.used, 256), 256, 0, st>>>(gp.f, gp.r, gp.map0, cm.n_groups, cm.used, T, out_index_ring[k & 3], traj);
         DTK_LAUNCHED();
       }
       CorrAssist as;
-      as.tmax = tensor ? tmax : nullptr; as.zero_word = hscratch; as.split_ready = tensor; as.no_thin = thin_free();
-      rc = launch_corr_maps(fv, descA, N, normA, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, split, st, as);
+      as.tkeys = tensor ? b.tkeys : nullptr; as.zero_word = b.hscratch; as.split_ready = tensor; as.no_thin = cm.no_thin;
+      rc = launch_corr_maps(fv, descA, N, normA, gp.f, gp.r, gp.m, gp.map0, cm.n_groups, cm.used, cm.maxm, b.maps, ms, b.plan,
+                            b.split, st, as);
       if (rc) return rc;
-      rc = launch_head(maps, used, ms, *g, *hw, out_index, traj, 3, 0, nullptr, hscratch, st, as.tmax, true);
+      rc = launch_head(b.maps, cm.used, ms, *g, *hw, out_index_ring[k & 3], traj, 3, 0, nullptr, b.hscratch, st, as.tkeys, true);
       if (rc) return rc;
     }
-  }
   }
   if (stop_after < 1) return DINOTRK_OK;
 
@@ -416,53 +476,104 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   if (stop_after < 2) return DINOTRK_OK;
 
   // ---- phase C: anchor re-tracking ---------------------------------------------------------------
+  // Three streams: the caller's stream runs the correlation GEMMs back to back; one auxiliary stream samples the
+  // descriptors of chunk k+1, another runs the head of chunk k, both while the GEMM of chunk k+1 owns the tensor cores
+  // (the head kernel is then launched with one CTA per SM so that it fits next to the GEMM's ~200 KB of shared memory;
+  // the rare full-map head launches cannot co-reside and simply wait for the GEMM's CTAs to retire).
   if (start_phase <= 2) {
-  {
-    ProfRange pr(PROF_ANCHOR_LIST, st);
-    anchor_lists_kernel<<<T, 256, 0, st>>>(cos_sims, N, T, anchor_th, d_cnt, d_qlist);
-    DTK_LAUNCHED();
-  }
-  std::vector<int> cnt(T);
-  DTK_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost, st));
-  DTK_CUDA(cudaStreamSynchronize(st));  // the one host sync: sizes of the anchor work lists
-  {
-    int a = 0;
-    long long item = 0;  // next work item: anchor frame a, item index within a (slot * T + i)
-    while (a < T) {
-      gb.clear();
-      int used = 0, maxm = 0;
-      while (a < T && used < ch && gb.n < gcap) {
-        long long tot = (long long)cnt[a] * T;
-        long long m = tot - item;
-        if (m > ch - used) m = ch - used;
-        if (m > 0) {
-          gb.push(a, used, (int)m, used, (int)item);
-          used += (int)m; item += m;
-          if ((int)m > maxm) maxm = (int)m;
+    {
+      ProfRange pr(PROF_ANCHOR_LIST, st);
+      anchor_lists_kernel<<<T, 256, 0, st>>>(cos_sims, N, T, anchor_th, d_cnt, d_qlist);
+      DTK_LAUNCHED();
+    }
+    std::vector<int> cnt(T);
+    DTK_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DTK_CUDA(cudaStreamSynchronize(st));  // the one host sync: sizes of the anchor work lists
+    metas.clear(); plan_host.clear();
+    {
+      int a = 0;
+      long long item = 0;  // next work item: anchor frame a, item index within a (slot * T + i)
+      while (a < T) {
+        gb.clear();
+        int used = 0, maxm = 0;
+        while (a < T && used < ch && gb.n < gcap) {
+          long long tot = (long long)cnt[a] * T;
+          long long m = tot - item;
+          if (m > ch - used) m = ch - used;
+          if (m > 0) {
+            gb.push(a, used, (int)m, used, (int)item);
+            used += (int)m; item += m;
+            if ((int)m > maxm) maxm = (int)m;
+          }
+          if (item >= tot) { item = 0; ++a; }
         }
-        if (item >= tot) { item = 0; ++a; }
+        if (used == 0) break;
+        commit_chunk(used, maxm);
       }
-      if (used == 0) break;
-      int rc = upload_groups();
-      if (rc) return rc;
+    }
+    int rc = upload_plan();
+    if (rc) return rc;
+    InferAsync* ia = infer_async();
+    const bool ovl = ia != nullptr && metas.size() > 1;
+    cudaStream_t sa = (ovl && ia->mode >= 2) ? ia->aux : st;    // head stream
+    cudaStream_t sb = ovl ? ia->aux2 : st;   // sampling stream
+    if (ovl) {
+      DTK_CUDA(cudaEventRecord(ia->fork, st));
+      DTK_CUDA(cudaStreamWaitEvent(sa, ia->fork, 0));
+      DTK_CUDA(cudaStreamWaitEvent(sb, ia->fork, 0));
+    }
+    auto enqueue_sample = [&](size_t k) -> int {   // descriptors of chunk k (buffer set k & 1)
+      const ChunkMeta& cm = metas[k];
+      const ChunkBufs& b = cb[k & 1];
+      const Grp gp = grp_of(k);
+      if (ovl && k >= 2) DTK_CUDA(cudaStreamWaitEvent(sb, ia->gemm[k & 1], 0));   // GEMM k-2 read the descriptors of this set
       {
-        ProfRange pr(PROF_SAMPLE, st);
+        ProfRange pr(PROF_SAMPLE, sb);
         // the split layout of launch_corr_gemm_tc for desc_rows = used: hi rows, then lo rows at the next 256-byte boundary
-        __half* c_hi = tensor ? reinterpret_cast<__half*>(split) : nullptr;
-        __half* c_lo = tensor ? reinterpret_cast<__half*>(reinterpret_cast<char*>(split) + align_up((size_t)used * C * 2, 256))
+        __half* c_hi = tensor ? reinterpret_cast<__half*>(b.split) : nullptr;
+        __half* c_lo = tensor ? reinterpret_cast<__half*>(reinterpret_cast<char*>(b.split) + align_up((size_t)cm.used * C * 2, 256))
                               : nullptr;
-        sample_anchor_kernel<<<used, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, traj, d_qlist, N, gf, gmap,
-                                                             gitem, gb.n, fb, descC, normC, out_index, c_hi, c_lo);
+        sample_anchor_kernel<<<cm.used, SAMPLE_THREADS, 0, sb>>>(tpc, T, C, P, g->h, g->w, pa, traj, d_qlist, N, gp.f, gp.map0,
+                                                                gp.item, cm.n_groups, fb, b.desc, b.norm, out_index_ring[k & 3], c_hi, c_lo);
         DTK_LAUNCHED();
       }
+      if (ovl) DTK_CUDA(cudaEventRecord(ia->sample[k & 1], sb));
+      return DINOTRK_OK;
+    };
+    // the full-map head of chunk j (usually an empty list) runs on the GEMM stream between two GEMMs: it needs ~70 KB of
+    // shared memory per CTA and could not co-reside with a GEMM anyway
+    auto head_full = [&](size_t j) -> int {
+      const ChunkBufs& b = cb[j & 1];
+      if (ovl) DTK_CUDA(cudaStreamWaitEvent(st, ia->head[j & 1], 0));   // fast head of chunk j (its list is complete)
+      return launch_head(b.maps, metas[j].used, ms, *g, *hw, out_index_ring[j & 3], anchors, 2, 0, nullptr, b.hscratch, st,
+                         tensor ? b.tkeys : nullptr, true, 0, 2);
+    };
+    if (!metas.empty() && (rc = enqueue_sample(0))) return rc;
+    for (size_t k = 0; k < metas.size(); ++k) {
+      const ChunkMeta& cm = metas[k];
+      const ChunkBufs& b = cb[k & 1];
+      const Grp gp = grp_of(k);
+      if (ovl) DTK_CUDA(cudaStreamWaitEvent(st, ia->sample[k & 1], 0));
+      if (k >= 2 && (rc = head_full(k - 2))) return rc;   // last reader of maps / keys / list of this buffer set
       CorrAssist as;
-      as.tmax = tensor ? tmax : nullptr; as.zero_word = hscratch; as.split_ready = tensor; as.no_thin = thin_free();
-      rc = launch_corr_maps(fv, descC, used, normC, gf, gr, gm, gmap, gb.n, used, maxm, maps, ms, plan, split, st, as);
+      as.tkeys = tensor ? b.tkeys : nullptr; as.zero_word = b.hscratch; as.split_ready = tensor; as.no_thin = cm.no_thin;
+      rc = launch_corr_maps(fv, b.desc, cm.used, b.norm, gp.f, gp.r, gp.m, gp.map0, cm.n_groups, cm.used, cm.maxm, b.maps, ms,
+                            b.plan, b.split, st, as);
       if (rc) return rc;
-      rc = launch_head(maps, used, ms, *g, *hw, out_index, anchors, 2, 0, nullptr, hscratch, st, as.tmax, true);
+      if (ovl) DTK_CUDA(cudaEventRecord(ia->gemm[k & 1], st));
+      if (k + 1 < metas.size() && (rc = enqueue_sample(k + 1))) return rc;
+      if (ovl) DTK_CUDA(cudaStreamWaitEvent(sa, ia->gemm[k & 1], 0));
+      rc = launch_head(b.maps, cm.used, ms, *g, *hw, out_index_ring[k & 3], anchors, 2, 0, nullptr, b.hscratch, sa, as.tkeys, true,
+                       (ovl && ia->mode >= 2) ? ia->head_ctas_per_sm : 0, 1);
       if (rc) return rc;
+      if (ovl) DTK_CUDA(cudaEventRecord(ia->head[k & 1], sa));
     }
-  }
+    for (size_t j = metas.size() >= 2 ? metas.size() - 2 : 0; j < metas.size(); ++j)
+      if ((rc = head_full(j))) return rc;
+    if (ovl) {
+      DTK_CUDA(cudaEventRecord(ia->join, sa));
+      DTK_CUDA(cudaStreamWaitEvent(st, ia->join, 0));
+    }
   }
   if (stop_after < 3) return DINOTRK_OK;
 

@@ -96,7 +96,9 @@ struct Tc2Cfg {
   static constexpr int kABytes = 128 * 128, kBBytes = (TC2_BN / 2) * 128;
   static constexpr int kStageBytes = Base::kOps * (kABytes + kBBytes);
   static constexpr int kStages = (Base::kOps == 2) ? 3 : 6;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 + 256 + (Base::kOps == 1 ? TC_EPI_SCRATCH : 0);
+  // no alignment slack: the kernel has no static shared memory, so the dynamic array starts 1024-byte aligned (trap otherwise)
+  // (the KB saved lets two head CTAs sit next to a correlation-GEMM CTA, inference.cu phase C)
+  static constexpr int kSmem = kStages * kStageBytes + 256 + (Base::kOps == 1 ? TC_EPI_SCRATCH : 0);
   static constexpr uint32_t kIdesc = tc::make_idesc(Base::kFmt, TC2_BM, TC2_BN);
 };
 
@@ -109,8 +111,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   using Base = TcCfg<MODE, TC2_BN>;
   using Cfg = Tc2Cfg<MODE>;
   constexpr int BN = TC2_BN;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ uint8_t smem_raw[];   // no static shared memory in this kernel: the dynamic window starts 1 KB-aligned
+  uint8_t* smem = smem_raw;
+  if (tc::smem_u32(smem) & 1023u) __trap();   // (checked: the 128B-swizzle atoms need 1024-byte aligned stage bases)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* full = bars;                       // [kStages]  (leader's copy is the one that is used)
   uint64_t* empty = bars + Cfg::kStages;       // [kStages]  per CTA (multicast commit)

@@ -507,11 +507,11 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
       if ((rc = make_tmap_2d(&tmQ, q16, (uint64_t)B * heads * N1, HD, FA_BQ, HD, TMAP_F16))) return rc;
       if ((rc = make_tmap_3d(&tmK, k16, (uint64_t)B * heads, N1, HD, FA_BKV, HD, TMAP_F16))) return rc;
       if ((rc = make_tmap_3d(&tmV, v16, (uint64_t)B * heads, HD, N1, HD, 64, TMAP_F16, (uint64_t)N1p8))) return rc;
-      // share of the exponentials evaluated on the FMA pipe (DTK_FA_POLY = 0 / 25 / 37 / 50 %, default 25)
+      // share of the exponentials evaluated on the FMA pipe (DTK_FA_POLY = 0 / 25 / 37 / 50 %, default 0)
       static int poly = -1;
       if (poly < 0) {
         const char* e = getenv("DTK_FA_POLY");
-        poly = e ? atoi(e) : 25;
+        poly = e ? atoi(e) : 0;   // measured on ViT-L (8108 tokens): the MUFU-only variant is the fastest
         DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0xA8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
