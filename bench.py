@@ -40,7 +40,7 @@ P = GEO_H * GEO_W
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--T", type=int, default=50)
@@ -85,46 +85,82 @@ def query_lattice(nq, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md's clocks line):
+    NVML from a Python thread every 20 ms; `nvidia-smi -lms` as the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((time.perf_counter(), float(sm), float(mx), int(bits)))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ts, line in self.rows:
-            if not (t0 <= ts <= t1 + 0.2):
-                continue
-            f = [x.strip() for x in line.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                bits = 0
+                for b, name in zip((0x8, 0x40, 0x20, 0x4), f[3:7]):
+                    if name.lower().startswith("active"):
+                        bits |= b
+                self.rows.append((time.perf_counter(), float(f[0]), float(f[1]), bits))
             except Exception:
                 continue
-            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
-                if val.lower().startswith("active"):
+
+    def stop(self, t0, t1):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        time.sleep(0.1)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, s_, m_, bits in self.rows:
+            if not (t0 <= ts <= t1):
+                continue
+            sm.append(s_); mx.append(m_)
+            for b, name in self.BITS.items():
+                if bits & b:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def measured_peaks():
@@ -184,16 +220,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals, descs = [], None
-    for i in range(args.warmup + args.steps):
+    # every step is one bounded sample (~15 s of host time at T=50, C=1024); the whole arm is kept within ~4 minutes:
+    # with large --steps only as many samples as fit are measured, and the line reports how many
+    vals, descs, budget_s, t_start = [], None, 240.0, time.perf_counter()
+    warm = min(args.warmup, 1)
+    for i in range(warm + args.steps):
+        t_s = time.perf_counter()
         v, cores, desc, total = cpu_reference_sample(args.T, args.C, args.nq, args.noise, seed=0,
                                                      max_anchor_calls=1)
-        if i >= args.warmup:
+        dt = time.perf_counter() - t_s
+        if i >= warm:
             vals.append(v)
         descs = desc
+        if vals and time.perf_counter() - t_start + dt > budget_s:
+            break
     value = statistics.mean(vals) if vals else 0.0
     line = {"impl": "reference", "metric": "query-points/sec (854x476, T=%d)" % args.T, "value": value,
-            "unit": "query-points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "unit": "query-points/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": warm,
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
             "ms_per_step": 1000.0 / value if value else None, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "T": args.T, "C": args.C, "query_points": args.nq},
@@ -257,7 +301,7 @@ def run_b200(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(0.1)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -344,6 +388,21 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def ncu_traffic(csv_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture (profiles/), bytes per launch."""
+    path = os.path.join(ROOT, "profiles", csv_name)
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, seen = 0.0, 0
+    for line in open(path):
+        f = line.strip().split(",")
+        if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and len(f) >= 3:
+            tot += float(f[2].strip('"')) * unit.get(f[1], 1.0)
+            seen += 1
+    return tot if seen == 2 else None
+
+
 def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks):
     """Algorithmic work per launch / average launch time for one kernel class."""
     ms_total, launches = stat
@@ -353,7 +412,11 @@ def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks):
         flops = 2.0 * maps_per_launch * P * args.C  # <d, F[p]> for every token of the target frame
         ach = flops / avg_s / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_sustained"], "traffic": None,
+                "frac": ach / peaks["tf_sustained"],
+                "traffic": ncu_traffic("ncu_r1_final_tc_gemm2.csv") if name == "corr_gemm" and args.precision == "fp16x3" else None,
+                "traffic_note": ("DRAM read + write bytes of one 16384-map launch (profiles/ncu_r1_final_tc_gemm2.csv); "
+                                 "algorithmic bytes of such a launch: maps out 531 MB + keys 4 MB + fp16 hi/lo operands "
+                                 "~110 MB = ~645 MB"),
                 "note": ("algorithmic FLOPs = 2*maps*P*C per launch; peak = sustained cuBLAS bf16 (%s). precision=%s: "
                          "fp16x3 executes 3 kind::f16 MMA passes (lo*hi, hi*lo, hi*hi) per algorithmic FLOP, so the tensor "
                          "pipe is busy ~3x this fraction; fp32 = exact FFMA GEMM on the CUDA cores") % (peaks["which"], args.precision),

@@ -485,13 +485,13 @@ constexpr int WMP = 16;   // pitch of the input window rows (15 used): float4 lo
 constexpr int WHC = 20;   // hidden window [position][16 channels], 20-float pitch: float4 reads of consecutive positions
                           // fall into distinct bank groups
 
-__global__ void __launch_bounds__(TMK_THREADS, 8)
+__global__ void __launch_bounds__(TMK_THREADS, 12)   // 40 registers: 12 CTAs per SM hide the per-map latency chain
 head_tm_kernel(const float* __restrict__ maps, const unsigned long long* __restrict__ tkeys, int n_tiles, int n_maps,
                HeadParams hp, dinotrk_head_weights wts, const int* __restrict__ out_index, float* __restrict__ out,
                int* __restrict__ aux, int* __restrict__ slow_list, int* __restrict__ slow_count) {
   __shared__ __align__(16) float sm_m[WM * WMP];          // input window, zero outside the map
   __shared__ __align__(16) float sm_h[WH * WH * WHC];     // hidden window, zero outside the map
-  __shared__ __align__(16) float sm_w2[16 * 12];          // output-layer weights [channel][9 taps + 3 pad]
+  __shared__ __align__(16) float sm_w2[4 * 9 * 4];        // output-layer weights [channel / 4][tap][channel % 4]
   __shared__ float sm_red[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = hp.h, w = hp.w, P = hp.P;
@@ -500,7 +500,7 @@ head_tm_kernel(const float* __restrict__ maps, const unsigned long long* __restr
 #pragma unroll
   for (int k = 0; k < 9; ++k) w1r[k] = wts.w1[ch][k];
   const float b1r = wts.b1[ch];
-  for (int i = tid; i < 16 * 12; i += TMK_THREADS) { const int o = i / 12, k = i - o * 12; sm_w2[i] = k < 9 ? wts.w2[o][k] : 0.f; }
+  for (int i = tid; i < 4 * 9 * 4; i += TMK_THREADS) { const int o4 = i / 36, k = (i / 4) % 9, j = i & 3; sm_w2[i] = wts.w2[o4 * 4 + j][k]; }
   __syncthreads();
 
   int map = blockIdx.x;
@@ -570,29 +570,26 @@ head_tm_kernel(const float* __restrict__ maps, const unsigned long long* __restr
     for (int y = rg; y < WH; y += TMK_THREADS / 16) {
       const int r = arow - 6 + y;
       const bool row_in = r >= 0 && r < h;
-      float in[3][16];
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(sm_m + (y + ky) * WMP + 4 * q);
-          in[ky][4 * q] = v.x; in[ky][4 * q + 1] = v.y; in[ky][4 * q + 2] = v.z; in[ky][4 * q + 3] = v.w;
-        }
+      // 3 x 3 input window sliding along the row: three new values per output (broadcast loads: the 16 channel
+      // threads of a row read the same addresses), few live registers -> 12 CTAs per SM
+      const float* m0 = sm_m + y * WMP;
+      float i00 = m0[0], i01 = m0[1], i10 = m0[WMP], i11 = m0[WMP + 1], i20 = m0[2 * WMP], i21 = m0[2 * WMP + 1];
 #pragma unroll
       for (int x = 0; x < WH; ++x) {
+        const float i02 = m0[x + 2], i12 = m0[WMP + x + 2], i22 = m0[2 * WMP + x + 2];
         float a = b1r;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) a = fmaf(w1r[ky * 3 + kx], in[ky][x + kx], a);
+        a = fmaf(w1r[0], i00, a); a = fmaf(w1r[1], i01, a); a = fmaf(w1r[2], i02, a);
+        a = fmaf(w1r[3], i10, a); a = fmaf(w1r[4], i11, a); a = fmaf(w1r[5], i12, a);
+        a = fmaf(w1r[6], i20, a); a = fmaf(w1r[7], i21, a); a = fmaf(w1r[8], i22, a);
         const int c = acol - 6 + x;
         sm_h[(y * WH + x) * WHC + ch] = (row_in && c >= 0 && c < w) ? fmaxf(a, 0.f) : 0.f;
+        i00 = i01; i01 = i02; i10 = i11; i11 = i12; i20 = i21; i21 = i22;
       }
     }
     __syncthreads();
     mout = warp_max(mout);
 
-    // ---- logits on the 11 x 11 box; thread = box pixel; channel-major accumulation, then the 3 x 3 taps ----
+    // ---- logits on the 11 x 11 box; thread = box pixel ----
     float z = -INFINITY;
     bool valid = false, indisc = false;
     float px = 0.f, py = 0.f;
@@ -603,26 +600,15 @@ head_tm_kernel(const float* __restrict__ maps, const unsigned long long* __restr
       if (valid) {
         float a = wts.b2;
 #pragma unroll
-        for (int o4 = 0; o4 < 4; ++o4) {
-          float4 hv[9];
+        for (int o4 = 0; o4 < 4; ++o4)
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-              hv[ky * 3 + kx] = *reinterpret_cast<const float4*>(sm_h + ((y + ky) * WH + x + kx) * WHC + o4 * 4);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 wa = *reinterpret_cast<const float4*>(sm_w2 + (o4 * 4 + j) * 12);
-            const float4 wb = *reinterpret_cast<const float4*>(sm_w2 + (o4 * 4 + j) * 12 + 4);
-            const float w8 = sm_w2[(o4 * 4 + j) * 12 + 8];
-            const float wk[9] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, w8};
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-              const float hvk = j == 0 ? hv[k].x : j == 1 ? hv[k].y : j == 2 ? hv[k].z : hv[k].w;
-              a = fmaf(wk[k], hvk, a);
+            for (int kx = 0; kx < 3; ++kx) {   // one float4 of hidden values (4 channels) x one float4 of weights per tap
+              const float4 hv = *reinterpret_cast<const float4*>(sm_h + ((y + ky) * WH + x + kx) * WHC + o4 * 4);
+              const float4 wv4 = *reinterpret_cast<const float4*>(sm_w2 + (o4 * 9 + ky * 3 + kx) * 4);
+              a = fmaf(wv4.x, hv.x, a); a = fmaf(wv4.y, hv.y, a); a = fmaf(wv4.z, hv.z, a); a = fmaf(wv4.w, hv.w, a);
             }
-          }
-        }
         z = a;
         const int dr = (r - arow) * hp.stride_px, dc = (c - acol) * hp.stride_px;
         indisc = dr * dr + dc * dc <= hp.radius2;

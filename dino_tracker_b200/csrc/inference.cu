@@ -222,16 +222,20 @@ struct InferAsync {
   cudaEvent_t fork, join, sample[2], gemm[2], head[2];
   int head_ctas_per_sm;
 };
+static int g_overlap_mode = -1;   // -1: DTK_OVERLAP or the default (1); see dinotrk_infer_set_overlap
 static InferAsync* infer_async() {
   static InferAsync ia;
-  static int state = 0;   // 0: not tried, 1: ready, -1: disabled / failed
+  static int state = 0;   // 0: not created, 1: ready, -1: creation failed
+  int mode = g_overlap_mode;
+  if (mode < 0) {
+    const char* e = getenv("DTK_OVERLAP");
+    mode = e ? atoi(e) : 1;
+  }
+  if (mode <= 0) return nullptr;
   if (state == 0) {
     state = -1;
-    const char* e = getenv("DTK_OVERLAP");
-    if (e && atoi(e) == 0) return nullptr;
-    ia.mode = e ? atoi(e) : 1;
     const char* hc = getenv("DTK_HEAD_OVERLAP_CTAS");
-    ia.head_ctas_per_sm = hc ? atoi(hc) : 1;
+    ia.head_ctas_per_sm = hc ? atoi(hc) : 2;
     if (cudaStreamCreateWithFlags(&ia.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaStreamCreateWithFlags(&ia.aux2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     cudaEvent_t* evs[] = {&ia.fork, &ia.join, &ia.sample[0], &ia.sample[1], &ia.gemm[0], &ia.gemm[1], &ia.head[0], &ia.head[1]};
@@ -239,7 +243,9 @@ static InferAsync* infer_async() {
       if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     state = 1;
   }
-  return state == 1 ? &ia : nullptr;
+  if (state != 1) return nullptr;
+  ia.mode = mode;
+  return &ia;
 }
 
 }  // namespace dtk
@@ -247,6 +253,12 @@ static InferAsync* infer_async() {
 using namespace dtk;
 
 extern "C" {
+
+int dinotrk_infer_set_overlap(int mode) {
+  DTK_CHECK_ARG(mode >= -1 && mode <= 2, "infer_set_overlap: mode must be -1 (default / DTK_OVERLAP), 0, 1 or 2");
+  g_overlap_mode = mode;
+  return DINOTRK_OK;
+}
 
 size_t dinotrk_corr_track_workspace_bytes(int total_maps, int n_groups, int C, const dinotrk_geom* g) {
   if (!g) return 0;

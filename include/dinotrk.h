@@ -129,6 +129,12 @@ int dinotrk_head(const float* maps, int n_maps, const dinotrk_geom* g,
  * the outputs of earlier phases are then inputs.  SYNCS the stream once when phase 2 runs (reads
  * the per-frame anchor counts back to size the anchor work lists). */
 size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N, int chunk_maps);
+/* Phase 2 pipelining across CUDA streams (process-wide; results are identical in every mode):
+ * 0 = everything on the caller's stream; 1 (default) = the descriptor sampling of chunk k+1 runs on an
+ * internal side stream under the correlation GEMM of chunk k; 2 = the head's fast path as well;
+ * -1 = back to the default / the DTK_OVERLAP environment variable.  All side-stream work is joined back
+ * into the caller's stream before dinotrk_infer returns. */
+int dinotrk_infer_set_overlap(int mode);
 int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
                   const dinotrk_head_weights* hw, const float* query_points, int N,
                   float anchor_th, float cos_th, int frame_batch, int start_phase, int stop_after,

@@ -242,3 +242,39 @@ def test_infer_medium_against_oracle(precision):
     assert (r["traj"].cpu() - aux["trajs"]).abs().max().item() <= XY_TOL
     assert torch.equal(r["occ"].bool().cpu(), o_ref)
     assert (r["cos_sims"].cpu() - aux["cos_sims"]).abs().max().item() <= 2e-5
+
+
+def test_infer_pipeline_modes_agree():
+    """Phase-C pipelining (side streams, double-buffered chunks, deferred full-map head) must not change a bit:
+    modes 0 / 1 / 2 and several chunk sizes against each other, and against the oracle."""
+    from dino_tracker_b200 import ModelInference, _lib, model_inference as mim
+    geo = Geometry()
+    T, C = 6, 128
+    feats, _ = synth.shifted_field_features(T, C, geo.h, geo.w, seed=41, noise=0.2, max_shift=2)
+    head = synth.head_weights("sharp", seed=41)
+    q = synth.lattice_query_points(5, 4, geo.H, geo.W, t_q=[i % T for i in range(20)], margin=30.0, jitter_seed=41)
+    model = make_model(geo, feats, head, "fp16x3")
+    mi = ModelInference(model, model.range_normalizer, 0.7, 0.6)
+    lib = _lib.load()
+    old = mim.DEFAULT_CHUNK_MAPS
+    results = {}
+    try:
+        for chunk in (256, 300, 16384):
+            for mode in (0, 1, 2):
+                assert lib.dinotrk_infer_set_overlap(mode) == 0
+                mim.DEFAULT_CHUNK_MAPS = chunk
+                r = mi.infer_all(q.to(DEV))
+                torch.cuda.synchronize()
+                results[(chunk, mode)] = {k: r[k].clone() for k in ("traj", "cos_sims", "anchors", "occ")}
+    finally:
+        mim.DEFAULT_CHUNK_MAPS = old
+        lib.dinotrk_infer_set_overlap(-1)
+    ref = results[(16384, 0)]
+    vis = ref["cos_sims"] >= 0.7
+    for key, r in results.items():
+        assert torch.equal(r["traj"], ref["traj"]) and torch.equal(r["cos_sims"], ref["cos_sims"]), key
+        assert torch.equal(r["occ"], ref["occ"]), key
+        assert torch.equal(r["anchors"][vis], ref["anchors"][vis]), key
+    t_ref, o_ref, aux = oi.infer(feats, q, head, geo, 0.7, 0.6, return_all=True)
+    assert (ref["traj"].cpu() - aux["trajs"]).abs().max().item() <= XY_TOL
+    assert torch.equal(ref["occ"].bool().cpu(), o_ref)
