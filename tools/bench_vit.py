@@ -19,7 +19,7 @@ def main():
     from dino_tracker_b200 import _lib
     _lib.load()
     r = bench.stage_timings(a, "cuda:0", _lib, bench.measured_peaks(), vit_only=True)
-    r["vit"]["fa_poly"] = os.environ.get("DTK_FA_POLY", "25")
+    r["vit"]["fa_poly"] = os.environ.get("DTK_FA_POLY", "0")
     print(json.dumps(r["vit"]))
 
 
