@@ -406,6 +406,36 @@ static int run_gemm_pair(const void* A, uint64_t a_rows, const void* Bm, uint64_
 
 constexpr int VIT_ROW_CHUNK = 1024;  // query rows per attention-score chunk
 
+// fused attention over fp16 q [B*heads][N1][64] (pre-scaled by 64^-1/2 * log2 e), k [B*heads][N1][64] and
+// v^T [B*heads][64][N1p] (row pitch N1p, a multiple of 8): out[b*N1 + n][h*64 + e], row pitch D, fp32 or fp16
+static int launch_flash(const __half* q16, const __half* k16, const __half* v16, int B, int heads, int N1, int N1p, int D,
+                        void* out, bool out_f16, cudaStream_t st) {
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_tmap_2d(&tmQ, q16, (uint64_t)B * heads * N1, HD, FA_BQ, HD, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tmK, k16, (uint64_t)B * heads, N1, HD, FA_BKV, HD, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tmV, v16, (uint64_t)B * heads, HD, N1, HD, 64, TMAP_F16, (uint64_t)N1p))) return rc;
+  // share of the exponentials evaluated on the FMA pipe (DTK_FA_POLY = 0 / 25 / 37 / 50 %, default 0)
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("DTK_FA_POLY");
+    poly = e ? atoi(e) : 0;   // measured on ViT-L (8108 tokens): the MUFU-only variant is the fastest
+    DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0xA8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0xAA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+  }
+  FlashParams fpar{N1, D, heads, out, out_f16 ? 1 : 0};
+  ProfRange pr(PROF_VIT_ATTN, st);
+  const dim3 fgrid(cdiv(N1, FA_BQ), B * heads);
+  if (poly <= 0) flash_attn_kernel<0><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
+  else if (poly <= 25) flash_attn_kernel<0x88><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
+  else if (poly <= 37) flash_attn_kernel<0xA8><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
+  else flash_attn_kernel<0xAA><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
 }  // namespace dtk
 
 using namespace dtk;
@@ -430,6 +460,14 @@ size_t dinotrk_vit_workspace_bytes(const dinotrk_vit_config* c, const dinotrk_ge
   b += align_up((size_t)c->heads * VIT_ROW_CHUNK * N1p * 4, 256);          // attention scores of one row chunk
   b += 4 * align_up((size_t)(c->heads + 2) * 4, 256) + 4096;               // plan tables
   return b;
+}
+
+int dinotrk_vit_attention(const void* q16, const void* k16, const void* vT16, int B, int heads, int N1, int N1p,
+                          float* out, void* stream) {
+  DTK_CHECK_ARG(q16 && k16 && vT16 && out, "vit_attention: null pointer");
+  DTK_CHECK_ARG(B > 0 && heads > 0 && N1 > 0 && N1p >= N1 && N1p % 8 == 0, "vit_attention: bad sizes");
+  return launch_flash(reinterpret_cast<const __half*>(q16), reinterpret_cast<const __half*>(k16),
+                      reinterpret_cast<const __half*>(vT16), B, heads, N1, N1p, heads * HD, out, false, (cudaStream_t)stream);
 }
 
 int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const dinotrk_vit_config* c,
@@ -510,28 +548,7 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
          : f16 ? run_gemm<EpiQKV16, 256, TcMode::F16>(y16, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st)
                : run_gemm<EpiQKV16, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st);
       if (rc) return rc;
-      CUtensorMap tmQ, tmK, tmV;
-      if ((rc = make_tmap_2d(&tmQ, q16, (uint64_t)B * heads * N1, HD, FA_BQ, HD, TMAP_F16))) return rc;
-      if ((rc = make_tmap_3d(&tmK, k16, (uint64_t)B * heads, N1, HD, FA_BKV, HD, TMAP_F16))) return rc;
-      if ((rc = make_tmap_3d(&tmV, v16, (uint64_t)B * heads, HD, N1, HD, 64, TMAP_F16, (uint64_t)N1p8))) return rc;
-      // share of the exponentials evaluated on the FMA pipe (DTK_FA_POLY = 0 / 25 / 37 / 50 %, default 0)
-      static int poly = -1;
-      if (poly < 0) {
-        const char* e = getenv("DTK_FA_POLY");
-        poly = e ? atoi(e) : 0;   // measured on ViT-L (8108 tokens): the MUFU-only variant is the fastest
-        DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0xA8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0xAA>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-      }
-      FlashParams fpar{N1, D, heads, f16 ? (void*)y16 : (void*)y, f16 ? 1 : 0};
-      ProfRange pr(PROF_VIT_ATTN, st);
-      const dim3 fgrid(cdiv(N1, FA_BQ), B * heads);
-      if (poly <= 0) flash_attn_kernel<0><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
-      else if (poly <= 25) flash_attn_kernel<0x88><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
-      else if (poly <= 37) flash_attn_kernel<0xA8><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
-      else flash_attn_kernel<0xAA><<<fgrid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, fpar);
-      DTK_LAUNCHED();
+      if ((rc = launch_flash(q16, k16, v16, B, heads, N1, N1p8, D, f16 ? (void*)y16 : (void*)y, f16, st))) return rc;
     } else {
       if ((rc = run_gemm<EpiQKV, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, EpiQKV{{}, q, k, vT, w[3], N1, D, heads, N1p},
                                       PROF_VIT_GEMM, st))) return rc;

@@ -213,6 +213,13 @@ size_t dinotrk_vit_workspace_bytes(const dinotrk_vit_config* c, const dinotrk_ge
 int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const dinotrk_vit_config* c,
                         const dinotrk_vit_weights* wt, float* out_tpc, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* The attention of one ViT block on its own (the fused tcgen05 kernel of dinotrk_vit_forward; head dim 64):
+ * q16 [B*heads][N1][64] fp16 ALREADY multiplied by 64^-1/2 * log2(e), k16 [B*heads][N1][64] fp16,
+ * vT16 [B*heads][64][N1p] fp16 (v transposed, row pitch N1p >= N1, a multiple of 8);
+ * out [B*N1][heads*64] fp32 = softmax(q k^T) v with head h in columns [64 h, 64 h + 64)
+ * (the layout of the reference's attn output before `proj`, dinov2 attention.py). */
+int dinotrk_vit_attention(const void* q16, const void* k16, const void* vT16, int B, int heads, int N1, int N1p,
+                          float* out, void* stream);
 
 /* ---- best buddies (preprocessing_dino_bb/extract_dino_best_buddies.py:12-54) ------------------------ */
 /* For every ordered pair k (source frame pair_src[k], target frame pair_tgt[k]; device int32[n_pairs]):

@@ -52,3 +52,57 @@ def test_vit_is_deterministic_and_batch_invariant():
     assert torch.equal(a, b), f"non-deterministic: {(a - b).abs().max().item()}"
     c = ex(video[1:4]).clone()
     assert torch.equal(a[1:4], c), f"batch-dependent: {(a[1:4] - c).abs().max().item()}"
+
+
+def _attention_reference(q, k, v):
+    """softmax(q k^T / 8) v in float64 from the fp16-rounded operands the kernel sees.  q: [BH][N][64] (unscaled)."""
+    s = torch.einsum("hnd,hmd->hnm", q.double(), k.double())
+    p = torch.softmax(s, dim=-1)
+    return torch.einsum("hnm,hmd->hnd", p, v.double())
+
+
+@pytest.mark.parametrize("case", ["random-small", "random-large", "ramp", "late-spike", "tail-1", "tail-63"])
+def test_fused_attention_against_float64(case):
+    """The attention kernel on its own (dinotrk_vit_attention): accumulator kept in TMEM across key tiles with a LAZY
+    running maximum -- 'ramp' and 'late-spike' make the row maxima jump by far more than 2^8 between key tiles, so the
+    tcgen05.ld / multiply / tcgen05.st rescale of the accumulator (row sums included) runs many times; the tail cases
+    end the keys 1 / 63 columns into the last 64-key tile."""
+    from dino_tracker_b200 import _lib
+    lib = _lib.load()
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(11)
+    B, heads = 2, 3
+    N1 = {"tail-1": 64 * 5 + 1, "tail-63": 64 * 4 + 63}.get(case, 700)
+    BH = B * heads
+    q = torch.randn(BH, N1, 64, generator=g)
+    k = torch.randn(BH, N1, 64, generator=g)
+    v = torch.randn(BH, N1, 64, generator=g)
+    if case == "random-large":
+        q *= 6.0
+    elif case == "ramp":          # score grows with the key index: ~16 log2 units per 64-key tile, every tile rescales
+        q[:, :, 0] = 4.0
+        k[:, :, 0] = torch.linspace(0, 240, N1)[None]
+    elif case == "late-spike":    # one late key dominates everything before it (row maxima jump by ~100 log2 units)
+        u = torch.sign(torch.randn(64, generator=g))
+        q = 0.2 * q + 3.0 * u
+        k[:, N1 - 70] = 3.0 * u
+    # the kernel's inputs: fp16, q pre-scaled by 64^-1/2 * log2(e)
+    scale = 0.125 * 1.4426950408889634
+    q16 = (q * scale).half()
+    k16 = k.half()
+    v16 = v.half()
+    ref = _attention_reference(q16.float() / scale / 8.0, k16.float(), v16.float())   # exp2(q16 . k) = exp((q16 / scale / 8) . k)
+    N1p = (N1 + 7) // 8 * 8
+    vT = torch.zeros(BH, 64, N1p, dtype=torch.half)
+    vT[:, :, :N1] = v16.transpose(1, 2)
+    out = torch.full((B * N1, heads * 64), float("nan"), device=dev)
+    qd, kd, vd = q16.to(dev).contiguous(), k16.to(dev).contiguous(), vT.to(dev).contiguous()
+    _lib.check(lib.dinotrk_vit_attention(_lib.ptr(qd), _lib.ptr(kd), _lib.ptr(vd), B, heads, N1, N1p, _lib.ptr(out),
+                                         _lib.stream_ptr()), "vit_attention")
+    torch.cuda.synchronize()
+    got = out.cpu().view(B, N1, heads, 64).permute(0, 2, 1, 3).reshape(BH, N1, 64).double()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    print(f"attention[{case}] max |diff| = {err:.3e} (max |ref| = {ref.abs().max().item():.3f})")
+    # fp16 P (2^-11 relative per probability) and fp16-exact operands: a few 1e-3 absolute on |v| ~ 1..4
+    assert err <= 2e-3
