@@ -14,6 +14,7 @@ from .model_inference import (ModelInference, generate_trajectory_input, generat
 
 from .vit import DinoV2Features, get_dino_features_video  # noqa: F401
 from .pipeline import build_tracker_from_video, track_video, save_dino_embed_video  # noqa: F401
+from .benchmark import infer_query_frames, save_predictions, run_videos  # noqa: F401
 
-__all__ = ["DinoV2Features", "get_dino_features_video", "build_tracker_from_video", "track_video", "save_dino_embed_video","Tracker", "ModelInference", "RangeNormalizer", "generate_trajectory_input", "generate_trajectory",
+__all__ = ["infer_query_frames", "save_predictions", "run_videos", "DinoV2Features", "get_dino_features_video", "build_tracker_from_video", "track_video", "save_dino_embed_video","Tracker", "ModelInference", "RangeNormalizer", "generate_trajectory_input", "generate_trajectory",
            "generate_trajectories"]

@@ -60,3 +60,19 @@ def test_shards_and_lpt():
     assert sorted(i for a in assign for i in a) == list(range(len(costs)))
     loads = [sum(costs[i] for i in a) for a in assign]
     assert max(loads) <= 1.5 * (sum(costs) / 4) or max(loads) == max(costs)
+
+
+def test_run_videos_covers_every_video_once():
+    """Multi-video launcher: LPT assignment, every video on exactly one rank, heaviest videos spread first."""
+    from dino_tracker_b200.benchmark import run_videos
+    ids = [f"v{i}" for i in range(7)]
+    costs = [50 * 256, 30 * 100, 90 * 400, 10 * 10, 60 * 256, 24 * 50, 80 * 300]
+    for world in (1, 2, 3, 8):
+        seen, loads = [], []
+        for rank in range(world):
+            r = run_videos(ids, costs, rank, world, lambda v: costs[ids.index(v)])
+            seen += list(r)
+            loads.append(sum(r.values()))
+        assert sorted(seen) == sorted(ids)
+        if world == 2:
+            assert max(loads) <= 0.6 * sum(costs)     # balanced: neither rank carries more than 60 %

@@ -54,3 +54,37 @@ def test_dino_embed_file_round_trip(tmp_path):
     assert saved.shape == (T, D, 13, 17) and saved.dtype == torch.float32 and saved.device.type == "cpu"
     m = Tracker(video=video.to("cuda:0"), dino_embed_path=path, device="cuda:0", delta_channels=[3, 4, 4, 4, D])
     assert torch.equal(m.dino_embed_video.cpu(), saved)
+
+
+def test_benchmark_query_frames_in_one_call(tmp_path):
+    """all query frames of a benchmark video through one inference call == the reference's per-frame loop
+    (inference_benchmark.py:36-41), bit for bit, and the same files on disk."""
+    from dino_tracker_b200 import ModelInference, Tracker, infer_query_frames, save_predictions, run_videos
+    geo = Geometry(H=98, W=126)
+    T, C = 6, 64
+    feats, _ = synth.shifted_field_features(T, C, geo.h, geo.w, seed=21, noise=0.2, max_shift=2)
+    video = synth.random_video(T, geo.H, geo.W, seed=22)
+    model = Tracker(video=video, dino_embed_video=feats, device="cuda:0", delta_channels=[3, 4, 4, 4, C])
+    model.tracker_head.load_state_dict(synth.head_weights("sharp", seed=5))
+    mi = ModelInference(model, model.range_normalizer, 0.7, 0.6)
+    qp = {}
+    for f, (nx, ny) in {0: (3, 2), 2: (2, 2), 5: (4, 1)}.items():   # TAP-Vid style: {query frame: N_f x 3 (x, y, t)}
+        qp[f] = synth.lattice_query_points(nx, ny, geo.H, geo.W, t_q=f, margin=14.0, jitter_seed=f).numpy()
+    got = infer_query_frames(mi, qp)
+    assert sorted(got) == [0, 2, 5]
+    for f in qp:
+        t_loop, o_loop = mi.infer(torch.from_numpy(qp[f]).to("cuda:0"))       # what the reference's loop does
+        assert torch.equal(got[f][0], t_loop) and torch.equal(got[f][1], o_loop)
+        t_ref, o_ref = oi.infer(model.refined_features.cpu().contiguous(), torch.from_numpy(qp[f]),
+                                synth.head_weights("sharp", seed=5), geo, 0.7, 0.6)
+        assert (got[f][0].cpu() - t_ref).abs().max().item() <= 1e-3 and torch.equal(got[f][1].cpu(), o_ref)
+    save_predictions(got, str(tmp_path / "trajectories"), str(tmp_path / "occlusions"))
+    for f in qp:
+        tr = np.load(tmp_path / "trajectories" / f"trajectories_{f}.npy")
+        oc = np.load(tmp_path / "occlusions" / f"occlusion_preds_{f}.npy")
+        assert tr.shape == (qp[f].shape[0], T, 2) and tr.dtype == np.float32 and oc.shape == (qp[f].shape[0], T) and oc.dtype == bool
+    # launcher: two ranks share three videos by cost; together they cover each video once
+    seen = []
+    for rank in range(2):
+        seen += list(run_videos(["a", "b", "c"], [5.0, 3.0, 2.0], rank, 2, lambda v: v.upper()).items())
+    assert sorted(seen) == [("a", "A"), ("b", "B"), ("c", "C")]
