@@ -133,7 +133,8 @@ size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N,
  * 0 = everything on the caller's stream; 1 (default) = the descriptor sampling of chunk k+1 runs on an
  * internal side stream under the correlation GEMM of chunk k; 2 = the head's fast path as well;
  * -1 = back to the default / the DTK_OVERLAP environment variable.  All side-stream work is joined back
- * into the caller's stream before dinotrk_infer returns. */
+ * into the caller's stream before dinotrk_infer returns.  The side streams and their events are one set per
+ * process (one process per GPU): with mode >= 1 do not run dinotrk_infer from two host threads at once. */
 int dinotrk_infer_set_overlap(int mode);
 int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
                   const dinotrk_head_weights* hw, const float* query_points, int N,
