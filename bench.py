@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--C", type=int, default=1024, help="feature dim: 1024 = ViT-L/14@15 (shipped config), 768 = ViT-B/14")
     ap.add_argument("--nq", type=int, default=256)
     ap.add_argument("--noise", type=float, default=0.25)
-    ap.add_argument("--chunk-maps", type=int, default=16384)
+    ap.add_argument("--chunk-maps", type=int, default=32768)
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp32"],
                     help="wide correlation groups: tcgen05 3xTF32 tensor cores, or the exact-fp32 FFMA GEMM")
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the cpu_baseline leg")
@@ -413,10 +413,12 @@ def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks):
         ach = flops / avg_s / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sustained"],
-                "traffic": ncu_traffic("ncu_r1_final_tc_gemm2.csv") if name == "corr_gemm" and args.precision == "fp16x3" else None,
-                "traffic_note": ("DRAM read + write bytes of one 16384-map launch (profiles/ncu_r1_final_tc_gemm2.csv); "
-                                 "algorithmic bytes of such a launch: maps out 531 MB + keys 4 MB + fp16 hi/lo operands "
-                                 "~110 MB = ~645 MB"),
+                "traffic": (ncu_traffic("ncu_r1_final_tc_gemm2.csv") * maps_per_launch / 16384.0
+                            if name == "corr_gemm" and args.precision == "fp16x3" and ncu_traffic("ncu_r1_final_tc_gemm2.csv") else None),
+                "traffic_note": ("DRAM read + write bytes per launch, from the ncu --set full capture of a 16384-map launch "
+                                 "(profiles/ncu_r1_final_tc_gemm2.csv: 704 MB = 43.0 KB per map) scaled to this run's maps per "
+                                 "launch; algorithmic bytes per map: 32.4 KB map out + 0.26 KB keys + ~6.7 KB fp16 hi/lo operands "
+                                 "= ~39.4 KB"),
                 "note": ("algorithmic FLOPs = 2*maps*P*C per launch; peak = sustained cuBLAS bf16 (%s). precision=%s: "
                          "fp16x3 executes 3 kind::f16 MMA passes (lo*hi, hi*lo, hi*hi) per algorithmic FLOP, so the tensor "
                          "pipe is busy ~3x this fraction; fp32 = exact FFMA GEMM on the CUDA cores") % (peaks["which"], args.precision),

@@ -15,7 +15,7 @@ from . import _lib
 from .range_normalizer import RangeNormalizer
 from .tracker import Tracker
 
-DEFAULT_CHUNK_MAPS = 16384   # maps per correlation/head chunk (32 KB each at 854x476); clamped to the work of the call
+DEFAULT_CHUNK_MAPS = 32768   # maps per correlation/head chunk (32 KB each at 854x476); clamped to the work of the call
 
 
 # ---- module-level helpers (models/model_inference.py:8-74) -------------------------------------

@@ -58,7 +58,8 @@ def test_dino_embed_file_round_trip(tmp_path):
 
 def test_benchmark_query_frames_in_one_call(tmp_path):
     """all query frames of a benchmark video through one inference call == the reference's per-frame loop
-    (inference_benchmark.py:36-41), bit for bit, and the same files on disk."""
+    (inference_benchmark.py:36-41) within the parity bar (group sizes differ, so thin groups of the loop run on the
+    exact-fp32 streaming kernel while the batched call runs them on the split-precision tensor GEMM), same files on disk."""
     from dino_tracker_b200 import ModelInference, Tracker, infer_query_frames, save_predictions, run_videos
     geo = Geometry(H=98, W=126)
     T, C = 6, 64
@@ -74,7 +75,7 @@ def test_benchmark_query_frames_in_one_call(tmp_path):
     assert sorted(got) == [0, 2, 5]
     for f in qp:
         t_loop, o_loop = mi.infer(torch.from_numpy(qp[f]).to("cuda:0"))       # what the reference's loop does
-        assert torch.equal(got[f][0], t_loop) and torch.equal(got[f][1], o_loop)
+        assert (got[f][0] - t_loop).abs().max().item() <= 1e-3 and torch.equal(got[f][1], o_loop)
         t_ref, o_ref = oi.infer(model.refined_features.cpu().contiguous(), torch.from_numpy(qp[f]),
                                 synth.head_weights("sharp", seed=5), geo, 0.7, 0.6)
         assert (got[f][0].cpu() - t_ref).abs().max().item() <= 1e-3 and torch.equal(got[f][1].cpu(), o_ref)
