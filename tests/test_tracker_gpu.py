@@ -278,3 +278,54 @@ def test_infer_pipeline_modes_agree():
     t_ref, o_ref, aux = oi.infer(feats, q, head, geo, 0.7, 0.6, return_all=True)
     assert (ref["traj"].cpu() - aux["trajs"]).abs().max().item() <= XY_TOL
     assert torch.equal(ref["occ"].bool().cpu(), o_ref)
+
+
+def test_full_size_properties():
+    """BASELINE.json config 2 at full size (854x476, T=50, C=1024, 256 query points, 652 800 correlation maps), where the
+    oracle would need a day: size-independent properties instead.
+      * query-order equivariance: permuting the query points permutes the outputs, bit for bit (every map's arithmetic is
+        independent of its row in the GEMM group);
+      * chunking invariance: 4 096-map chunks (160 chunks, pipelined) == 32 768-map chunks, bit for bit;
+      * precision: the split-fp16 tensor path against the exact-fp32 FFMA path: |dxy| <= 1e-3 px, identical occlusion;
+      * semantics: the synthetic video is a translating field; every track follows the known shift of its frame."""
+    import bench
+    from bench_inputs import sharp_head
+    from dino_tracker_b200 import ModelInference, Tracker, model_inference as mim
+    T, C, nq = 50, 1024, 256
+    feats = bench.synth_video_features(T, C, DEV, 1234, 0.25)
+    video = torch.zeros(T, 3, bench.H, bench.W, device=DEV)
+    q = bench.query_lattice(nq, 0).to(DEV)
+    old = mim.DEFAULT_CHUNK_MAPS
+    try:
+        res = {}
+        for prec in ("fp16x3", "fp32"):
+            m = Tracker(video=video, dino_embed_video=feats, device=DEV, delta_channels=[3, 4, 4, 4, C], corr_precision=prec)
+            m.tracker_head.load_state_dict(sharp_head(0))
+            mi = ModelInference(m, m.range_normalizer, 0.7, 0.6)
+            mim.DEFAULT_CHUNK_MAPS = 32768
+            res[prec] = mi.infer_all(q)
+            if prec == "fp16x3":
+                perm = torch.randperm(nq, generator=torch.Generator().manual_seed(0)).to(DEV)
+                rp = mi.infer_all(q[perm])
+                mim.DEFAULT_CHUNK_MAPS = 4096
+                rc = mi.infer_all(q)
+            del m, mi
+        a = res["fp16x3"]
+        assert torch.equal(rp["traj"], a["traj"][perm]) and torch.equal(rp["occ"], a["occ"][perm])
+        assert torch.equal(rp["cos_sims"], a["cos_sims"][perm])
+        assert torch.equal(rc["traj"], a["traj"]) and torch.equal(rc["occ"], a["occ"]) and torch.equal(rc["anchors"], a["anchors"])
+        b = res["fp32"]
+        assert (a["traj"] - b["traj"]).abs().max().item() <= XY_TOL
+        assert torch.equal(a["occ"], b["occ"])
+        # every frame is an anchor frame on this workload: 256 * 50 * 51 maps
+        assert int((a["cos_sims"] >= 0.7).sum().item()) == nq * T
+        # the field translates by whole tokens: frame t shows frame 0 shifted by (dy_t, dx_t) tokens (same recurrence as
+        # bench.synth_video_features), so every track must follow -7 px * shift_t to within half a token
+        cg = torch.Generator().manual_seed(1234)
+        shifts = torch.zeros(T, 2, dtype=torch.long)
+        for t in range(1, T):
+            shifts[t] = (shifts[t - 1] + torch.randint(-1, 2, (2,), generator=cg)).clamp(-3, 3)
+        expect = a["traj"][:, :1, :2].cpu() - 7.0 * shifts[:, [1, 0]].float()[None]       # (x, y) <- (dx, dy)
+        assert (a["traj"][:, :, :2].cpu() - expect).abs().max().item() < 3.5
+    finally:
+        mim.DEFAULT_CHUNK_MAPS = old
