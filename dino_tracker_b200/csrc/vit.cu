@@ -4,10 +4,12 @@
 // token-major feature video [T][P][C]   (models/extractor.py:41-85,137-150; utils.py:32-72; the block arithmetic is
 // facebookresearch/dinov2's -- parity unpinned).
 //
-// Every contraction (patch embedding, qkv, q.k^T, p.v, proj, fc1, fc2) runs on the tcgen05 GEMM of tcgemm.cuh in
-// TF32 with fp32 accumulation in TMEM; bias / position embedding / GELU / LayerScale + residual / head scatter are
-// epilogues on the accumulator.  Round 1 materialises the attention scores per (frame, row chunk) in a workspace
-// (tensor-core GEMM -> row softmax -> tensor-core GEMM); the fused flash-style kernel is the next step.
+// Default path (gemm_f16 = 1, attn_materialized = 0): fp16 operands / fp32 accumulation everywhere.  The linear layers
+// (patch embedding, qkv, proj, fc1, fc2) run on the tcgen05 GEMMs of tcgemm.cuh / tcgemm2.cuh (CTA pairs when gemm_pair = 1)
+// with bias / position embedding / GELU / LayerScale + residual / head scatter as coalesced epilogues on the accumulator;
+// the residual stream stays fp32.  Attention is the fused kernel of flash.cuh (scores never leave the SM).
+// Validation path (attn_materialized = 1): TF32 GEMMs, attention scores materialised per (frame, row chunk) in a workspace
+// (tensor-core GEMM -> row softmax -> tensor-core GEMM).
 #include "common.cuh"
 #include "corr.cuh"
 #include "tcgemm.cuh"
