@@ -424,12 +424,18 @@ def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks):
                          "pipe is busy ~3x this fraction; fp32 = exact FFMA GEMM on the CUDA cores") % (peaks["which"], args.precision),
                 "executed_mma_tflops": ach * 3 if args.precision == "fp16x3" else None}
     if name == "head":
-        flops = 4.67e6 * maps_per_launch  # 2 x (144 + 144) FMA per token, SURVEY.md 8a row a7
+        # the fast path evaluates the refiner exactly on the 13x13 / 11x11 windows: 169*16*9 + 121*16*9 = 41 760 FMA per map
+        # (the reference's full-map formulation, SURVEY.md 8a row a7, is 4.67 MFLOP per map: 56x more)
+        flops = 2.0 * 41760 * maps_per_launch
         ach = flops / avg_s / 1e12
         pk = fp32_peak_tflops(clocks)
         return {"kernel": name, "bound": "fp32-cuda-core", "achieved": ach, "peak": pk, "unit": "TFLOP/s",
                 "frac": ach / pk, "traffic": None,
-                "note": "refiner convs are exact-fp32 CUDA-core work; peak = 148 SMs x 128 lanes x 2 x max SM clock"}
+                "reference_formulation_tflops": 4.67e6 * maps_per_launch / avg_s / 1e12,
+                "note": ("exact-fp32 CUDA-core work of the windowed refiner (83.5 kFLOP per map; the full-map formulation the "
+                         "reference evaluates is 4.67 MFLOP per map and is only run for uncertified maps); the kernel is "
+                         "issue / latency bound, not FMA bound (profiles/ncu_r1_final_head_tm.csv: 5.8 k warp instructions per "
+                         "map, issue slots 55 % busy); peak = 148 SMs x 128 lanes x 2 x max SM clock")}
     # HBM-bound streaming kernels: feature bytes read once per launch
     nbytes = maps_per_launch * 0  # filled by the dedicated probe
     return {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
