@@ -60,6 +60,8 @@ SIGNATURES = {
     "dinotrk_head": (c_int, [_P, c_int, POINTER(Geom), POINTER(HeadWeights), _P, _P, c_int, c_int, _P, _P, _P]),
     "dinotrk_infer_workspace_bytes": (c_size_t, [c_int, c_int, POINTER(Geom), c_int, c_int]),
     "dinotrk_infer_set_overlap": (c_int, [c_int]),
+    "dinotrk_infer_max_chunks": (c_size_t, [c_int, c_int, c_int]),
+    "dinotrk_infer_plan": (c_int, [c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P]),
     "dinotrk_infer": (c_int, [POINTER(Features), POINTER(Geom), POINTER(HeadWeights), _P, c_int, c_float, c_float,
                               c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "dinotrk_traj_cos_sims": (c_int, [_P, c_int, c_int, POINTER(Geom), _P, _P, c_int, _P, _P, c_size_t, _P]),

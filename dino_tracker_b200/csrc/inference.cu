@@ -9,6 +9,7 @@
 //   B  cos-sims     : d[n][i] sampled along the trajectory . d[n][t_q]            -> cos[n][i]
 //   C  anchors      : for every anchor frame a, descriptors e[n][i] (a in A_n)    -> anchors[n][a][i]
 //   D  occlusion    : lower medians over anchors, threshold, OR with cos < th     -> occ[n][i]
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -215,6 +216,60 @@ struct GroupBuf {  // host mirror of the per-chunk group arrays: [frame | row0 |
   }
 };
 
+// ---- chunk planning (host only) ---------------------------------------------------------------------------------
+// A phase's work items are cut into chunks of <= ch correlation maps; inside a chunk, items of the same target
+// frame form one group = [frame | first descriptor row | number of rows m | first map | first item] (GroupBuf order).
+//   kind 0 (trajectories): items = (frame t, query row n), t-major; descriptor rows are the N query rows.
+//   kind 1 (anchors): items of anchor frame a = cnt[a] * T pairs (slot, i), a-major; descriptor rows are per chunk.
+struct ChunkMeta { int used, maxm, n_groups; bool no_thin; };
+static void plan_chunks(int kind, int T, int N, const int* cnt, int ch, int gcap, std::vector<ChunkMeta>& metas,
+                        std::vector<int>& plan_host) {
+  metas.clear(); plan_host.clear();
+  GroupBuf gb(gcap);
+  auto commit_chunk = [&](int used, int maxm) {
+    bool no_thin = true;
+    for (int k = 0; k < gb.n; ++k) no_thin = no_thin && gb.v[2 * gb.cap + k] > STREAM_MAX_M;
+    metas.push_back(ChunkMeta{used, maxm, gb.n, no_thin});
+    plan_host.insert(plan_host.end(), gb.v.begin(), gb.v.end());
+  };
+  if (kind == 0) {
+    int t = 0, row = 0;  // next work item: (frame t, query row)
+    while (t < T) {
+      gb.clear();
+      int used = 0, maxm = 0;
+      while (t < T && used < ch && gb.n < gcap) {
+        int m = N - row;
+        if (m > ch - used) m = ch - used;
+        gb.push(t, row, m, used, 0);
+        used += m; row += m;
+        if (m > maxm) maxm = m;
+        if (row == N) { row = 0; ++t; }
+      }
+      commit_chunk(used, maxm);
+    }
+  } else {
+    int a = 0;
+    long long item = 0;  // next work item: anchor frame a, item index within a (slot * T + i)
+    while (a < T) {
+      gb.clear();
+      int used = 0, maxm = 0;
+      while (a < T && used < ch && gb.n < gcap) {
+        long long tot = (long long)cnt[a] * T;
+        long long m = tot - item;
+        if (m > ch - used) m = ch - used;
+        if (m > 0) {
+          gb.push(a, used, (int)m, used, (int)item);
+          used += (int)m; item += m;
+          if ((int)m > maxm) maxm = (int)m;
+        }
+        if (item >= tot) { item = 0; ++a; }
+      }
+      if (used == 0) break;
+      commit_chunk(used, maxm);
+    }
+  }
+}
+
 // auxiliary stream + events of the phase-C pipeline (one set per process; DTK_OVERLAP=0 disables the overlap)
 struct InferAsync {
   int mode;                 // 1: sampling overlapped with the GEMMs (default); 2: sampling and the head fast path
@@ -254,6 +309,31 @@ using namespace dtk;
 
 extern "C" {
 
+static int infer_chunk_maps(int chunk_maps) { return chunk_maps > 0 ? chunk_maps : 4096; }
+// upper bound on the number of chunks of one phase (phase C has the most work items: N * T * T)
+static size_t infer_max_chunks(int T, int N, size_t ch) { return ((size_t)N * T * T + ch - 1) / ch + 2; }
+
+size_t dinotrk_infer_max_chunks(int T, int N, int chunk_maps) { return infer_max_chunks(T, N, (size_t)infer_chunk_maps(chunk_maps)); }
+
+int dinotrk_infer_plan(int kind, int T, int N, const int* anchor_counts, int chunk_maps, int* groups, int* meta,
+                       int max_chunks, int* n_chunks) {
+  DTK_CHECK_ARG((kind == 0 || kind == 1) && T > 0 && N >= 0 && n_chunks, "infer_plan: bad arguments");
+  DTK_CHECK_ARG(kind == 0 || anchor_counts, "infer_plan: kind 1 needs the per-frame anchor counts");
+  const int ch = infer_chunk_maps(chunk_maps), gcap = T + 2;
+  std::vector<ChunkMeta> metas;
+  std::vector<int> plan_host;
+  plan_chunks(kind, T, N, anchor_counts, ch, gcap, metas, plan_host);
+  *n_chunks = (int)metas.size();
+  DTK_CHECK_ARG((int)metas.size() <= max_chunks || (!groups && !meta), "infer_plan: %zu chunks, room for %d", metas.size(), max_chunks);
+  if (groups) std::copy(plan_host.begin(), plan_host.end(), groups);
+  if (meta)
+    for (size_t k = 0; k < metas.size(); ++k) {
+      meta[4 * k] = metas[k].used; meta[4 * k + 1] = metas[k].maxm; meta[4 * k + 2] = metas[k].n_groups;
+      meta[4 * k + 3] = metas[k].no_thin ? 1 : 0;
+    }
+  return DINOTRK_OK;
+}
+
 int dinotrk_infer_set_overlap(int mode) {
   DTK_CHECK_ARG(mode >= -1 && mode <= 2, "infer_set_overlap: mode must be -1 (default / DTK_OVERLAP), 0, 1 or 2");
   g_overlap_mode = mode;
@@ -292,9 +372,6 @@ int dinotrk_corr_track(const dinotrk_features* feat, const dinotrk_geom* g,
   return launch_head(maps, total_maps, ms, *g, *hw, out_index, out, out_stride, out_mode, nullptr, hscratch, st);
 }
 
-static int infer_chunk_maps(int chunk_maps) { return chunk_maps > 0 ? chunk_maps : 4096; }
-// upper bound on the number of chunks of one phase (phase C has the most work items: N * T * T)
-static size_t infer_max_chunks(int T, int N, size_t ch) { return ((size_t)N * T * T + ch - 1) / ch + 2; }
 
 size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N, int chunk_maps) {
   if (!g) return 0;
@@ -405,16 +482,8 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
 
   // The chunks of a phase are planned on the host in one go and their group arrays uploaded with ONE copy, so the
   // per-chunk launches below never block the host (a pageable cudaMemcpyAsync per chunk would).
-  struct ChunkMeta { int used, maxm, n_groups; bool no_thin; };
   std::vector<ChunkMeta> metas;
   std::vector<int> plan_host;
-  GroupBuf gb(gcap);
-  auto commit_chunk = [&](int used, int maxm) {
-    bool no_thin = true;
-    for (int k = 0; k < gb.n; ++k) no_thin = no_thin && gb.v[2 * gb.cap + k] > STREAM_MAX_M;
-    metas.push_back(ChunkMeta{used, maxm, gb.n, no_thin});
-    plan_host.insert(plan_host.end(), gb.v.begin(), gb.v.end());
-  };
   auto upload_plan = [&]() -> int {
     DTK_CHECK_ARG(metas.size() <= max_chunks, "infer: chunk plan exceeds its bound (%zu > %zu)", metas.size(), max_chunks);
     if (!plan_host.empty())
@@ -441,23 +510,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
         if (rc) return rc;
       }
     }
-    metas.clear(); plan_host.clear();
-    {
-      int t = 0, row = 0;  // next work item: (frame t, query row)
-      while (t < T) {
-        gb.clear();
-        int used = 0, maxm = 0;
-        while (t < T && used < ch && gb.n < gcap) {
-          int m = N - row;
-          if (m > ch - used) m = ch - used;
-          gb.push(t, row, m, used, 0);
-          used += m; row += m;
-          if (m > maxm) maxm = m;
-          if (row == N) { row = 0; ++t; }
-        }
-        commit_chunk(used, maxm);
-      }
-    }
+    plan_chunks(0, T, N, nullptr, ch, gcap, metas, plan_host);
     int rc = upload_plan();
     if (rc) return rc;
     for (size_t k = 0; k < metas.size(); ++k) {
@@ -501,28 +554,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
     std::vector<int> cnt(T);
     DTK_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTK_CUDA(cudaStreamSynchronize(st));  // the one host sync: sizes of the anchor work lists
-    metas.clear(); plan_host.clear();
-    {
-      int a = 0;
-      long long item = 0;  // next work item: anchor frame a, item index within a (slot * T + i)
-      while (a < T) {
-        gb.clear();
-        int used = 0, maxm = 0;
-        while (a < T && used < ch && gb.n < gcap) {
-          long long tot = (long long)cnt[a] * T;
-          long long m = tot - item;
-          if (m > ch - used) m = ch - used;
-          if (m > 0) {
-            gb.push(a, used, (int)m, used, (int)item);
-            used += (int)m; item += m;
-            if ((int)m > maxm) maxm = (int)m;
-          }
-          if (item >= tot) { item = 0; ++a; }
-        }
-        if (used == 0) break;
-        commit_chunk(used, maxm);
-      }
-    }
+    plan_chunks(1, T, N, cnt.data(), ch, gcap, metas, plan_host);
     int rc = upload_plan();
     if (rc) return rc;
     InferAsync* ia = infer_async();

@@ -129,6 +129,15 @@ int dinotrk_head(const float* maps, int n_maps, const dinotrk_geom* g,
  * the outputs of earlier phases are then inputs.  SYNCS the stream once when phase 2 runs (reads
  * the per-frame anchor counts back to size the anchor work lists). */
 size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N, int chunk_maps);
+/* Host-only helper (no GPU needed): the chunk plan dinotrk_infer uses.  kind 0 = trajectory phase (items = every
+ * (frame, query row) pair), kind 1 = anchor phase (anchor_counts[a] * T items per anchor frame a).  Chunks hold
+ * <= chunk_maps correlation maps; inside a chunk the items of one target frame form a group.  Outputs (either may be
+ * NULL to just count): groups [n_chunks][5][T + 2] int32 = per chunk {frame, first descriptor row, rows m, first map,
+ * first item} x group; meta [n_chunks][4] = {maps used, largest m, number of groups, 1 if no group is thin};
+ * *n_chunks.  dinotrk_infer_max_chunks bounds n_chunks (and sizes dinotrk_infer's workspace). */
+size_t dinotrk_infer_max_chunks(int T, int N, int chunk_maps);
+int dinotrk_infer_plan(int kind, int T, int N, const int* anchor_counts, int chunk_maps, int* groups, int* meta,
+                       int max_chunks, int* n_chunks);
 /* Phase 2 pipelining across CUDA streams (process-wide; results are identical in every mode):
  * 0 = everything on the caller's stream; 1 (default) = the descriptor sampling of chunk k+1 runs on an
  * internal side stream under the correlation GEMM of chunk k; 2 = the head's fast path as well;
