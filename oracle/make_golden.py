@@ -136,6 +136,133 @@ def gen_bb_case(name, H, W, T, C, seed):
     print(name, {k: v["cos_sims"].shape[0] for k, v in res.items()})
 
 
+def gen_posembed_case(name, cases, dim, n_pos, seed):
+    """The reference-owned pieces of the ViT stage (row a1): VitExtractor._fix_pos_enc (models/extractor.py:57-85), the
+    position-embedding interpolation for stride-7 overlapping patches, run from the live reference on a seeded table.
+    DINOv2 calls it as interpolate_pos_encoding(x, w, h) with (w, h) = x.shape[2:] of the B x 3 x H x W input, i.e.
+    w = image HEIGHT and h = image WIDTH."""
+    import types
+    ref_harness.install("cpu")
+    from models.extractor import VitExtractor
+    fn = VitExtractor._fix_pos_enc(14, (7, 7))
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.randn(1, 1 + n_pos * n_pos, dim, generator=g)
+    out = dict(dim=np.array(dim), n_pos=np.array(n_pos), seed=np.array(seed), pos_embed=pos.numpy(),
+               cases=np.array(cases))
+    holder = types.SimpleNamespace(pos_embed=pos)
+    for (H, W) in cases:
+        n_h, n_w = 1 + (H - 14) // 7, 1 + (W - 14) // 7
+        x = torch.zeros(1, 1 + n_h * n_w, dim)
+        res = fn(holder, x, H, W)
+        assert res.shape == (1, 1 + n_h * n_w, dim)
+        out[f"out_{H}x{W}"] = res.numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    print(name, cases)
+
+
+VIT_CASE = dict(model_name="dinov2_vits14", dim=384, heads=6, depth=2, layer=1, H=98, W=126, T=1, seed=51, std=0.05)
+
+
+def hf_dinov2_layer(dim, heads, sd, i):
+    """Block i of a DINOv2 hub state dict as a ``transformers`` Dinov2Layer: an implementation of the DINOv2 block that is
+    independent of oracle/vit.py (also used by tests/test_vit_oracle_cpu.py)."""
+    from transformers import Dinov2Config
+    from transformers.models.dinov2.modeling_dinov2 import Dinov2Layer
+    cfg = Dinov2Config(hidden_size=dim, num_attention_heads=heads, num_hidden_layers=1, mlp_ratio=4, layer_norm_eps=1e-6,
+                       hidden_act="gelu", layerscale_value=1.0, use_swiglu_ffn=False, qkv_bias=True,
+                       attention_probs_dropout_prob=0.0, hidden_dropout_prob=0.0, drop_path_rate=0.0)
+    cfg._attn_implementation = "eager"
+    layer = Dinov2Layer(cfg).eval()
+    p = f"blocks.{i}."
+    qkv_w, qkv_b = sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"]
+    mapped = {
+        "norm1.weight": sd[p + "norm1.weight"], "norm1.bias": sd[p + "norm1.bias"],
+        "norm2.weight": sd[p + "norm2.weight"], "norm2.bias": sd[p + "norm2.bias"],
+        "attention.attention.query.weight": qkv_w[:dim], "attention.attention.query.bias": qkv_b[:dim],
+        "attention.attention.key.weight": qkv_w[dim:2 * dim], "attention.attention.key.bias": qkv_b[dim:2 * dim],
+        "attention.attention.value.weight": qkv_w[2 * dim:], "attention.attention.value.bias": qkv_b[2 * dim:],
+        "attention.output.dense.weight": sd[p + "attn.proj.weight"], "attention.output.dense.bias": sd[p + "attn.proj.bias"],
+        "layer_scale1.lambda1": sd[p + "ls1.gamma"], "layer_scale2.lambda1": sd[p + "ls2.gamma"],
+        "mlp.fc1.weight": sd[p + "mlp.fc1.weight"], "mlp.fc1.bias": sd[p + "mlp.fc1.bias"],
+        "mlp.fc2.weight": sd[p + "mlp.fc2.weight"], "mlp.fc2.bias": sd[p + "mlp.fc2.bias"],
+    }
+    assert set(mapped) == set(layer.state_dict())
+    layer.load_state_dict(mapped)
+    return layer
+
+
+def vit_case_state_dict(cfg=VIT_CASE):
+    from . import vit as ovit
+    g = torch.Generator().manual_seed(cfg["seed"])
+    sd = ovit.random_state_dict(cfg["depth"], cfg["dim"], g, n_pos=37, std=cfg["std"])
+    for i in range(cfg["depth"]):   # LayerScale away from 1 so that its placement matters
+        sd[f"blocks.{i}.ls1.gamma"] = 0.5 + torch.rand(cfg["dim"], generator=g)
+        sd[f"blocks.{i}.ls2.gamma"] = 0.5 + torch.rand(cfg["dim"], generator=g)
+    return sd
+
+
+def gen_vit_case(name, cfg=VIT_CASE):
+    """Row a1 through the LIVE reference: utils.get_dino_features_video + models/extractor.VitExtractor (ImageNet
+    normalisation, stride-7 re-striding of the patch convolution, _fix_pos_enc, block hooks, tap point, cls drop,
+    rearrange) run unmodified; only ``torch.hub.load`` -- the network download of facebookresearch/dinov2 -- is replaced by
+    a stand-in with the DinoVisionTransformer surface the extractor touches (patch_embed.proj, cls_token, pos_embed,
+    interpolate_pos_encoding, blocks[i] with .attn.qkv / .attn.attn_drop hook points, forward = prepare tokens + blocks),
+    whose blocks are ``transformers``' Dinov2Layer (independent of oracle/vit.py) carrying seeded weights."""
+    import torch.nn as nn
+    ref_harness.install("cpu")
+    import utils as ref_utils
+    sd = vit_case_state_dict(cfg)
+    dim, heads = cfg["dim"], cfg["heads"]
+
+    class Block(nn.Module):
+        def __init__(self, i):
+            super().__init__()
+            self.layer = hf_dinov2_layer(dim, heads, sd, i)
+            self.attn = nn.Module()                       # hook points only (the extractor registers, never reads, them)
+            self.attn.qkv = nn.Identity()
+            self.attn.attn_drop = nn.Identity()
+
+        def forward(self, x):
+            out = self.layer(x)
+            return out[0] if isinstance(out, (tuple, list)) else out
+
+    class StandIn(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.patch_embed = nn.Module()
+            self.patch_embed.proj = nn.Conv2d(3, dim, 14, stride=14)
+            self.patch_embed.proj.weight.data.copy_(sd["patch_embed.proj.weight"])
+            self.patch_embed.proj.bias.data.copy_(sd["patch_embed.proj.bias"])
+            self.cls_token = nn.Parameter(sd["cls_token"].clone())
+            self.pos_embed = nn.Parameter(sd["pos_embed"].clone())
+            self.blocks = nn.ModuleList([Block(i) for i in range(cfg["depth"])])
+
+        def interpolate_pos_encoding(self, x, w, h):      # replaced by the reference (set_overlapping_patches)
+            raise AssertionError("the reference must install its own position-embedding interpolation")
+
+        def forward(self, x):                             # DinoVisionTransformer.prepare_tokens_with_masks + blocks
+            B, nc, w, h = x.shape
+            x = self.patch_embed.proj(x).flatten(2).transpose(1, 2)
+            x = torch.cat((self.cls_token.expand(B, -1, -1), x), dim=1)
+            x = x + self.interpolate_pos_encoding(x, w, h)
+            for blk in self.blocks:
+                x = blk(x)
+            return x
+
+    video = synth.random_video(cfg["T"], cfg["H"], cfg["W"], seed=cfg["seed"] + 1)
+    real_load = torch.hub.load
+    torch.hub.load = lambda repo, model_name, *a, **kw: StandIn().eval()
+    try:
+        with torch.no_grad():
+            feats = ref_utils.get_dino_features_video(video, model_name=cfg["model_name"], stride=7, layer=cfg["layer"],
+                                                      device="cpu")
+    finally:
+        torch.hub.load = real_load
+    out = dict(features=feats.numpy(), shape=np.array(feats.shape))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    print(name, tuple(feats.shape), float(feats.abs().max()))
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(8)
@@ -144,6 +271,8 @@ def main():
     gen_delta_case("delta_small", 98, 126, 3, [3, 8, 12, 16, 24], seed=21)
     gen_delta_case("delta_full_geom", 476, 854, 1, [3, 4, 4, 4, 8], seed=22)
     gen_bb_case("bb_small", 98, 126, 3, 16, seed=31)
+    gen_posembed_case("posembed", [(476, 854), (98, 126), (112, 140), (518, 518)], dim=6, n_pos=37, seed=41)
+    gen_vit_case("vit_small")
 
 
 if __name__ == "__main__":

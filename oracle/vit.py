@@ -1,11 +1,14 @@
 """Oracle restatement of the DINOv2 ViT feature extractor.
 
-Test infrastructure (see ``oracle/__init__.py``).  PARITY UNPINNED: the block arithmetic
-belongs to facebookresearch/dinov2 (torch.hub, unpinned ``main``; call site
-models/extractor.py:26), which is absent from the reference tree and this image.  The block
-math below restates the published DINOv2 ``DinoVisionTransformer`` (pre-LN block, LayerNorm
-eps 1e-6, MHA with scale head_dim**-0.5, LayerScale, MLP 4x with exact GELU); everything the
-reference itself defines is restated from its source: stride patch (models/extractor.py:41-55),
+Test infrastructure (see ``oracle/__init__.py``).  Pinning: the reference's own code on this
+row (everything listed below from models/extractor.py and utils.py) is pinned by golden
+vectors produced by the live reference (tests/golden/vit_small.npz, posembed.npz;
+oracle/make_golden.py gen_vit_case / gen_posembed_case).  The block arithmetic belongs to
+facebookresearch/dinov2 (torch.hub, unpinned ``main``; call site models/extractor.py:26),
+which is absent from the reference tree and this image: the block math below restates the
+published DINOv2 ``DinoVisionTransformer`` (pre-LN block, LayerNorm eps 1e-6, MHA with scale
+head_dim**-0.5, LayerScale, MLP 4x with exact GELU) and is cross-checked against
+``transformers``' Dinov2Layer; everything the reference itself defines is restated from its source: stride patch (models/extractor.py:41-55),
 pos-embed interpolation (:57-85), tap point = output of block ``layer`` before the final norm
 (:112-116,137-150), ImageNet normalisation, cls drop and C x h x w layout (utils.py:44-67).
 State-dict keys are the DINOv2 hub names so real checkpoints load unchanged.

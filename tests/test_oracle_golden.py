@@ -100,3 +100,36 @@ def test_best_buddies_matches_reference():
     tc = a["target_coords"].numpy()
     ia = np.lexsort((tc[:, 0], tc[:, 1]))  # ascending token order = (y, x)
     assert np.array_equal(a["target_coords"].numpy()[ia], b["source_coords"].numpy())
+
+
+def test_pos_embed_interpolation_matches_reference():
+    """ViT row a1, the reference-owned part: VitExtractor._fix_pos_enc (models/extractor.py:57-85) run from the live
+    reference on a seeded 37x37 table, four resolutions incl. the 854x476 bench geometry.  Both the oracle's restatement
+    and the product's host-side copy (the table is interpolated once per model on the host, then uploaded) must
+    reproduce it exactly."""
+    from oracle import vit as ovit
+    from dino_tracker_b200.vit import interpolate_pos_embed as product_interp
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "posembed.npz")))
+    pos = torch.from_numpy(g["pos_embed"])
+    for H, W in g["cases"]:
+        n_h, n_w = 1 + (int(H) - 14) // 7, 1 + (int(W) - 14) // 7
+        ref = g[f"out_{int(H)}x{int(W)}"]
+        assert ref.shape == (1, 1 + n_h * n_w, pos.shape[-1])
+        assert np.array_equal(ovit.interpolate_pos_embed(pos, n_h, n_w).numpy(), ref)
+        assert np.array_equal(product_interp(pos, n_h, n_w).numpy(), ref)
+
+
+def test_vit_stage_matches_reference_pipeline():
+    """Row a1 through the live reference: utils.get_dino_features_video + VitExtractor run unmodified (normalisation,
+    re-strided patch convolution, position-embedding fix, hooks, tap, cls drop, layout); only torch.hub's download of
+    facebookresearch/dinov2 is replaced by a stand-in whose blocks are transformers' Dinov2Layer (oracle/make_golden.py
+    gen_vit_case).  The oracle's restatement reproduces the stored features."""
+    from oracle import make_golden as mg
+    from oracle import vit as ovit
+    cfg = mg.VIT_CASE
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "vit_small.npz")))
+    sd = mg.vit_case_state_dict(cfg)
+    video = synth.random_video(cfg["T"], cfg["H"], cfg["W"], seed=cfg["seed"] + 1)
+    mine = ovit.dino_features_video(video, sd, cfg["heads"], cfg["layer"]).numpy()
+    assert mine.shape == tuple(g["shape"])
+    assert np.abs(mine - g["features"]).max() <= 1e-5 * np.abs(g["features"]).max()

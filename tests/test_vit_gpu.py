@@ -1,6 +1,6 @@
 """GPU tests: tcgen05 ViT (fp16-operand GEMMs on CTA pairs or single CTAs + fused attention; TF32 GEMMs + materialised
-attention as the validation path) against the fp32 oracle restatement (parity unpinned: the DINOv2 block arithmetic is
-third-party, see oracle/vit.py), and the attention kernel on its own against float64."""
+attention as the validation path) against the fp32 oracle restatement (itself pinned to the live reference pipeline and to
+transformers' DINOv2 block, see oracle/vit.py), and the attention kernel on its own against float64."""
 import numpy as np
 import pytest
 import torch
