@@ -107,3 +107,24 @@ def test_fused_attention_against_float64(case):
     print(f"attention[{case}] max |diff| = {err:.3e} (max |ref| = {ref.abs().max().item():.3f})")
     # fp16 P (2^-11 relative per probability) and fp16-exact operands: a few 1e-3 absolute on |v| ~ 1..4
     assert err <= 2e-3
+
+
+def test_vit_matches_reference_pipeline_golden():
+    """CUDA ViT against the features the LIVE reference pipeline produced (tests/golden/vit_small.npz: the reference's
+    get_dino_features_video / VitExtractor around a stand-in hub model with transformers' DINOv2 blocks; dim 384, 6 heads,
+    2 blocks, tap 1, 98x126 frame)."""
+    import os
+    from oracle import make_golden as mg
+    from dino_tracker_b200.vit import DinoV2Features
+    cfg = mg.VIT_CASE
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vit_small.npz")))
+    sd = mg.vit_case_state_dict(cfg)
+    video = synth.random_video(cfg["T"], cfg["H"], cfg["W"], seed=cfg["seed"] + 1)
+    ex = DinoV2Features(sd, heads=cfg["heads"], layer=cfg["layer"], device="cuda:0")
+    got = ex.features_chw(video).cpu().numpy()
+    ref = g["features"]
+    assert got.shape == ref.shape
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref).max()
+    print(f"ViT vs reference-pipeline golden: max |diff| = {err:.3e} (max |ref| = {scale:.3f})")
+    assert err <= 5e-3 * scale
