@@ -128,8 +128,22 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
-def stream_ptr():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """Current torch stream of ``device`` (default: the current device).  The library launches on the CURRENT device,
+    so callers that own a device wrap their calls in ``torch.cuda.device(dev)`` (see ``on_device``)."""
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def on_device(fn):
+    """Method decorator: run with ``self._dev`` as the current CUDA device (kernels, streams and the library's
+    per-device state then all belong to the model's device, whatever the caller's current device is)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with torch.cuda.device(self._dev):
+            return fn(self, *a, **kw)
+    return wrapped
 
 
 def require_cuda(device):

@@ -28,6 +28,11 @@ def token_coords(H, W, step=7, patch=14, device="cpu"):
 @torch.no_grad()
 def nearest_neighbours(tpc, norms, geom, pairs, hi=None, lo=None, pairs_per_launch=48):
     """pairs: list of ordered (s, t).  Returns nn_idx [n_pairs][P] int32, nn_cos [n_pairs][P] fp32 (device)."""
+    with torch.cuda.device(tpc.device):   # the library launches on the current device
+        return _nearest_neighbours(tpc, norms, geom, pairs, hi, lo, pairs_per_launch)
+
+
+def _nearest_neighbours(tpc, norms, geom, pairs, hi, lo, pairs_per_launch):
     lib = _lib.load()
     dev = tpc.device
     T, P, C = tpc.shape
@@ -56,8 +61,13 @@ def nearest_neighbours(tpc, norms, geom, pairs, hi=None, lo=None, pairs_per_laun
 def best_buddies(features_chw, H, W, stride=7, patch=14, device="cuda:0", rank=0, world=1, unordered_pairs=None):
     """features_chw: T x C x h x w.  Returns the reference's dict for the unordered pairs owned by this rank
     (both orientations of each): {'s_t': {...}, 't_s': {...}}."""
-    lib = _lib.load()
     dev = _lib.require_cuda(device)
+    with torch.cuda.device(dev):
+        return _best_buddies(features_chw, H, W, stride, patch, dev, rank, world, unordered_pairs)
+
+
+def _best_buddies(features_chw, H, W, stride, patch, dev, rank, world, unordered_pairs):
+    lib = _lib.load()
     T, C, h, w = features_chw.shape
     geom = _lib.make_geom((h - 1) * stride + patch, (w - 1) * stride + patch, patch, stride, 35)
     assert (geom.h, geom.w) == (h, w)

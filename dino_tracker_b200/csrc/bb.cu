@@ -168,7 +168,8 @@ int dinotrk_best_buddies_pairs(const dinotrk_features* feat, const dinotrk_geom*
   if ((rc = make_tmap_2d(&tmA_lo, feat->lo, (uint64_t)T * P, C, TC_BM, Cfg::kBK, TMAP_F16))) return rc;
   if ((rc = make_tmap_3d(&tmB_hi, feat->hi, T, P, C, TC_BN, Cfg::kBK, TMAP_F16))) return rc;
   if ((rc = make_tmap_3d(&tmB_lo, feat->lo, T, P, C, TC_BN, Cfg::kBK, TMAP_F16))) return rc;
-  static bool attr = false;
+  static PerDev<bool> attr_dev;
+  bool& attr = attr_dev.get();
   if (!attr) {
     DTK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TcMode::F16X3, BBEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr = true;

@@ -52,6 +52,19 @@ struct ProfRange {
   ~ProfRange() { if (on) prof_end(st); }
 };
 
+// per-device cache slot for values that belong to a device's context (function attributes, occupancy queries,
+// auxiliary streams): indexed by the CURRENT device, so a second GPU in the same process gets its own
+constexpr int DTK_MAX_DEVICES = 64;
+template <typename T>
+struct PerDev {
+  T v[DTK_MAX_DEVICES] = {};
+  T& get() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[(d >= 0 && d < DTK_MAX_DEVICES) ? d : 0];
+  }
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

@@ -268,7 +268,8 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
                                    assist.split_ready);
       if (rc) return rc;
     } else {
-      static bool attr_set = false;
+      static PerDev<bool> attr_dev;
+      bool& attr_set = attr_dev.get();
       if (!attr_set) {
         DTK_CUDA(cudaFuncSetAttribute(corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         attr_set = true;
@@ -287,7 +288,8 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
     const int variant = max_group_m <= 2 ? 0 : (max_group_m <= 4 ? 1 : 2);
     const int maxm = variant == 0 ? 2 : (variant == 1 ? 4 : 8);
     size_t smem = (size_t)maxm * C * sizeof(float);
-    static size_t attr_smem[3] = {0, 0, 0};
+    static PerDev<size_t[3]> attr_smem_dev;
+    size_t (&attr_smem)[3] = attr_smem_dev.get();
     auto kern = variant == 0 ? corr_stream_kernel<2, 8> : (variant == 1 ? corr_stream_kernel<4, 8> : corr_stream_kernel<8, 4>);
     if (smem > 48 * 1024 && smem > attr_smem[variant]) {
       DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -171,7 +171,8 @@ int launch_corr_gemm_tc(const void* tpc_hi, const void* tpc_lo, const float* nor
   if ((rc = make_tmap_2d(&tmA_lo, d_lo, desc_rows, C, TC_BM, Cfg::kBK, TMAP_F16))) return rc;
   if ((rc = make_tmap_3d(&tmB_hi, tpc_hi, T, P, C, b_box, Cfg::kBK, TMAP_F16))) return rc;
   if ((rc = make_tmap_3d(&tmB_lo, tpc_lo, T, P, C, b_box, Cfg::kBK, TMAP_F16))) return rc;
-  static bool attr = false;
+  static PerDev<bool> attr_dev;
+  bool& attr = attr_dev.get();
   if (!attr) {
     DTK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<TcMode::F16X3, CorrEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmem));

@@ -292,7 +292,8 @@ static int conv_gemm(const __half* a_hi, const __half* a_lo, int rows, int Kp, c
   if ((rc = make_tmap_3d(&tB_hi, w_hi, 1, Cout, Kp, BN, Cfg::kBK, TMAP_F16))) return rc;
   if ((rc = make_tmap_3d(&tB_lo, w_lo, 1, Cout, Kp, BN, Cfg::kBK, TMAP_F16))) return rc;
   auto kern = tc_gemm_kernel<TcMode::F16X3, EpiConv, BN>;
-  static bool attr = false;
+  static PerDev<bool> attr_dev;
+  bool& attr = attr_dev.get();
   if (!attr) {
     DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr = true;
@@ -333,7 +334,8 @@ static int launch_conv_tc(const float* in, const __half* w_hi, const __half* w_l
 }
 
 static int launch_conv(const float* in, const float* wgt, const float* bias, float* out, ConvShape cs, cudaStream_t st) {
-  static bool attr = false;
+  static PerDev<bool> attr_dev;
+  bool& attr = attr_dev.get();
   if (!attr) {
     DTK_CUDA(cudaFuncSetAttribute(conv5x5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM));
     attr = true;

@@ -695,7 +695,8 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
       DTK_LAUNCHED();
     }
     if (tkeys != nullptr) {
-      static int per_sm_tm = 0;
+      static PerDev<int> per_sm_dev;
+      int& per_sm_tm = per_sm_dev.get();
       if (per_sm_tm == 0) {
         DTK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tm, head_tm_kernel, TMK_THREADS, 0));
         if (per_sm_tm < 1) per_sm_tm = 1;
@@ -708,7 +709,8 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
       DTK_LAUNCHED();
     } else {
       size_t smem = (size_t)(lin_elems + WM * WM + 3 + 16 * WH * WH + 32) * sizeof(float) + 4 * sizeof(unsigned long long);
-      static size_t attr_w = 0;
+      static PerDev<size_t> attr_w_dev;
+      size_t& attr_w = attr_w_dev.get();
       if (smem > attr_w) {
         DTK_CUDA(cudaFuncSetAttribute(head_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_w = smem;
@@ -727,7 +729,8 @@ int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geo
   const int nwarps = cdiv(g.h, 4);
   const int threads = nwarps * 32;
   size_t smem = (size_t)(2 * lin_elems + 2 * nwarps * 2 * 128 + 6 * 32) * sizeof(float) + 32 * sizeof(unsigned long long);
-  static size_t attr_smem[4] = {0, 0, 0, 0};
+  static PerDev<size_t[4]> attr_smem_dev;
+  size_t (&attr_smem)[4] = attr_smem_dev.get();
   const bool wrap = g.w <= 124;                 // tile 31 of every band lies outside the map
   const int variant = (threads <= 576 ? 0 : 2) + (wrap ? 0 : 1);  // <= 576 threads: 112 registers/thread; else 64
   auto kern = variant == 0 ? head_kernel<576, true> : variant == 1 ? head_kernel<576, false>

@@ -278,9 +278,12 @@ struct InferAsync {
   int head_ctas_per_sm;
 };
 static int g_overlap_mode = -1;   // -1: DTK_OVERLAP or the default (1); see dinotrk_infer_set_overlap
+struct InferAsyncSlot { InferAsync ia; int state; };   // state 0: not created, 1: ready, -1: creation failed
 static InferAsync* infer_async() {
-  static InferAsync ia;
-  static int state = 0;   // 0: not created, 1: ready, -1: creation failed
+  static PerDev<InferAsyncSlot> slots;   // streams and events belong to the device they were created on
+  InferAsyncSlot& slot = slots.get();
+  InferAsync& ia = slot.ia;
+  int& state = slot.state;
   int mode = g_overlap_mode;
   if (mode < 0) {
     const char* e = getenv("DTK_OVERLAP");
@@ -401,7 +404,8 @@ int dinotrk_traj_cos_sims(const float* tpc, int T, int C, const dinotrk_geom* g,
   DTK_CHECK_ARG(T > 0 && C > 0 && C % 4 == 0 && N >= 0, "traj_cos_sims: bad sizes");
   if (N == 0) return DINOTRK_OK;
   size_t smem = (size_t)2 * C * sizeof(float);
-  static size_t attr = 0;
+  static PerDev<size_t> attr_dev;
+  size_t& attr = attr_dev.get();
   if (smem > 48 * 1024 && smem > attr) {
     DTK_CUDA(cudaFuncSetAttribute(traj_cos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
@@ -419,7 +423,8 @@ int dinotrk_occlusion(const float* traj, const float* cos_sims, const float* anc
   if (N == 0) return DINOTRK_OK;
   size_t smem = (size_t)(4 + OCC_THREADS / 32) * T * sizeof(float);
   DTK_CHECK_ARG(smem <= 200 * 1024, "occlusion: T=%d too large", T);
-  static size_t attr = 0;
+  static PerDev<size_t> attr_dev;
+  size_t& attr = attr_dev.get();
   if (smem > 48 * 1024 && smem > attr) {
     DTK_CUDA(cudaFuncSetAttribute(occlusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;

@@ -351,7 +351,8 @@ static int run_gemm(const void* A, uint64_t a_rows, const void* Bm, uint64_t b_b
   if ((rc = make_tmap_2d(&tmA, A, a_rows, K, TC_BM, Cfg::kBK, kT, ld))) return rc;
   if ((rc = make_tmap_3d(&tmB, Bm, b_batch, b_rows, K, BN, Cfg::kBK, kT, ld))) return rc;
   auto kern = tc_gemm_kernel<MODE, Epi, BN>;
-  static bool attr = false;  // one static per template instantiation
+  static PerDev<bool> attr_dev;  // one static per template instantiation
+  bool& attr = attr_dev.get();
   if (!attr) {
     DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr = true;
@@ -389,7 +390,8 @@ static int run_gemm_pair(const void* A, uint64_t a_rows, const void* Bm, uint64_
   if ((rc = make_tmap_2d(&tmA, A, a_rows, K, 128, Base::kBK, TMAP_F16))) return rc;
   if ((rc = make_tmap_3d(&tmB, Bm, 1, b_rows, K, TC2_BN / 2, Base::kBK, TMAP_F16))) return rc;
   auto kern = tc_gemm2_kernel<TcMode::F16, Epi>;
-  static bool attr = false;
+  static PerDev<bool> attr_dev;
+  bool& attr = attr_dev.get();
   if (!attr) {
     DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr = true;

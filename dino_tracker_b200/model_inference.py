@@ -54,6 +54,25 @@ def generate_trajectories(query_points, video, model, range_normalizer, dst_rang
 
 def _run_phases(model: Tracker, query_points, start, stop, batch_size, anchor_th=0.5, cos_th=0.5, traj=None,
                 cos_sims=None, anchors=None, use_raw_features=False, chunk_maps=None):
+    with torch.cuda.device(model._dev):   # the library launches on the current device
+        return _run_phases_on_device(model, query_points, start, stop, batch_size, anchor_th, cos_th, traj, cos_sims,
+                                     anchors, use_raw_features, chunk_maps)
+
+
+def _traj3(traj, T, dev):
+    """Trajectories as N x T x 3 (x, y, t).  The reference's occlusion / anchor code only reads [..., :2]
+    (models/model_inference.py:137,191), so N x T x 2 -- what ``infer`` returns -- is accepted and completed with t."""
+    traj = traj.to(device=dev, dtype=torch.float32)
+    if traj.dim() != 3 or traj.shape[1] != T or traj.shape[2] not in (2, 3):
+        raise ValueError(f"trajectories must be N x {T} x 2 or N x {T} x 3, got {tuple(traj.shape)}")
+    if traj.shape[2] == 2:
+        t = torch.arange(T, device=dev, dtype=torch.float32)[None, :, None].expand(traj.shape[0], T, 1)
+        traj = torch.cat([traj, t], dim=2)
+    return traj.contiguous()
+
+
+def _run_phases_on_device(model: Tracker, query_points, start, stop, batch_size, anchor_th, cos_th, traj,
+                          cos_sims, anchors, use_raw_features, chunk_maps):
     if chunk_maps is None:
         chunk_maps = DEFAULT_CHUNK_MAPS   # module attribute: read at call time (bench.py --chunk-maps sets it)
     chunk_maps = int(min(chunk_maps, max(256, query_points.shape[0] * model.video.shape[0] ** 2)))
@@ -71,7 +90,7 @@ def _run_phases(model: Tracker, query_points, start, stop, batch_size, anchor_th
     if traj is None:
         traj = torch.zeros(N, T, 3, device=dev, dtype=torch.float32)
     else:
-        traj = traj.to(device=dev, dtype=torch.float32).contiguous()
+        traj = _traj3(traj, T, dev)
     if stop >= 1:
         cos_sims = torch.zeros(N, T, device=dev, dtype=torch.float32) if cos_sims is None else \
             cos_sims.to(device=dev, dtype=torch.float32).contiguous()
@@ -89,7 +108,7 @@ def _run_phases(model: Tracker, query_points, start, stop, batch_size, anchor_th
     _lib.check(lib.dinotrk_infer(
         ctypes.byref(feat), ctypes.byref(geom), ctypes.byref(model.head_weights()), _lib.ptr(q), N,
         float(anchor_th), float(cos_th), fb, start, stop, chunk_maps, _lib.ptr(traj), _lib.ptr(cos_sims),
-        _lib.ptr(anchors), _lib.ptr(occ), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "infer")
+        _lib.ptr(anchors), _lib.ptr(occ), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)), "infer")
     return {"traj": traj, "cos_sims": cos_sims, "anchors": anchors, "occ": occ}
 
 
@@ -137,13 +156,21 @@ class ModelInference(torch.nn.Module):
     def _occlusion(self, traj, cos_sims, anchors, anch_th, cos_th):
         lib = _lib.load()
         dev = self.model._dev
-        traj = traj.to(device=dev, dtype=torch.float32).contiguous()
         cos_sims = cos_sims.to(device=dev, dtype=torch.float32).contiguous()
-        anchors = anchors.to(device=dev, dtype=torch.float32).contiguous()
         N, T = cos_sims.shape
+        traj = _traj3(traj, T, dev)                     # the kernel reads (x, y, t) triples
+        anchors = anchors.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(anchors.shape) != (N, T, T, 2) or traj.shape[0] != N:
+            raise ValueError(f"occlusion: anchors must be {N} x {T} x {T} x 2 and trajectories {N} x {T} x 2|3")
+        # the reference takes a median over an empty anchor set and raises; say so instead of calling everything visible
+        n_anchor = (cos_sims >= anch_th).sum(dim=1)
+        if N and int(n_anchor.min()) == 0:
+            raise ValueError("occlusion: query point %d has no anchor frame (cos-sim >= %.3f); the reference fails here too"
+                             % (int(n_anchor.argmin()), anch_th))
         occ = torch.zeros(N, T, device=dev, dtype=torch.uint8)
-        _lib.check(lib.dinotrk_occlusion(_lib.ptr(traj), _lib.ptr(cos_sims), _lib.ptr(anchors), N, T, float(anch_th),
-                                         float(cos_th), _lib.ptr(occ), _lib.stream_ptr()), "occlusion")
+        with torch.cuda.device(dev):
+            _lib.check(lib.dinotrk_occlusion(_lib.ptr(traj), _lib.ptr(cos_sims), _lib.ptr(anchors), N, T, float(anch_th),
+                                             float(cos_th), _lib.ptr(occ), _lib.stream_ptr(dev)), "occlusion")
         return occ.bool()
 
     def compute_occlusion(self, trajectories, trajs_cos_sims, anchor_trajectories: Dict[int, torch.Tensor]):

@@ -53,18 +53,19 @@ class Tracker(nn.Module):
         self.corr_precision = corr_precision
         self._refined_tpc = None
         self._refined_norms = None
-        self._split_cache = {}
         self._head_cache = (None, None)
+        self._local = None   # (refined tpc, norms) of the last uncached forward (training-style call)
 
-        if _adopt_tpc is not None:            # token-major features straight from the in-process ViT stage (no copy)
-            self._dino_tpc = _adopt_tpc
-            self._dino_norms = torch.empty(_adopt_tpc.shape[:2], device=self._dev, dtype=torch.float32)
-            _lib.check(self._lib.dinotrk_token_norms(_lib.ptr(_adopt_tpc), _lib.ptr(self._dino_norms), _adopt_tpc.shape[0],
-                                                      _adopt_tpc.shape[2], _adopt_tpc.shape[1], _lib.stream_ptr()), "token_norms")
-        elif dino_embed_video is not None:    # in-process features given as T x C x h x w
-            self._set_dino(dino_embed_video)
-        else:
-            self.load_dino_embed_video()
+        with torch.cuda.device(self._dev):
+            if _adopt_tpc is not None:            # token-major features straight from the in-process ViT stage (no copy)
+                self._dino_tpc = _adopt_tpc
+                self._dino_norms = torch.empty(_adopt_tpc.shape[:2], device=self._dev, dtype=torch.float32)
+                _lib.check(self._lib.dinotrk_token_norms(_lib.ptr(_adopt_tpc), _lib.ptr(self._dino_norms), _adopt_tpc.shape[0],
+                                                          _adopt_tpc.shape[2], _adopt_tpc.shape[1], _lib.stream_ptr(self._dev)), "token_norms")
+            elif dino_embed_video is not None:    # in-process features given as T x C x h x w
+                self._set_dino(dino_embed_video)
+            else:
+                self.load_dino_embed_video()
         C = self._dino_tpc.shape[-1]
         channels = list(delta_channels) if delta_channels is not None else [3, 64, 128, 256, C]
         self.delta_dino = DeltaDINO(channels=channels, vit_stride=stride).to(self._dev)
@@ -78,6 +79,7 @@ class Tracker(nn.Module):
         T, P, C = tpc.shape
         return tpc.view(T, self._geom.h, self._geom.w, C).permute(0, 3, 1, 2)
 
+    @_lib.on_device
     def _pack(self, chw):
         """T x C x h x w (any device) -> token-major [T][P][C] + per-token norms on the GPU."""
         chw = _as_f32(chw, self._dev)
@@ -88,21 +90,26 @@ class Tracker(nn.Module):
         tpc = torch.empty(T, h * w, C, device=self._dev, dtype=torch.float32)
         norms = torch.empty(T, h * w, device=self._dev, dtype=torch.float32)
         _lib.check(self._lib.dinotrk_pack_features(_lib.ptr(chw), _lib.ptr(tpc), _lib.ptr(norms), T, C, h * w,
-                                                    _lib.stream_ptr()), "pack_features")
+                                                    _lib.stream_ptr(self._dev)), "pack_features")
         return tpc, norms
 
+    @_lib.on_device
     def features_struct(self, tpc, norms):
         """C struct for a [T][P][C] feature video (+ its cached fp16 hi/lo split in fp16x3 mode)."""
         if self.corr_precision != "fp16x3" or tpc.shape[-1] % 8:
             return _lib.make_features(tpc, norms)
-        key = (tpc.data_ptr(), tpc._version, tuple(tpc.shape))
-        if self._split_cache.get("key") != key:
+        # The split lives ON the tensor object it was computed from: a fresh feature tensor (uncached forward,
+        # re-cached embeddings) never inherits the split of a dead tensor that happened to own the same address.
+        # Feature tensors are written once by the kernel that creates them; _version guards torch-level in-place edits.
+        split = getattr(tpc, "_dtk_split", None)
+        if split is None or split[0] != tpc._version:
             hi = torch.empty(tpc.shape, device=tpc.device, dtype=torch.float16)
             lo = torch.empty(tpc.shape, device=tpc.device, dtype=torch.float16)
             _lib.check(self._lib.dinotrk_split_fp16(_lib.ptr(tpc), _lib.ptr(hi), _lib.ptr(lo), tpc.numel(),
-                                                     _lib.stream_ptr()), "split_fp16")
-            self._split_cache = {"key": key, "hi": hi, "lo": lo}
-        return _lib.make_features(tpc, norms, self._split_cache["hi"], self._split_cache["lo"])
+                                                     _lib.stream_ptr(self._dev)), "split_fp16")
+            split = (tpc._version, hi, lo)
+            tpc._dtk_split = split
+        return _lib.make_features(tpc, norms, split[1], split[2])
 
     def _set_dino(self, chw):
         self._dino_tpc, self._dino_norms = self._pack(chw)
@@ -149,6 +156,7 @@ class Tracker(nn.Module):
             return refined, residual, raw
         return refined, residual
 
+    @_lib.on_device
     def _refined_for(self, idx):
         dino = self._dino_tpc[idx].contiguous()
         frames = _as_f32(self.video[idx.to(self.video.device)], self._dev)
@@ -209,6 +217,7 @@ class Tracker(nn.Module):
         desc, _ = self._sample(tpc, source_points, frames_set, normalized=True)
         return desc
 
+    @_lib.on_device
     def _sample(self, tpc, points, frames_set, normalized):
         pts = _as_f32(points, self._dev)
         B = pts.shape[0]
@@ -218,7 +227,7 @@ class Tracker(nn.Module):
         fs = frames_set.to(device=self._dev, dtype=torch.int32).contiguous()
         _lib.check(self._lib.dinotrk_sample_descriptors(
             _lib.ptr(tpc), tpc.shape[0], C, ctypes.byref(self._geom), _lib.ptr(pts), B, _lib.ptr(fs), fs.shape[0],
-            1 if normalized else 0, _lib.ptr(desc), _lib.ptr(dn), _lib.stream_ptr()), "sample_descriptors")
+            1 if normalized else 0, _lib.ptr(desc), _lib.ptr(dn), _lib.stream_ptr(self._dev)), "sample_descriptors")
         return desc, dn
 
     # ------------------------------------------------------------------ forward
@@ -229,12 +238,24 @@ class Tracker(nn.Module):
             return self._refined_tpc, self._refined_norms, None
         # no cache (training-style call): refine just the requested frames; indices become set slots
         tpc, norms = self._refined_for(frames_set_t.to(self._dev).long())
+        self._local = (tpc, norms)
         return tpc, norms, "local"
 
+    @_lib.on_device
     def forward(self, inp, use_raw_features=False):
         """models/tracker.py:303-325.  inp = (source_points B x 3 px, source_frame_indices B,
         target_frame_indices B, frames_set_t N).  Returns B x 2 in [-1, 1]."""
         src_pts, src_idx, tgt_idx, frames_set_t = inp
+        # the reference indexes tensors with these (IndexError when out of range); the kernels would read out of bounds
+        fs_host = frames_set_t.detach().to("cpu").long()
+        n_set, n_frames = int(fs_host.numel()), int(self._dino_tpc.shape[0])
+        if n_set == 0 or int(fs_host.min()) < 0 or int(fs_host.max()) >= n_frames:
+            raise IndexError(f"frames_set_t must hold frame indices in [0, {n_frames}), got {fs_host.tolist()}")
+        for name, idx in (("source_frame_indices", src_idx), ("target_frame_indices", tgt_idx)):
+            ih = idx.detach().to("cpu").long()
+            if ih.numel() and (int(ih.min()) < 0 or int(ih.max()) >= n_set):
+                raise IndexError(f"{name} must index the frame set (size {n_set})")
+        self._local = None
         tpc, norms, mode = self._features_for_forward(frames_set_t, use_raw_features)
         self._last_frames = (frames_set_t, use_raw_features)
         B = src_pts.shape[0]
@@ -262,7 +283,7 @@ class Tracker(nn.Module):
             ctypes.byref(feat), ctypes.byref(self._geom), ctypes.byref(self.head_weights()),
             _lib.ptr(desc), _lib.ptr(dn), _lib.ptr(grp[0]), _lib.ptr(grp[1]), _lib.ptr(grp[2]), _lib.ptr(grp[3]),
             n_groups, B, int(counts.max()), _lib.ptr(out_index), _lib.ptr(out), 2, 1,
-            _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "corr_track")
+            _lib.ptr(ws), ws_bytes, _lib.stream_ptr(self._dev)), "corr_track")
         return out
 
     # the reference stores gathered copies of the frame set on every call (models/tracker.py:322-323);
@@ -270,8 +291,18 @@ class Tracker(nn.Module):
     @property
     def frame_embeddings(self):
         fs, raw = self._last_frames
-        src = self.dino_embed_video if (raw or self._refined_tpc is None) else self.refined_features
+        if not raw and self._local is not None:   # uncached forward: the refined embeddings of that frame set
+            return self._chw_view(self._local[0])
+        src = self.dino_embed_video if raw else self.refined_features
         return src[fs.to(self._dev).long()]
+
+    @property
+    def residual_embeddings(self):
+        """models/tracker.py:319-321: refined - raw of the last forward's frame set."""
+        fs, raw = self._last_frames
+        if raw:
+            return None
+        return self.frame_embeddings - self.raw_embeddings
 
     @property
     def raw_embeddings(self):

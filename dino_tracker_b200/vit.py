@@ -93,6 +93,7 @@ class DinoV2Features(torch.nn.Module):
         return self._pos_cache[key]
 
     @torch.no_grad()
+    @_lib.on_device
     def forward(self, video01):
         """video01: T x 3 x H x W in [0, 1] (any device).  Returns tpc [T][P][C] (cuda)."""
         lib = self._lib

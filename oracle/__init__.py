@@ -34,3 +34,16 @@ Pinning status (see DESIGN.md "Oracle"):
     checkpoint's own block code equals the published definition both other
     implementations follow.
 """
+
+
+def use_exact_fp32():
+    """fp32 arithmetic for the oracle on a CUDA device: TF32 off for matmuls and convolutions (the
+    tensor-core shortcuts PyTorch may otherwise take), so that ``oracle.*`` on ``cuda`` is the same
+    fp32 computation as on the CPU up to summation order."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.set_float32_matmul_precision("highest")
+    except Exception:  # pragma: no cover
+        pass

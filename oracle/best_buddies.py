@@ -22,7 +22,7 @@ def best_buddies_pair(fs: torch.Tensor, ft: torch.Tensor, coords: torch.Tensor):
     aff = aff / torch.clamp(fs.norm(dim=1)[:, None] * ft.norm(dim=1)[None], min=1e-08)
     s_max = torch.argmax(aff, dim=1)
     t_max = torch.argmax(aff, dim=0)
-    rng = torch.arange(fs.shape[0])
+    rng = torch.arange(fs.shape[0], device=fs.device)
     s_bb = rng == t_max[s_max]
     t_bb = s_max[s_bb]
     return {"source_coords": coords[s_bb], "target_coords": coords[t_bb],

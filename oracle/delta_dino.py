@@ -18,7 +18,7 @@ def blur_pool(x: torch.Tensor) -> torch.Tensor:
     (left 1, right 2, top 1, bottom 2), depthwise outer([1,3,3,1])/64, stride 2
     (third-party adobe/antialiased-cnns; call site models/networks/delta_dino.py:44)."""
     C = x.shape[1]
-    a = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    a = torch.tensor([1.0, 3.0, 3.0, 1.0], device=x.device)
     filt = a[:, None] * a[None, :]
     filt = (filt / filt.sum())[None, None].repeat(C, 1, 1, 1)
     return F.conv2d(F.pad(x, (1, 2, 1, 2), mode="reflect"), filt, stride=2, groups=C)
@@ -47,8 +47,8 @@ def align_cnn_to_vit(cnn: torch.Tensor, vit_hw, patch=14, vit_stride=7, cnn_stri
     vh, vw = vit_hw
     ch, cw = cnn.shape[-2:]
     c_br = [(ch - 1) * cnn_stride, (cw - 1) * cnn_stride]
-    vit_x = torch.arange(vw, dtype=torch.float32) * vit_stride + patch / 2.0
-    vit_y = torch.arange(vh, dtype=torch.float32) * vit_stride + patch / 2.0
+    vit_x = torch.arange(vw, dtype=torch.float32, device=cnn.device) * vit_stride + patch / 2.0
+    vit_y = torch.arange(vh, dtype=torch.float32, device=cnn.device) * vit_stride + patch / 2.0
     gx, gy = torch.meshgrid(-1.0 - (1.0 / c_br[1]) + (2.0 * vit_x / c_br[1]),
                             -1 - (1.0 / c_br[0]) + (2.0 * vit_y / c_br[0]), indexing="xy")
     grid = torch.stack([gx, gy], dim=-1)[None].expand(cnn.shape[0], -1, -1, -1)

@@ -12,11 +12,12 @@ from .tracker import (Geometry, normalize_points_for_sampling, sample_descriptor
 def trajectory_input(query_point, T, start_t, end_t):
     """models/model_inference.py:8-34."""
     rest = end_t - start_t
+    dev = query_point.device
     src_pts = query_point[None].repeat(rest, 1)
     frames_set_t = torch.cat([query_point[2:3].to(torch.float32),
-                              torch.arange(start_t, end_t, dtype=torch.float32)]).int()
-    src_idx = torch.zeros(rest, dtype=torch.long)
-    tgt_idx = torch.arange(rest, dtype=torch.long) + 1
+                              torch.arange(start_t, end_t, dtype=torch.float32, device=dev)]).int()
+    src_idx = torch.zeros(rest, dtype=torch.long, device=dev)
+    tgt_idx = torch.arange(rest, dtype=torch.long, device=dev) + 1
     return src_pts, src_idx, tgt_idx, frames_set_t
 
 
@@ -45,7 +46,7 @@ def compute_trajectory_cos_sims(features, trajectories, query_points, geo: Geome
     pn = normalize_points_for_sampling(trajectories, geo)  # broadcast over N x T x 3
     d = sample_descriptors(features, pn.reshape(-1, 3)).reshape(N, T, -1)
     qf = query_points[:, 2].long()
-    dq = d[torch.arange(N), qf]
+    dq = d[torch.arange(N, device=d.device), qf]
     return F.cosine_similarity(dq[:, None], d, dim=-1)
 
 
@@ -54,20 +55,21 @@ def anchor_predictions(features, preds, anchor_frames, head_sd, geo: Geometry, b
     """models/model_inference.py:130-154 -> M x T x 2: for every anchor frame a, the track of
     preds[i] (living in frame i) into frame a."""
     T = preds.shape[0]
+    dev = preds.device
     bs = T if batch_size is None else batch_size
     out = []
     for a in anchor_frames.tolist():
         coords = []
         for i in range(0, T, bs):
             e = min(i + bs, T)
-            frames_set_t = torch.cat([torch.tensor([a]), torch.arange(i, e)]).int()
-            src_idx = torch.arange(1, frames_set_t.shape[0])
-            tgt_idx = torch.zeros(frames_set_t.shape[0] - 1, dtype=torch.long)
+            frames_set_t = torch.cat([torch.tensor([a], device=dev), torch.arange(i, e, device=dev)]).int()
+            src_idx = torch.arange(1, frames_set_t.shape[0], device=dev)
+            tgt_idx = torch.zeros(frames_set_t.shape[0] - 1, dtype=torch.long, device=dev)
             inp = (preds[i:e], src_idx, tgt_idx, frames_set_t)
             coords.append(unnormalize_xy(tracker_forward(features, inp, head_sd, geo, faithful), geo))
         out.append(torch.cat(coords)[:, :2])
     if not out:
-        return torch.zeros(0, T, 2)
+        return torch.zeros(0, T, 2, device=dev)
     return torch.stack(out)
 
 
@@ -77,7 +79,7 @@ def compute_anchor_trajectories(features, trajectories, cos_sims, head_sd, geo, 
     N, T = trajectories.shape[:2]
     res = {}
     for n in range(N):
-        anchors = torch.arange(T)[cos_sims[n] >= anchor_th]
+        anchors = torch.arange(T, device=cos_sims.device)[cos_sims[n] >= anchor_th]
         res[n] = anchor_predictions(features, trajectories[n], anchors, head_sd, geo, batch_size,
                                     faithful)
     return res

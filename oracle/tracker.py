@@ -1,7 +1,10 @@
 """Oracle restatement of the tracker forward.
 
-Test infrastructure (see ``oracle/__init__.py``).  Plain PyTorch fp32 on CPU; the
-explicit formulas below are also the specification the CUDA kernels follow.
+Test infrastructure (see ``oracle/__init__.py``).  Plain PyTorch fp32; the explicit formulas
+below are also the specification the CUDA kernels follow.  Device-agnostic: every tensor is
+created on the device of the inputs, so the same code is the CPU oracle (goldens, small cases)
+and -- on ``cuda`` with TF32 off (``oracle.use_exact_fp32()``) -- the fp32 oracle for
+BASELINE.json's full-size configurations and the reference's PyTorch-CUDA comparator.
 """
 import math
 from dataclasses import dataclass
@@ -50,8 +53,8 @@ class Geometry:
 def normalize_points_for_sampling(points: torch.Tensor, geo: Geometry) -> torch.Tensor:
     """models/tracker.py:77-94 -- ``a * points + b`` with a=[aw,ah,1], b=[bw,bh,0] in fp32."""
     aw, ah, bw, bh = geo.point_affine()
-    a = torch.tensor([[aw, ah, 1]], dtype=torch.float32)
-    b = torch.tensor([[bw, bh, 0]], dtype=torch.float32)
+    a = torch.tensor([[aw, ah, 1]], dtype=torch.float32, device=points.device)
+    b = torch.tensor([[bw, bh, 0]], dtype=torch.float32, device=points.device)
     return a * points + b
 
 
@@ -62,7 +65,7 @@ def _unnormalize_clip(coord: torch.Tensor, size: int) -> torch.Tensor:
     return torch.clamp(x, min=0.0, max=float(size - 1))
 
 
-def sample_descriptors(features: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
+def sample_descriptors(features: torch.Tensor, points: torch.Tensor, frames_set=None) -> torch.Tensor:
     """models/tracker.py:96-111 + utils.py:75-101 (5-D ``grid_sample``), restated explicitly.
 
     features: N x C x h x w (the frame set).  points: B x 3 = (x_n, y_n, idx) with
@@ -73,8 +76,13 @@ def sample_descriptors(features: torch.Tensor, points: torch.Tensor) -> torch.Te
     weight onto a neighbouring frame -- reproduced here.
     Trilinear weights and the corner accumulation order follow ATen's
     ``grid_sampler_3d`` (tnw, tne, tsw, tse, bnw, bne, bsw, bse).
+
+    ``frames_set`` (optional, N ints): ``features`` is then the WHOLE video and slot z of the
+    frame set is ``features[frames_set[z]]`` -- the same values as sampling the gathered copy
+    ``features[frames_set]`` (models/tracker.py:316), without materialising it.
     """
-    N, C, h, w = features.shape
+    _, C, h, w = features.shape
+    N = features.shape[0] if frames_set is None else frames_set.shape[0]
     pts = points.to(torch.float32)
     tn = pts[:, 2].clone()
     if N > 1:
@@ -95,28 +103,41 @@ def sample_descriptors(features: torch.Tensor, points: torch.Tensor) -> torch.Te
         (x0, y1, z1, (x1 - ix) * (iy - y0) * (iz - z0)),
         (x1, y1, z1, (ix - x0) * (iy - y0) * (iz - z0)),
     ]
-    out = torch.zeros(pts.shape[0], C, dtype=torch.float32)
+    out = torch.zeros(pts.shape[0], C, dtype=torch.float32, device=features.device)
+    fs = None if frames_set is None else frames_set.long()
     for xi, yi, zi, wt in corners:
         ok = (xi >= 0) & (xi <= w - 1) & (yi >= 0) & (yi <= h - 1) & (zi >= 0) & (zi <= N - 1)
         xi = xi.clamp(0, w - 1).long(); yi = yi.clamp(0, h - 1).long(); zi = zi.clamp(0, N - 1).long()
-        vals = features[zi, :, yi, xi]  # B x C
+        vals = features[zi if fs is None else fs[zi], :, yi, xi]  # B x C
         out = out + torch.where(ok[:, None], vals * wt[:, None], torch.zeros_like(vals))
     return out
 
 
 # --------------------------------------------------------------------------- a5
 def corr_maps(source_desc: torch.Tensor, frames: torch.Tensor, target_idx: torch.Tensor,
-              faithful_einsum: bool = False) -> torch.Tensor:
+              faithful_einsum: bool = False, frames_set=None) -> torch.Tensor:
     """models/tracker.py:158-169.  source_desc B x C, frames N x C x h x w, target_idx B.
 
     corr[b] = <s_b, F[tgt_b][:, r, c]> / max(|s_b| * |F[tgt_b][:, r, c]|, 1e-8)  -> B x 1 x h x w.
     ``faithful_einsum=True`` reproduces the reference's cost profile (all B x N maps,
-    then the diagonal pick); the default computes only the B needed maps.
+    then the diagonal pick); the default computes only the B needed maps.  With
+    ``frames_set`` the target of map b is ``frames[frames_set[target_idx[b]]]`` (``frames`` =
+    the whole video, no gathered copy) and maps sharing a target frame are one matrix product.
     """
     tgt = target_idx.long()
-    if faithful_einsum:
+    if frames_set is not None and not faithful_einsum:
+        tf = frames_set.long()[tgt]
+        B = source_desc.shape[0]
+        _, C, h, w = frames.shape
+        corr = torch.empty(B, h, w, dtype=torch.float32, device=frames.device)
+        fnorm = torch.empty(B, h, w, dtype=torch.float32, device=frames.device)
+        for f in torch.unique(tf).tolist():
+            sel = tf == f
+            corr[sel] = (source_desc[sel] @ frames[f].reshape(C, h * w)).reshape(-1, h, w)
+            fnorm[sel] = frames[f].norm(dim=0)
+    elif faithful_einsum:
         vol = torch.einsum("bc,nchw->bnhw", source_desc, frames)
-        corr = vol[torch.arange(source_desc.shape[0]), tgt]
+        corr = vol[torch.arange(source_desc.shape[0], device=vol.device), tgt]
         fnorm = frames.norm(dim=1)[tgt]
     else:
         sel = frames[tgt]  # B x C x h x w
@@ -175,7 +196,7 @@ def head_forward(cost_relu: torch.Tensor, head_sd: dict, geo: Geometry, return_a
     p = torch.softmax(z.reshape(B, 1, -1), dim=2).reshape(B, h, w)
     xs, ys = token_pixel_grid(geo)
     gy, gx = torch.meshgrid(ys, xs, indexing="ij")
-    grid = torch.stack((gx, gy), -1)  # h x w x 2 (x, y), int64
+    grid = torch.stack((gx, gy), -1).to(cost_relu.device)  # h x w x 2 (x, y), int64
     hs = geo.patch // 2
     centre = torch.stack((col * geo.stride + hs, row * geo.stride + hs), dim=-1)  # B x 2
     mask = torch.norm((grid[None] - centre[:, None, None]).to(torch.float32), dim=-1) <= geo.radius
@@ -187,7 +208,7 @@ def head_forward(cost_relu: torch.Tensor, head_sd: dict, geo: Geometry, return_a
         hm[fb] = (hm[fb] + uniform[:, None, None]) * mask[fb]
         s[fb] = hm[fb].sum(dim=(1, 2))
     point = (grid[None] * hm[..., None]).sum(dim=(1, 2)) / s[:, None]
-    norm = torch.tensor([geo.W, geo.H], dtype=torch.float32) - 1
+    norm = torch.tensor([geo.W, geo.H], dtype=torch.float32, device=point.device) - 1
     out = point / norm
     out = (1 - (-1)) * out + (-1)
     if return_aux:
@@ -198,7 +219,7 @@ def head_forward(cost_relu: torch.Tensor, head_sd: dict, geo: Geometry, return_a
 def unnormalize_xy(coords: torch.Tensor, geo: Geometry) -> torch.Tensor:
     """RangeNormalizer.unnormalize(src=(-1,1), dims=[0,1]) (data/dataset.py:39-53) as
     called in models/model_inference.py:52,144: (v - (-1)) / (1 - (-1)) * (W-1, H-1)."""
-    norm = torch.tensor([geo.W, geo.H], dtype=torch.float32) - 1
+    norm = torch.tensor([geo.W, geo.H], dtype=torch.float32, device=coords.device) - 1
     x = (coords - (-1)) / (1 - (-1))
     return x * norm
 
@@ -212,11 +233,14 @@ def tracker_forward(features: torch.Tensor, inp, head_sd: dict, geo: Geometry,
     target_frame_indices B, frames_set_t N).  Returns B x 2 in [-1, 1].
     """
     src_pts, src_idx, tgt_idx, frames_set_t = inp
-    frames = features[frames_set_t.long()]  # models/tracker.py:316 (gather copy)
-    if faithful:
-        _ = features[frames_set_t.long()]  # models/tracker.py:317: second, unused gather
     pn = normalize_points_for_sampling(src_pts.to(torch.float32), geo)
     pts = torch.cat([pn[:, :-1], src_idx[:, None].to(torch.float32)], dim=1)
-    desc = sample_descriptors(frames, pts)
-    corr = corr_maps(desc, frames, tgt_idx, faithful_einsum=faithful)
+    if faithful:   # the reference's cost profile: two gathered copies of the frame set, B x N einsum
+        frames = features[frames_set_t.long()]  # models/tracker.py:316 (gather copy)
+        _ = features[frames_set_t.long()]  # models/tracker.py:317: second, unused gather
+        desc = sample_descriptors(frames, pts)
+        corr = corr_maps(desc, frames, tgt_idx, faithful_einsum=True)
+    else:          # same values, frame set addressed through its index vector
+        desc = sample_descriptors(features, pts, frames_set_t)
+        corr = corr_maps(desc, features, tgt_idx, frames_set=frames_set_t)
     return head_forward(torch.relu(corr), head_sd, geo)

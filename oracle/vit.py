@@ -89,8 +89,8 @@ def block_forward(x, sd, i, heads):
 def vit_tokens(frames01: torch.Tensor, sd: dict, heads: int, layer: int, stride: int = 7,
                patch: int = 14, return_all=False):
     """frames01: B x 3 x H x W in [0, 1].  Returns block-``layer`` output B x (1+h*w) x D."""
-    mean = torch.tensor(IMAGENET_MEAN)[None, :, None, None]
-    std = torch.tensor(IMAGENET_STD)[None, :, None, None]
+    mean = torch.tensor(IMAGENET_MEAN, device=frames01.device)[None, :, None, None]
+    std = torch.tensor(IMAGENET_STD, device=frames01.device)[None, :, None, None]
     x = (frames01 - mean) / std  # torchvision Normalize, utils.py:46,55
     x = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=stride)
     B, D, n_h, n_w = x.shape
