@@ -53,6 +53,10 @@ def parse():
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the cpu_baseline leg")
     ap.add_argument("--stream-probe", type=int, default=1, help="0: skip the dedicated corr_stream HBM probe")
     ap.add_argument("--stages", type=int, default=1, help="0: skip the ViT / delta-DINO / best-buddies stage timings")
+    ap.add_argument("--head", default="sharp", choices=["sharp", "well", "mixed"], help="refiner weights of the timed step")
+    ap.add_argument("--path", type=int, default=-1, help="anchor-phase pipeline: -1 automatic, 0 full-map, 1 coarse pass + exact window")
+    ap.add_argument("--torch-cuda-baseline", type=int, default=1, help="0: skip timing the reference's PyTorch path on cuda:0")
+    ap.add_argument("--second-head", type=int, default=1, help="0: skip the extra timing with the mixed-sign head")
     return ap.parse_args()
 
 
@@ -176,11 +180,32 @@ def measured_peaks():
 _CPU_FEATS = {}
 
 
-def cpu_reference_sample(T, C, nq, noise, seed=0, max_anchor_calls=6):
-    """Times the oracle's FAITHFUL restatement of the reference path on the host cores, on a bounded sample:
-    one query point -- its trajectory call (1 model() call over T+1 frames), the cos-sim pass, up to
-    ``max_anchor_calls`` anchor model() calls (extrapolated to this query point's anchor count) and the
-    occlusion step.  Returns (query-points/s, cores, description)."""
+def head_weights_for(kind):
+    """Refiner weights of the timed step: 'sharp' (bench_inputs.sharp_head: positive, dominant centre tap -- like a trained
+    head), 'well' (U(0.2, 1) everywhere: blurry softmax) or 'mixed' (mixed-sign kernels).  Same draws as oracle/synth.py."""
+    from bench_inputs import sharp_head
+    import numpy as np
+    if kind == "sharp":
+        return sharp_head(0)
+    rs = np.random.RandomState(1000)
+
+    def u(lo, hi, *shape):
+        return torch.from_numpy(rs.uniform(lo, hi, size=shape).astype(np.float32))
+    if kind == "well":
+        return {"cnn_refiner.0.weight": u(0.2, 1, 16, 1, 3, 3), "cnn_refiner.0.bias": u(0.2, 1, 16),
+                "cnn_refiner.2.weight": u(0.2, 1, 1, 16, 3, 3), "cnn_refiner.2.bias": u(0.2, 1, 1)}
+    w1 = u(-0.5, 1, 16, 1, 3, 3); w2 = u(-0.5, 1, 1, 16, 3, 3)
+    return {"cnn_refiner.0.weight": w1, "cnn_refiner.0.bias": u(-0.2, 0.2, 16),
+            "cnn_refiner.2.weight": w2, "cnn_refiner.2.bias": u(-0.2, 0.2, 1)}
+
+
+def cpu_reference_sample(T, C, nq, noise, seed=0, anchor_calls=3, samples=3):
+    """Times the oracle's FAITHFUL restatement of the reference path (same gathers and B x N einsum per model() call,
+    models/tracker.py:303-325) on the host cores, on a bounded sample of the workload: one query point -- per sample its
+    trajectory model() call and ``anchor_calls`` anchor model() calls (one untimed warm-up call first), plus the cos-sim
+    pass and the occlusion step once.  A query point costs  traj + cos + (#anchors) x anchor-call + occlusion; the value
+    uses the MEDIAN call times over ``samples`` samples, the spread (min .. max over samples) is reported next to it.
+    Returns (query-points/s, cores, description, seconds per query point, spread dict)."""
     from oracle import inference as oi
     from oracle.tracker import Geometry
     from bench_inputs import sharp_head
@@ -194,26 +219,69 @@ def cpu_reference_sample(T, C, nq, noise, seed=0, max_anchor_calls=6):
     head = sharp_head(0)
     q = query_lattice(nq, seed)[nq // 2 + 3: nq // 2 + 4].clone()
     with torch.no_grad():
-        t0 = time.perf_counter()
-        traj = oi.compute_trajectories(feats, q, head, geo, None, faithful=True)
-        t_a = time.perf_counter() - t0
+        traj = oi.compute_trajectories(feats, q, head, geo, None, faithful=True)          # warm-up (+ the values we need)
         t0 = time.perf_counter()
         cos = oi.compute_trajectory_cos_sims(feats, traj, q, geo)
         t_b = time.perf_counter() - t0
         anchors = torch.arange(T)[cos[0] >= 0.7]
         m = int(anchors.numel())
-        k = min(m, max_anchor_calls)
+        k = max(1, min(m, anchor_calls))
+        t_traj, t_anchor = [], []
+        part = None
+        for s_ in range(samples):
+            t0 = time.perf_counter()
+            oi.compute_trajectories(feats, q, head, geo, None, faithful=True)
+            t_traj.append(time.perf_counter() - t0)
+            sel = anchors[(torch.arange(k) + s_ * k) % max(m, 1)] if m else anchors
+            t0 = time.perf_counter()
+            part = oi.anchor_predictions(feats, traj[0], sel, head, geo, None, faithful=True)
+            t_anchor.append((time.perf_counter() - t0) / max(len(sel), 1))
         t0 = time.perf_counter()
-        part = oi.anchor_predictions(feats, traj[0], anchors[:k], head, geo, None, faithful=True)
-        t_c = (time.perf_counter() - t0) * (m / max(k, 1))
-        t0 = time.perf_counter()
-        green = part.repeat((m + k - 1) // max(k, 1), 1, 1)[:m] if k else part
+        green = part.repeat((m + k - 1) // k, 1, 1)[:m] if m else part
         oi.occlusion_for_query(green, traj[0, :, :2], cos[0], 0.7, 0.6)
         t_d = time.perf_counter() - t0
-    total = t_a + t_b + t_c + t_d
-    desc = (f"1 query point of the T={T}, C={C} workload: trajectory model() call {t_a:.2f}s + cos-sims {t_b:.2f}s + "
-            f"{k} of {m} anchor model() calls (extrapolated x{m / max(k, 1):.1f}) {t_c:.2f}s + occlusion {t_d:.3f}s")
-    return 1.0 / total, cores, desc, total
+    per_qp = [t_traj[i] + t_b + m * t_anchor[i] + t_d for i in range(samples)]
+    total = statistics.median(per_qp)
+    spread = {"samples": samples, "anchor_calls_per_sample": k, "s_per_query_point_min": min(per_qp),
+              "s_per_query_point_median": total, "s_per_query_point_max": max(per_qp),
+              "traj_call_s_median": statistics.median(t_traj), "anchor_call_s_median": statistics.median(t_anchor)}
+    desc = (f"1 query point of the T={T}, C={C} workload on {cores} host threads: median over {samples} samples of "
+            f"[trajectory model() call {statistics.median(t_traj):.2f}s + {k} anchor model() calls "
+            f"{statistics.median(t_anchor):.2f}s each, extrapolated to this point's {m} anchors] + cos-sims {t_b:.2f}s + "
+            f"occlusion {t_d:.3f}s; per-query-point seconds min/median/max = {min(per_qp):.1f}/{total:.1f}/{max(per_qp):.1f}")
+    return 1.0 / total, cores, desc, total, spread
+
+
+def torch_cuda_reference_sample(T, C, nq, noise, dev, n_points=2):
+    """The reference's PyTorch path on THIS GPU (the north star's >= 10x comparator): the oracle's faithful
+    restatement (per model() call: two gathered copies of the frame set, B x N einsum, refiner convolutions, softmax --
+    models/tracker.py:303-325, models/model_inference.py:37-216) run by torch on ``dev`` with torch's default precision
+    flags (fp32 matmul; cuDNN convolutions may use TF32, as they would for the reference), for ``n_points`` complete query
+    points (trajectory, cos-sims, every anchor call, occlusion) after one warm-up point."""
+    from oracle import inference as oi
+    from oracle.tracker import Geometry
+    from bench_inputs import sharp_head
+    geo = Geometry()
+    feats = synth_video_features(T, C, dev, 1234, noise)
+    head = {k: v.to(dev) for k, v in sharp_head(0).items()}
+    q_all = query_lattice(nq, 0).to(dev)
+    idx = [nq // 2 + 3, 5, nq - 7, nq // 3][: n_points + 1]
+    with torch.no_grad():
+        oi.infer(feats, q_all[idx[:1]], head, geo, 0.7, 0.6, faithful=True)            # warm-up: cuBLAS / cuDNN plans
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, _, aux = oi.infer(feats, q_all[idx[1:]], head, geo, 0.7, 0.6, faithful=True, return_all=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    n = len(idx) - 1
+    calls = n + int(sum(int(a.shape[0]) for a in aux["anchors"].values()))
+    del feats
+    torch.cuda.empty_cache()
+    return {"value": n / dt, "unit": "query-points/s", "device": torch.cuda.get_device_name(0), "kind": "port",
+            "sample": (f"{n} complete query points of the T={T}, C={C} workload ({calls} model() calls, {dt / calls * 1e3:.1f} ms each), "
+                       f"the oracle's faithful restatement of the reference path run by torch {torch.__version__} on the GPU, "
+                       f"fp32, after one warm-up point"),
+            "s_per_query_point": dt / n}
 
 
 def run_reference(args):
@@ -226,8 +294,7 @@ def run_reference(args):
     warm = min(args.warmup, 1)
     for i in range(warm + args.steps):
         t_s = time.perf_counter()
-        v, cores, desc, total = cpu_reference_sample(args.T, args.C, args.nq, args.noise, seed=0,
-                                                     max_anchor_calls=1)
+        v, cores, desc, total, _ = cpu_reference_sample(args.T, args.C, args.nq, args.noise, seed=0, anchor_calls=1, samples=1)
         dt = time.perf_counter() - t_s
         if i >= warm:
             vals.append(v)
@@ -278,10 +345,10 @@ def run_b200(args):
     model = Tracker(video=video, dino_embed_video=feats, device=dev, delta_channels=[3, 4, 4, 4, C],
                     corr_precision=args.precision)
     del feats
-    from bench_inputs import sharp_head
-    model.tracker_head.load_state_dict(sharp_head(0))
+    model.tracker_head.load_state_dict(head_weights_for(args.head))
     from dino_tracker_b200 import model_inference as _mi_mod
     _mi_mod.DEFAULT_CHUNK_MAPS = args.chunk_maps
+    _lib.check(lib.dinotrk_infer_set_path(args.path), "infer_set_path")
     mi = ModelInference(model, model.range_normalizer, 0.7, 0.6)
     q_host = query_lattice(nq, 0).pin_memory()
     q_dev = q_host.to(dev)
@@ -298,6 +365,7 @@ def run_b200(args):
     n_anch = (r["cos_sims"] >= 0.7).sum(dim=1).float()
     maps_per_step = int(nq * T + n_anch.sum().item() * T)
     torch.cuda.synchronize()
+    path_stats = _lib.infer_stats()
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -353,14 +421,39 @@ def run_b200(args):
     value = world * nq * args.steps / (ms / 1000.0)
     e2e_value = world * nq * args.steps / (e2e_ms / 1000.0)
 
-    # ---- roofline of the dominant kernel (per-class CUDA-event times from inside the timed region)
-    total_prof = sum(v[0] for v in prof.values()) or 1.0
-    kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps,
-                   "share": v[0] / total_prof} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
-    dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
-    roofline = kernel_roofline(dom, prof[dom], args, maps_per_step, peaks, clocks)
-    extra = {k: kernel_roofline(k, prof[k], args, maps_per_step, peaks, clocks)
-             for k in ("corr_gemm", "head", "corr_stream") if k in prof and k != dom}
+    # ---- per-kernel-class times.  The timed region overlaps kernels across streams, so its event brackets include
+    # cross-stream waits; the per-kernel figures (and the roofline) come from a separate pass with the overlap switched
+    # off (everything on one stream: a bracket = the kernels' own time), run right after the timed region.
+    _lib.check(lib.dinotrk_infer_set_overlap(0), "set_overlap")
+    step_resident(); torch.cuda.synchronize()
+    _lib.profile_enable(True); _lib.profile_collect()
+    clean_steps = 3
+    ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ce0.record()
+    for _ in range(clean_steps):
+        step_resident()
+    ce1.record(); torch.cuda.synchronize()
+    clean = _lib.profile_collect()
+    _lib.profile_enable(False)
+    _lib.check(lib.dinotrk_infer_set_overlap(-1), "set_overlap")
+    serial_ms = ce0.elapsed_time(ce1) / clean_steps
+    total_clean = sum(v[0] for v in clean.values()) or 1.0
+    kernels = {k: {"ms_per_step": v[0] / clean_steps, "launches_per_step": v[1] / clean_steps, "share": v[0] / total_clean,
+                   "ms_per_step_in_timed_region_brackets": prof.get(k, (0.0, 0))[0] / args.steps}
+               for k, v in sorted(clean.items(), key=lambda kv: -kv[1][0])}
+    clean_stat = {k: (v[0] * args.steps / clean_steps, v[1] * args.steps / clean_steps) for k, v in clean.items()}
+    dom = max(clean.items(), key=lambda kv: kv[1][0])[0]
+    roofline = kernel_roofline(dom, clean_stat[dom], args, maps_per_step, peaks, clocks, path_stats)
+    extra = {k: kernel_roofline(k, clean_stat[k], args, maps_per_step, peaks, clocks, path_stats)
+             for k in ("corr_gemm", "xw_coarse_gemm", "xw_exact_gemm", "xw_head", "head", "corr_stream") if k in clean_stat and k != dom}
+    corr_ms = sum(clean[k][0] for k in ("corr_gemm", "xw_coarse_gemm", "xw_exact_gemm") if k in clean) / clean_steps
+    if corr_ms > 0:
+        ach = 2.0 * maps_per_step * P * C / (corr_ms / 1e3) / 1e12
+        extra["correlation_total"] = {"kernels": [k for k in ("corr_gemm", "xw_coarse_gemm", "xw_exact_gemm") if k in clean],
+                                      "bound": "tensor", "ms_per_step": corr_ms, "achieved": ach, "peak": peaks["tf_sustained"],
+                                      "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
+                                      "note": "all correlation GEMM kernels of a step together against the algorithmic 2*P*C FLOPs of "
+                                              "every map (what the reference's formulation computes per map)"}
     if args.stream_probe:
         extra["corr_stream_probe"] = stream_probe(model, mi, lib, _lib, args, peaks)
 
@@ -371,18 +464,49 @@ def run_b200(args):
                        "anchors_per_query_mean": n_anch.mean().item(), "corr_maps_per_step": maps_per_step,
                        "parallelism": f"video-parallel x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (1.66 GB feature video per step; no explicit flush)",
-                       "chunk_maps": args.chunk_maps, "corr_precision": args.precision},
+                       "chunk_maps": args.chunk_maps, "corr_precision": args.precision, "head_kind": args.head,
+                       "anchor_pipeline": path_stats["pipeline"],
+                       "anchor_maps_exact_window": path_stats["exact_window"], "anchor_maps_full_map": path_stats["full_map"],
+                       "exact_window_fraction": (path_stats["exact_window"] / max(path_stats["anchor_maps"], 1)
+                                                 if path_stats["pipeline"] == "exact-window" else None)},
             "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": extra,
-            "kernels": kernels, "peaks": peaks}
+            "kernels": kernels, "kernels_note": "per-class CUDA-event times of a separate overlap-off pass (%d steps, %.2f ms per "
+                                                "serialised step); see the comment in bench.py" % (clean_steps, serial_ms),
+            "peaks": peaks}
+    if args.second_head and world == 1 and args.head != "mixed":
+        # the same step with mixed-sign refiner weights: whatever the head's certificate cannot cover goes through the
+        # full-map refiner (a trained checkpoint's weights are not known here; this is the unfavourable end)
+        model.tracker_head.load_state_dict(head_weights_for("mixed"))
+        for _ in range(2):
+            step_resident()
+        torch.cuda.synchronize()
+        st2 = _lib.infer_stats()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(3):
+            step_resident()
+        m1.record(); torch.cuda.synchronize()
+        ms2 = m0.elapsed_time(m1) / 3
+        line["second_head"] = {"head_kind": "mixed", "value": nq / (ms2 / 1e3), "unit": "query-points/s", "ms_per_step": ms2,
+                               "anchor_pipeline": st2["pipeline"], "anchor_maps_exact_window": st2["exact_window"],
+                               "anchor_maps_full_map": st2["full_map"]}
+        model.tracker_head.load_state_dict(head_weights_for(args.head))
+    if args.torch_cuda_baseline and world == 1:
+        del model, mi
+        torch.cuda.empty_cache()
+        line["torch_cuda_baseline"] = torch_cuda_reference_sample(T, C, nq, args.noise, dev)
+        line["torch_cuda_baseline"]["speedup_e2e"] = e2e_value / line["torch_cuda_baseline"]["value"]
+        model = mi = None
     if args.stages and world == 1:
         line["stages"] = stage_timings(args, dev, _lib, peaks)
         fs = line["stages"]["per_video_feature_stage_s"]
         line["stages"]["query_points_per_s_from_pixels"] = nq / (fs + ms / args.steps / 1000.0)
     if args.cpu_baseline and world == 1:
-        v, cores, desc, _ = cpu_reference_sample(T, C, nq, args.noise, seed=0, max_anchor_calls=3)
-        line["cpu_baseline"] = {"value": v, "unit": "query-points/s", "cores": cores, "kind": "port", "sample": desc}
+        v, cores, desc, _, spread = cpu_reference_sample(T, C, nq, args.noise, seed=0, anchor_calls=3, samples=3)
+        line["cpu_baseline"] = {"value": v, "unit": "query-points/s", "cores": cores, "kind": "port", "sample": desc,
+                                "spread": spread}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -403,41 +527,64 @@ def ncu_traffic(csv_name):
     return tot if seen == 2 else None
 
 
-def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks):
-    """Algorithmic work per launch / average launch time for one kernel class."""
+def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks, path_stats=None):
+    """Algorithmic work per launch / average launch time for one kernel class (DESIGN.md section 4 states the per-unit figures)."""
     ms_total, launches = stat
     avg_s = ms_total / 1000.0 / max(launches, 1)
-    maps_per_launch = maps_per_step * args.steps / max(launches, 1)
+    anchor_maps = (path_stats or {}).get("anchor_maps", 0)
+    xw = (path_stats or {}).get("pipeline") == "exact-window"
+    # maps a launch of this class processes: the exact-window kernels only see the anchor phase
+    if name.startswith("xw_"):
+        maps_total = anchor_maps * args.steps
+    elif name in ("corr_gemm", "head", "head_full") and xw:
+        maps_total = (maps_per_step - anchor_maps + (path_stats or {}).get("full_map", 0)) * args.steps
+    else:
+        maps_total = maps_per_step * args.steps
+    maps_per_launch = maps_total / max(launches, 1)
+    tensor_note = "peak = sustained cuBLAS bf16 (%s)" % peaks["which"]
+    if name == "xw_coarse_gemm":
+        flops = 2.0 * maps_per_launch * P * args.C
+        ach = flops / avg_s / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tf_sustained"], "traffic": ncu_traffic("ncu_r2_xw_coarse.csv"),
+                "traffic_note": "DRAM read + write bytes per launch from the committed ncu --set full capture of this kernel "
+                                "(profiles/ncu_r2_xw_coarse.csv), null until captured; algorithmic bytes per map: fp16 operands "
+                                "(descriptor 2 KB + its share of the frame's 16.6 MB) + 384 B of tile keys -- no map is stored",
+                "note": "single kind::f16 pass over the hi halves: executed MMA FLOPs = algorithmic 2*maps*P*C; " + tensor_note,
+                "maps_per_launch": maps_per_launch, "ms_per_launch": avg_s * 1e3}
+    if name == "xw_exact_gemm":
+        flops_exec = 2.0 * maps_per_launch * 480 * args.C * 3 * (128.0 / max(args.T if args.T <= 128 else 125, 1))
+        flops_alg = 2.0 * maps_per_launch * 225 * args.C
+        ach = flops_alg / avg_s / 1e12
+        return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tf_sustained"], "traffic": ncu_traffic("ncu_r2_xw_exact.csv"),
+                "executed_mma_tflops": flops_exec / avg_s / 1e12,
+                "note": "algorithmic = the 15 x 15 window the head needs per map (2*225*C FLOPs); executed = 3 split-precision "
+                        "passes x 480 box columns x 128 UMMA rows per cell of T maps; " + tensor_note,
+                "maps_per_launch": maps_per_launch, "ms_per_launch": avg_s * 1e3}
     if name in ("corr_gemm", "best_buddies", "vit_gemm", "delta_conv"):
         flops = 2.0 * maps_per_launch * P * args.C  # <d, F[p]> for every token of the target frame
         ach = flops / avg_s / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sustained"],
-                "traffic": (ncu_traffic("ncu_r1_final_tc_gemm2.csv") * maps_per_launch / 16384.0
-                            if name == "corr_gemm" and args.precision == "fp16x3" and ncu_traffic("ncu_r1_final_tc_gemm2.csv") else None),
-                "traffic_note": ("DRAM read + write bytes per launch, from the ncu --set full capture of a 16384-map launch "
-                                 "(profiles/ncu_r1_final_tc_gemm2.csv: 704 MB = 43.0 KB per map) scaled to this run's maps per "
-                                 "launch; algorithmic bytes per map: 32.4 KB map out + 0.26 KB keys + ~6.7 KB fp16 hi/lo operands "
-                                 "= ~39.4 KB"),
-                "note": ("algorithmic FLOPs = 2*maps*P*C per launch; peak = sustained cuBLAS bf16 (%s). precision=%s: "
+                "traffic": None,
+                "note": ("algorithmic FLOPs = 2*maps*P*C per launch; %s. precision=%s: "
                          "fp16x3 executes 3 kind::f16 MMA passes (lo*hi, hi*lo, hi*hi) per algorithmic FLOP, so the tensor "
-                         "pipe is busy ~3x this fraction; fp32 = exact FFMA GEMM on the CUDA cores") % (peaks["which"], args.precision),
-                "executed_mma_tflops": ach * 3 if args.precision == "fp16x3" else None}
-    if name == "head":
-        # the fast path evaluates the refiner exactly on the 13x13 / 11x11 windows: 169*16*9 + 121*16*9 = 41 760 FMA per map
+                         "pipe is busy ~3x this fraction; fp32 = exact FFMA GEMM on the CUDA cores") % (tensor_note, args.precision),
+                "executed_mma_tflops": ach * 3 if args.precision == "fp16x3" else None,
+                "maps_per_launch": maps_per_launch, "ms_per_launch": avg_s * 1e3}
+    if name in ("head", "xw_head"):
+        # the windowed refiner: 169*16*9 + 121*16*9 = 41 760 FMA per map
         # (the reference's full-map formulation, SURVEY.md 8a row a7, is 4.67 MFLOP per map: 56x more)
         flops = 2.0 * 41760 * maps_per_launch
         ach = flops / avg_s / 1e12
         pk = fp32_peak_tflops(clocks)
         return {"kernel": name, "bound": "fp32-cuda-core", "achieved": ach, "peak": pk, "unit": "TFLOP/s",
-                "frac": ach / pk, "traffic": None,
+                "frac": ach / pk, "traffic": None, "ns_per_map": avg_s * 1e9 / max(maps_per_launch, 1),
                 "reference_formulation_tflops": 4.67e6 * maps_per_launch / avg_s / 1e12,
                 "note": ("exact-fp32 CUDA-core work of the windowed refiner (83.5 kFLOP per map; the full-map formulation the "
-                         "reference evaluates is 4.67 MFLOP per map and is only run for uncertified maps); the kernel is "
-                         "issue / latency bound, not FMA bound (profiles/ncu_r1_final_head_tm.csv: 5.8 k warp instructions per "
-                         "map, issue slots 55 % busy); peak = 148 SMs x 128 lanes x 2 x max SM clock")}
-    # HBM-bound streaming kernels: feature bytes read once per launch
-    nbytes = maps_per_launch * 0  # filled by the dedicated probe
+                         "reference evaluates is 4.67 MFLOP per map and is only run for uncertified maps); "
+                         "peak = 148 SMs x 128 lanes x 2 x max SM clock")}
     return {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
             "traffic": None, "note": "see roofline_other.corr_stream_probe"}
 

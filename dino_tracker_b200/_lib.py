@@ -60,6 +60,8 @@ SIGNATURES = {
     "dinotrk_head": (c_int, [_P, c_int, POINTER(Geom), POINTER(HeadWeights), _P, _P, c_int, c_int, _P, _P, _P]),
     "dinotrk_infer_workspace_bytes": (c_size_t, [c_int, c_int, POINTER(Geom), c_int, c_int]),
     "dinotrk_infer_set_overlap": (c_int, [c_int]),
+    "dinotrk_infer_set_path": (c_int, [c_int]),
+    "dinotrk_infer_last_stats": (c_int, [POINTER(ctypes.c_longlong), c_int]),
     "dinotrk_infer_max_chunks": (c_size_t, [c_int, c_int, c_int]),
     "dinotrk_infer_plan": (c_int, [c_int, c_int, c_int, _P, c_int, _P, _P, c_int, _P]),
     "dinotrk_infer": (c_int, [POINTER(Features), POINTER(Geom), POINTER(HeadWeights), _P, c_int, c_float, c_float,
@@ -183,6 +185,13 @@ def profile_collect():
     cnt = (c_ulonglong * n)()
     check(lib.dinotrk_profile_collect(ms, cnt, n), "profile_collect")
     return {lib.dinotrk_profile_class_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}
+
+
+def infer_stats():
+    """{anchor-phase maps, finished by the exact-window path, re-done by the full-map path, pipeline} of the last infer."""
+    a = (ctypes.c_longlong * 4)()
+    check(load().dinotrk_infer_last_stats(a, 4), "infer_last_stats")
+    return {"anchor_maps": int(a[0]), "exact_window": int(a[1]), "full_map": int(a[2]), "pipeline": "exact-window" if a[3] else "full-map"}
 
 
 def launch_count():

@@ -62,6 +62,23 @@ int make_tmap_3d(CUtensorMap* map, const void* base, uint64_t batch, uint64_t ro
   return encode(map, base, 3, dims, strides, box, elem);
 }
 
+// rank-4 map over a [d3][d2][d1][d0] tensor (d0 contiguous): used for {channels, w, h, T} boxes of the feature video
+int make_tmap_4d(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                 const uint32_t box[4], int elem) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return DINOTRK_ECUDA; }
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t s[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapDataType dt = elem == TMAP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                         : elem == TMAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = fn(map, dt, 4, const_cast<void*>(base), d, s, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (4-d) failed (%d)", (int)r); return DINOTRK_ECUDA; }
+  return DINOTRK_OK;
+}
+
 // x = hi + lo (+ residual <= 2^-22 |x| in the fp16 normal range): hi = rn_fp16(x), lo = rn_fp16(x - hi)
 __global__ void split_f16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, size_t n4) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

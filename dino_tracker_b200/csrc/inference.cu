@@ -15,8 +15,11 @@
 #include "common.cuh"
 #include "corr.cuh"
 #include "sample.cuh"
+#include "xwin.cuh"
 
 namespace dtk {
+
+constexpr int TC2_BM_ROWS = 256;   // M tile of the CTA-pair GEMM (tcgemm2.cuh: TC2_BM)
 
 // ---------------------------------------------------------------------------------- phase A helpers
 // descriptors of the query points: frames_set = [t_q, s..e-1], set index 0 (model_inference.py:8-34)
@@ -222,8 +225,9 @@ struct GroupBuf {  // host mirror of the per-chunk group arrays: [frame | row0 |
 //   kind 0 (trajectories): items = (frame t, query row n), t-major; descriptor rows are the N query rows.
 //   kind 1 (anchors): items of anchor frame a = cnt[a] * T pairs (slot, i), a-major; descriptor rows are per chunk.
 struct ChunkMeta { int used, maxm, n_groups; bool no_thin; };
+// align: anchor-phase chunks are cut at multiples of `align` items per frame (T for the exact-window path: whole cells).
 static void plan_chunks(int kind, int T, int N, const int* cnt, int ch, int gcap, std::vector<ChunkMeta>& metas,
-                        std::vector<int>& plan_host) {
+                        std::vector<int>& plan_host, int align = 1) {
   metas.clear(); plan_host.clear();
   GroupBuf gb(gcap);
   auto commit_chunk = [&](int used, int maxm) {
@@ -256,7 +260,11 @@ static void plan_chunks(int kind, int T, int N, const int* cnt, int ch, int gcap
       while (a < T && used < ch && gb.n < gcap) {
         long long tot = (long long)cnt[a] * T;
         long long m = tot - item;
-        if (m > ch - used) m = ch - used;
+        if (m > ch - used) {
+          m = (long long)((ch - used) / align) * align;
+          if (m == 0 && used > 0) break;            // chunk full up to the alignment
+          if (m == 0) m = align;                    // (ch >= align is guaranteed by the caller)
+        }
         if (m > 0) {
           gb.push(a, used, (int)m, used, (int)item);
           used += (int)m; item += m;
@@ -267,6 +275,42 @@ static void plan_chunks(int kind, int T, int N, const int* cnt, int ch, int gcap
       if (used == 0) break;
       commit_chunk(used, maxm);
     }
+  }
+}
+
+// ---- cells of the exact-window path (xwin.cuh): the <= 128 source frames of one (query slot, anchor frame) ----
+struct CellPlan {
+  std::vector<int> v;               // per chunk: [row0 | m | frame | group] x (cells of the chunk), chunks back to back
+  std::vector<size_t> first;        // first cell of chunk k in v's cell numbering (size chunks + 1)
+  std::vector<int> tiles;           // per chunk: (gcap + 1) prefix of ceil(m / 256) per group (coarse GEMM)
+  int max_m = 0;
+};
+static void plan_cells(int T, int gcap, const std::vector<ChunkMeta>& metas, const std::vector<int>& plan_host, CellPlan& cp) {
+  const int nb = (T + XW_MAX_CELL - 1) / XW_MAX_CELL, rb = (T + nb - 1) / nb;
+  cp.v.clear(); cp.first.assign(1, 0); cp.tiles.clear(); cp.max_m = 0;
+  std::vector<int> r0, mm, fr, gr;
+  for (size_t k = 0; k < metas.size(); ++k) {
+    const int* gb = plan_host.data() + k * 5 * gcap;
+    r0.clear(); mm.clear(); fr.clear(); gr.clear();
+    int pre = 0;
+    for (int g = 0; g < metas[k].n_groups; ++g) {
+      const int frame = gb[g], row0 = gb[gcap + g], m = gb[2 * gcap + g];
+      cp.tiles.push_back(pre);
+      pre += (m + TC2_BM_ROWS - 1) / TC2_BM_ROWS;
+      for (int s0 = 0; s0 < m; s0 += T)
+        for (int b = 0; b < T; b += rb) {
+          const int cm = std::min(rb, T - b);
+          r0.push_back(row0 + s0 + b); mm.push_back(cm); fr.push_back(frame); gr.push_back(g);
+          cp.max_m = std::max(cp.max_m, cm);
+        }
+    }
+    for (int g = metas[k].n_groups; g <= gcap; ++g) cp.tiles.push_back(pre);
+    const size_t n = r0.size();
+    cp.v.insert(cp.v.end(), r0.begin(), r0.end());
+    cp.v.insert(cp.v.end(), mm.begin(), mm.end());
+    cp.v.insert(cp.v.end(), fr.begin(), fr.end());
+    cp.v.insert(cp.v.end(), gr.begin(), gr.end());
+    cp.first.push_back(cp.first.back() + n);
   }
 }
 
@@ -306,17 +350,65 @@ static InferAsync* infer_async() {
   return &ia;
 }
 
+// events, pinned counters and selection of the exact-window pipeline (one set per device)
+constexpr int XW_RING = 4;
+struct XwAsync {
+  int state;                                   // 0: not created, 1: ready, -1: failed
+  cudaEvent_t sample[XW_RING], done[XW_RING], freed[XW_RING];
+  int* host_cnt;                               // pinned: [XW_RING] queue totals + [16] phase-A uncertified counts
+};
+static XwAsync* xw_async() {
+  static PerDev<XwAsync> slots;
+  XwAsync& xa = slots.get();
+  if (xa.state == 0) {
+    xa.state = -1;
+    for (int k = 0; k < XW_RING; ++k) {
+      if (cudaEventCreateWithFlags(&xa.sample[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&xa.done[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&xa.freed[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaHostAlloc(&xa.host_cnt, (XW_RING + 16) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    xa.state = 1;
+  }
+  return xa.state == 1 ? &xa : nullptr;
+}
+static int g_xw_path = -1;                     // -1: automatic (DTK_XW or on), 0: full-map path only, 1: exact-window path
+static long long g_infer_stats[4] = {0, 0, 0, 0};   // anchor-phase maps | of them on the exact-window path | queued | path used
+
 }  // namespace dtk
 
 using namespace dtk;
 
 extern "C" {
 
-static int infer_chunk_maps(int chunk_maps) { return chunk_maps > 0 ? chunk_maps : 4096; }
-// upper bound on the number of chunks of one phase (phase C has the most work items: N * T * T)
-static size_t infer_max_chunks(int T, int N, size_t ch) { return ((size_t)N * T * T + ch - 1) / ch + 2; }
+int dinotrk_infer_set_path(int path) {
+  DTK_CHECK_ARG(path >= -1 && path <= 1, "infer_set_path: -1 (automatic), 0 (full-map GEMM + head) or 1 (coarse pass + exact window)");
+  g_xw_path = path;
+  return DINOTRK_OK;
+}
 
-size_t dinotrk_infer_max_chunks(int T, int N, int chunk_maps) { return infer_max_chunks(T, N, (size_t)infer_chunk_maps(chunk_maps)); }
+int dinotrk_infer_last_stats(long long* out, int n) {
+  DTK_CHECK_ARG(out && n >= 4, "infer_last_stats: need 4 slots");
+  for (int i = 0; i < 4; ++i) out[i] = g_infer_stats[i];
+  return DINOTRK_OK;
+}
+
+static int infer_chunk_maps(int chunk_maps) { return chunk_maps > 0 ? chunk_maps : 4096; }
+// chunks of the anchor phase hold whole (query, anchor frame) cells of T maps: never smaller than T
+static int infer_chunk_eff(int chunk_maps, int T) { const int c = infer_chunk_maps(chunk_maps); return c > T ? c : T; }
+// upper bound on the number of chunks of one phase (phase C has the most work items: N * T * T)
+// (anchor-phase chunks are cut at whole cells of T maps: a full chunk holds at least the largest multiple of T <= ch)
+static size_t infer_max_chunks(int T, int N, size_t ch) {
+  size_t cap = (ch / (size_t)T) * (size_t)T;
+  if (cap < (size_t)T) cap = T;
+  return ((size_t)N * T * T + cap - 1) / cap + 2;
+}
+
+// (planner entry point: plain chunks of `chunk_maps` maps, cut anywhere)
+size_t dinotrk_infer_max_chunks(int T, int N, int chunk_maps) {
+  const size_t ch = (size_t)infer_chunk_maps(chunk_maps);
+  return ((size_t)N * T * T + ch - 1) / ch + 2;
+}
 
 int dinotrk_infer_plan(int kind, int T, int N, const int* anchor_counts, int chunk_maps, int* groups, int* meta,
                        int max_chunks, int* n_chunks) {
@@ -378,7 +470,7 @@ int dinotrk_corr_track(const dinotrk_features* feat, const dinotrk_geom* g,
 
 size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N, int chunk_maps) {
   if (!g) return 0;
-  const size_t ch = infer_chunk_maps(chunk_maps), ms = dinotrk_map_stride(g);
+  const size_t ch = infer_chunk_eff(chunk_maps, T), ms = dinotrk_map_stride(g);
   const int gcap = T + 2;
   size_t b = 0;
   b += align_up((size_t)N * C * 4, 256) + align_up((size_t)N * 4, 256);   // descA, normA
@@ -393,7 +485,19 @@ size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N,
   b += 4 * align_up(ch * 4, 256);                                          // out_index ring
   b += align_up(infer_max_chunks(T, N, ch) * 5 * gcap * 4, 256);           // group arrays of every chunk of a phase
   b += align_up((size_t)T * 4, 256) + align_up((size_t)T * N * 4, 256);    // cnt, qlist
-  return b + 8192;
+  // exact-window pipeline: ring of XW_RING chunk sets (descriptors fp32 + fp16 hi/lo, norms, out_index, keys, boxes),
+  // the cells of every chunk of the phase, coarse-GEMM tile prefixes, compact group arrays of the full-map queue
+  const size_t chx = ch;
+  const int nb = (T + XW_MAX_CELL - 1) / XW_MAX_CELL;
+  const size_t max_cells_chunk = chx + 2;                                  // cells have >= 1 row
+  size_t x = 0;
+  x += align_up(chx * C * 4, 256) + align_up(chx * 4, 256) + corr_tc_workspace_bytes((int)chx, C) + 256 + align_up(chx * 4, 256);
+  x += xw_chunk_bytes((int)chx, (int)max_cells_chunk, cdiv(g->h * g->w, CORR_TILE), gcap);
+  b += XW_RING * x;
+  b += align_up((size_t)N * T * nb * 16 + 64, 256);                         // cells of all chunks
+  b += align_up(infer_max_chunks(T, N, ch) * (gcap + 1) * 4, 256);         // coarse tile prefixes per chunk
+  b += align_up((size_t)4 * gcap * 4, 256) + align_up(64 * 4, 256);        // compact group arrays, phase-A counters
+  return b + 16384;
 }
 
 int dinotrk_traj_cos_sims(const float* tpc, int T, int C, const dinotrk_geom* g, const float* traj,
@@ -456,7 +560,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   if (N == 0) return DINOTRK_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = g->h * g->w, ms = dinotrk_map_stride(g);
-  const int ch = infer_chunk_maps(chunk_maps);
+  const int ch = infer_chunk_eff(chunk_maps, T);
   const int fb = frame_batch > 0 ? (frame_batch < T ? frame_batch : T) : T;
   const int gcap = T + 2;
   const PointAffine pa = make_point_affine(*g);
@@ -482,6 +586,29 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   int* d_groups = ar.take<int>(max_chunks * 5 * gcap);
   int* d_cnt = ar.take<int>(T);
   int* d_qlist = ar.take<int>((size_t)T * N);
+  struct XwSet { float* desc; float* norm; float* split; int* out_index; XwChunk xc; } xr[XW_RING];
+  const int n_tiles_map = cdiv(P, CORR_TILE);
+  for (int k = 0; k < XW_RING; ++k) {
+    xr[k].desc = ar.take<float>((size_t)ch * C);
+    xr[k].norm = ar.take<float>(ch);
+    xr[k].split = ar.take<float>(corr_tc_workspace_bytes(ch, C) / 4);
+    xr[k].out_index = ar.take<int>(ch);
+    XwChunk& x = xr[k].xc;
+    x.key1 = ar.take<unsigned long long>((size_t)ch * n_tiles_map);
+    x.max2 = ar.take<float>((size_t)ch * n_tiles_map);
+    x.cand = ar.take<int>((size_t)ch * XW_MAX_CAND);
+    x.stat = ar.take<int>(ch);
+    x.cell_of = ar.take<int>(ch);
+    x.slow_list = ar.take<int>(ch);
+    x.box_org = ar.take<int2>((size_t)ch + 2);
+    x.xbox = ar.take<float>((size_t)ch * XW_COLS);
+    x.slow_cnt = ar.take<int>(gcap + 1);
+  }
+  const int cell_nb = (T + XW_MAX_CELL - 1) / XW_MAX_CELL;
+  int* d_cells = ar.take<int>((size_t)N * T * cell_nb * 4 + 16);
+  int* d_tiles = ar.take<int>(max_chunks * (gcap + 1));
+  int* d_cgrp = ar.take<int>((size_t)4 * gcap);
+  int* d_cntA = ar.take<int>(64);
   DTK_CHECK_ARG(ar.ok(), "infer: workspace arena overflow");
   const bool tensor = fv.tensor();   // tensor-core GEMM: tile keys for the head, fp16 split fused into the samplers
 
@@ -501,6 +628,8 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
     return Grp{b, b + gcap, b + 2 * gcap, b + 3 * gcap, b + 4 * gcap};
   };
 
+  int n_chunks_A = 0;
+  long long maps_A = 0;
   // ---- phase A: trajectories -------------------------------------------------------------------
   if (start_phase <= 0) {
     {
@@ -534,7 +663,11 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
       if (rc) return rc;
       rc = launch_head(b.maps, cm.used, ms, *g, *hw, out_index_ring[k & 3], traj, 3, 0, nullptr, b.hscratch, st, as.tkeys, true);
       if (rc) return rc;
+      if (k < 16)   // uncertified maps of this chunk: the anchor phase chooses its pipeline from their share
+        DTK_CUDA(cudaMemcpyAsync(d_cntA + k, b.hscratch, sizeof(int), cudaMemcpyDeviceToDevice, st));
     }
+    n_chunks_A = (int)std::min<size_t>(metas.size(), 16);
+    maps_A = (long long)N * T;
   }
   if (stop_after < 1) return DINOTRK_OK;
 
@@ -557,8 +690,124 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
       DTK_LAUNCHED();
     }
     std::vector<int> cnt(T);
+    // pipeline of the anchor phase: coarse pass + exact window (xwin.cuh) on the tensor path, unless disabled
+    bool use_xw = tensor && g->radius <= 5 * g->stride && n_tiles_map <= 64;
+    int pathsel = g_xw_path;
+    if (pathsel < 0) { const char* e = getenv("DTK_XW"); if (e) pathsel = atoi(e) != 0 ? 1 : 0; }
+    if (pathsel == 0) use_xw = false;
+    XwAsync* xa = use_xw ? xw_async() : nullptr;
+    if (!xa) use_xw = false;
+    if (xa && n_chunks_A > 0)
+      DTK_CUDA(cudaMemcpyAsync(xa->host_cnt + XW_RING, d_cntA, (size_t)n_chunks_A * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTK_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTK_CUDA(cudaStreamSynchronize(st));  // the one host sync: sizes of the anchor work lists
+    if (use_xw && pathsel < 0 && n_chunks_A > 0) {
+      // head weights the certificate cannot handle send (almost) every map to the full-map kernels anyway: the trajectory
+      // phase just showed it; skip the exact-window attempt then.  (Depends on the weights and the video only.)
+      long long unc = 0;
+      for (int k = 0; k < n_chunks_A; ++k) unc += xa->host_cnt[XW_RING + k];
+      if (unc * 4 > maps_A) use_xw = false;
+    }
+    long long maps_C = 0;
+    for (int a = 0; a < T; ++a) maps_C += (long long)cnt[a] * T;
+    g_infer_stats[0] = maps_C; g_infer_stats[1] = 0; g_infer_stats[2] = 0; g_infer_stats[3] = use_xw ? 1 : 0;
+    if (use_xw) {
+      plan_chunks(1, T, N, cnt.data(), ch, gcap, metas, plan_host, T);
+      int rc = upload_plan();
+      if (rc) return rc;
+      CellPlan cp;
+      plan_cells(T, gcap, metas, plan_host, cp);
+      DTK_CHECK_ARG(cp.first.back() * 4 <= (size_t)N * T * cell_nb * 4 + 16, "infer: cell plan exceeds its bound");
+      if (!cp.v.empty()) DTK_CUDA(cudaMemcpyAsync(d_cells, cp.v.data(), cp.v.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      if (!cp.tiles.empty()) DTK_CUDA(cudaMemcpyAsync(d_tiles, cp.tiles.data(), cp.tiles.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      InferAsync* ia = infer_async();
+      const bool ovl = ia != nullptr && metas.size() > 1;
+      cudaStream_t sb = ovl ? ia->aux2 : st;   // sampling stream
+      if (ovl) {
+        DTK_CUDA(cudaEventRecord(ia->fork, st));
+        DTK_CUDA(cudaStreamWaitEvent(sb, ia->fork, 0));
+      }
+      auto hi_of = [&](const XwSet& x, int rows) { (void)rows; return reinterpret_cast<char*>(x.split); };
+      auto lo_of = [&](const XwSet& x, int rows) { return reinterpret_cast<char*>(x.split) + align_up((size_t)rows * C * 2, 256); };
+      auto cells_of = [&](size_t k) {
+        XwCells c;
+        const int n = (int)(cp.first[k + 1] - cp.first[k]);
+        const int* base = d_cells + 4 * cp.first[k];
+        c.row0 = base; c.m = base + n; c.frame = base + 2 * n; c.group = base + 3 * n; c.n_cells = n; c.max_m = cp.max_m;
+        return c;
+      };
+      auto enqueue_sample_x = [&](size_t k) -> int {
+        const ChunkMeta& cm = metas[k];
+        const XwSet& x = xr[k % XW_RING];
+        const Grp gp = grp_of(k);
+        if (ovl && k >= XW_RING) DTK_CUDA(cudaStreamWaitEvent(sb, xa->freed[k % XW_RING], 0));   // chunk k - 4 is through
+        {
+          ProfRange pr(PROF_SAMPLE, sb);
+          sample_anchor_kernel<<<cm.used, SAMPLE_THREADS, 0, sb>>>(tpc, T, C, P, g->h, g->w, pa, traj, d_qlist, N, gp.f, gp.map0,
+                                                                  gp.item, cm.n_groups, fb, x.desc, x.norm, x.out_index,
+                                                                  reinterpret_cast<__half*>(hi_of(x, cm.used)),
+                                                                  reinterpret_cast<__half*>(lo_of(x, cm.used)));
+          DTK_LAUNCHED();
+        }
+        if (ovl) DTK_CUDA(cudaEventRecord(xa->sample[k % XW_RING], sb));
+        return DINOTRK_OK;
+      };
+      // full-map path for the queued maps of chunk j (host knows how many): compact -> split-precision GEMM over all
+      // tokens -> head kernels of head.cu, on buffer set cb[0]
+      auto finish = [&](size_t j) -> int {
+        DTK_CUDA(cudaEventSynchronize(xa->done[j % XW_RING]));
+        const int n_slow = xa->host_cnt[j % XW_RING];
+        const ChunkMeta& cm = metas[j];
+        const XwSet& x = xr[j % XW_RING];
+        const Grp gp = grp_of(j);
+        DTK_CHECK_ARG(n_slow >= 0 && n_slow <= cm.used, "infer: corrupt full-map queue (%d of %d)", n_slow, cm.used);
+        g_infer_stats[1] += cm.used - n_slow; g_infer_stats[2] += n_slow;
+        if (n_slow > 0) {
+          const ChunkBufs& b = cb[0];
+          char* c_hi = reinterpret_cast<char*>(b.split);
+          char* c_lo = c_hi + align_up((size_t)n_slow * C * 2, 256);
+          int rc2 = launch_xw_compact(x.desc, hi_of(x, cm.used), lo_of(x, cm.used), x.norm, x.out_index, C, gp.f, gp.map0, cm.n_groups,
+                                      n_slow, x.xc, b.desc, c_hi, c_lo, b.norm, out_index_ring[0], d_cgrp, gcap, st);
+          if (rc2) return rc2;
+          CorrAssist as;
+          as.tkeys = b.tkeys; as.zero_word = b.hscratch; as.split_ready = true; as.no_thin = false;
+          const int mg = n_slow > STREAM_MAX_M + 1 ? n_slow : STREAM_MAX_M + 1;   // group sizes live on the device: plan for both kinds
+          rc2 = launch_corr_maps(fv, b.desc, n_slow, b.norm, d_cgrp, d_cgrp + gcap, d_cgrp + 2 * gcap, d_cgrp + 3 * gcap,
+                                 cm.n_groups, n_slow, mg, b.maps, ms, b.plan, b.split, st, as);
+          if (rc2) return rc2;
+          rc2 = launch_head(b.maps, n_slow, ms, *g, *hw, out_index_ring[0], anchors, 2, 0, nullptr, b.hscratch, st, b.tkeys, true);
+          if (rc2) return rc2;
+        }
+        DTK_CUDA(cudaEventRecord(xa->freed[j % XW_RING], st));
+        return DINOTRK_OK;
+      };
+      if (!metas.empty() && (rc = enqueue_sample_x(0))) return rc;
+      for (size_t k = 0; k < metas.size(); ++k) {
+        const ChunkMeta& cm = metas[k];
+        const XwSet& x = xr[k % XW_RING];
+        const Grp gp = grp_of(k);
+        const XwCells cells = cells_of(k);
+        if (ovl) DTK_CUDA(cudaStreamWaitEvent(st, xa->sample[k % XW_RING], 0));
+        if ((rc = launch_xw_coarse(fv, hi_of(x, cm.used), cm.used, x.norm, gp.f, gp.r, gp.m, gp.map0, d_tiles + k * (gcap + 1),
+                                   cm.n_groups, cm.used / TC2_BM_ROWS + cm.n_groups, x.xc, st))) return rc;
+        if ((rc = launch_xw_plan(cells, x.norm, cm.n_groups, *g, x.xc, st))) return rc;
+        if ((rc = launch_xw_gemm(fv, *g, hi_of(x, cm.used), lo_of(x, cm.used), cm.used, cells, x.xc, st))) return rc;
+        if ((rc = launch_xw_head(fv, *g, *hw, cells, x.norm, gp.map0, cm.used, x.out_index, anchors, 2, 0, x.xc, st, cm.n_groups)))
+          return rc;
+        DTK_CUDA(cudaMemcpyAsync(xa->host_cnt + (k % XW_RING), x.xc.slow_cnt + cm.n_groups, sizeof(int), cudaMemcpyDeviceToHost, st));
+        DTK_CUDA(cudaEventRecord(xa->done[k % XW_RING], st));
+        if (k + 1 < metas.size() && (rc = enqueue_sample_x(k + 1))) return rc;
+        if (k >= 2 && (rc = finish(k - 2))) return rc;
+      }
+      for (size_t j = metas.size() >= 2 ? metas.size() - 2 : 0; j < metas.size(); ++j)
+        if ((rc = finish(j))) return rc;
+      if (ovl) {
+        DTK_CUDA(cudaEventRecord(ia->join, sb));
+        DTK_CUDA(cudaStreamWaitEvent(st, ia->join, 0));
+      }
+      if (stop_after < 3) return DINOTRK_OK;
+      return dinotrk_occlusion(traj, cos_sims, anchors, N, T, anchor_th, cos_th, occ, stream);
+    }
     plan_chunks(1, T, N, cnt.data(), ch, gcap, metas, plan_host);
     int rc = upload_plan();
     if (rc) return rc;

@@ -1,0 +1,715 @@
+// Coarse pass + exact window (see xwin.cuh): kernels and launchers.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "corr.cuh"
+#include "tcgemm.cuh"
+#include "tcgemm2.cuh"
+#include "xwin.cuh"
+
+namespace dtk {
+
+int make_tmap_4d(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                 const uint32_t box[4], int elem);   // corr_tc.cu
+
+// ====================================================================================================== 1. coarse GEMM
+// Epilogue of the single-pass kind::f16 GEMM over the `hi` halves: nothing is stored per token.  Per (map, 256-token tile):
+// key1 = bits(max) << 32 | (0x7fffffff - first token holding it), max2 = second largest value (>= 0).  Values are the same
+// expression as the exact path, relu(acc / max(|d| |F|, 1e-8)), with a fast division (its error is part of XW_EPS).
+struct CoarseEpi {
+  const float* norms;
+  const float* desc_norm;
+  const int* grp_frame;
+  const int* grp_row0;
+  const int* grp_map0;
+  unsigned long long* key1;
+  float* max2;
+  int n_tiles, P;
+  struct State { float m1, m2; int tok; };
+  __device__ __forceinline__ void tile_begin(State& s) const { s.m1 = -1.f; s.m2 = -1.f; s.tok = 0; }
+  __device__ __forceinline__ void tile_end(State& s, int g, int r, int nt) const {
+    const size_t o = (size_t)(grp_map0[g] + r) * n_tiles + nt;
+    key1[o] = ((unsigned long long)__float_as_uint(s.m1 + 0.f) << 32) | (unsigned)(0x7fffffff - s.tok);
+    max2[o] = fmaxf(s.m2, 0.f);
+  }
+  __device__ __forceinline__ void operator()(State& s, int g, int r, int col0, const float (&f)[32], int ncols) const {
+    const float dn = desc_norm[grp_row0[g] + r];
+    const float* fn = norms + (size_t)grp_frame[g] * P + col0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols) {
+        const float v = fmaxf(__fdividef(f[i], fmaxf(dn * __ldg(fn + i), 1e-8f)), 0.f);
+        if (v > s.m1) { s.m2 = s.m1; s.m1 = v; s.tok = col0 + i; } else s.m2 = fmaxf(s.m2, v);
+      }
+  }
+};
+
+int launch_xw_coarse(const FeatView& fv, const void* desc_hi, int desc_rows, const float* desc_norm, const int* grp_frame,
+                     const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
+                     int max_tiles, const XwChunk& xc, cudaStream_t st) {
+  using Cfg = Tc2Cfg<TcMode::F16>;
+  using Base = TcCfg<TcMode::F16, TC2_BN>;
+  static_assert(TC2_BN == CORR_TILE, "coarse keys are per 256-token tile");
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_2d(&tmA, desc_hi, desc_rows, fv.C, 128, Base::kBK, TMAP_F16))) return rc;
+  if ((rc = make_tmap_3d(&tmB, fv.hi, fv.T, fv.P, fv.C, TC2_BN / 2, Base::kBK, TMAP_F16))) return rc;
+  auto kern = tc_gemm2_kernel<TcMode::F16, CoarseEpi>;
+  static PerDev<bool> attr_dev;
+  bool& attr = attr_dev.get();
+  if (!attr) {
+    DTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr = true;
+  }
+  TcProblem pb{grp_frame, grp_row0, grp_m, tile_start, n_groups, fv.P, fv.C};
+  CoarseEpi epi{fv.norms, desc_norm, grp_frame, grp_row0, grp_map0, xc.key1, xc.max2, cdiv(fv.P, CORR_TILE), fv.P};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles_bound = max_tiles * cdiv(fv.P, TC2_BN);
+  int grid = 2 * (tiles_bound < sms / 2 ? tiles_bound : sms / 2);
+  if (grid < 2) grid = 2;
+  ProfRange pr(PROF_XW_COARSE, st);
+  kern<<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmA, tmB, tmB, pb, epi);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+// ====================================================================================================== 2. plan
+// One warp per cell.  Per map (lane = tile): global coarse maximum, candidate tiles (max1 >= gmax - 2 eps), ambiguity (some
+// tile's SECOND value is also within 2 eps: an arg-max candidate whose token we do not know).  Per cell: the lower medians of
+// the maps' coarse arg-max row / column give the box centre; a map fits if every candidate lies within +-XW_SLACK of it.
+constexpr int PLAN_WARPS = 4;
+__global__ void __launch_bounds__(PLAN_WARPS * 32)
+xw_plan_kernel(XwCells cells, const float* __restrict__ desc_norm, int n_groups, int n_tiles, int w,
+               const unsigned long long* __restrict__ key1, const float* __restrict__ max2, int* __restrict__ cand,
+               int* __restrict__ stat, int* __restrict__ cell_of, int2* __restrict__ box_org, int* __restrict__ slow_cnt) {
+  __shared__ short s_r[PLAN_WARPS][XW_MAX_CELL], s_c[PLAN_WARPS][XW_MAX_CELL];
+  __shared__ unsigned char s_ok[PLAN_WARPS][XW_MAX_CELL];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gw = blockIdx.x * PLAN_WARPS + wid, nw = gridDim.x * PLAN_WARPS;
+  if (gw == 0)   // zero the queue counters of this chunk (n_groups per-group counts + the total)
+    for (int i = lane; i <= n_groups; i += 32) slow_cnt[i] = 0;
+  for (int cell = gw; cell < cells.n_cells; cell += nw) {
+    const int row0 = cells.row0[cell], m = cells.m[cell];
+    for (int r = 0; r < m; ++r) {
+      const int map = row0 + r;
+      const unsigned long long* k1 = key1 + (size_t)map * n_tiles;
+      const float* k2 = max2 + (size_t)map * n_tiles;
+      unsigned long long kk[2] = {0ull, 0ull};
+      float v2[2] = {0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int t = lane + 32 * q;
+        if (t < n_tiles) { kk[q] = __ldg(k1 + t); v2[q] = __ldg(k2 + t); }
+      }
+      unsigned long long gk = kk[0] > kk[1] ? kk[0] : kk[1];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, gk, o); gk = t > gk ? t : gk; }
+      const float gmax = __uint_as_float((unsigned)(gk >> 32));
+      const int ptok = 0x7fffffff - (int)(gk & 0xffffffffu);
+      const float th = gmax - 2.f * XW_EPS;
+      bool amb = false;
+      int ncand = 0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int t = lane + 32 * q;
+        const bool in = t < n_tiles;
+        const bool isc = in && __uint_as_float((unsigned)(kk[q] >> 32)) >= th;
+        const unsigned cm = __ballot_sync(0xffffffffu, isc);
+        amb = amb || __any_sync(0xffffffffu, in && v2[q] >= th);
+        const int rank = ncand + __popc(cm & ((1u << lane) - 1u));
+        if (isc && rank < XW_MAX_CAND) cand[(size_t)map * XW_MAX_CAND + rank] = 0x7fffffff - (int)(kk[q] & 0xffffffffu);
+        ncand += __popc(cm);
+      }
+      // a (near-)zero map has no meaningful arg-max candidates; a tiny descriptor norm voids the error bound
+      amb = amb || ncand > XW_MAX_CAND || !(gmax > 4.f * XW_EPS) || !(desc_norm[map] >= 1e-6f);
+      if (lane >= ncand && lane < XW_MAX_CAND) cand[(size_t)map * XW_MAX_CAND + lane] = -1;
+      if (lane == 0) {
+        s_r[wid][r] = (short)(ptok / w);
+        s_c[wid][r] = (short)(ptok - (ptok / w) * w);
+        s_ok[wid][r] = amb ? 0 : 1;
+        cell_of[map] = cell;
+      }
+    }
+    __syncwarp();
+    // lower medians over the unambiguous maps
+    int nv = 0;
+    for (int r = lane; r < m; r += 32) nv += s_ok[wid][r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    int med_r = -1, med_c = -1;
+    if (nv > 0) {
+      const int want = (nv - 1) / 2;
+      for (int r = lane; r < m; r += 32) {
+        if (!s_ok[wid][r]) continue;
+        int rk_r = 0, rk_c = 0;
+        const int vr = s_r[wid][r], vc = s_c[wid][r];
+        for (int q = 0; q < m; ++q) {
+          if (!s_ok[wid][q]) continue;
+          rk_r += (s_r[wid][q] < vr) || (s_r[wid][q] == vr && q < r);
+          rk_c += (s_c[wid][q] < vc) || (s_c[wid][q] == vc && q < r);
+        }
+        if (rk_r == want) med_r = vr;
+        if (rk_c == want) med_c = vc;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        med_r = max(med_r, __shfl_xor_sync(0xffffffffu, med_r, o));
+        med_c = max(med_c, __shfl_xor_sync(0xffffffffu, med_c, o));
+      }
+    }
+    __syncwarp();   // cand[] of this cell was written by this warp's lanes above
+    int n_fit = 0;
+    for (int r = lane; r < m; r += 32) {
+      const int map = row0 + r;
+      bool fit = s_ok[wid][r] != 0;
+      if (fit) {
+#pragma unroll
+        for (int q = 0; q < XW_MAX_CAND; ++q) {
+          const int tok = cand[(size_t)map * XW_MAX_CAND + q];
+          if (tok >= 0) {
+            const int tr = tok / w, tc_ = tok - tr * w;
+            fit = fit && abs(tr - med_r) <= XW_SLACK && abs(tc_ - med_c) <= XW_SLACK;
+          }
+        }
+      }
+      stat[map] = fit ? 0 : 1;
+      n_fit += fit ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_fit += __shfl_xor_sync(0xffffffffu, n_fit, o);
+    if (lane == 0)
+      box_org[cell] = n_fit > 0 ? make_int2(med_r - XW_BOX / 2, med_c - XW_BOX / 2) : make_int2(0, INT_MIN);
+    __syncwarp();
+  }
+}
+
+int launch_xw_plan(const XwCells& cells, const float* desc_norm, int n_groups, const dinotrk_geom& g, const XwChunk& xc,
+                   cudaStream_t st) {
+  const int n_tiles = cdiv(g.h * g.w, CORR_TILE);
+  DTK_CHECK_ARG(n_tiles <= 64, "exact-window path: token grid too large (%d tiles)", n_tiles);
+  DTK_CHECK_ARG(cells.max_m <= XW_MAX_CELL, "exact-window path: cell of %d rows", cells.max_m);
+  if (cells.n_cells <= 0) return DINOTRK_OK;
+  int grid = cdiv(cells.n_cells, PLAN_WARPS);
+  if (grid > 148 * 8) grid = 148 * 8;
+  ProfRange pr(PROF_XW_PLAN, st);
+  xw_plan_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(cells, desc_norm, n_groups, n_tiles, g.w, xc.key1, xc.max2, xc.cand, xc.stat,
+                                                   xc.cell_of, xc.box_org, xc.slow_cnt);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+// ====================================================================================================== 3. exact box GEMM
+// Persistent, warp-specialised (same roles as tc_gemm_kernel).  One "tile" = one cell: D[128 rows x 480 columns] in TMEM =
+// the cell's descriptors against the 21 x 21 box tokens (3 N-parts of 7 box rows), split precision (lo*hi + hi*lo + hi*hi
+// per K step, in the full-map GEMM's order).  A K-block of the descriptors (hi, lo) is loaded once and used by the three
+// parts; the box rows arrive as 4-D TMA boxes {64 channels, 21 columns, 7 rows, 1 frame} of the [T][h][w][C] feature video,
+// zero-filled outside the token grid.
+template <int AROWS>
+struct XwCfg {
+  static constexpr int kBK = 64;                            // fp16 elements per 128-byte swizzle row
+  static constexpr int kABytes = AROWS * 128;               // one operand half (hi or lo) of the descriptor K-block
+  static constexpr int kAStage = 2 * kABytes, kAStages = 2;
+  static constexpr int kBBytes = XW_PART_N * 128;           // 160 rows reserved, 147 written
+  static constexpr int kBStage = 2 * kBBytes, kBStages = AROWS == 64 ? 4 : 3;
+  static constexpr int kBTx = 2 * XW_PART_ROWS * XW_BOX * 128;
+  static constexpr int kSmem = kAStages * kAStage + kBStages * kBStage + 256 + TC_EPI_SCRATCH;
+  static constexpr uint32_t kIdesc = tc::make_idesc(0, 128, XW_PART_N);
+};
+
+namespace tc {
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+}  // namespace tc
+
+template <int AROWS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+xw_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, XwCells cells,
+               const int2* __restrict__ box_org, float* __restrict__ xbox, int K) {
+  using Cfg = XwCfg<AROWS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (tc::smem_u32(smem) & 1023u) __trap();   // no static shared memory in this kernel: the window starts 1 KB-aligned
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + Cfg::kAStages * Cfg::kAStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + Cfg::kBStages * Cfg::kBStage);
+  uint64_t* a_full = bars;                          // [2]
+  uint64_t* a_empty = a_full + Cfg::kAStages;       // [2]
+  uint64_t* b_full = a_empty + Cfg::kAStages;       // [kBStages]
+  uint64_t* b_empty = b_full + Cfg::kBStages;       // [kBStages]
+  uint64_t* tfull = b_empty + Cfg::kBStages;        // [1]
+  uint64_t* tempty = tfull + 1;                     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+  float* epi_scratch = reinterpret_cast<float*>(b_ring + Cfg::kBStages * Cfg::kBStage + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = (K + Cfg::kBK - 1) / Cfg::kBK;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA_hi); tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_hi); tc::prefetch_tmap(&tmB_lo);
+    for (int s = 0; s < Cfg::kAStages; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < Cfg::kBStages; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    tc::mbar_init(tfull, 1); tc::mbar_init(tempty, 4);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (tc::elect_one()) {
+      int as = 0, aph = 0, bs = 0, bph = 0;
+      for (int cell = blockIdx.x; cell < cells.n_cells; cell += gridDim.x) {
+        const int2 org = box_org[cell];
+        if (org.y == INT_MIN) continue;            // every map of the cell takes the full-map path
+        const int arow = cells.row0[cell], frame = cells.frame[cell];
+        for (int kb = 0; kb < KB; ++kb) {
+          const int k0 = kb * Cfg::kBK;
+          tc::mbar_wait(&a_empty[as], aph ^ 1);
+          uint8_t* sa = a_ring + as * Cfg::kAStage;
+          tc::mbar_expect_tx(&a_full[as], Cfg::kAStage);
+          tc::tma_load_2d(&tmA_hi, &a_full[as], sa, k0, arow);
+          tc::tma_load_2d(&tmA_lo, &a_full[as], sa + Cfg::kABytes, k0, arow);
+          if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
+          for (int part = 0; part < XW_PARTS; ++part) {
+            tc::mbar_wait(&b_empty[bs], bph ^ 1);
+            uint8_t* sb = b_ring + bs * Cfg::kBStage;
+            tc::mbar_expect_tx(&b_full[bs], Cfg::kBTx);
+            tc::tma_load_4d(&tmB_hi, &b_full[bs], sb, k0, org.y, org.x + part * XW_PART_ROWS, frame);
+            tc::tma_load_4d(&tmB_lo, &b_full[bs], sb + Cfg::kBBytes, k0, org.y, org.x + part * XW_PART_ROWS, frame);
+            if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int as = 0, aph = 0, bs = 0, bph = 0, it = 0;
+    for (int cell = blockIdx.x; cell < cells.n_cells; cell += gridDim.x) {
+      if (box_org[cell].y == INT_MIN) continue;
+      tc::mbar_wait(tempty, (it & 1) ^ 1);
+      tc::fence_after_sync();
+      for (int kb = 0; kb < KB; ++kb) {
+        tc::mbar_wait(&a_full[as], aph);
+        const uint32_t sa = tc::smem_u32(a_ring + as * Cfg::kAStage);
+        for (int part = 0; part < XW_PARTS; ++part) {
+          tc::mbar_wait(&b_full[bs], bph);
+          tc::fence_after_sync();
+          if (tc::elect_one()) {
+            const uint32_t sb = tc::smem_u32(b_ring + bs * Cfg::kBStage);
+            const uint32_t tmem_d = tmem_base + part * XW_PART_N;
+#pragma unroll
+            for (int ks = 0; ks < Cfg::kBK / 16; ++ks) {
+              const uint32_t koff = ks * 32;
+              const uint64_t a_hi = tc::smem_desc_sw128(sa + koff), a_lo = tc::smem_desc_sw128(sa + Cfg::kABytes + koff);
+              const uint64_t b_hi = tc::smem_desc_sw128(sb + koff), b_lo = tc::smem_desc_sw128(sb + Cfg::kBBytes + koff);
+              const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+              tc::mma_ss<false>(tmem_d, a_lo, b_hi, Cfg::kIdesc, first);   // same order as tc_gemm_kernel (F16X3)
+              tc::mma_ss<false>(tmem_d, a_hi, b_lo, Cfg::kIdesc, 1u);
+              tc::mma_ss<false>(tmem_d, a_hi, b_hi, Cfg::kIdesc, 1u);
+            }
+            tc::mma_commit(&b_empty[bs]);
+            if (part == XW_PARTS - 1) {
+              tc::mma_commit(&a_empty[as]);
+              if (kb == KB - 1) tc::mma_commit(tfull);
+            }
+          }
+          __syncwarp();
+          if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+        }
+        if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
+      }
+      ++it;
+    }
+  } else {
+    // ===================== epilogue: raw accumulator rows -> xbox (coalesced through a per-warp transpose) ==========
+    const int quad = warp & 3;
+    float* sw = epi_scratch + (warp - 2) * (32 * 36);
+    int it = 0;
+    for (int cell = blockIdx.x; cell < cells.n_cells; cell += gridDim.x) {
+      if (box_org[cell].y == INT_MIN) continue;
+      const int m = cells.m[cell], map0 = cells.row0[cell];
+      tc::mbar_wait(tfull, it & 1);
+      tc::fence_after_sync();
+      const int row_base = quad * 32;
+      if (row_base < m) {
+        const uint32_t taddr = tmem_base + ((uint32_t)row_base << 16);
+#pragma unroll 1
+        for (int c = 0; c < XW_COLS; c += 32) {
+          uint32_t v[32];
+          tc::tmem_ld32(taddr + c, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(sw + lane * 36 + i) =
+                make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          __syncwarp();
+          const int c4 = (lane & 7) * 4, r4 = lane >> 3;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int rr = q * 4 + r4;
+            if (row_base + rr < m)
+              *reinterpret_cast<float4*>(xbox + (size_t)(map0 + row_base + rr) * XW_COLS + c + c4) =
+                  *reinterpret_cast<const float4*>(sw + rr * 36 + c4);
+          }
+          __syncwarp();
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tempty);
+      ++it;
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc::fence_after_sync();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_hi, const void* desc_lo, int desc_rows,
+                   const XwCells& cells, const XwChunk& xc, cudaStream_t st) {
+  if (cells.n_cells <= 0) return DINOTRK_OK;
+  DTK_CHECK_ARG(fv.C % 8 == 0 && cells.max_m <= XW_MAX_CELL, "exact-window GEMM: bad sizes");
+  const bool small = cells.max_m <= 64;
+  const int arows = small ? 64 : 128;
+  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  int rc;
+  if ((rc = make_tmap_2d(&tA_hi, desc_hi, desc_rows, fv.C, arows, 64, TMAP_F16))) return rc;
+  if ((rc = make_tmap_2d(&tA_lo, desc_lo, desc_rows, fv.C, arows, 64, TMAP_F16))) return rc;
+  const uint64_t dims[4] = {(uint64_t)fv.C, (uint64_t)g.w, (uint64_t)g.h, (uint64_t)fv.T};
+  const uint64_t strides[3] = {(uint64_t)fv.C * 2, (uint64_t)g.w * fv.C * 2, (uint64_t)fv.P * fv.C * 2};
+  const uint32_t box[4] = {64, XW_BOX, XW_PART_ROWS, 1};
+  if ((rc = make_tmap_4d(&tB_hi, fv.hi, dims, strides, box, TMAP_F16))) return rc;
+  if ((rc = make_tmap_4d(&tB_lo, fv.lo, dims, strides, box, TMAP_F16))) return rc;
+  static PerDev<bool> attr_dev;
+  bool& attr = attr_dev.get();
+  if (!attr) {
+    DTK_CUDA(cudaFuncSetAttribute(xw_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, XwCfg<64>::kSmem));
+    DTK_CUDA(cudaFuncSetAttribute(xw_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, XwCfg<128>::kSmem));
+    attr = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = cells.n_cells < sms ? cells.n_cells : sms;
+  ProfRange pr(PROF_XW_GEMM, st);
+  if (small)
+    xw_gemm_kernel<64><<<grid, TC_THREADS, XwCfg<64>::kSmem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, cells, xc.box_org, xc.xbox, fv.C);
+  else
+    xw_gemm_kernel<128><<<grid, TC_THREADS, XwCfg<128>::kSmem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, cells, xc.box_org, xc.xbox, fv.C);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+// ====================================================================================================== 4. head
+// One warp per map.  Exact values v = relu(acc / max(|d| |F|, 1e-8)) (the full-map GEMM's epilogue expression) are formed
+// from the raw accumulators of xbox on demand: at the candidates (-> exact first arg-max) and on the 15 x 15 window.  Then
+// the refiner on the window (hidden layer 13 x 13 x 16 in two channel halves, logits on 11 x 11), softmax sums, the
+// certificate of head.cu with   m_out = max(exact window values outside the 7 x 7 core,
+//                                             per tile: (its max token inside the core ? second value : max) + XW_EPS)
+// and either the track point or a place in the group's full-map queue.
+constexpr int XH_WARPS = 8;
+constexpr int XH_MP = 17;      // input window pitch
+constexpr int XH_HP = 12;      // hidden window [position][8 channels], 12-float pitch (conflict-free float4 reads)
+constexpr int XWM = 15, XWH = 13, XWB = 11;
+constexpr int XH_W2 = 160, XH_MWIN = 256, XH_PER_WARP = XH_MWIN + 2032;    // floats (XWM * XH_MP = 255, XWH^2 * XH_HP = 2028)
+constexpr int XH_SMEM = (XH_W2 + XH_WARPS * XH_PER_WARP) * 4;
+
+struct XhParams {
+  int h, w, P, n_tiles;
+  int stride_px, half_patch, radius2;
+  float normW, normH;
+  int out_stride, out_mode;
+  float P1[16], P2[16];
+};
+
+__global__ void __launch_bounds__(XH_WARPS * 32, 3)
+xw_head_kernel(int n_maps, XhParams hp, dinotrk_head_weights wts, const float* __restrict__ norms,
+               const float* __restrict__ desc_norm, const int* __restrict__ cell_frame, const int* __restrict__ cell_group,
+               const int* __restrict__ grp_map0, const int* __restrict__ cell_of, const int2* __restrict__ box_org,
+               const int* __restrict__ stat, const int* __restrict__ cand, const unsigned long long* __restrict__ key1,
+               const float* __restrict__ max2, const float* __restrict__ xbox, const int* __restrict__ out_index,
+               float* __restrict__ out, int* __restrict__ slow_cnt, int* __restrict__ slow_list, int n_groups) {
+  extern __shared__ __align__(16) float xh_smem[];     // [w2: 160] then per warp [input window: 256 | hidden window: 2032]
+  float* sm_w2 = xh_smem;                              // [half][tap][channel % 8]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 2 * 9 * 8; i += blockDim.x) { const int hh = i / 72, k = (i / 8) % 9, j = i & 7; sm_w2[i] = wts.w2[hh * 8 + j][k]; }
+  __syncthreads();
+  float* mm = xh_smem + XH_W2 + wid * XH_PER_WARP;
+  float* hh_ = mm + XH_MWIN;
+  const int h = hp.h, w = hp.w, P = hp.P;
+  const int c8 = lane & 7, pg = lane >> 3;
+
+  for (int map = blockIdx.x * XH_WARPS + wid; map < n_maps; map += gridDim.x * XH_WARPS) {
+    const int cell = cell_of[map];
+    const int g = cell_group[cell];
+    bool slow = stat[map] != 0;
+    int amax = 0;
+    float mout = 0.f, zmax = 0.f;
+    float tot[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (!slow) {
+      const int2 org = box_org[cell];
+      const float* fn = norms + (size_t)cell_frame[cell] * P;
+      const float* xr = xbox + (size_t)map * XW_COLS;
+      const float dn = desc_norm[map];
+      // ---- exact first arg-max among the candidates (every lane, redundantly: <= 4 loads) ----
+      float best = -1.f;
+      amax = -1;
+#pragma unroll
+      for (int q = 0; q < XW_MAX_CAND; ++q) {
+        const int tok = __ldg(cand + (size_t)map * XW_MAX_CAND + q);
+        if (tok >= 0) {
+          const int tr = tok / w, tcn = tok - tr * w;
+          const float v = fmaxf(__fdiv_rn(__ldg(xr + xw_col(tr - org.x, tcn - org.y)), fmaxf(__fmul_rn(dn, __ldg(fn + tok)), 1e-8f)), 0.f);
+          if (v > best || (v == best && tok < amax)) { best = v; amax = tok; }
+        }
+      }
+      const int arow = amax / w, acol = amax - arow * w;
+      // ---- coarse bound on everything outside the window, from the tile keys ----
+      for (int t = lane; t < hp.n_tiles; t += 32) {
+        const unsigned long long k = __ldg(key1 + (size_t)map * hp.n_tiles + t);
+        const int tk = 0x7fffffff - (int)(k & 0xffffffffu);
+        const int tr = tk / w, tcn = tk - tr * w;
+        const bool in_core = abs(tr - arow) <= 3 && abs(tcn - acol) <= 3;
+        const float b = in_core ? __ldg(max2 + (size_t)map * hp.n_tiles + t) : __uint_as_float((unsigned)(k >> 32));
+        mout = fmaxf(mout, b + XW_EPS);
+      }
+      // ---- exact input window (15 x 15, zero outside the map) + exact part of m_out ----
+#pragma unroll
+      for (int q = 0; q < (XWM * 16 + 31) / 32; ++q) {
+        const int i = lane + 32 * q;
+        const int y = i >> 4, x = i & 15;
+        const int r = arow - 7 + y, c = acol - 7 + x;
+        float v = 0.f;
+        if (y < XWM && x < XWM && r >= 0 && r < h && c >= 0 && c < w) {
+          const int tok = r * w + c;
+          v = fmaxf(__fdiv_rn(__ldg(xr + xw_col(r - org.x, c - org.y)), fmaxf(__fmul_rn(dn, __ldg(fn + tok)), 1e-8f)), 0.f);
+          if (!(abs(r - arow) <= 3 && abs(c - acol) <= 3)) mout = fmaxf(mout, v);
+        }
+        if (y < XWM && x < XWM) mm[y * XH_MP + x] = v;
+      }
+      __syncwarp();
+      // ---- refiner: hidden layer in two channel halves, output layer accumulated per box pixel ----
+      float acc[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = wts.b2;
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        const int ch = hf * 8 + c8;
+        float w1r[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w1r[k] = wts.w1[ch][k];
+        const float b1r = wts.b1[ch];
+        for (int y = pg; y < XWH; y += 4) {
+          const int r = arow - 6 + y;
+          const bool row_in = r >= 0 && r < h;
+          const float* m0 = mm + y * XH_MP;
+          float i00 = m0[0], i01 = m0[1], i10 = m0[XH_MP], i11 = m0[XH_MP + 1], i20 = m0[2 * XH_MP], i21 = m0[2 * XH_MP + 1];
+#pragma unroll
+          for (int x = 0; x < XWH; ++x) {
+            const float i02 = m0[x + 2], i12 = m0[XH_MP + x + 2], i22 = m0[2 * XH_MP + x + 2];
+            float a = b1r;
+            a = fmaf(w1r[0], i00, a); a = fmaf(w1r[1], i01, a); a = fmaf(w1r[2], i02, a);
+            a = fmaf(w1r[3], i10, a); a = fmaf(w1r[4], i11, a); a = fmaf(w1r[5], i12, a);
+            a = fmaf(w1r[6], i20, a); a = fmaf(w1r[7], i21, a); a = fmaf(w1r[8], i22, a);
+            const int c = acol - 6 + x;
+            hh_[(y * XWH + x) * XH_HP + c8] = (row_in && c >= 0 && c < w) ? fmaxf(a, 0.f) : 0.f;
+            i00 = i01; i01 = i02; i10 = i11; i11 = i12; i20 = i21; i21 = i22;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int p = lane + 32 * q;
+          if (p < XWB * XWB) {
+            const int y = p / XWB, x = p - y * XWB;
+            float a = acc[q];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const float* hb = hh_ + ((y + ky) * XWH + x + kx) * XH_HP;
+                const float4 h0 = *reinterpret_cast<const float4*>(hb), h1 = *reinterpret_cast<const float4*>(hb + 4);
+                const float* wb = sm_w2 + (hf * 9 + ky * 3 + kx) * 8;
+                const float4 w0 = *reinterpret_cast<const float4*>(wb), w1_ = *reinterpret_cast<const float4*>(wb + 4);
+                a = fmaf(w0.x, h0.x, a); a = fmaf(w0.y, h0.y, a); a = fmaf(w0.z, h0.z, a); a = fmaf(w0.w, h0.w, a);
+                a = fmaf(w1_.x, h1.x, a); a = fmaf(w1_.y, h1.y, a); a = fmaf(w1_.z, h1.z, a); a = fmaf(w1_.w, h1.w, a);
+              }
+            acc[q] = a;
+          }
+        }
+        __syncwarp();
+      }
+      // ---- softmax sums on the box / the disc ----
+      float z[4];
+      bool valid[4], indisc[4];
+      float px[4], py[4];
+      zmax = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = lane + 32 * q;
+        valid[q] = false; indisc[q] = false; z[q] = -INFINITY; px[q] = py[q] = 0.f;
+        if (p < XWB * XWB) {
+          const int y = p / XWB, x = p - y * XWB;
+          const int r = arow - 5 + y, c = acol - 5 + x;
+          valid[q] = r >= 0 && r < h && c >= 0 && c < w;
+          if (valid[q]) {
+            z[q] = acc[q];
+            const int dr = (r - arow) * hp.stride_px, dc = (c - acol) * hp.stride_px;
+            indisc[q] = dr * dr + dc * dc <= hp.radius2;
+            px[q] = (float)(hp.half_patch + c * hp.stride_px);
+            py[q] = (float)(hp.half_patch + r * hp.stride_px);
+          }
+        }
+        zmax = fmaxf(zmax, z[q]);
+      }
+      zmax = warp_max(zmax);
+      mout = warp_max(mout);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float e = valid[q] ? expf(z[q] - zmax) : 0.f;
+        tot[0] += e;
+        if (indisc[q]) { tot[1] += e; tot[2] = fmaf(px[q], e, tot[2]); tot[3] = fmaf(py[q], e, tot[3]); }
+        tot[4] += valid[q] ? 1.f : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 5; ++q) tot[q] = warp_sum(tot[q]);
+    }
+    if (lane == 0) {
+      bool certified = false;
+      if (!slow) {
+        // every logit outside the box:  z <= b2 + sum_o P2_o * relu(b1_o + P1_o * mout)   (head.cu, same certificate)
+        float F = wts.b2;
+#pragma unroll
+        for (int o = 0; o < 16; ++o) F = fmaf(hp.P2[o], fmaxf(fmaf(hp.P1[o], mout, wts.b1[o]), 0.f), F);
+        const float rest = ((float)P - tot[4]) * expf(fminf(F - zmax, 80.f));
+        certified = tot[1] >= 2e-8f * (tot[0] + rest) && tot[1] > 0.f && isfinite(rest);
+      }
+      if (certified) {
+        const float px_ = __fdiv_rn(tot[2], tot[1]), py_ = __fdiv_rn(tot[3], tot[1]);
+        float nx = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(px_, hp.normW)), -1.f);
+        float ny = __fadd_rn(__fmul_rn(2.f, __fdiv_rn(py_, hp.normH)), -1.f);
+        if (hp.out_mode == 0) {
+          nx = __fmul_rn(__fdiv_rn(__fadd_rn(nx, 1.f), 2.f), hp.normW);
+          ny = __fmul_rn(__fdiv_rn(__fadd_rn(ny, 1.f), 2.f), hp.normH);
+        }
+        const size_t oi = (size_t)(out_index ? out_index[map] : map) * hp.out_stride;
+        out[oi] = nx; out[oi + 1] = ny;
+      } else {
+        const int pos = atomicAdd(slow_cnt + g, 1);
+        slow_list[grp_map0[g] + pos] = map;
+        atomicAdd(slow_cnt + n_groups, 1);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int launch_xw_head(const FeatView& fv, const dinotrk_geom& g, const dinotrk_head_weights& hw, const XwCells& cells,
+                   const float* desc_norm, const int* grp_map0, int n_maps, const int* out_index, float* out, int out_stride,
+                   int out_mode, const XwChunk& xc, cudaStream_t st, int n_groups) {
+  if (n_maps <= 0) return DINOTRK_OK;
+  DTK_CHECK_ARG(g.radius <= 5 * g.stride, "exact-window path: disc radius %d exceeds 5 tokens", g.radius);
+  XhParams hp;
+  hp.h = g.h; hp.w = g.w; hp.P = g.h * g.w; hp.n_tiles = cdiv(hp.P, CORR_TILE);
+  hp.stride_px = g.stride; hp.half_patch = g.patch / 2; hp.radius2 = g.radius * g.radius;
+  hp.normW = (float)(g.W - 1); hp.normH = (float)(g.H - 1);
+  hp.out_stride = out_stride; hp.out_mode = out_mode;
+  for (int o = 0; o < 16; ++o) {
+    float p1 = 0.f, p2 = 0.f;
+    for (int k = 0; k < 9; ++k) { p1 += hw.w1[o][k] > 0.f ? hw.w1[o][k] : 0.f; p2 += hw.w2[o][k] > 0.f ? hw.w2[o][k] : 0.f; }
+    hp.P1[o] = p1 * (1.f + 1e-6f); hp.P2[o] = p2 * (1.f + 1e-6f);
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = cdiv(n_maps, XH_WARPS);
+  if (grid > sms * 3) grid = sms * 3;
+  static PerDev<bool> attr_dev;
+  bool& attr = attr_dev.get();
+  if (!attr) {
+    DTK_CUDA(cudaFuncSetAttribute(xw_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XH_SMEM));
+    attr = true;
+  }
+  ProfRange pr(PROF_XW_HEAD, st);
+  xw_head_kernel<<<grid, XH_WARPS * 32, XH_SMEM, st>>>(n_maps, hp, hw, fv.norms, desc_norm, cells.frame, cells.group, grp_map0,
+                                                 xc.cell_of, xc.box_org, xc.stat, xc.cand, xc.key1, xc.max2, xc.xbox, out_index,
+                                                 out, xc.slow_cnt, xc.slow_list, n_groups);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+// ====================================================================================================== 5. full-map queue
+// One block per queued map: copies its descriptor (fp32 + fp16 hi / lo), norm and output slot to compact row b; block 0
+// also writes the compact group arrays.  Rows of a group keep their queue order (arbitrary, results do not depend on it).
+__global__ void __launch_bounds__(128)
+xw_compact_kernel(const float4* __restrict__ desc, const uint4* __restrict__ dhi, const uint4* __restrict__ dlo,
+                  const float* __restrict__ desc_norm, const int* __restrict__ out_index, int C, const int* __restrict__ grp_frame,
+                  const int* __restrict__ grp_map0, int n_groups, const int* __restrict__ slow_cnt,
+                  const int* __restrict__ slow_list, float4* __restrict__ c_desc, uint4* __restrict__ c_hi, uint4* __restrict__ c_lo,
+                  float* __restrict__ c_norm, int* __restrict__ c_out_index, int* __restrict__ cgrp, int gcap) {
+  __shared__ int s_g, s_pos;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int pre = 0, gsel = -1, psel = 0;
+    for (int g = 0; g < n_groups; ++g) {
+      const int c = slow_cnt[g];
+      if (b == 0) { cgrp[g] = grp_frame[g]; cgrp[gcap + g] = pre; cgrp[2 * gcap + g] = c; cgrp[3 * gcap + g] = pre; }
+      if (gsel < 0 && b < pre + c) { gsel = g; psel = b - pre; }
+      pre += c;
+    }
+    s_g = gsel; s_pos = psel;
+  }
+  __syncthreads();
+  if (s_g < 0) return;
+  const int src = slow_list[grp_map0[s_g] + s_pos];
+  for (int i = threadIdx.x; i < C / 4; i += blockDim.x) c_desc[(size_t)b * (C / 4) + i] = desc[(size_t)src * (C / 4) + i];
+  if (dhi != nullptr)
+    for (int i = threadIdx.x; i < C / 8; i += blockDim.x) {
+      c_hi[(size_t)b * (C / 8) + i] = dhi[(size_t)src * (C / 8) + i];
+      c_lo[(size_t)b * (C / 8) + i] = dlo[(size_t)src * (C / 8) + i];
+    }
+  if (threadIdx.x == 0) { c_norm[b] = desc_norm[src]; c_out_index[b] = out_index[src]; }
+}
+
+int launch_xw_compact(const float* desc, const void* desc_hi, const void* desc_lo, const float* desc_norm,
+                      const int* out_index, int C, const int* grp_frame, const int* grp_map0, int n_groups, int n_slow,
+                      const XwChunk& xc, float* c_desc, void* c_hi, void* c_lo, float* c_norm, int* c_out_index, int* cgrp,
+                      int gcap, cudaStream_t st) {
+  if (n_slow <= 0) return DINOTRK_OK;
+  ProfRange pr(PROF_MISC, st);
+  xw_compact_kernel<<<n_slow, 128, 0, st>>>(reinterpret_cast<const float4*>(desc), reinterpret_cast<const uint4*>(desc_hi),
+                                            reinterpret_cast<const uint4*>(desc_lo), desc_norm, out_index, C, grp_frame, grp_map0,
+                                            n_groups, xc.slow_cnt, xc.slow_list, reinterpret_cast<float4*>(c_desc),
+                                            reinterpret_cast<uint4*>(c_hi), reinterpret_cast<uint4*>(c_lo), c_norm, c_out_index, cgrp,
+                                            gcap);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
+size_t xw_chunk_bytes(int chunk_maps, int max_cells, int n_tiles, int gcap) {
+  const size_t ch = (size_t)chunk_maps;
+  size_t b = 0;
+  b += align_up(ch * n_tiles * 8, 256) + align_up(ch * n_tiles * 4, 256);              // key1, max2
+  b += align_up(ch * XW_MAX_CAND * 4, 256) + 3 * align_up(ch * 4, 256);                // cand, stat, cell_of, slow_list
+  b += align_up((size_t)max_cells * 8, 256);                                           // box_org
+  b += align_up(ch * XW_COLS * 4, 256);                                                // xbox
+  b += align_up((size_t)(gcap + 1) * 4, 256);                                          // slow_cnt
+  return b + 2048;
+}
+
+}  // namespace dtk

@@ -145,6 +145,20 @@ int dinotrk_infer_plan(int kind, int T, int N, const int* anchor_counts, int chu
  * into the caller's stream before dinotrk_infer returns.  The side streams and their events are one set per
  * process (one process per GPU): with mode >= 1 do not run dinotrk_infer from two host threads at once. */
 int dinotrk_infer_set_overlap(int mode);
+/* Pipeline of the anchor re-tracking phase (process-wide):
+ *  1 = coarse pass + exact window: one single-pass fp16 GEMM keeps per map and 256-token tile only (max, its token, second
+ *      value); the fp32-faithful split-precision contraction is then evaluated only on a 21 x 21 token box around the
+ *      arg-max of each (query, anchor frame) cell, and a warp-per-map head consumes those values -- no correlation map is
+ *      ever written.  Maps whose arg-max cannot be resolved from the coarse pass (near ties), that leave their cell's box
+ *      or that fail the head's certificate are re-done by pipeline 0; no result depends on a coarse value.
+ *  0 = full maps: split-precision GEMM over all tokens into chunk buffers + the head kernels (the round-1 pipeline).
+ * -1 (default) = 1 when the feature struct carries fp16 hi / lo halves (tensor path), unless the trajectory phase just
+ *      showed that the head's certificate fails for more than a quarter of the maps (ill-conditioned refiner weights);
+ *      the DTK_XW environment variable (0 / 1) overrides.
+ * dinotrk_infer_last_stats: {anchor-phase maps, maps finished by the exact-window path, maps re-done by the full-map path,
+ * pipeline used} of the last dinotrk_infer call that ran the anchor phase. */
+int dinotrk_infer_set_path(int path);
+int dinotrk_infer_last_stats(long long* out, int n);
 int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
                   const dinotrk_head_weights* hw, const float* query_points, int N,
                   float anchor_th, float cos_th, int frame_batch, int start_phase, int stop_after,

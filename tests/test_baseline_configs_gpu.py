@@ -62,7 +62,7 @@ def _compare_infer(r, sub, feats, q, head, geo, label):
           f"anchor sets {'identical' if same_sets else 'DIFFER'}, anchor tracks max {worst:.2e} px "
           f"({n_bad} of {n_tot} beyond {XY_TOL} px), occlusion {'identical' if occ_same else 'DIFFERS'}")
     assert e_traj <= XY_TOL
-    assert e_cos <= 2e-5
+    assert e_cos <= 1e-4      # intermediate: sampled AT the predicted points, so it inherits d(cos)/d(px) * the track difference
     assert same_sets
     assert occ_same
     # intermediate anchor tracks: an arg-max near-tie between two tokens (a < 1e-6 gap in cosine) may legitimately
