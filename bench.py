@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--path", type=int, default=-1, help="anchor-phase pipeline: -1 automatic, 0 full-map, 1 coarse pass + exact window")
     ap.add_argument("--torch-cuda-baseline", type=int, default=1, help="0: skip timing the reference's PyTorch path on cuda:0")
     ap.add_argument("--second-head", type=int, default=1, help="0: skip the extra timing with the mixed-sign head")
+    ap.add_argument("--multi", type=int, default=1, help="0: skip the config 3 / 4 / 5 blocks (bench_multi.py)")
+    ap.add_argument("--config3-vit", type=int, default=1, help="0: config 3 without the ViT stage (tracker + delta-DINO only)")
     return ap.parse_args()
 
 
@@ -412,6 +414,23 @@ def run_b200(args):
         ms, e2e_ms = tt[0].item(), tt[1].item()
     else:
         e2e_ms = e2e_s * 1000.0
+    # ---- BASELINE configs 3 / 4 / 5 (every rank takes part; rank 0 keeps the blocks)
+    multi_blocks = {}
+    if args.multi and C == 1024:
+        import bench_multi
+        import bench as _self
+        c_map = (ms / args.steps / 1e3) / float(nq * T * (T + 1))
+        mi_keep, model_keep = mi, model
+        for name, fn in (("config4", lambda: bench_multi.config4(dist, rank, world, dev, _self)),
+                         ("config3", lambda: bench_multi.config3(dist, rank, world, dev, _self, c_map, 0.0155, bool(args.config3_vit))),
+                         ("config5", lambda: bench_multi.config5(dist, rank, world, dev, _self))):
+            try:
+                multi_blocks[name] = fn()
+            except Exception as ex:  # a failed block must not take the headline line with it
+                multi_blocks[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -475,6 +494,9 @@ def run_b200(args):
             "kernels": kernels, "kernels_note": "per-class CUDA-event times of a separate overlap-off pass (%d steps, %.2f ms per "
                                                 "serialised step); see the comment in bench.py" % (clean_steps, serial_ms),
             "peaks": peaks}
+    for k_, v_ in multi_blocks.items():
+        if v_ is not None:
+            line[k_] = v_
     if args.second_head and world == 1 and args.head != "mixed":
         # the same step with mixed-sign refiner weights: whatever the head's certificate cannot cover goes through the
         # full-map refiner (a trained checkpoint's weights are not known here; this is the unfavourable end)

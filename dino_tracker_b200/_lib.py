@@ -76,6 +76,7 @@ SIGNATURES = {
     "dinotrk_best_buddies_workspace_bytes": (c_size_t, [c_int, c_int]),
     "dinotrk_best_buddies_pairs": (c_int, [POINTER(Features), POINTER(Geom), _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "dinotrk_bb_mutual": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "dinotrk_bb_nms": (c_int, [_P, c_int, POINTER(Geom), c_float, c_float, c_int, _P, _P, _P]),
     "dinotrk_profile_classes": (c_int, []),
     "dinotrk_profile_class_name": (c_char_p, [c_int]),
     "dinotrk_profile_enable": (None, [c_int]),

@@ -51,7 +51,7 @@ def save_predictions(predictions: Mapping[int, tuple], trajectories_dir: str, oc
 def run_videos(video_ids: Sequence, costs: Sequence[float], rank: int, world: int,
                run_one: Callable[[object], Dict[int, tuple]]):
     """Multi-video launcher: videos are dealt to ranks by longest-processing-time-first on ``costs``
-    (e.g. T x number of query points); every rank runs ``run_one(video_id)`` for its share -- no data-path
+    (``parallel.video_cost``: N_q * T * (T + 1) * c_map + T * c_frame); every rank runs ``run_one(video_id)`` for its share -- no data-path
     collective.  Returns {video_id: run_one(video_id)} for this rank's videos."""
     mine = lpt_assign(list(costs), world)[rank]
     return {video_ids[i]: run_one(video_ids[i]) for i in mine}

@@ -122,6 +122,79 @@ __global__ void bb_mutual_kernel(const int* __restrict__ nn_st, const int* __res
   mutual[i] = nn_ts[g * P + nn_st[i]] == n ? 1 : 0;
 }
 
+// ---- best-buddy peak filter (preprocessing_dino_bb/compute_dino_bb_nms.py:12-66) ---------------------------------------
+// Per similarity map of one source point against a target frame, the reference keeps the 400 largest values, puts a
+// (2 box_size)^2 box on each, runs greedy NMS (torchvision.ops.batched_nms: descending score, a box is dropped when its
+// IoU with an already KEPT box exceeds the threshold) and reports the two largest kept values and their ratio r.  Greedy
+// NMS keeps the maximum first; the second kept box is therefore the highest-scoring candidate whose IoU with the
+// maximum's box is <= threshold -- provided it is among the 400 largest values.  So per map: arg-max, the best value
+// outside the maximum's suppression zone, and a rank test (fewer than `topk` values strictly above it).  Nothing is
+// sorted.  Box arithmetic in fp32 as torchvision does it: inter / (area_a + area_b - inter) > thresh.
+constexpr int NMS_THREADS = 256;
+__global__ void __launch_bounds__(NMS_THREADS)
+bb_nms_kernel(const float* __restrict__ maps, int n_maps, int map_stride, int P, int w, int stride_px, int half_patch,
+              float box, float iou_thresh, int topk, float* __restrict__ peak_affs, float* __restrict__ r_out) {
+  __shared__ unsigned long long s_key[NMS_THREADS / 32];
+  __shared__ float s_f[NMS_THREADS / 32];
+  __shared__ int s_i[NMS_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int map = blockIdx.x; map < n_maps; map += gridDim.x) {
+    const float* m = maps + (size_t)map * map_stride;
+    // first arg-max (values are >= 0 after the ReLU of the correlation epilogue; a negative similarity can never be one of
+    // the reported peaks: the reference multiplies by the keep mask and takes a top-2 over values that include zeros)
+    unsigned long long key = 0ull;
+    for (int i = tid; i < P; i += NMS_THREADS) {
+      const unsigned long long k = ((unsigned long long)__float_as_uint(m[i] + 0.f) << 32) | (unsigned)(0x7fffffff - i);
+      key = k > key ? k : key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
+    if (lane == 0) s_key[warp] = key;
+    __syncthreads();
+    unsigned long long kb = s_key[0];
+#pragma unroll
+    for (int k = 1; k < NMS_THREADS / 32; ++k) kb = s_key[k] > kb ? s_key[k] : kb;
+    const int amax = 0x7fffffff - (int)(kb & 0xffffffffu);
+    const float vmax = __uint_as_float((unsigned)(kb >> 32));
+    const float ax = (float)(half_patch + (amax % w) * stride_px), ay = (float)(half_patch + (amax / w) * stride_px);
+    const float ax1 = ax - box, ax2 = ax + box, ay1 = ay - box, ay2 = ay + box;
+    const float area = (ax2 - ax1) * (ay2 - ay1);
+    // best value whose box survives next to the maximum's box
+    float v2 = 0.f;
+    for (int i = tid; i < P; i += NMS_THREADS) {
+      if (i == amax) continue;
+      const float x = (float)(half_patch + (i % w) * stride_px), y = (float)(half_patch + (i / w) * stride_px);
+      const float iw = fmaxf(fminf(ax2, x + box) - fmaxf(ax1, x - box), 0.f);
+      const float ih = fmaxf(fminf(ay2, y + box) - fmaxf(ay1, y - box), 0.f);
+      const float inter = iw * ih;
+      const float iou = inter / (area + area - inter);
+      if (!(iou > iou_thresh)) v2 = fmaxf(v2, m[i]);
+    }
+    v2 = warp_max(v2);
+    if (lane == 0) s_f[warp] = v2;
+    __syncthreads();
+    v2 = s_f[0];
+#pragma unroll
+    for (int k = 1; k < NMS_THREADS / 32; ++k) v2 = fmaxf(v2, s_f[k]);
+    // is it among the `topk` largest values of the map?
+    int above = 0;
+    for (int i = tid; i < P; i += NMS_THREADS) above += m[i] > v2 ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+    if (lane == 0) s_i[warp] = above;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int k = 0; k < NMS_THREADS / 32; ++k) tot += s_i[k];
+      const float second = tot < topk ? v2 : 0.f;
+      peak_affs[2 * (size_t)map] = vmax;
+      peak_affs[2 * (size_t)map + 1] = second;
+      r_out[map] = __fdiv_rn(second, vmax);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void bb_plan_kernel(int n_pairs, int P, const int* __restrict__ src, int* row0, int* m, int* tile_start) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int tiles = (P + TC_BM - 1) / TC_BM;
@@ -191,6 +264,20 @@ int dinotrk_best_buddies_pairs(const dinotrk_features* feat, const dinotrk_geom*
                                                                   n_tiles, n_pairs, 2e-4f, nn_idx, nn_cos);
     DTK_LAUNCHED();
   }
+  return DINOTRK_OK;
+}
+
+int dinotrk_bb_nms(const float* maps, int n_maps, const dinotrk_geom* g, float box_size, float iou_thresh, int topk,
+                   float* peak_affs, float* r, void* stream) {
+  DTK_CHECK_ARG(maps && g && peak_affs && r && n_maps >= 0 && topk > 0 && box_size > 0.f, "bb_nms: bad arguments");
+  if (n_maps == 0) return DINOTRK_OK;
+  const int P = g->h * g->w;
+  DTK_CHECK_ARG(topk <= P, "bb_nms: topk %d exceeds the %d tokens of a map (torch.topk would fail too)", topk, P);
+  int grid = n_maps < 148 * 8 ? n_maps : 148 * 8;
+  ProfRange pr(PROF_BB, (cudaStream_t)stream);
+  bb_nms_kernel<<<grid, NMS_THREADS, 0, (cudaStream_t)stream>>>(maps, n_maps, dinotrk_map_stride(g), P, g->w, g->stride, g->patch / 2,
+                                                                box_size, iou_thresh, topk, peak_affs, r);
+  DTK_LAUNCHED();
   return DINOTRK_OK;
 }
 

@@ -252,7 +252,9 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
   const float* tpc = fv.tpc;
   const float* norms = fv.norms;
   const int C = fv.C, P = fv.P;
-  const int stream_max = STREAM_MAX_M;
+  // all_wide: every non-empty group goes through the GEMM, whatever its size (the full-map queue of the exact-window
+  // pipeline: a map's arithmetic must not depend on how many other maps of its frame were queued with it)
+  const int stream_max = assist.all_wide ? 0 : STREAM_MAX_M;
   if (max_group_m > stream_max || tkeys != nullptr || assist.zero_word != nullptr) {
     ProfRange pr(PROF_MISC, st);
     corr_plan_kernel<<<1, 32, 0, st>>>(grp_m, n_groups, stream_max, tile_rows, tile_start, grp_map0, tkeys, n_tiles,
@@ -282,7 +284,7 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
       DTK_LAUNCHED();
     }
   }
-  if (!assist.no_thin) {
+  if (!assist.no_thin && !assist.all_wide) {
     // thin groups (there may be none; CTAs of wide groups exit at once).  Three instantiations: <= 2 or <= 4 descriptors
     // with 8 rows in flight per warp (pure streaming), <= 8 descriptors with 4 rows.
     const int variant = max_group_m <= 2 ? 0 : (max_group_m <= 4 ? 1 : 2);

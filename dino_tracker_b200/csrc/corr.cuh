@@ -30,6 +30,7 @@ struct CorrAssist {
   int* zero_word = nullptr;
   bool split_ready = false;
   bool no_thin = false;
+  bool all_wide = false;   // no streaming kernel: groups of any size > 0 are GEMM tiles
 };
 
 size_t corr_plan_bytes(int n_groups);

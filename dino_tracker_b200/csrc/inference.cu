@@ -770,8 +770,8 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
                                       n_slow, x.xc, b.desc, c_hi, c_lo, b.norm, out_index_ring[0], d_cgrp, gcap, st);
           if (rc2) return rc2;
           CorrAssist as;
-          as.tkeys = b.tkeys; as.zero_word = b.hscratch; as.split_ready = true; as.no_thin = false;
-          const int mg = n_slow > STREAM_MAX_M + 1 ? n_slow : STREAM_MAX_M + 1;   // group sizes live on the device: plan for both kinds
+          as.tkeys = b.tkeys; as.zero_word = b.hscratch; as.split_ready = true; as.no_thin = true; as.all_wide = true;
+          const int mg = n_slow;   // (group sizes live on the device; with all_wide any size is a GEMM tile)
           rc2 = launch_corr_maps(fv, b.desc, n_slow, b.norm, d_cgrp, d_cgrp + gcap, d_cgrp + 2 * gcap, d_cgrp + 3 * gcap,
                                  cm.n_groups, n_slow, mg, b.maps, ms, b.plan, b.split, st, as);
           if (rc2) return rc2;

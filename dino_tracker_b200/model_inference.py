@@ -131,6 +131,18 @@ class ModelInference(torch.nn.Module):
         """models/model_inference.py:110-126 -> N x T."""
         return _run_phases(self.model, query_points, 1, 1, None, traj=trajectories)["cos_sims"]
 
+    def _get_model_preds_at_anchors(self, model, range_normalizer, preds, anchor_indices, batch_size=None):
+        """models/model_inference.py:130-154 for ONE query point: ``preds`` T x 3 (its trajectory), ``anchor_indices`` the
+        anchor frames -> M x T x 2, the track of every ``preds[i]`` (living in frame i) into every anchor frame.  Same work
+        list as the anchor phase of ``infer`` (one device call instead of the reference's M x ceil(T / batch) model() calls)."""
+        T = preds.shape[0]
+        dev = model._dev
+        cos = torch.zeros(1, T, device=dev, dtype=torch.float32)
+        idx = torch.as_tensor(anchor_indices, device=dev).long().reshape(-1)
+        cos[0, idx] = 1.0
+        r = _run_phases(model, torch.zeros(1, 3, device=dev), 2, 2, batch_size, anchor_th=0.5, traj=preds[None], cos_sims=cos)
+        return r["anchors"][0][idx]
+
     def compute_anchor_trajectories(self, trajectories: torch.Tensor, cos_sims: torch.Tensor,
                                     batch_size=None) -> Dict[int, torch.Tensor]:
         """models/model_inference.py:156-165 -> {n: M_n x T x 2} (rows = anchor frames, ascending)."""

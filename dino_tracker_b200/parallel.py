@@ -1,8 +1,8 @@
 """Single-node multi-GPU sharding of the hot path: one process per GPU, ``torch.distributed``
 (NCCL on GPUs; the host logic below is backend-agnostic and is tested with ``gloo`` on CPU).
 
-* video-parallel (configs 2/3): videos dealt to ranks by longest-processing-time-first on T * N_q; no data-path
-  collective.
+* video-parallel (configs 2/3): videos dealt to ranks by longest-processing-time-first on ``video_cost`` =
+  N_q * T * (T + 1) * c_map + T * c_frame; no data-path collective.
 * frame-sharded long video (config 4): rank r owns a contiguous block of frames, runs ViT + delta-DINO for them
   writing straight into its slice of the full ``[T][P][C]`` buffer, then ONE in-place all-gather of the refined
   features (each (query, frame) correlation map needs only that frame + one descriptor, so any frame sharding is
@@ -27,8 +27,15 @@ def query_shard(N: int, world: int, rank: int):
     return frame_shard(N, world, rank)
 
 
+def video_cost(T: int, n_query_points: int, c_map: float = 2.5e-8, c_frame: float = 1.55e-2) -> float:
+    """Seconds one video costs on one GPU: every query point is tracked into every frame (T maps) and, from each of its T
+    track points, re-tracked into every anchor frame (<= T * T maps) -> N_q * T * (T + 1) correlation maps; the feature
+    stage (ViT + delta-DINO) is per frame.  Defaults: measured on B200 (exact-window pipeline; ViT-L/14@15)."""
+    return n_query_points * T * (T + 1) * c_map + T * c_frame
+
+
 def lpt_assign(costs: Sequence[float], world: int) -> List[List[int]]:
-    """Longest-processing-time-first assignment of videos to ranks (cost = T * N_q)."""
+    """Longest-processing-time-first assignment of videos to ranks (costs: ``video_cost`` per video)."""
     order = sorted(range(len(costs)), key=lambda i: -costs[i])
     loads = [0.0] * world
     out = [[] for _ in range(world)]

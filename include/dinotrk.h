@@ -256,6 +256,12 @@ int dinotrk_best_buddies_pairs(const dinotrk_features* feat, const dinotrk_geom*
                                void* workspace, size_t workspace_bytes, void* stream);
 /* mutual[k][n] = (nn_ts[k][nn_st[k][n]] == n): source token n of pair k is a best buddy. */
 int dinotrk_bb_mutual(const int* nn_st, const int* nn_ts, int n_pairs, int P, uint8_t* mutual, void* stream);
+/* Peak filter of the best-buddy pairs (preprocessing_dino_bb/compute_dino_bb_nms.py:12-66, get_bb_sim_indices): maps =
+ * [n_maps][dinotrk_map_stride] similarity maps of the source points against the target frame (dinotrk_corr_maps). Per map:
+ * peak_affs[2] = the two largest values that survive box NMS (boxes of +-box_size px around the token centres, greedy,
+ * IoU threshold, restricted to the `topk` largest values), r = second / first. */
+int dinotrk_bb_nms(const float* maps, int n_maps, const dinotrk_geom* g, float box_size, float iou_thresh, int topk,
+                   float* peak_affs, float* r, void* stream);
 
 /* ---- per-kernel-class device timing (CUDA events on the launching stream; bench.py roofline) ------ */
 int dinotrk_profile_classes(void);

@@ -136,6 +136,41 @@ def gen_bb_case(name, H, W, T, C, seed):
     print(name, {k: v["cos_sims"].shape[0] for k, v in res.items()})
 
 
+def gen_bb_nms_case(name, H, W, T, C, seed):
+    """Live preprocessing_dino_bb/compute_dino_bb_nms.py (compute_bb_nms + compute_max_r over every pair) on the best
+    buddies the live extract script finds; the token grid needs >= 400 tokens (torch.topk(k=400))."""
+    import argparse
+    import tempfile
+    ref_harness.install("cpu")
+    from preprocessing_dino_bb import compute_dino_bb_nms as nms
+    from preprocessing_dino_bb import extract_dino_best_buddies as bb
+    from preprocessing_dino_bb.dino_bb_utils import create_meshgrid
+    from .tracker import Geometry
+    geo = Geometry(H=H, W=W)
+    assert geo.P >= 400
+    feats, _ = synth.shifted_field_features(T, C, geo.h, geo.w, seed=seed, noise=0.5, max_shift=2)
+    d = tempfile.mkdtemp()
+    torch.save(feats, os.path.join(d, "f.pt"))
+    args = argparse.Namespace(dino_emb_path=os.path.join(d, "f.pt"), h=H, w=W, stride=7, out_path=os.path.join(d, "out", "bb.pt"))
+    bb.run(args)
+    dino_bb = torch.load(args.out_path)
+    coords = create_meshgrid(h=H, w=W, step=7)
+    for key in list(dino_bb.keys()):                       # run() of compute_dino_bb_nms.py:85-110 with our geometry's grid
+        if dino_bb[key].get("r", None) is not None:
+            continue
+        sf, tf = (int(x) for x in key.split("_"))
+        a = nms.compute_bb_nms(dino_bb[f"{sf}_{tf}"], sf, tf, feats, coords, 7, 50, 0.2)
+        b = nms.compute_bb_nms(dino_bb[f"{tf}_{sf}"], tf, sf, feats, coords, 7, 50, 0.2)
+        a, b = nms.compute_max_r(a, b)
+        dino_bb[key], dino_bb[f"{tf}_{sf}"] = a, b
+    out = dict(HWTC=np.array([H, W, T, C]), seed=np.array(seed))
+    for k, v in dino_bb.items():
+        for kk in ("source_coords", "target_coords", "cos_sims", "peak_affs", "r"):
+            out[f"{k}.{kk}"] = v[kk].numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    print(name, {k: (v["r"].shape[0], float(v["r"].max())) for k, v in dino_bb.items()})
+
+
 def gen_posembed_case(name, cases, dim, n_pos, seed):
     """The reference-owned pieces of the ViT stage (row a1): VitExtractor._fix_pos_enc (models/extractor.py:57-85), the
     position-embedding interpolation for stride-7 overlapping patches, run from the live reference on a seeded table.
@@ -271,6 +306,7 @@ def main():
     gen_delta_case("delta_small", 98, 126, 3, [3, 8, 12, 16, 24], seed=21)
     gen_delta_case("delta_full_geom", 476, 854, 1, [3, 4, 4, 4, 8], seed=22)
     gen_bb_case("bb_small", 98, 126, 3, 16, seed=31)
+    gen_bb_nms_case("bb_nms_small", 154, 210, 3, 16, seed=32)
     gen_posembed_case("posembed", [(476, 854), (98, 126), (112, 140), (518, 518)], dim=6, n_pos=37, seed=41)
     gen_vit_case("vit_small")
 
