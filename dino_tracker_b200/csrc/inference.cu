@@ -598,6 +598,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
     x.max2 = ar.take<float>((size_t)ch * n_tiles_map);
     x.cand = ar.take<int>((size_t)ch * XW_MAX_CAND);
     x.stat = ar.take<int>(ch);
+    x.pinfo = ar.take<int>(ch);
     x.cell_of = ar.take<int>(ch);
     x.slow_list = ar.take<int>(ch);
     x.box_org = ar.take<int2>((size_t)ch + 2);
@@ -790,7 +791,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
         if (ovl) DTK_CUDA(cudaStreamWaitEvent(st, xa->sample[k % XW_RING], 0));
         if ((rc = launch_xw_coarse(fv, hi_of(x, cm.used), cm.used, x.norm, gp.f, gp.r, gp.m, gp.map0, d_tiles + k * (gcap + 1),
                                    cm.n_groups, cm.used / TC2_BM_ROWS + cm.n_groups, x.xc, st))) return rc;
-        if ((rc = launch_xw_plan(cells, x.norm, cm.n_groups, *g, x.xc, st))) return rc;
+        if ((rc = launch_xw_plan(cells, x.norm, cm.n_groups, *g, x.xc, st, cm.used))) return rc;
         if ((rc = launch_xw_gemm(fv, *g, hi_of(x, cm.used), lo_of(x, cm.used), cm.used, cells, x.xc, st))) return rc;
         if ((rc = launch_xw_head(fv, *g, *hw, cells, x.norm, gp.map0, cm.used, x.out_index, anchors, 2, 0, x.xc, st, cm.n_groups)))
           return rc;

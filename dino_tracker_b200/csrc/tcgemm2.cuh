@@ -232,11 +232,9 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       tc::mbar_wait(&tfull[buf], aphase);
       tc::fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tc::tmem_ld32(taddr + c, v);
-        tc::tmem_ld_wait();
+      // column blocks of 32; the TMEM load of the next block is in flight while this one is consumed (the epilogue warps
+      // have their scheduler to themselves, so nothing else hides that latency)
+      auto consume = [&](const uint32_t (&v)[32], int c) {
         const int ncols = min(32, pb.N - (n0 + c));
         if constexpr (EpiCoalesced<Epi>::value) {
           if (!epi.direct(n0 + c)) {
@@ -259,7 +257,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
               }
             }
             __syncwarp();
-            continue;
+            return;
           }
         }
         if (row_ok && ncols > 0) {
@@ -267,6 +265,19 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
           epi(est, g, r, n0 + c, f, ncols);
+        }
+      };
+      {
+        uint32_t va[32], vb[32];
+        tc::tmem_ld32(taddr, va);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          tc::tmem_ld_wait();
+          tc::tmem_ld32(taddr + c + 32, vb);
+          consume(va, c);
+          tc::tmem_ld_wait();
+          if (c + 64 < BN) tc::tmem_ld32(taddr + c + 64, va);
+          consume(vb, c + 32);
         }
       }
       if (row_ok) epi.tile_end(est, g, r, n0 / BN);

@@ -25,22 +25,49 @@ struct CoarseEpi {
   unsigned long long* key1;
   float* max2;
   int n_tiles, P;
-  struct State { float m1, m2; int tok; };
-  __device__ __forceinline__ void tile_begin(State& s) const { s.m1 = -1.f; s.m2 = -1.f; s.tok = 0; }
+  // The epilogue warps are alone on their schedulers, so every dependent instruction costs its full latency: the 32 values of
+  // a column block are formed as 32 independent chains (all norm loads first), and the (max, first token, second value)
+  // statistics run in four interleaved branch-free accumulators (columns = lane of the accumulator mod 4), merged per tile.
+  struct State { float m1[4], m2[4]; int tok[4]; float dn; };
+  __device__ __forceinline__ void tile_begin(State& s) const {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { s.m1[a] = -1.f; s.m2[a] = -1.f; s.tok[a] = 0x7fffffff; }
+    s.dn = -1.f;
+  }
   __device__ __forceinline__ void tile_end(State& s, int g, int r, int nt) const {
+    float m1 = s.m1[0], m2 = s.m2[0];
+    int tok = s.tok[0];
+#pragma unroll
+    for (int a = 1; a < 4; ++a) {   // top-2 of the union; equal maxima -> the smaller token (first arg-max)
+      m2 = fmaxf(fmaxf(m2, s.m2[a]), fminf(m1, s.m1[a]));
+      const bool take = s.m1[a] > m1 || (s.m1[a] == m1 && s.tok[a] < tok);
+      tok = take ? s.tok[a] : tok;
+      m1 = fmaxf(m1, s.m1[a]);
+    }
     const size_t o = (size_t)(grp_map0[g] + r) * n_tiles + nt;
-    key1[o] = ((unsigned long long)__float_as_uint(s.m1 + 0.f) << 32) | (unsigned)(0x7fffffff - s.tok);
-    max2[o] = fmaxf(s.m2, 0.f);
+    key1[o] = ((unsigned long long)__float_as_uint(fmaxf(m1, 0.f)) << 32) | (unsigned)(0x7fffffff - tok);
+    max2[o] = fmaxf(m2, 0.f);
   }
   __device__ __forceinline__ void operator()(State& s, int g, int r, int col0, const float (&f)[32], int ncols) const {
-    const float dn = desc_norm[grp_row0[g] + r];
+    if (s.dn < 0.f) s.dn = desc_norm[grp_row0[g] + r];
+    const float dn = s.dn;
     const float* fn = norms + (size_t)grp_frame[g] * P + col0;
+    float t[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols) {
-        const float v = fmaxf(__fdividef(f[i], fmaxf(dn * __ldg(fn + i), 1e-8f)), 0.f);
-        if (v > s.m1) { s.m2 = s.m1; s.m1 = v; s.tok = col0 + i; } else s.m2 = fmaxf(s.m2, v);
-      }
+    for (int i = 0; i < 32; ++i) t[i] = __ldg(fn + (i < ncols ? i : 0));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float v = fmaxf(__fdividef(f[i], fmaxf(dn * t[i], 1e-8f)), 0.f);
+      t[i] = i < ncols ? v : -1.f;      // columns past the end of the map never win
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int a = i & 3;
+      const float v = t[i];
+      s.m2[a] = fmaxf(s.m2[a], fminf(s.m1[a], v));
+      s.tok[a] = v > s.m1[a] ? col0 + i : s.tok[a];      // strict: the first token of this accumulator holding its maximum
+      s.m1[a] = fmaxf(s.m1[a], v);
+    }
   }
 };
 
@@ -76,70 +103,79 @@ int launch_xw_coarse(const FeatView& fv, const void* desc_hi, int desc_rows, con
 }
 
 // ====================================================================================================== 2. plan
-// One warp per cell.  Per map (lane = tile): global coarse maximum, candidate tiles (max1 >= gmax - 2 eps), ambiguity (some
-// tile's SECOND value is also within 2 eps: an arg-max candidate whose token we do not know).  Per cell: the lower medians of
-// the maps' coarse arg-max row / column give the box centre; a map fits if every candidate lies within +-XW_SLACK of it.
-constexpr int PLAN_WARPS = 4;
+// (a) one warp per MAP (lane = tile): global coarse maximum, candidate tiles (max1 >= gmax - 2 eps), ambiguity (some tile's
+//     SECOND value is also within 2 eps: an arg-max candidate whose token is unknown).  Writes the candidate tokens and
+//     pinfo[map] = coarse arg-max token, or -1 - token if the map is ambiguous.
+// (b) one warp per CELL: the lower medians of the unambiguous maps' coarse arg-max row / column give the box centre; a map
+//     fits if every candidate lies within +-XW_SLACK of it.
+constexpr int PLAN_WARPS = 8;
 __global__ void __launch_bounds__(PLAN_WARPS * 32)
-xw_plan_kernel(XwCells cells, const float* __restrict__ desc_norm, int n_groups, int n_tiles, int w,
-               const unsigned long long* __restrict__ key1, const float* __restrict__ max2, int* __restrict__ cand,
-               int* __restrict__ stat, int* __restrict__ cell_of, int2* __restrict__ box_org, int* __restrict__ slow_cnt) {
+xw_cand_kernel(int n_maps, const float* __restrict__ desc_norm, int n_groups, int n_tiles, const unsigned long long* __restrict__ key1,
+               const float* __restrict__ max2, int* __restrict__ cand, int* __restrict__ pinfo, int* __restrict__ slow_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5), nw = gridDim.x * PLAN_WARPS;
+  if (gw == 0)   // zero the queue counters of this chunk (n_groups per-group counts + the total)
+    for (int i = lane; i <= n_groups; i += 32) slow_cnt[i] = 0;
+  for (int map = gw; map < n_maps; map += nw) {
+    const unsigned long long* k1 = key1 + (size_t)map * n_tiles;
+    const float* k2 = max2 + (size_t)map * n_tiles;
+    unsigned long long kk[2] = {0ull, 0ull};
+    float v2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int t = lane + 32 * q;
+      if (t < n_tiles) { kk[q] = __ldg(k1 + t); v2[q] = __ldg(k2 + t); }
+    }
+    unsigned long long gk = kk[0] > kk[1] ? kk[0] : kk[1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, gk, o); gk = t > gk ? t : gk; }
+    const float gmax = __uint_as_float((unsigned)(gk >> 32));
+    const int ptok = 0x7fffffff - (int)(gk & 0xffffffffu);
+    const float th = gmax - 2.f * XW_EPS;
+    bool amb = false;
+    int ncand = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int t = lane + 32 * q;
+      const bool in = t < n_tiles;
+      const bool isc = in && __uint_as_float((unsigned)(kk[q] >> 32)) >= th;
+      const unsigned cm = __ballot_sync(0xffffffffu, isc);
+      amb = amb || __any_sync(0xffffffffu, in && v2[q] >= th);
+      const int rank = ncand + __popc(cm & ((1u << lane) - 1u));
+      if (isc && rank < XW_MAX_CAND) cand[(size_t)map * XW_MAX_CAND + rank] = 0x7fffffff - (int)(kk[q] & 0xffffffffu);
+      ncand += __popc(cm);
+    }
+    // a (near-)zero map has no meaningful arg-max candidates; a tiny descriptor norm voids the error bound
+    amb = amb || ncand > XW_MAX_CAND || !(gmax > 4.f * XW_EPS) || !(desc_norm[map] >= 1e-6f);
+    if (lane >= ncand && lane < XW_MAX_CAND) cand[(size_t)map * XW_MAX_CAND + lane] = -1;
+    if (lane == 0) pinfo[map] = amb ? -1 - ptok : ptok;
+  }
+}
+
+__global__ void __launch_bounds__(PLAN_WARPS * 32)
+xw_cell_kernel(XwCells cells, int w, const int* __restrict__ cand, const int* __restrict__ pinfo, int* __restrict__ stat,
+               int* __restrict__ cell_of, int2* __restrict__ box_org) {
   __shared__ short s_r[PLAN_WARPS][XW_MAX_CELL], s_c[PLAN_WARPS][XW_MAX_CELL];
   __shared__ unsigned char s_ok[PLAN_WARPS][XW_MAX_CELL];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int gw = blockIdx.x * PLAN_WARPS + wid, nw = gridDim.x * PLAN_WARPS;
-  if (gw == 0)   // zero the queue counters of this chunk (n_groups per-group counts + the total)
-    for (int i = lane; i <= n_groups; i += 32) slow_cnt[i] = 0;
   for (int cell = gw; cell < cells.n_cells; cell += nw) {
     const int row0 = cells.row0[cell], m = cells.m[cell];
-    for (int r = 0; r < m; ++r) {
-      const int map = row0 + r;
-      const unsigned long long* k1 = key1 + (size_t)map * n_tiles;
-      const float* k2 = max2 + (size_t)map * n_tiles;
-      unsigned long long kk[2] = {0ull, 0ull};
-      float v2[2] = {0.f, 0.f};
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int t = lane + 32 * q;
-        if (t < n_tiles) { kk[q] = __ldg(k1 + t); v2[q] = __ldg(k2 + t); }
-      }
-      unsigned long long gk = kk[0] > kk[1] ? kk[0] : kk[1];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, gk, o); gk = t > gk ? t : gk; }
-      const float gmax = __uint_as_float((unsigned)(gk >> 32));
-      const int ptok = 0x7fffffff - (int)(gk & 0xffffffffu);
-      const float th = gmax - 2.f * XW_EPS;
-      bool amb = false;
-      int ncand = 0;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int t = lane + 32 * q;
-        const bool in = t < n_tiles;
-        const bool isc = in && __uint_as_float((unsigned)(kk[q] >> 32)) >= th;
-        const unsigned cm = __ballot_sync(0xffffffffu, isc);
-        amb = amb || __any_sync(0xffffffffu, in && v2[q] >= th);
-        const int rank = ncand + __popc(cm & ((1u << lane) - 1u));
-        if (isc && rank < XW_MAX_CAND) cand[(size_t)map * XW_MAX_CAND + rank] = 0x7fffffff - (int)(kk[q] & 0xffffffffu);
-        ncand += __popc(cm);
-      }
-      // a (near-)zero map has no meaningful arg-max candidates; a tiny descriptor norm voids the error bound
-      amb = amb || ncand > XW_MAX_CAND || !(gmax > 4.f * XW_EPS) || !(desc_norm[map] >= 1e-6f);
-      if (lane >= ncand && lane < XW_MAX_CAND) cand[(size_t)map * XW_MAX_CAND + lane] = -1;
-      if (lane == 0) {
-        s_r[wid][r] = (short)(ptok / w);
-        s_c[wid][r] = (short)(ptok - (ptok / w) * w);
-        s_ok[wid][r] = amb ? 0 : 1;
-        cell_of[map] = cell;
-      }
+    int nv = 0;
+    for (int r = lane; r < m; r += 32) {
+      const int pi = __ldg(pinfo + row0 + r);
+      const int ptok = pi >= 0 ? pi : -1 - pi;
+      s_r[wid][r] = (short)(ptok / w);
+      s_c[wid][r] = (short)(ptok - (ptok / w) * w);
+      s_ok[wid][r] = pi >= 0 ? 1 : 0;
+      nv += pi >= 0 ? 1 : 0;
+      cell_of[row0 + r] = cell;
     }
     __syncwarp();
-    // lower medians over the unambiguous maps
-    int nv = 0;
-    for (int r = lane; r < m; r += 32) nv += s_ok[wid][r];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
     int med_r = -1, med_c = -1;
-    if (nv > 0) {
+    if (nv > 0) {   // lower medians over the unambiguous maps
       const int want = (nv - 1) / 2;
       for (int r = lane; r < m; r += 32) {
         if (!s_ok[wid][r]) continue;
@@ -159,20 +195,19 @@ xw_plan_kernel(XwCells cells, const float* __restrict__ desc_norm, int n_groups,
         med_c = max(med_c, __shfl_xor_sync(0xffffffffu, med_c, o));
       }
     }
-    __syncwarp();   // cand[] of this cell was written by this warp's lanes above
     int n_fit = 0;
     for (int r = lane; r < m; r += 32) {
       const int map = row0 + r;
       bool fit = s_ok[wid][r] != 0;
       if (fit) {
+        const int4 cd = __ldg(reinterpret_cast<const int4*>(cand) + map);
+        const int ct[4] = {cd.x, cd.y, cd.z, cd.w};
 #pragma unroll
-        for (int q = 0; q < XW_MAX_CAND; ++q) {
-          const int tok = cand[(size_t)map * XW_MAX_CAND + q];
-          if (tok >= 0) {
-            const int tr = tok / w, tc_ = tok - tr * w;
+        for (int q = 0; q < XW_MAX_CAND; ++q)
+          if (ct[q] >= 0) {
+            const int tr = ct[q] / w, tc_ = ct[q] - tr * w;
             fit = fit && abs(tr - med_r) <= XW_SLACK && abs(tc_ - med_c) <= XW_SLACK;
           }
-        }
       }
       stat[map] = fit ? 0 : 1;
       n_fit += fit ? 1 : 0;
@@ -186,16 +221,20 @@ xw_plan_kernel(XwCells cells, const float* __restrict__ desc_norm, int n_groups,
 }
 
 int launch_xw_plan(const XwCells& cells, const float* desc_norm, int n_groups, const dinotrk_geom& g, const XwChunk& xc,
-                   cudaStream_t st) {
+                   cudaStream_t st, int n_maps) {
+  static_assert(XW_MAX_CAND == 4, "candidates are read as one int4");
   const int n_tiles = cdiv(g.h * g.w, CORR_TILE);
   DTK_CHECK_ARG(n_tiles <= 64, "exact-window path: token grid too large (%d tiles)", n_tiles);
   DTK_CHECK_ARG(cells.max_m <= XW_MAX_CELL, "exact-window path: cell of %d rows", cells.max_m);
-  if (cells.n_cells <= 0) return DINOTRK_OK;
-  int grid = cdiv(cells.n_cells, PLAN_WARPS);
-  if (grid > 148 * 8) grid = 148 * 8;
+  if (cells.n_cells <= 0 || n_maps <= 0) return DINOTRK_OK;
   ProfRange pr(PROF_XW_PLAN, st);
-  xw_plan_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(cells, desc_norm, n_groups, n_tiles, g.w, xc.key1, xc.max2, xc.cand, xc.stat,
-                                                   xc.cell_of, xc.box_org, xc.slow_cnt);
+  int grid = cdiv(n_maps, PLAN_WARPS);
+  if (grid > 148 * 8) grid = 148 * 8;
+  xw_cand_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(n_maps, desc_norm, n_groups, n_tiles, xc.key1, xc.max2, xc.cand, xc.pinfo, xc.slow_cnt);
+  DTK_LAUNCHED();
+  grid = cdiv(cells.n_cells, PLAN_WARPS);
+  if (grid > 148 * 8) grid = 148 * 8;
+  xw_cell_kernel<<<grid, PLAN_WARPS * 32, 0, st>>>(cells, g.w, xc.cand, xc.pinfo, xc.stat, xc.cell_of, xc.box_org);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }
@@ -705,7 +744,7 @@ size_t xw_chunk_bytes(int chunk_maps, int max_cells, int n_tiles, int gcap) {
   const size_t ch = (size_t)chunk_maps;
   size_t b = 0;
   b += align_up(ch * n_tiles * 8, 256) + align_up(ch * n_tiles * 4, 256);              // key1, max2
-  b += align_up(ch * XW_MAX_CAND * 4, 256) + 3 * align_up(ch * 4, 256);                // cand, stat, cell_of, slow_list
+  b += align_up(ch * XW_MAX_CAND * 4, 256) + 4 * align_up(ch * 4, 256);                // cand, stat, pinfo, cell_of, slow_list
   b += align_up((size_t)max_cells * 8, 256);                                           // box_org
   b += align_up(ch * XW_COLS * 4, 256);                                                // xbox
   b += align_up((size_t)(gcap + 1) * 4, 256);                                          // slow_cnt

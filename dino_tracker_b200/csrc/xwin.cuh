@@ -41,6 +41,7 @@ struct XwChunk {          // device buffers of one chunk in flight (all sized fo
   unsigned long long* key1;   // [maps][n_tiles]  coarse tile maximum << 32 | (0x7fffffff - first token)
   float* max2;                // [maps][n_tiles]  second largest coarse value of the tile
   int* cand;                  // [maps][XW_MAX_CAND] candidate tokens (-1 = none)
+  int* pinfo;                 // [maps] coarse arg-max token, or -1 - token for an ambiguous map (plan scratch)
   int* stat;                  // [maps] 0: exact-window path, 1: full-map path
   int* cell_of;               // [maps] cell index
   int2* box_org;              // [cells] (first box row, first box column); x = INT_MIN: skip the cell
@@ -63,7 +64,7 @@ int launch_xw_coarse(const FeatView& fv, const void* desc_hi, int desc_rows, con
                      const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
                      int max_tiles, const XwChunk& xc, cudaStream_t st);
 int launch_xw_plan(const XwCells& cells, const float* desc_norm, int n_groups, const dinotrk_geom& g, const XwChunk& xc,
-                   cudaStream_t st);
+                   cudaStream_t st, int n_maps);
 int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_hi, const void* desc_lo, int desc_rows,
                    const XwCells& cells, const XwChunk& xc, cudaStream_t st);
 int launch_xw_head(const FeatView& fv, const dinotrk_geom& g, const dinotrk_head_weights& hw, const XwCells& cells,
