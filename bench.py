@@ -486,6 +486,7 @@ def run_b200(args):
                        "chunk_maps": args.chunk_maps, "corr_precision": args.precision, "head_kind": args.head,
                        "anchor_pipeline": path_stats["pipeline"],
                        "anchor_maps_exact_window": path_stats["exact_window"], "anchor_maps_full_map": path_stats["full_map"],
+                       "anchor_maps_full_map_by_certificate": path_stats.get("full_map_by_certificate"),
                        "exact_window_fraction": (path_stats["exact_window"] / max(path_stats["anchor_maps"], 1)
                                                  if path_stats["pipeline"] == "exact-window" else None)},
             "e2e": {"value": e2e_value, "unit": "query-points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

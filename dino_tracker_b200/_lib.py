@@ -190,9 +190,10 @@ def profile_collect():
 
 def infer_stats():
     """{anchor-phase maps, finished by the exact-window path, re-done by the full-map path, pipeline} of the last infer."""
-    a = (ctypes.c_longlong * 4)()
-    check(load().dinotrk_infer_last_stats(a, 4), "infer_last_stats")
-    return {"anchor_maps": int(a[0]), "exact_window": int(a[1]), "full_map": int(a[2]), "pipeline": "exact-window" if a[3] else "full-map"}
+    a = (ctypes.c_longlong * 5)()
+    check(load().dinotrk_infer_last_stats(a, 5), "infer_last_stats")
+    return {"anchor_maps": int(a[0]), "exact_window": int(a[1]), "full_map": int(a[2]), "pipeline": "exact-window" if a[3] else "full-map",
+            "full_map_by_certificate": int(a[4])}
 
 
 def launch_count():

@@ -148,6 +148,70 @@ __global__ void sample_anchor_kernel(const float* __restrict__ tpc, int T, int C
   if (threadIdx.x == 0) out_index[j] = (n * T + a) * T + i;
 }
 
+// The descriptor of work item (n, i, a) -- trajectory point traj[n][i] sampled from the frame set [a, i0..e-1] at slot
+// i - i0 + 1 -- does not depend on the anchor frame a unless the fp32 round trip of the slot index (utils.py:96-99) leaks
+// weight onto slot 0.  So every (n, i) is sampled ONCE (fp16 hi / lo halves + norm, what the tensor-path GEMMs consume) and
+// flagged if slot 0 takes part; per chunk, unflagged items are row copies, flagged ones are sampled as before.
+__global__ void sample_unique_kernel(const float* __restrict__ tpc, int T, int C, int P, int h, int w, PointAffine pa,
+                                     const float* __restrict__ traj, int frame_batch, __half* __restrict__ u_hi,
+                                     __half* __restrict__ u_lo, float* __restrict__ u_norm, int* __restrict__ u_flag) {
+  const int u = blockIdx.x;                 // n * T + i
+  const int i = u % T;
+  const int i0 = (i / frame_batch) * frame_batch, e = min(i0 + frame_batch, T);
+  const float* pt = traj + (size_t)u * 3;
+  float x = __fadd_rn(__fmul_rn(pa.aw, pt[0]), pa.bw);
+  float y = __fadd_rn(__fmul_rn(pa.ah, pt[1]), pa.bh);
+  TriCorners c = tri_setup(x, y, (float)(i - i0 + 1), e - i0 + 1, h, w);
+  bool slot0 = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) slot0 = slot0 || (c.z0 == 0 && c.tok[k] >= 0 && c.wxy[k][0] != 0.f);
+  if (threadIdx.x == 0) u_flag[u] = slot0 ? 1 : 0;
+  if (slot0) return;                        // depends on the anchor frame: sampled per work item
+  const int f0 = i0 + c.z0 - 1;
+  const int f1 = c.z1 < 0 ? -1 : i0 + c.z1 - 1;
+  sample_point(tpc, C, P, c, f0, f1, nullptr, u_norm + u, u_hi + (size_t)u * C, u_lo + (size_t)u * C);
+}
+
+// descriptors (fp16 hi / lo + norm) and output slots of one chunk of anchor work items, from the unique samples
+__global__ void gather_anchor_kernel(const float* __restrict__ tpc, int T, int C, int P, int h, int w, PointAffine pa,
+                                     const float* __restrict__ traj, const int* __restrict__ qlist, int N,
+                                     const int* __restrict__ grp_frame, const int* __restrict__ grp_map0,
+                                     const int* __restrict__ grp_item0, int n_groups, int frame_batch,
+                                     const __half* __restrict__ u_hi, const __half* __restrict__ u_lo,
+                                     const float* __restrict__ u_norm, const int* __restrict__ u_flag,
+                                     float* __restrict__ dnorm, int* __restrict__ out_index, __half* __restrict__ desc_hi,
+                                     __half* __restrict__ desc_lo) {
+  const int j = blockIdx.x;
+  int lo = 0, hi = n_groups - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (grp_map0[mid] <= j) lo = mid; else hi = mid - 1;
+  }
+  const int a = grp_frame[lo];
+  const int uu = grp_item0[lo] + (j - grp_map0[lo]);
+  const int slot = uu / T, i = uu - slot * T;
+  const int n = qlist[(size_t)a * N + slot];
+  const size_t u = (size_t)n * T + i;
+  if (threadIdx.x == 0) out_index[j] = (n * T + a) * T + i;
+  if (!u_flag[u]) {
+    const uint4* sh = reinterpret_cast<const uint4*>(u_hi + u * C);
+    const uint4* sl = reinterpret_cast<const uint4*>(u_lo + u * C);
+    uint4* dh = reinterpret_cast<uint4*>(desc_hi + (size_t)j * C);
+    uint4* dl = reinterpret_cast<uint4*>(desc_lo + (size_t)j * C);
+    for (int k = threadIdx.x; k < C / 8; k += blockDim.x) { dh[k] = __ldg(sh + k); dl[k] = __ldg(sl + k); }
+    if (threadIdx.x == 0) dnorm[j] = u_norm[u];
+    return;
+  }
+  const int i0 = (i / frame_batch) * frame_batch, e = min(i0 + frame_batch, T);
+  const float* pt = traj + u * 3;
+  float x = __fadd_rn(__fmul_rn(pa.aw, pt[0]), pa.bw);
+  float y = __fadd_rn(__fmul_rn(pa.ah, pt[1]), pa.bh);
+  TriCorners c = tri_setup(x, y, (float)(i - i0 + 1), e - i0 + 1, h, w);
+  int f0 = c.z0 == 0 ? a : i0 + c.z0 - 1;
+  int f1 = c.z1 < 0 ? -1 : (c.z1 == 0 ? a : i0 + c.z1 - 1);
+  sample_point(tpc, C, P, c, f0, f1, nullptr, dnorm + j, desc_hi + (size_t)j * C, desc_lo + (size_t)j * C);
+}
+
 // ---------------------------------------------------------------------------------- phase D
 // model_inference.py:169-177.  One block per query point, one warp per column i.
 // D[a][i] = |anchors[n][a][i] - traj[n][a]| for a in A_n; med[i] = lower median over a
@@ -355,7 +419,7 @@ constexpr int XW_RING = 4;
 struct XwAsync {
   int state;                                   // 0: not created, 1: ready, -1: failed
   cudaEvent_t sample[XW_RING], done[XW_RING], freed[XW_RING];
-  int* host_cnt;                               // pinned: [XW_RING] queue totals + [16] phase-A uncertified counts
+  int* host_cnt;                               // pinned: [XW_RING][2] queue totals / uncertified + [16] phase-A uncertified counts
 };
 static XwAsync* xw_async() {
   static PerDev<XwAsync> slots;
@@ -367,13 +431,13 @@ static XwAsync* xw_async() {
       if (cudaEventCreateWithFlags(&xa.done[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&xa.freed[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
-    if (cudaHostAlloc(&xa.host_cnt, (XW_RING + 16) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&xa.host_cnt, (2 * XW_RING + 16) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) return nullptr;
     xa.state = 1;
   }
   return xa.state == 1 ? &xa : nullptr;
 }
 static int g_xw_path = -1;                     // -1: automatic (DTK_XW or on), 0: full-map path only, 1: exact-window path
-static long long g_infer_stats[4] = {0, 0, 0, 0};   // anchor-phase maps | of them on the exact-window path | queued | path used
+static long long g_infer_stats[5] = {0, 0, 0, 0, 0};   // anchor-phase maps | on the exact-window path | queued | path used | queued by the certificate
 
 }  // namespace dtk
 
@@ -388,8 +452,8 @@ int dinotrk_infer_set_path(int path) {
 }
 
 int dinotrk_infer_last_stats(long long* out, int n) {
-  DTK_CHECK_ARG(out && n >= 4, "infer_last_stats: need 4 slots");
-  for (int i = 0; i < 4; ++i) out[i] = g_infer_stats[i];
+  DTK_CHECK_ARG(out && n >= 4, "infer_last_stats: need at least 4 slots");
+  for (int i = 0; i < (n < 5 ? n : 5); ++i) out[i] = g_infer_stats[i];
   return DINOTRK_OK;
 }
 
@@ -491,9 +555,10 @@ size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N,
   const int nb = (T + XW_MAX_CELL - 1) / XW_MAX_CELL;
   const size_t max_cells_chunk = chx + 2;                                  // cells have >= 1 row
   size_t x = 0;
-  x += align_up(chx * C * 4, 256) + align_up(chx * 4, 256) + corr_tc_workspace_bytes((int)chx, C) + 256 + align_up(chx * 4, 256);
-  x += xw_chunk_bytes((int)chx, (int)max_cells_chunk, cdiv(g->h * g->w, CORR_TILE), gcap);
+  x += align_up(chx * 4, 256) + corr_tc_workspace_bytes((int)chx, C) + 256 + align_up(chx * 4, 256);   // norms, hi / lo, out_index
+  x += xw_chunk_bytes((int)chx, (int)max_cells_chunk, cdiv(g->h * g->w, XW_TILE), gcap);
   b += XW_RING * x;
+  b += 2 * align_up((size_t)N * T * C * 2, 256) + 2 * align_up((size_t)N * T * 4, 256);   // unique descriptors (hi, lo, norm, flag)
   b += align_up((size_t)N * T * nb * 16 + 64, 256);                         // cells of all chunks
   b += align_up(infer_max_chunks(T, N, ch) * (gcap + 1) * 4, 256);         // coarse tile prefixes per chunk
   b += align_up((size_t)4 * gcap * 4, 256) + align_up(64 * 4, 256);        // compact group arrays, phase-A counters
@@ -586,10 +651,13 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   int* d_groups = ar.take<int>(max_chunks * 5 * gcap);
   int* d_cnt = ar.take<int>(T);
   int* d_qlist = ar.take<int>((size_t)T * N);
-  struct XwSet { float* desc; float* norm; float* split; int* out_index; XwChunk xc; } xr[XW_RING];
-  const int n_tiles_map = cdiv(P, CORR_TILE);
+  struct XwSet { float* norm; float* split; int* out_index; XwChunk xc; } xr[XW_RING];
+  const int n_tiles_map = cdiv(P, XW_TILE);     // coarse keys per map
+  __half* u_hi = ar.take<__half>((size_t)N * T * C);
+  __half* u_lo = ar.take<__half>((size_t)N * T * C);
+  float* u_norm = ar.take<float>((size_t)N * T);
+  int* u_flag = ar.take<int>((size_t)N * T);
   for (int k = 0; k < XW_RING; ++k) {
-    xr[k].desc = ar.take<float>((size_t)ch * C);
     xr[k].norm = ar.take<float>(ch);
     xr[k].split = ar.take<float>(corr_tc_workspace_bytes(ch, C) / 4);
     xr[k].out_index = ar.take<int>(ch);
@@ -603,7 +671,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
     x.slow_list = ar.take<int>(ch);
     x.box_org = ar.take<int2>((size_t)ch + 2);
     x.xbox = ar.take<float>((size_t)ch * XW_COLS);
-    x.slow_cnt = ar.take<int>(gcap + 1);
+    x.slow_cnt = ar.take<int>(gcap + 2);
   }
   const int cell_nb = (T + XW_MAX_CELL - 1) / XW_MAX_CELL;
   int* d_cells = ar.take<int>((size_t)N * T * cell_nb * 4 + 16);
@@ -699,19 +767,19 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
     XwAsync* xa = use_xw ? xw_async() : nullptr;
     if (!xa) use_xw = false;
     if (xa && n_chunks_A > 0)
-      DTK_CUDA(cudaMemcpyAsync(xa->host_cnt + XW_RING, d_cntA, (size_t)n_chunks_A * sizeof(int), cudaMemcpyDeviceToHost, st));
+      DTK_CUDA(cudaMemcpyAsync(xa->host_cnt + 2 * XW_RING, d_cntA, (size_t)n_chunks_A * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTK_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTK_CUDA(cudaStreamSynchronize(st));  // the one host sync: sizes of the anchor work lists
     if (use_xw && pathsel < 0 && n_chunks_A > 0) {
       // head weights the certificate cannot handle send (almost) every map to the full-map kernels anyway: the trajectory
       // phase just showed it; skip the exact-window attempt then.  (Depends on the weights and the video only.)
       long long unc = 0;
-      for (int k = 0; k < n_chunks_A; ++k) unc += xa->host_cnt[XW_RING + k];
+      for (int k = 0; k < n_chunks_A; ++k) unc += xa->host_cnt[2 * XW_RING + k];
       if (unc * 4 > maps_A) use_xw = false;
     }
     long long maps_C = 0;
     for (int a = 0; a < T; ++a) maps_C += (long long)cnt[a] * T;
-    g_infer_stats[0] = maps_C; g_infer_stats[1] = 0; g_infer_stats[2] = 0; g_infer_stats[3] = use_xw ? 1 : 0;
+    g_infer_stats[0] = maps_C; g_infer_stats[1] = 0; g_infer_stats[2] = 0; g_infer_stats[3] = use_xw ? 1 : 0; g_infer_stats[4] = 0;
     if (use_xw) {
       plan_chunks(1, T, N, cnt.data(), ch, gcap, metas, plan_host, T);
       int rc = upload_plan();
@@ -744,9 +812,9 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
         if (ovl && k >= XW_RING) DTK_CUDA(cudaStreamWaitEvent(sb, xa->freed[k % XW_RING], 0));   // chunk k - 4 is through
         {
           ProfRange pr(PROF_SAMPLE, sb);
-          sample_anchor_kernel<<<cm.used, SAMPLE_THREADS, 0, sb>>>(tpc, T, C, P, g->h, g->w, pa, traj, d_qlist, N, gp.f, gp.map0,
-                                                                  gp.item, cm.n_groups, fb, x.desc, x.norm, x.out_index,
-                                                                  reinterpret_cast<__half*>(hi_of(x, cm.used)),
+          gather_anchor_kernel<<<cm.used, SAMPLE_THREADS, 0, sb>>>(tpc, T, C, P, g->h, g->w, pa, traj, d_qlist, N, gp.f, gp.map0,
+                                                                  gp.item, cm.n_groups, fb, u_hi, u_lo, u_norm, u_flag, x.norm,
+                                                                  x.out_index, reinterpret_cast<__half*>(hi_of(x, cm.used)),
                                                                   reinterpret_cast<__half*>(lo_of(x, cm.used)));
           DTK_LAUNCHED();
         }
@@ -757,7 +825,8 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
       // tokens -> head kernels of head.cu, on buffer set cb[0]
       auto finish = [&](size_t j) -> int {
         DTK_CUDA(cudaEventSynchronize(xa->done[j % XW_RING]));
-        const int n_slow = xa->host_cnt[j % XW_RING];
+        const int n_slow = xa->host_cnt[2 * (j % XW_RING)];
+        g_infer_stats[4] += xa->host_cnt[2 * (j % XW_RING) + 1];
         const ChunkMeta& cm = metas[j];
         const XwSet& x = xr[j % XW_RING];
         const Grp gp = grp_of(j);
@@ -767,7 +836,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
           const ChunkBufs& b = cb[0];
           char* c_hi = reinterpret_cast<char*>(b.split);
           char* c_lo = c_hi + align_up((size_t)n_slow * C * 2, 256);
-          int rc2 = launch_xw_compact(x.desc, hi_of(x, cm.used), lo_of(x, cm.used), x.norm, x.out_index, C, gp.f, gp.map0, cm.n_groups,
+          int rc2 = launch_xw_compact(nullptr, hi_of(x, cm.used), lo_of(x, cm.used), x.norm, x.out_index, C, gp.f, gp.map0, cm.n_groups,
                                       n_slow, x.xc, b.desc, c_hi, c_lo, b.norm, out_index_ring[0], d_cgrp, gcap, st);
           if (rc2) return rc2;
           CorrAssist as;
@@ -782,6 +851,15 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
         DTK_CUDA(cudaEventRecord(xa->freed[j % XW_RING], st));
         return DINOTRK_OK;
       };
+      {   // every (query, source frame) descriptor once; the per-chunk kernels copy rows
+        ProfRange pr(PROF_SAMPLE, st);
+        sample_unique_kernel<<<N * T, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, traj, fb, u_hi, u_lo, u_norm, u_flag);
+        DTK_LAUNCHED();
+      }
+      if (ovl) {   // (the fork above was recorded before this launch: make the sampling stream wait for it)
+        DTK_CUDA(cudaEventRecord(ia->fork, st));
+        DTK_CUDA(cudaStreamWaitEvent(sb, ia->fork, 0));
+      }
       if (!metas.empty() && (rc = enqueue_sample_x(0))) return rc;
       for (size_t k = 0; k < metas.size(); ++k) {
         const ChunkMeta& cm = metas[k];
@@ -795,7 +873,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
         if ((rc = launch_xw_gemm(fv, *g, hi_of(x, cm.used), lo_of(x, cm.used), cm.used, cells, x.xc, st))) return rc;
         if ((rc = launch_xw_head(fv, *g, *hw, cells, x.norm, gp.map0, cm.used, x.out_index, anchors, 2, 0, x.xc, st, cm.n_groups)))
           return rc;
-        DTK_CUDA(cudaMemcpyAsync(xa->host_cnt + (k % XW_RING), x.xc.slow_cnt + cm.n_groups, sizeof(int), cudaMemcpyDeviceToHost, st));
+        DTK_CUDA(cudaMemcpyAsync(xa->host_cnt + 2 * (k % XW_RING), x.xc.slow_cnt + cm.n_groups, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         DTK_CUDA(cudaEventRecord(xa->done[k % XW_RING], st));
         if (k + 1 < metas.size() && (rc = enqueue_sample_x(k + 1))) return rc;
         if (k >= 2 && (rc = finish(k - 2))) return rc;

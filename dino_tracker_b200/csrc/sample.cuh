@@ -9,7 +9,7 @@ namespace dtk {
 constexpr int SAMPLE_THREADS = 128;
 
 // All SAMPLE_THREADS threads of the block call this with identical arguments.
-// out[C] = sum over the (up to) 8 in-bounds corners, accumulated in ATen's order; norm_out (optional)
+// out[C] (optional) = sum over the (up to) 8 in-bounds corners, accumulated in ATen's order; norm_out (optional)
 // receives |out|_2 (source_embeddings.norm(dim=1), models/tracker.py:164).  Corners whose weight is exactly 0 are not
 // read (x + 0 * v = x for finite v: same value).  out_hi / out_lo (optional, [C] fp16 each) receive the split
 // out = hi + lo that the tensor-core correlation GEMM consumes (same rounding as split_f16_kernel).
@@ -40,7 +40,7 @@ __device__ __forceinline__ void sample_point(const float* __restrict__ tpc, int 
         acc.z = fmaf(v.z, wts[k], acc.z); acc.w = fmaf(v.w, wts[k], acc.w);
       }
     }
-    reinterpret_cast<float4*>(out)[i] = acc;
+    if (out != nullptr) reinterpret_cast<float4*>(out)[i] = acc;
     if (out_hi != nullptr) {
       __half h0 = __float2half_rn(acc.x), h1 = __float2half_rn(acc.y), h2 = __float2half_rn(acc.z), h3 = __float2half_rn(acc.w);
       __half l0 = __float2half_rn(acc.x - __half2float(h0)), l1 = __float2half_rn(acc.y - __half2float(h1));

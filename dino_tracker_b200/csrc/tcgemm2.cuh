@@ -103,8 +103,11 @@ struct Tc2Cfg {
 };
 
 // pb.tile_start: prefix of ceil(m / 256) per group.  Same Epi contract as tc_gemm_kernel.
-template <TcMode MODE, class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+// EPI_WARPS = 4: warps 2..5 own one TMEM lane quadrant each (all 256 columns of a tile); EPI_WARPS = 8 (direct epilogues only):
+// two warps per quadrant, each covering 128 columns -- the epilogue functor then sees "tiles" of 128 columns
+// (tile_end's n_tile index = 2 * (n0 / 256) + half).  Launch with 64 + 32 * EPI_WARPS threads.
+template <TcMode MODE, class Epi, int EPI_WARPS = 4>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcProblem pb,
                 Epi epi) {
@@ -122,6 +125,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* epi_scratch = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
   static_assert(!EpiCoalesced<Epi>::value || Base::kOps == 1, "coalesced epilogues need the scratch of the single-pass modes");
+  static_assert(EPI_WARPS == 4 || (EPI_WARPS == 8 && !EpiCoalesced<Epi>::value), "8 epilogue warps: direct epilogues only");
+  constexpr int EPI_COLS = BN / (EPI_WARPS / 4);   // columns of a tile one epilogue warp covers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc::cluster_ctarank();
@@ -135,7 +140,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     tc::prefetch_tmap(&tmA_hi); tc::prefetch_tmap(&tmB_hi);
     if (Base::kOps == 2) { tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_lo); }
     for (int s = 0; s < Cfg::kStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], 8); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&tfull[b], 1); tc::mbar_init(&tempty[b], 2 * EPI_WARPS); }
     tc::mbar_fence_init();
   }
   tc::cluster_sync_all();                       // barrier inits visible cluster-wide before any remote use
@@ -219,6 +224,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } else if (warp >= 2) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
     const int quad = warp & 3;
+    const int chalf = ((warp - 2) >> 2) * EPI_COLS;   // first column of this warp's share of the tile
     int it = 0;
     const uint32_t tempty_leader0 = tc::mapa(tc::smem_u32(&tempty[0]), 0), tempty_leader1 = tc::mapa(tc::smem_u32(&tempty[1]), 0);
     for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
@@ -231,10 +237,11 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       epi.tile_begin(est);
       tc::mbar_wait(&tfull[buf], aphase);
       tc::fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN + chalf;
       // column blocks of 32; the TMEM load of the next block is in flight while this one is consumed (the epilogue warps
       // have their scheduler to themselves, so nothing else hides that latency)
-      auto consume = [&](const uint32_t (&v)[32], int c) {
+      auto consume = [&](const uint32_t (&v)[32], int cc) {
+        const int c = chalf + cc;
         const int ncols = min(32, pb.N - (n0 + c));
         if constexpr (EpiCoalesced<Epi>::value) {
           if (!epi.direct(n0 + c)) {
@@ -271,16 +278,16 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         uint32_t va[32], vb[32];
         tc::tmem_ld32(taddr, va);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
+        for (int c = 0; c < EPI_COLS; c += 64) {
           tc::tmem_ld_wait();
           tc::tmem_ld32(taddr + c + 32, vb);
           consume(va, c);
           tc::tmem_ld_wait();
-          if (c + 64 < BN) tc::tmem_ld32(taddr + c + 64, va);
+          if (c + 64 < EPI_COLS) tc::tmem_ld32(taddr + c + 64, va);
           consume(vb, c + 32);
         }
       }
-      if (row_ok) epi.tile_end(est, g, r, n0 / BN);
+      if (row_ok) epi.tile_end(est, g, r, (n0 + chalf) / EPI_COLS);
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);

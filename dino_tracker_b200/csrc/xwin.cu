@@ -35,6 +35,7 @@ struct CoarseEpi {
     s.dn = -1.f;
   }
   __device__ __forceinline__ void tile_end(State& s, int g, int r, int nt) const {
+    if (nt >= n_tiles) return;   // second half of the last GEMM tile lies completely past the end of the map
     float m1 = s.m1[0], m2 = s.m2[0];
     int tok = s.tok[0];
 #pragma unroll
@@ -76,12 +77,12 @@ int launch_xw_coarse(const FeatView& fv, const void* desc_hi, int desc_rows, con
                      int max_tiles, const XwChunk& xc, cudaStream_t st) {
   using Cfg = Tc2Cfg<TcMode::F16>;
   using Base = TcCfg<TcMode::F16, TC2_BN>;
-  static_assert(TC2_BN == CORR_TILE, "coarse keys are per 256-token tile");
+  static_assert(TC2_BN == 2 * XW_TILE, "coarse keys are per half GEMM tile (8 epilogue warps)");
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_2d(&tmA, desc_hi, desc_rows, fv.C, 128, Base::kBK, TMAP_F16))) return rc;
   if ((rc = make_tmap_3d(&tmB, fv.hi, fv.T, fv.P, fv.C, TC2_BN / 2, Base::kBK, TMAP_F16))) return rc;
-  auto kern = tc_gemm2_kernel<TcMode::F16, CoarseEpi>;
+  auto kern = tc_gemm2_kernel<TcMode::F16, CoarseEpi, 8>;
   static PerDev<bool> attr_dev;
   bool& attr = attr_dev.get();
   if (!attr) {
@@ -89,7 +90,7 @@ int launch_xw_coarse(const FeatView& fv, const void* desc_hi, int desc_rows, con
     attr = true;
   }
   TcProblem pb{grp_frame, grp_row0, grp_m, tile_start, n_groups, fv.P, fv.C};
-  CoarseEpi epi{fv.norms, desc_norm, grp_frame, grp_row0, grp_map0, xc.key1, xc.max2, cdiv(fv.P, CORR_TILE), fv.P};
+  CoarseEpi epi{fv.norms, desc_norm, grp_frame, grp_row0, grp_map0, xc.key1, xc.max2, cdiv(fv.P, XW_TILE), fv.P};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -97,7 +98,7 @@ int launch_xw_coarse(const FeatView& fv, const void* desc_hi, int desc_rows, con
   int grid = 2 * (tiles_bound < sms / 2 ? tiles_bound : sms / 2);
   if (grid < 2) grid = 2;
   ProfRange pr(PROF_XW_COARSE, st);
-  kern<<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmA, tmB, tmB, pb, epi);
+  kern<<<grid, 64 + 32 * 8, Cfg::kSmem, st>>>(tmA, tmA, tmB, tmB, pb, epi);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }
@@ -114,8 +115,8 @@ xw_cand_kernel(int n_maps, const float* __restrict__ desc_norm, int n_groups, in
                const float* __restrict__ max2, int* __restrict__ cand, int* __restrict__ pinfo, int* __restrict__ slow_cnt) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * PLAN_WARPS + (threadIdx.x >> 5), nw = gridDim.x * PLAN_WARPS;
-  if (gw == 0)   // zero the queue counters of this chunk (n_groups per-group counts + the total)
-    for (int i = lane; i <= n_groups; i += 32) slow_cnt[i] = 0;
+  if (gw == 0)   // zero the queue counters of this chunk (n_groups per-group counts + the total + the uncertified count)
+    for (int i = lane; i <= n_groups + 1; i += 32) slow_cnt[i] = 0;
   for (int map = gw; map < n_maps; map += nw) {
     const unsigned long long* k1 = key1 + (size_t)map * n_tiles;
     const float* k2 = max2 + (size_t)map * n_tiles;
@@ -223,7 +224,7 @@ xw_cell_kernel(XwCells cells, int w, const int* __restrict__ cand, const int* __
 int launch_xw_plan(const XwCells& cells, const float* desc_norm, int n_groups, const dinotrk_geom& g, const XwChunk& xc,
                    cudaStream_t st, int n_maps) {
   static_assert(XW_MAX_CAND == 4, "candidates are read as one int4");
-  const int n_tiles = cdiv(g.h * g.w, CORR_TILE);
+  const int n_tiles = cdiv(g.h * g.w, XW_TILE);
   DTK_CHECK_ARG(n_tiles <= 64, "exact-window path: token grid too large (%d tiles)", n_tiles);
   DTK_CHECK_ARG(cells.max_m <= XW_MAX_CELL, "exact-window path: cell of %d rows", cells.max_m);
   if (cells.n_cells <= 0 || n_maps <= 0) return DINOTRK_OK;
@@ -463,9 +464,9 @@ int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_h
 // and either the track point or a place in the group's full-map queue.
 constexpr int XH_WARPS = 8;
 constexpr int XH_MP = 17;      // input window pitch
-constexpr int XH_HP = 12;      // hidden window [position][8 channels], 12-float pitch (conflict-free float4 reads)
+constexpr int XH_HP = 8;       // hidden window [position][8 channels]: the 4 row groups of a warp hit disjoint bank octets
 constexpr int XWM = 15, XWH = 13, XWB = 11;
-constexpr int XH_W2 = 160, XH_MWIN = 256, XH_PER_WARP = XH_MWIN + 2032;    // floats (XWM * XH_MP = 255, XWH^2 * XH_HP = 2028)
+constexpr int XH_W2 = 0, XH_MWIN = 256, XH_PER_WARP = XH_MWIN + 1352;      // floats (XWM * XH_MP = 255, XWH^2 * XH_HP = 1352)
 constexpr int XH_SMEM = (XH_W2 + XH_WARPS * XH_PER_WARP) * 4;
 
 struct XhParams {
@@ -476,6 +477,141 @@ struct XhParams {
   float P1[16], P2[16];
 };
 
+// Window, refiner and softmax sums of one map (one warp).  INTERIOR: the 15 x 15 window lies inside the token grid (no
+// zero padding anywhere: the per-position bounds tests drop out -- the common case away from the frame border).
+template <bool INTERIOR>
+__device__ __forceinline__ void xw_refine(const XhParams& hp, const dinotrk_head_weights& wts, float* __restrict__ mm,
+                                          float* __restrict__ hh_, const float* __restrict__ xr, const float* __restrict__ fn,
+                                          float dn, int2 org, int arow, int acol, int lane, float& mout, float& zmax,
+                                          float (&tot)[5]) {
+  const int h = hp.h, w = hp.w;
+  const int c8 = lane & 7, pg = lane >> 3;
+  // ---- exact input window (15 x 15, zero outside the map) + exact part of m_out ----
+#pragma unroll
+  for (int q = 0; q < (XWM * 16 + 31) / 32; ++q) {
+    const int i = lane + 32 * q;
+    const int y = i >> 4, x = i & 15;
+    const int r = arow - 7 + y, c = acol - 7 + x;
+    float v = 0.f;
+    if (y < XWM && x < XWM && (INTERIOR || (r >= 0 && r < h && c >= 0 && c < w))) {
+      const int tok = r * w + c;
+      v = fmaxf(__fdiv_rn(__ldg(xr + xw_col(r - org.x, c - org.y)), fmaxf(__fmul_rn(dn, __ldg(fn + tok)), 1e-8f)), 0.f);
+      if (!(abs(r - arow) <= 3 && abs(c - acol) <= 3)) mout = fmaxf(mout, v);
+    }
+    if (y < XWM && x < XWM) mm[y * XH_MP + x] = v;
+  }
+  __syncwarp();
+  // ---- refiner.  Lane = (channel c8 of the current half of 8, row group pg).  Hidden layer: the lane's channel on the
+  // rows pg, pg + 4, ... of the 13 x 13 window, a 3 x 3 input window sliding along the row (weights in registers), stored
+  // [position][8 channels].  Output layer: the SAME lane layout -- the lane accumulates its channel's contribution to
+  // the logits of box rows pg, pg + 4, pg + 8 (again sliding along the row: 3 new shared-memory words per 9 FMAs), both
+  // halves into the same accumulators; the 8 channel lanes of a row group are then summed by shuffles.  (Thread = pixel
+  // with float4 reads of [position][channel] costs 4x the shared-memory wavefronts, which is what bounds this kernel.)
+  float acc[3 * XWB];
+#pragma unroll
+  for (int q = 0; q < 3 * XWB; ++q) acc[q] = 0.f;
+#pragma unroll 1
+  for (int hf = 0; hf < 2; ++hf) {
+    const int ch = hf * 8 + c8;
+    {
+      float w1r[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w1r[k] = wts.w1[ch][k];
+      const float b1r = wts.b1[ch];
+      for (int y = pg; y < XWH; y += 4) {
+        const int r = arow - 6 + y;
+        const bool row_in = r >= 0 && r < h;
+        const float* m0 = mm + y * XH_MP;
+        float i00 = m0[0], i01 = m0[1], i10 = m0[XH_MP], i11 = m0[XH_MP + 1], i20 = m0[2 * XH_MP], i21 = m0[2 * XH_MP + 1];
+#pragma unroll
+        for (int x = 0; x < XWH; ++x) {
+          const float i02 = m0[x + 2], i12 = m0[XH_MP + x + 2], i22 = m0[2 * XH_MP + x + 2];
+          float a = b1r;
+          a = fmaf(w1r[0], i00, a); a = fmaf(w1r[1], i01, a); a = fmaf(w1r[2], i02, a);
+          a = fmaf(w1r[3], i10, a); a = fmaf(w1r[4], i11, a); a = fmaf(w1r[5], i12, a);
+          a = fmaf(w1r[6], i20, a); a = fmaf(w1r[7], i21, a); a = fmaf(w1r[8], i22, a);
+          const int c = acol - 6 + x;
+          hh_[(y * XWH + x) * XH_HP + c8] = (INTERIOR || (row_in && c >= 0 && c < w)) ? fmaxf(a, 0.f) : 0.f;
+          i00 = i01; i01 = i02; i10 = i11; i11 = i12; i20 = i21; i21 = i22;
+        }
+      }
+    }
+    __syncwarp();
+    {
+      float w2r[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) w2r[k] = wts.w2[ch][k];
+#pragma unroll
+      for (int yi = 0; yi < 3; ++yi) {
+        const int y = pg + 4 * yi;
+        if (y < XWB) {
+          const float* h0 = hh_ + (y * XWH) * XH_HP + c8;
+          float i00 = h0[0], i01 = h0[XH_HP], i10 = h0[XWH * XH_HP], i11 = h0[(XWH + 1) * XH_HP];
+          float i20 = h0[2 * XWH * XH_HP], i21 = h0[(2 * XWH + 1) * XH_HP];
+#pragma unroll
+          for (int x = 0; x < XWB; ++x) {
+            const float i02 = h0[(x + 2) * XH_HP], i12 = h0[(XWH + x + 2) * XH_HP], i22 = h0[(2 * XWH + x + 2) * XH_HP];
+            float a = acc[yi * XWB + x];
+            a = fmaf(w2r[0], i00, a); a = fmaf(w2r[1], i01, a); a = fmaf(w2r[2], i02, a);
+            a = fmaf(w2r[3], i10, a); a = fmaf(w2r[4], i11, a); a = fmaf(w2r[5], i12, a);
+            a = fmaf(w2r[6], i20, a); a = fmaf(w2r[7], i21, a); a = fmaf(w2r[8], i22, a);
+            acc[yi * XWB + x] = a;
+            i00 = i01; i01 = i02; i10 = i11; i11 = i12; i20 = i21; i21 = i22;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // sum over the 8 channel lanes (and thereby over the 16 channels); lane c8 == x & 7 publishes pixel (y, x)
+  float* zb = mm;                                  // the input window is dead: reuse it for the 121 logits
+#pragma unroll
+  for (int yi = 0; yi < 3; ++yi) {
+    const int y = pg + 4 * yi;
+#pragma unroll
+    for (int x = 0; x < XWB; ++x) {
+      float v = acc[yi * XWB + x];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (y < XWB && c8 == (x & 7)) zb[y * XWB + x] = v + wts.b2;
+    }
+  }
+  __syncwarp();
+  // ---- softmax sums on the box / the disc (thread = box pixel) ----
+  float z[4];
+  bool valid[4], indisc[4];
+  float px[4], py[4];
+  zmax = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int p = lane + 32 * q;
+    valid[q] = false; indisc[q] = false; z[q] = -INFINITY; px[q] = py[q] = 0.f;
+    if (p < XWB * XWB) {
+      const int y = p / XWB, x = p - y * XWB;
+      const int r = arow - 5 + y, c = acol - 5 + x;
+      valid[q] = INTERIOR || (r >= 0 && r < h && c >= 0 && c < w);
+      if (valid[q]) {
+        z[q] = zb[p];
+        const int dr = (r - arow) * hp.stride_px, dc = (c - acol) * hp.stride_px;
+        indisc[q] = dr * dr + dc * dc <= hp.radius2;
+        px[q] = (float)(hp.half_patch + c * hp.stride_px);
+        py[q] = (float)(hp.half_patch + r * hp.stride_px);
+      }
+    }
+    zmax = fmaxf(zmax, z[q]);
+  }
+  zmax = warp_max(zmax);
+  mout = warp_max(mout);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float e = valid[q] ? expf(z[q] - zmax) : 0.f;
+    tot[0] += e;
+    if (indisc[q]) { tot[1] += e; tot[2] = fmaf(px[q], e, tot[2]); tot[3] = fmaf(py[q], e, tot[3]); }
+    tot[4] += valid[q] ? 1.f : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(XH_WARPS * 32, 3)
 xw_head_kernel(int n_maps, XhParams hp, dinotrk_head_weights wts, const float* __restrict__ norms,
                const float* __restrict__ desc_norm, const int* __restrict__ cell_frame, const int* __restrict__ cell_group,
@@ -483,11 +619,8 @@ xw_head_kernel(int n_maps, XhParams hp, dinotrk_head_weights wts, const float* _
                const int* __restrict__ stat, const int* __restrict__ cand, const unsigned long long* __restrict__ key1,
                const float* __restrict__ max2, const float* __restrict__ xbox, const int* __restrict__ out_index,
                float* __restrict__ out, int* __restrict__ slow_cnt, int* __restrict__ slow_list, int n_groups) {
-  extern __shared__ __align__(16) float xh_smem[];     // [w2: 160] then per warp [input window: 256 | hidden window: 2032]
-  float* sm_w2 = xh_smem;                              // [half][tap][channel % 8]
+  extern __shared__ __align__(16) float xh_smem[];     // per warp [input window: 256 | hidden window: 1352]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 2 * 9 * 8; i += blockDim.x) { const int hh = i / 72, k = (i / 8) % 9, j = i & 7; sm_w2[i] = wts.w2[hh * 8 + j][k]; }
-  __syncthreads();
   float* mm = xh_smem + XH_W2 + wid * XH_PER_WARP;
   float* hh_ = mm + XH_MWIN;
   const int h = hp.h, w = hp.w, P = hp.P;
@@ -527,104 +660,11 @@ xw_head_kernel(int n_maps, XhParams hp, dinotrk_head_weights wts, const float* _
         const float b = in_core ? __ldg(max2 + (size_t)map * hp.n_tiles + t) : __uint_as_float((unsigned)(k >> 32));
         mout = fmaxf(mout, b + XW_EPS);
       }
-      // ---- exact input window (15 x 15, zero outside the map) + exact part of m_out ----
-#pragma unroll
-      for (int q = 0; q < (XWM * 16 + 31) / 32; ++q) {
-        const int i = lane + 32 * q;
-        const int y = i >> 4, x = i & 15;
-        const int r = arow - 7 + y, c = acol - 7 + x;
-        float v = 0.f;
-        if (y < XWM && x < XWM && r >= 0 && r < h && c >= 0 && c < w) {
-          const int tok = r * w + c;
-          v = fmaxf(__fdiv_rn(__ldg(xr + xw_col(r - org.x, c - org.y)), fmaxf(__fmul_rn(dn, __ldg(fn + tok)), 1e-8f)), 0.f);
-          if (!(abs(r - arow) <= 3 && abs(c - acol) <= 3)) mout = fmaxf(mout, v);
-        }
-        if (y < XWM && x < XWM) mm[y * XH_MP + x] = v;
-      }
-      __syncwarp();
-      // ---- refiner: hidden layer in two channel halves, output layer accumulated per box pixel ----
-      float acc[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = wts.b2;
-#pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        const int ch = hf * 8 + c8;
-        float w1r[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) w1r[k] = wts.w1[ch][k];
-        const float b1r = wts.b1[ch];
-        for (int y = pg; y < XWH; y += 4) {
-          const int r = arow - 6 + y;
-          const bool row_in = r >= 0 && r < h;
-          const float* m0 = mm + y * XH_MP;
-          float i00 = m0[0], i01 = m0[1], i10 = m0[XH_MP], i11 = m0[XH_MP + 1], i20 = m0[2 * XH_MP], i21 = m0[2 * XH_MP + 1];
-#pragma unroll
-          for (int x = 0; x < XWH; ++x) {
-            const float i02 = m0[x + 2], i12 = m0[XH_MP + x + 2], i22 = m0[2 * XH_MP + x + 2];
-            float a = b1r;
-            a = fmaf(w1r[0], i00, a); a = fmaf(w1r[1], i01, a); a = fmaf(w1r[2], i02, a);
-            a = fmaf(w1r[3], i10, a); a = fmaf(w1r[4], i11, a); a = fmaf(w1r[5], i12, a);
-            a = fmaf(w1r[6], i20, a); a = fmaf(w1r[7], i21, a); a = fmaf(w1r[8], i22, a);
-            const int c = acol - 6 + x;
-            hh_[(y * XWH + x) * XH_HP + c8] = (row_in && c >= 0 && c < w) ? fmaxf(a, 0.f) : 0.f;
-            i00 = i01; i01 = i02; i10 = i11; i11 = i12; i20 = i21; i21 = i22;
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int p = lane + 32 * q;
-          if (p < XWB * XWB) {
-            const int y = p / XWB, x = p - y * XWB;
-            float a = acc[q];
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                const float* hb = hh_ + ((y + ky) * XWH + x + kx) * XH_HP;
-                const float4 h0 = *reinterpret_cast<const float4*>(hb), h1 = *reinterpret_cast<const float4*>(hb + 4);
-                const float* wb = sm_w2 + (hf * 9 + ky * 3 + kx) * 8;
-                const float4 w0 = *reinterpret_cast<const float4*>(wb), w1_ = *reinterpret_cast<const float4*>(wb + 4);
-                a = fmaf(w0.x, h0.x, a); a = fmaf(w0.y, h0.y, a); a = fmaf(w0.z, h0.z, a); a = fmaf(w0.w, h0.w, a);
-                a = fmaf(w1_.x, h1.x, a); a = fmaf(w1_.y, h1.y, a); a = fmaf(w1_.z, h1.z, a); a = fmaf(w1_.w, h1.w, a);
-              }
-            acc[q] = a;
-          }
-        }
-        __syncwarp();
-      }
-      // ---- softmax sums on the box / the disc ----
-      float z[4];
-      bool valid[4], indisc[4];
-      float px[4], py[4];
-      zmax = -INFINITY;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int p = lane + 32 * q;
-        valid[q] = false; indisc[q] = false; z[q] = -INFINITY; px[q] = py[q] = 0.f;
-        if (p < XWB * XWB) {
-          const int y = p / XWB, x = p - y * XWB;
-          const int r = arow - 5 + y, c = acol - 5 + x;
-          valid[q] = r >= 0 && r < h && c >= 0 && c < w;
-          if (valid[q]) {
-            z[q] = acc[q];
-            const int dr = (r - arow) * hp.stride_px, dc = (c - acol) * hp.stride_px;
-            indisc[q] = dr * dr + dc * dc <= hp.radius2;
-            px[q] = (float)(hp.half_patch + c * hp.stride_px);
-            py[q] = (float)(hp.half_patch + r * hp.stride_px);
-          }
-        }
-        zmax = fmaxf(zmax, z[q]);
-      }
-      zmax = warp_max(zmax);
-      mout = warp_max(mout);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float e = valid[q] ? expf(z[q] - zmax) : 0.f;
-        tot[0] += e;
-        if (indisc[q]) { tot[1] += e; tot[2] = fmaf(px[q], e, tot[2]); tot[3] = fmaf(py[q], e, tot[3]); }
-        tot[4] += valid[q] ? 1.f : 0.f;
-      }
+      // ---- window, refiner, softmax sums ----
+      if (arow >= 7 && arow + 7 < h && acol >= 7 && acol + 7 < w)
+        xw_refine<true>(hp, wts, mm, hh_, xr, fn, dn, org, arow, acol, lane, mout, zmax, tot);
+      else
+        xw_refine<false>(hp, wts, mm, hh_, xr, fn, dn, org, arow, acol, lane, mout, zmax, tot);
 #pragma unroll
       for (int q = 0; q < 5; ++q) tot[q] = warp_sum(tot[q]);
     }
@@ -652,6 +692,7 @@ xw_head_kernel(int n_maps, XhParams hp, dinotrk_head_weights wts, const float* _
         const int pos = atomicAdd(slow_cnt + g, 1);
         slow_list[grp_map0[g] + pos] = map;
         atomicAdd(slow_cnt + n_groups, 1);
+        if (!slow) atomicAdd(slow_cnt + n_groups + 1, 1);   // (statistics: queued by the certificate, not by the plan)
       }
     }
     __syncwarp();
@@ -664,7 +705,7 @@ int launch_xw_head(const FeatView& fv, const dinotrk_geom& g, const dinotrk_head
   if (n_maps <= 0) return DINOTRK_OK;
   DTK_CHECK_ARG(g.radius <= 5 * g.stride, "exact-window path: disc radius %d exceeds 5 tokens", g.radius);
   XhParams hp;
-  hp.h = g.h; hp.w = g.w; hp.P = g.h * g.w; hp.n_tiles = cdiv(hp.P, CORR_TILE);
+  hp.h = g.h; hp.w = g.w; hp.P = g.h * g.w; hp.n_tiles = cdiv(hp.P, XW_TILE);
   hp.stride_px = g.stride; hp.half_patch = g.patch / 2; hp.radius2 = g.radius * g.radius;
   hp.normW = (float)(g.W - 1); hp.normH = (float)(g.H - 1);
   hp.out_stride = out_stride; hp.out_mode = out_mode;
@@ -716,7 +757,8 @@ xw_compact_kernel(const float4* __restrict__ desc, const uint4* __restrict__ dhi
   __syncthreads();
   if (s_g < 0) return;
   const int src = slow_list[grp_map0[s_g] + s_pos];
-  for (int i = threadIdx.x; i < C / 4; i += blockDim.x) c_desc[(size_t)b * (C / 4) + i] = desc[(size_t)src * (C / 4) + i];
+  if (desc != nullptr)   // (the fp32 copy only feeds the non-tensor GEMMs)
+    for (int i = threadIdx.x; i < C / 4; i += blockDim.x) c_desc[(size_t)b * (C / 4) + i] = desc[(size_t)src * (C / 4) + i];
   if (dhi != nullptr)
     for (int i = threadIdx.x; i < C / 8; i += blockDim.x) {
       c_hi[(size_t)b * (C / 8) + i] = dhi[(size_t)src * (C / 8) + i];
@@ -747,7 +789,7 @@ size_t xw_chunk_bytes(int chunk_maps, int max_cells, int n_tiles, int gcap) {
   b += align_up(ch * XW_MAX_CAND * 4, 256) + 4 * align_up(ch * 4, 256);                // cand, stat, pinfo, cell_of, slow_list
   b += align_up((size_t)max_cells * 8, 256);                                           // box_org
   b += align_up(ch * XW_COLS * 4, 256);                                                // xbox
-  b += align_up((size_t)(gcap + 1) * 4, 256);                                          // slow_cnt
+  b += align_up((size_t)(gcap + 2) * 4, 256);                                          // slow_cnt
   return b + 2048;
 }
 

@@ -33,12 +33,13 @@ constexpr int XW_PARTS = 3, XW_PART_ROWS = 7, XW_PART_N = 160;   // 3 N-parts of
 constexpr int XW_COLS = XW_PARTS * XW_PART_N;                    // accumulator columns per map (raw dump pitch)
 constexpr int XW_MAX_CELL = 128;      // rows (source frames) per cell = UMMA M
 constexpr int XW_MAX_CAND = 4;
+constexpr int XW_TILE = 128;          // tokens per coarse key (the coarse GEMM's 8 epilogue warps cover 128 columns each)
 
 // column of box token (by, bx) in a map's accumulator row
 __host__ __device__ inline int xw_col(int by, int bx) { return (by / XW_PART_ROWS) * XW_PART_N + (by % XW_PART_ROWS) * XW_BOX + bx; }
 
 struct XwChunk {          // device buffers of one chunk in flight (all sized for chunk_maps maps)
-  unsigned long long* key1;   // [maps][n_tiles]  coarse tile maximum << 32 | (0x7fffffff - first token)
+  unsigned long long* key1;   // [maps][n_tiles]  coarse maximum of a XW_TILE-token tile << 32 | (0x7fffffff - first token)
   float* max2;                // [maps][n_tiles]  second largest coarse value of the tile
   int* cand;                  // [maps][XW_MAX_CAND] candidate tokens (-1 = none)
   int* pinfo;                 // [maps] coarse arg-max token, or -1 - token for an ambiguous map (plan scratch)
