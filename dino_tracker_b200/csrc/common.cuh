@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost nothing unless a profiler injects itself
+
 #include "dinotrk.h"
 
 namespace dtk {
@@ -64,6 +66,12 @@ struct PerDev {
     cudaGetDevice(&d);
     return v[(d >= 0 && d < DTK_MAX_DEVICES) ? d : 0];
   }
+};
+
+// NVTX range over a host-side phase (nsys / ncu --nvtx): the four phases of dinotrk_infer, the ViT and delta-DINO stages
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -247,7 +247,7 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
                      cudaStream_t st, const CorrAssist& assist) {
   if (n_groups <= 0 || total_maps <= 0) return DINOTRK_OK;
   unsigned long long* tkeys = fv.tensor() ? assist.tkeys : nullptr;
-  const int tile_rows = fv.tensor() ? corr_tc_tile_rows() : BM;   // rows per GEMM M tile (256 on CTA pairs)
+  const int tile_rows = fv.tensor() ? (assist.small_tiles ? 128 : corr_tc_tile_rows()) : BM;   // rows per GEMM M tile
   const int n_tiles = cdiv(fv.P, CORR_TILE);
   const float* tpc = fv.tpc;
   const float* norms = fv.norms;
@@ -267,7 +267,7 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
     if (fv.tensor()) {
       int rc = launch_corr_gemm_tc(fv.hi, fv.lo, norms, fv.T, C, P, desc, desc_rows, desc_norm, grp_frame, grp_row0,
                                    grp_m, grp_map0, tile_start, n_groups, max_tiles, maps, map_stride, split_ws, st, tkeys,
-                                   assist.split_ready);
+                                   assist.split_ready, tile_rows);
       if (rc) return rc;
     } else {
       static PerDev<bool> attr_dev;

@@ -31,6 +31,7 @@ struct CorrAssist {
   bool split_ready = false;
   bool no_thin = false;
   bool all_wide = false;   // no streaming kernel: groups of any size > 0 are GEMM tiles
+  bool small_tiles = false;   // tensor path: 128-row single-CTA tiles instead of 256-row CTA-pair tiles (many tiny groups)
 };
 
 size_t corr_plan_bytes(int n_groups);
@@ -46,7 +47,7 @@ int launch_corr_gemm_tc(const void* tpc_hi, const void* tpc_lo, const float* nor
                         const float* desc, int desc_rows, const float* desc_norm, const int* grp_frame,
                         const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
                         int max_tiles, float* maps, int map_stride, float* desc_split_ws, cudaStream_t st,
-                        unsigned long long* tkeys = nullptr, bool split_ready = false);
+                        unsigned long long* tkeys = nullptr, bool split_ready = false, int tile_rows = 0 /* 0: default */);
 int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st);
 
 int launch_head(const float* maps, int n_maps, int map_stride, const dinotrk_geom& g,

@@ -173,7 +173,7 @@ int launch_corr_gemm_tc(const void* tpc_hi, const void* tpc_lo, const float* nor
                         const float* desc, int desc_rows, const float* desc_norm, const int* grp_frame,
                         const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
                         int max_tiles, float* maps, int map_stride, float* desc_split_ws, cudaStream_t st,
-                        unsigned long long* tkeys, bool split_ready) {
+                        unsigned long long* tkeys, bool split_ready, int tile_rows) {
   using Cfg = TcCfg<TcMode::F16X3>;
   static_assert(TC_BN == CORR_TILE, "the tile maxima are per GEMM N tile");
   DTK_CHECK_ARG(C % 8 == 0, "corr (tensor path): C must be a multiple of 8");
@@ -181,7 +181,7 @@ int launch_corr_gemm_tc(const void* tpc_hi, const void* tpc_lo, const float* nor
   char* d_lo = d_hi + align_up((size_t)desc_rows * C * 2, 256);
   int rc = split_ready ? DINOTRK_OK : launch_split_f16(desc, d_hi, d_lo, (size_t)desc_rows * C, st);
   if (rc) return rc;
-  const bool pairs = corr_tc_tile_rows() == TC2_BM;   // tile_start was planned with this M tile
+  const bool pairs = (tile_rows > 0 ? tile_rows : corr_tc_tile_rows()) == TC2_BM;   // tile_start was planned with this M tile
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   const uint32_t b_box = pairs ? TC2_BN / 2 : TC_BN;   // a CTA of a pair stages half of the B tile
   if ((rc = make_tmap_2d(&tmA_hi, d_hi, desc_rows, C, TC_BM, Cfg::kBK, TMAP_F16))) return rc;

@@ -444,6 +444,7 @@ int dinotrk_delta_refine(const float* frames, int B, int H, int W, const int* ch
                          const float* const* bias, const float* dino_tpc, const float* ixs, const float* iys,
                          int h, int w, float* refined_tpc, float* norms, void* workspace, size_t workspace_bytes,
                          void* stream) {
+  NvtxRange nvtx_range("dinotrk.delta_refine");
   PeerOut none{};
   return delta_refine_impl(frames, B, H, W, channels, wgt, bias, dino_tpc, ixs, iys, h, w, refined_tpc, norms, workspace,
                            workspace_bytes, none, stream);
@@ -454,6 +455,7 @@ int dinotrk_delta_refine_tc(const float* frames, int B, int H, int W, const int*
                             const float* iys, int h, int w, float* refined_tpc, float* norms, void* workspace,
                             size_t workspace_bytes, float* const* peer_bases, int n_peers, size_t first_frame,
                             void* stream) {
+  NvtxRange nvtx_range("dinotrk.delta_refine");
   DTK_CHECK_ARG(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_bases), "delta_refine_tc: bad peer list");
   PeerOut po{};
   po.n = n_peers;
@@ -468,6 +470,7 @@ int dinotrk_delta_refine_allgather(const float* frames, int B, int H, int W, con
                                    int h, int w, float* refined_tpc, float* norms, void* workspace,
                                    size_t workspace_bytes, float* const* peer_bases, int n_peers, size_t first_frame,
                                    void* stream) {
+  NvtxRange nvtx_range("dinotrk.delta_refine");
   DTK_CHECK_ARG(n_peers >= 0 && n_peers <= 8 && (n_peers == 0 || peer_bases), "delta_refine_allgather: bad peer list");
   PeerOut po{};
   po.n = n_peers;

@@ -290,8 +290,10 @@ struct GroupBuf {  // host mirror of the per-chunk group arrays: [frame | row0 |
 //   kind 1 (anchors): items of anchor frame a = cnt[a] * T pairs (slot, i), a-major; descriptor rows are per chunk.
 struct ChunkMeta { int used, maxm, n_groups; bool no_thin; };
 // align: anchor-phase chunks are cut at multiples of `align` items per frame (T for the exact-window path: whole cells).
-static void plan_chunks(int kind, int T, int N, const int* cnt, int ch, int gcap, std::vector<ChunkMeta>& metas,
-                        std::vector<int>& plan_host, int align = 1) {
+// first_cap > 0: capacity of the first anchor-phase chunk only (the probe chunk of the exact-window pipeline).
+static void plan_chunks(int kind, int T, int N, const int* cnt, int ch_all, int gcap, std::vector<ChunkMeta>& metas,
+                        std::vector<int>& plan_host, int align = 1, int first_cap = 0) {
+  int ch = ch_all;
   metas.clear(); plan_host.clear();
   GroupBuf gb(gcap);
   auto commit_chunk = [&](int used, int maxm) {
@@ -321,6 +323,7 @@ static void plan_chunks(int kind, int T, int N, const int* cnt, int ch, int gcap
     while (a < T) {
       gb.clear();
       int used = 0, maxm = 0;
+      ch = (metas.empty() && first_cap > 0 && first_cap < ch_all) ? first_cap : ch_all;
       while (a < T && used < ch && gb.n < gcap) {
         long long tot = (long long)cnt[a] * T;
         long long m = tot - item;
@@ -416,6 +419,7 @@ static InferAsync* infer_async() {
 
 // events, pinned counters and selection of the exact-window pipeline (one set per device)
 constexpr int XW_RING = 4;
+constexpr int XW_PROBE_MAPS = 4096;   // size of the probe chunk (automatic pipeline choice)
 struct XwAsync {
   int state;                                   // 0: not created, 1: ready, -1: failed
   cudaEvent_t sample[XW_RING], done[XW_RING], freed[XW_RING];
@@ -561,7 +565,10 @@ size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N,
   b += 2 * align_up((size_t)N * T * C * 2, 256) + 2 * align_up((size_t)N * T * 4, 256);   // unique descriptors (hi, lo, norm, flag)
   b += align_up((size_t)N * T * nb * 16 + 64, 256);                         // cells of all chunks
   b += align_up(infer_max_chunks(T, N, ch) * (gcap + 1) * 4, 256);         // coarse tile prefixes per chunk
-  b += align_up((size_t)4 * gcap * 4, 256) + align_up(64 * 4, 256);        // compact group arrays, phase-A counters
+  {
+    const size_t sg = std::min<size_t>(infer_max_chunks(T, N, ch) * (size_t)gcap, 16384);
+    b += align_up(4 * sg * 4, 256) + align_up((sg + 1) * 4, 256) + align_up(64 * 4, 256);   // queue group arrays + tile plan, phase-A counters
+  }
   return b + 16384;
 }
 
@@ -676,7 +683,9 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   const int cell_nb = (T + XW_MAX_CELL - 1) / XW_MAX_CELL;
   int* d_cells = ar.take<int>((size_t)N * T * cell_nb * 4 + 16);
   int* d_tiles = ar.take<int>(max_chunks * (gcap + 1));
-  int* d_cgrp = ar.take<int>((size_t)4 * gcap);
+  const int sg_cap = (int)std::min<size_t>(max_chunks * (size_t)gcap, 16384);   // groups of the accumulated full-map queue
+  int* d_cgrp = ar.take<int>((size_t)4 * sg_cap);
+  int* d_splan = ar.take<int>((size_t)sg_cap + 1);
   int* d_cntA = ar.take<int>(64);
   DTK_CHECK_ARG(ar.ok(), "infer: workspace arena overflow");
   const bool tensor = fv.tensor();   // tensor-core GEMM: tile keys for the head, fp16 split fused into the samplers
@@ -701,6 +710,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   long long maps_A = 0;
   // ---- phase A: trajectories -------------------------------------------------------------------
   if (start_phase <= 0) {
+    NvtxRange nv("dinotrk.infer.A.trajectories");
     {
       ProfRange pr(PROF_SAMPLE, st);
       sample_query_kernel<<<N, SAMPLE_THREADS, 0, st>>>(tpc, T, C, P, g->h, g->w, pa, query_points, descA, normA);
@@ -742,6 +752,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
 
   // ---- phase B: cosine similarities along the trajectories --------------------------------------
   if (start_phase <= 1) {
+    NvtxRange nv("dinotrk.infer.B.cos_sims");
     int rc = dinotrk_traj_cos_sims(tpc, T, C, g, traj, query_points, N, cos_sims, nullptr, 0, stream);
     if (rc) return rc;
   }
@@ -753,6 +764,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   // (the head kernel is then launched with one CTA per SM so that it fits next to the GEMM's ~200 KB of shared memory;
   // the rare full-map head launches cannot co-reside and simply wait for the GEMM's CTAs to retire).
   if (start_phase <= 2) {
+    NvtxRange nv("dinotrk.infer.C.anchors");
     {
       ProfRange pr(PROF_ANCHOR_LIST, st);
       anchor_lists_kernel<<<T, 256, 0, st>>>(cos_sims, N, T, anchor_th, d_cnt, d_qlist);
@@ -780,10 +792,18 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
     long long maps_C = 0;
     for (int a = 0; a < T; ++a) maps_C += (long long)cnt[a] * T;
     g_infer_stats[0] = maps_C; g_infer_stats[1] = 0; g_infer_stats[2] = 0; g_infer_stats[3] = use_xw ? 1 : 0; g_infer_stats[4] = 0;
+    size_t k0 = 0;            // first chunk of the full-map pipeline (> 0 after an exact-window probe)
+    bool planned = false;
     if (use_xw) {
-      plan_chunks(1, T, N, cnt.data(), ch, gcap, metas, plan_host, T);
+      // automatic mode: the first chunk is a small probe; if the head's certificate sends more than a quarter of it to the
+      // full-map queue (refiner weights whose outside-the-box logit bound needs the exact map), the rest of the phase runs
+      // the full-map pipeline directly.  The probe is the same set of work items for every chunk size >= XW_PROBE_MAPS.
+      const bool probing = pathsel < 0;
+      const int probe_cap = std::max(T, (XW_PROBE_MAPS / T) * T);
+      plan_chunks(1, T, N, cnt.data(), ch, gcap, metas, plan_host, T, probing ? probe_cap : 0);
       int rc = upload_plan();
       if (rc) return rc;
+      planned = true;
       CellPlan cp;
       plan_cells(T, gcap, metas, plan_host, cp);
       DTK_CHECK_ARG(cp.first.back() * 4 <= (size_t)N * T * cell_nb * 4 + 16, "infer: cell plan exceeds its bound");
@@ -821,8 +841,22 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
         if (ovl) DTK_CUDA(cudaEventRecord(xa->sample[k % XW_RING], sb));
         return DINOTRK_OK;
       };
-      // full-map path for the queued maps of chunk j (host knows how many): compact -> split-precision GEMM over all
-      // tokens -> head kernels of head.cu, on buffer set cb[0]
+      // Full-map queue.  The queued maps of chunk j (the host knows how many once the chunk's head has run) are appended to
+      // ONE compact descriptor array (buffer set cb[0]); the queue is worked off -- split-precision GEMM over all tokens on
+      // 128-row tiles + the head kernels of head.cu -- when it is full and at the end of the phase.
+      int q_rows = 0, q_groups = 0;
+      auto flush = [&]() -> int {
+        if (q_rows == 0) return DINOTRK_OK;
+        const ChunkBufs& b = cb[0];
+        CorrAssist as;
+        as.tkeys = b.tkeys; as.zero_word = b.hscratch; as.split_ready = true; as.no_thin = true; as.all_wide = true; as.small_tiles = true;
+        int rc2 = launch_corr_maps(fv, nullptr, ch, b.norm, d_cgrp, d_cgrp + sg_cap, d_cgrp + 2 * sg_cap, d_cgrp + 3 * sg_cap, q_groups,
+                                   q_rows, q_rows, b.maps, ms, d_splan, b.split, st, as);
+        if (rc2) return rc2;
+        rc2 = launch_head(b.maps, q_rows, ms, *g, *hw, out_index_ring[0], anchors, 2, 0, nullptr, b.hscratch, st, b.tkeys, true);
+        q_rows = q_groups = 0;
+        return rc2;
+      };
       auto finish = [&](size_t j) -> int {
         DTK_CUDA(cudaEventSynchronize(xa->done[j % XW_RING]));
         const int n_slow = xa->host_cnt[2 * (j % XW_RING)];
@@ -833,20 +867,17 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
         DTK_CHECK_ARG(n_slow >= 0 && n_slow <= cm.used, "infer: corrupt full-map queue (%d of %d)", n_slow, cm.used);
         g_infer_stats[1] += cm.used - n_slow; g_infer_stats[2] += n_slow;
         if (n_slow > 0) {
+          if (q_rows + n_slow > ch || q_groups + cm.n_groups > sg_cap) {
+            int rc2 = flush();
+            if (rc2) return rc2;
+          }
           const ChunkBufs& b = cb[0];
           char* c_hi = reinterpret_cast<char*>(b.split);
-          char* c_lo = c_hi + align_up((size_t)n_slow * C * 2, 256);
+          char* c_lo = c_hi + align_up((size_t)ch * C * 2, 256);          // layout of a descriptor array of `ch` rows
           int rc2 = launch_xw_compact(nullptr, hi_of(x, cm.used), lo_of(x, cm.used), x.norm, x.out_index, C, gp.f, gp.map0, cm.n_groups,
-                                      n_slow, x.xc, b.desc, c_hi, c_lo, b.norm, out_index_ring[0], d_cgrp, gcap, st);
+                                      n_slow, x.xc, nullptr, c_hi, c_lo, b.norm, out_index_ring[0], d_cgrp, sg_cap, st, q_rows, q_groups);
           if (rc2) return rc2;
-          CorrAssist as;
-          as.tkeys = b.tkeys; as.zero_word = b.hscratch; as.split_ready = true; as.no_thin = true; as.all_wide = true;
-          const int mg = n_slow;   // (group sizes live on the device; with all_wide any size is a GEMM tile)
-          rc2 = launch_corr_maps(fv, b.desc, n_slow, b.norm, d_cgrp, d_cgrp + gcap, d_cgrp + 2 * gcap, d_cgrp + 3 * gcap,
-                                 cm.n_groups, n_slow, mg, b.maps, ms, b.plan, b.split, st, as);
-          if (rc2) return rc2;
-          rc2 = launch_head(b.maps, n_slow, ms, *g, *hw, out_index_ring[0], anchors, 2, 0, nullptr, b.hscratch, st, b.tkeys, true);
-          if (rc2) return rc2;
+          q_rows += n_slow; q_groups += cm.n_groups;
         }
         DTK_CUDA(cudaEventRecord(xa->freed[j % XW_RING], st));
         return DINOTRK_OK;
@@ -861,6 +892,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
         DTK_CUDA(cudaStreamWaitEvent(sb, ia->fork, 0));
       }
       if (!metas.empty() && (rc = enqueue_sample_x(0))) return rc;
+      size_t n_finished = 0, k_end = metas.size();
       for (size_t k = 0; k < metas.size(); ++k) {
         const ChunkMeta& cm = metas[k];
         const XwSet& x = xr[k % XW_RING];
@@ -875,23 +907,38 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
           return rc;
         DTK_CUDA(cudaMemcpyAsync(xa->host_cnt + 2 * (k % XW_RING), x.xc.slow_cnt + cm.n_groups, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         DTK_CUDA(cudaEventRecord(xa->done[k % XW_RING], st));
+        if (k == 0 && probing && metas.size() > 1) {   // the probe: wait for it, look at the certificate's verdicts
+          if ((rc = finish(0))) return rc;
+          n_finished = 1;
+          if (g_infer_stats[4] * 4 > (long long)cm.used) { k_end = 1; break; }
+        }
         if (k + 1 < metas.size() && (rc = enqueue_sample_x(k + 1))) return rc;
-        if (k >= 2 && (rc = finish(k - 2))) return rc;
+        while (n_finished + 2 <= k)
+          if ((rc = finish(n_finished++))) return rc;
       }
-      for (size_t j = metas.size() >= 2 ? metas.size() - 2 : 0; j < metas.size(); ++j)
-        if ((rc = finish(j))) return rc;
+      while (n_finished < k_end)
+        if ((rc = finish(n_finished++))) return rc;
+      if ((rc = flush())) return rc;
       if (ovl) {
         DTK_CUDA(cudaEventRecord(ia->join, sb));
         DTK_CUDA(cudaStreamWaitEvent(st, ia->join, 0));
       }
-      if (stop_after < 3) return DINOTRK_OK;
-      return dinotrk_occlusion(traj, cos_sims, anchors, N, T, anchor_th, cos_th, occ, stream);
+      if (k_end == metas.size()) {
+        if (stop_after < 3) return DINOTRK_OK;
+        NvtxRange nvd("dinotrk.infer.D.occlusion");
+        return dinotrk_occlusion(traj, cos_sims, anchors, N, T, anchor_th, cos_th, occ, stream);
+      }
+      k0 = k_end;                       // switched: chunks k0.. on the full-map pipeline below (same plan)
+      g_infer_stats[3] = 0;
     }
-    plan_chunks(1, T, N, cnt.data(), ch, gcap, metas, plan_host);
-    int rc = upload_plan();
-    if (rc) return rc;
+    if (!planned) {
+      plan_chunks(1, T, N, cnt.data(), ch, gcap, metas, plan_host);
+      int rc0 = upload_plan();
+      if (rc0) return rc0;
+    }
+    int rc = DINOTRK_OK;
     InferAsync* ia = infer_async();
-    const bool ovl = ia != nullptr && metas.size() > 1;
+    const bool ovl = ia != nullptr && metas.size() > k0 + 1;
     cudaStream_t sa = (ovl && ia->mode >= 2) ? ia->aux : st;    // head stream
     cudaStream_t sb = ovl ? ia->aux2 : st;   // sampling stream
     if (ovl) {
@@ -903,7 +950,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
       const ChunkMeta& cm = metas[k];
       const ChunkBufs& b = cb[k & 1];
       const Grp gp = grp_of(k);
-      if (ovl && k >= 2) DTK_CUDA(cudaStreamWaitEvent(sb, ia->gemm[k & 1], 0));   // GEMM k-2 read the descriptors of this set
+      if (ovl && k >= k0 + 2) DTK_CUDA(cudaStreamWaitEvent(sb, ia->gemm[k & 1], 0));   // GEMM k-2 read the descriptors of this set
       {
         ProfRange pr(PROF_SAMPLE, sb);
         // the split layout of launch_corr_gemm_tc for desc_rows = used: hi rows, then lo rows at the next 256-byte boundary
@@ -925,13 +972,13 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
       return launch_head(b.maps, metas[j].used, ms, *g, *hw, out_index_ring[j & 3], anchors, 2, 0, nullptr, b.hscratch, st,
                          tensor ? b.tkeys : nullptr, true, 0, 2);
     };
-    if (!metas.empty() && (rc = enqueue_sample(0))) return rc;
-    for (size_t k = 0; k < metas.size(); ++k) {
+    if (k0 < metas.size() && (rc = enqueue_sample(k0))) return rc;
+    for (size_t k = k0; k < metas.size(); ++k) {
       const ChunkMeta& cm = metas[k];
       const ChunkBufs& b = cb[k & 1];
       const Grp gp = grp_of(k);
       if (ovl) DTK_CUDA(cudaStreamWaitEvent(st, ia->sample[k & 1], 0));
-      if (k >= 2 && (rc = head_full(k - 2))) return rc;   // last reader of maps / keys / list of this buffer set
+      if (k >= k0 + 2 && (rc = head_full(k - 2))) return rc;   // last reader of maps / keys / list of this buffer set
       CorrAssist as;
       as.tkeys = tensor ? b.tkeys : nullptr; as.zero_word = b.hscratch; as.split_ready = tensor; as.no_thin = cm.no_thin;
       rc = launch_corr_maps(fv, b.desc, cm.used, b.norm, gp.f, gp.r, gp.m, gp.map0, cm.n_groups, cm.used, cm.maxm, b.maps, ms,
@@ -945,7 +992,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
       if (rc) return rc;
       if (ovl) DTK_CUDA(cudaEventRecord(ia->head[k & 1], sa));
     }
-    for (size_t j = metas.size() >= 2 ? metas.size() - 2 : 0; j < metas.size(); ++j)
+    for (size_t j = std::max(k0, metas.size() >= 2 ? metas.size() - 2 : 0); j < metas.size(); ++j)
       if ((rc = head_full(j))) return rc;
     if (ovl) {
       DTK_CUDA(cudaEventRecord(ia->join, sa));
@@ -955,6 +1002,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   if (stop_after < 3) return DINOTRK_OK;
 
   // ---- phase D: occlusion --------------------------------------------------------------------------
+  NvtxRange nvd("dinotrk.infer.D.occlusion");
   return dinotrk_occlusion(traj, cos_sims, anchors, N, T, anchor_th, cos_th, occ, stream);
 }
 

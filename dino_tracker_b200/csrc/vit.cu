@@ -477,6 +477,7 @@ int dinotrk_vit_attention(const void* q16, const void* k16, const void* vT16, in
 int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const dinotrk_vit_config* c,
                         const dinotrk_vit_weights* wt, float* out_tpc, void* workspace, size_t workspace_bytes,
                         void* stream) {
+  NvtxRange nvtx_range("dinotrk.vit_forward");
   DTK_CHECK_ARG(frames && g && c && wt && out_tpc && wt->blocks, "vit_forward: null pointer");
   const int D = c->dim, heads = c->heads, P = g->h * g->w, N1 = P + 1, Kp = vit_kp(c);
   DTK_CHECK_ARG(D == heads * HD && D % 64 == 0 && D <= 2048, "vit_forward: dim must be heads x 64 (<= 2048)");

@@ -741,21 +741,26 @@ xw_compact_kernel(const float4* __restrict__ desc, const uint4* __restrict__ dhi
                   const float* __restrict__ desc_norm, const int* __restrict__ out_index, int C, const int* __restrict__ grp_frame,
                   const int* __restrict__ grp_map0, int n_groups, const int* __restrict__ slow_cnt,
                   const int* __restrict__ slow_list, float4* __restrict__ c_desc, uint4* __restrict__ c_hi, uint4* __restrict__ c_lo,
-                  float* __restrict__ c_norm, int* __restrict__ c_out_index, int* __restrict__ cgrp, int gcap) {
+                  float* __restrict__ c_norm, int* __restrict__ c_out_index, int* __restrict__ cgrp, int gcap, int row_base,
+                  int grp_base) {
   __shared__ int s_g, s_pos;
-  const int b = blockIdx.x;
+  const int bb = blockIdx.x;
   if (threadIdx.x == 0) {
     int pre = 0, gsel = -1, psel = 0;
     for (int g = 0; g < n_groups; ++g) {
       const int c = slow_cnt[g];
-      if (b == 0) { cgrp[g] = grp_frame[g]; cgrp[gcap + g] = pre; cgrp[2 * gcap + g] = c; cgrp[3 * gcap + g] = pre; }
-      if (gsel < 0 && b < pre + c) { gsel = g; psel = b - pre; }
+      if (bb == 0) {
+        cgrp[grp_base + g] = grp_frame[g]; cgrp[gcap + grp_base + g] = row_base + pre; cgrp[2 * gcap + grp_base + g] = c;
+        cgrp[3 * gcap + grp_base + g] = row_base + pre;
+      }
+      if (gsel < 0 && bb < pre + c) { gsel = g; psel = bb - pre; }
       pre += c;
     }
     s_g = gsel; s_pos = psel;
   }
   __syncthreads();
   if (s_g < 0) return;
+  const int b = row_base + bb;
   const int src = slow_list[grp_map0[s_g] + s_pos];
   if (desc != nullptr)   // (the fp32 copy only feeds the non-tensor GEMMs)
     for (int i = threadIdx.x; i < C / 4; i += blockDim.x) c_desc[(size_t)b * (C / 4) + i] = desc[(size_t)src * (C / 4) + i];
@@ -770,14 +775,14 @@ xw_compact_kernel(const float4* __restrict__ desc, const uint4* __restrict__ dhi
 int launch_xw_compact(const float* desc, const void* desc_hi, const void* desc_lo, const float* desc_norm,
                       const int* out_index, int C, const int* grp_frame, const int* grp_map0, int n_groups, int n_slow,
                       const XwChunk& xc, float* c_desc, void* c_hi, void* c_lo, float* c_norm, int* c_out_index, int* cgrp,
-                      int gcap, cudaStream_t st) {
+                      int gcap, cudaStream_t st, int row_base, int grp_base) {
   if (n_slow <= 0) return DINOTRK_OK;
   ProfRange pr(PROF_MISC, st);
   xw_compact_kernel<<<n_slow, 128, 0, st>>>(reinterpret_cast<const float4*>(desc), reinterpret_cast<const uint4*>(desc_hi),
                                             reinterpret_cast<const uint4*>(desc_lo), desc_norm, out_index, C, grp_frame, grp_map0,
                                             n_groups, xc.slow_cnt, xc.slow_list, reinterpret_cast<float4*>(c_desc),
                                             reinterpret_cast<uint4*>(c_hi), reinterpret_cast<uint4*>(c_lo), c_norm, c_out_index, cgrp,
-                                            gcap);
+                                            gcap, row_base, grp_base);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }

@@ -71,11 +71,11 @@ int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_h
 int launch_xw_head(const FeatView& fv, const dinotrk_geom& g, const dinotrk_head_weights& hw, const XwCells& cells,
                    const float* desc_norm, const int* grp_map0, int n_maps, const int* out_index, float* out, int out_stride,
                    int out_mode, const XwChunk& xc, cudaStream_t st, int n_groups);
-// Gathers the queued maps' descriptor rows (fp32, hi, lo, norm, out_index) into compact arrays and builds their
-// group arrays ([frame | row0 | m | map0] x n_groups at cgrp).  n_slow = host copy of slow_cnt[n_groups].
+// Appends the queued maps' descriptor rows (fp32 optional, hi, lo, norm, out_index) to compact arrays at row_base and their
+// group arrays ([frame | row0 | m | map0] x gcap, entries grp_base ..) to cgrp.  n_slow = host copy of slow_cnt[n_groups].
 int launch_xw_compact(const float* desc, const void* desc_hi, const void* desc_lo, const float* desc_norm,
                       const int* out_index, int C, const int* grp_frame, const int* grp_map0, int n_groups, int n_slow,
                       const XwChunk& xc, float* c_desc, void* c_hi, void* c_lo, float* c_norm, int* c_out_index, int* cgrp,
-                      int gcap, cudaStream_t st);
+                      int gcap, cudaStream_t st, int row_base = 0, int grp_base = 0);
 
 }  // namespace dtk

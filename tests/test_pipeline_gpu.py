@@ -89,3 +89,58 @@ def test_benchmark_query_frames_in_one_call(tmp_path):
     for rank in range(2):
         seen += list(run_videos(["a", "b", "c"], [5.0, 3.0, 2.0], rank, 2, lambda v: v.upper()).items())
     assert sorted(seen) == [("a", "A"), ("b", "B"), ("c", "C")]
+
+
+def test_reference_entry_point_call_sequence_through_the_dropin(tmp_path):
+    """The exact call sequence of the reference's entry points (dino_tracker.py::get_model :86-108, inference_grid.py::run
+    :12-41, inference_benchmark.py::run :14-41) against the drop-in ``models`` package: constructor kwargs, ``.to(device)``,
+    checkpoint files + ``load_weights(iter)``, ``ModelInference(model=..., range_normalizer=..., ...)``, ``model.video.shape``,
+    ``infer(query_points=..., batch_size=...)``, ``[..., :2].cpu().detach().numpy()`` -- results against the oracle.
+    (The scripts themselves need the reference tree, its dataset folders and config files; tests/test_dropin_surface.py
+    checks by AST walk that nothing they touch is missing here.)"""
+    import os
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(ROOT, "dino_tracker_b200", "dropin"))
+    for m in [k for k in list(sys.modules) if k == "models" or k.startswith("models.")]:
+        del sys.modules[m]
+    try:
+        from models.model_inference import ModelInference          # inference_grid.py:6
+        from models.tracker import Tracker                         # dino_tracker.py (from models.tracker import Tracker)
+        device = "cuda:0"
+        geo = Geometry(H=98, W=126)
+        T, C = 5, 32
+        feats, _ = synth.shifted_field_features(T, C, geo.h, geo.w, seed=61, noise=0.15, max_shift=2)
+        video = synth.random_video(T, geo.H, geo.W, seed=62).to(device)
+        emb_path = str(tmp_path / "dino_embeddings" / "dino_embed_video.pt")
+        os.makedirs(os.path.dirname(emb_path))
+        torch.save(feats, emb_path)
+        ckpt = tmp_path / "models" / "dino_tracker"
+        os.makedirs(ckpt)
+        head = synth.head_weights("sharp", seed=61)
+        dsd = od.random_state_dict([3, 64, 128, 256, C], torch.Generator().manual_seed(63), last_std=0.01)
+        torch.save(head, ckpt / "tracker_head_100.pt")
+        torch.save(dsd, ckpt / "delta_dino_100.pt")
+        tracker_args = {"video": video, "device": device, "dino_embed_path": emb_path, "dino_patch_size": 14, "stride": 7,
+                        "ckpt_path": str(ckpt), "cyc_n_frames": 4, "cyc_batch_size_per_frame": 256,
+                        "cyc_fg_points_ratio": 0.7, "cyc_thresh": 4}
+        model = Tracker(**tracker_args).to(device)                 # dino_tracker.py:102
+        model.load_weights(100)                                    # inference_grid.py:18
+        model_inference = ModelInference(model=model, range_normalizer=model.range_normalizer,
+                                         anchor_cosine_similarity_threshold=0.7, cosine_similarity_threshold=0.6)
+        model_video_h, model_video_w = model.video.shape[-2], model.video.shape[-1]
+        assert (model_video_h, model_video_w) == (geo.H, geo.W)
+        q = synth.lattice_query_points(3, 2, geo.H, geo.W, t_q=[0, 1, 2, 3, 4, 0], margin=14.0, jitter_seed=61).to(device)
+        traj, occ = model_inference.infer(q, batch_size=None)      # inference_grid.py:38
+        t_np, o_np = traj[..., :2].cpu().detach().numpy(), occ.cpu().detach().numpy()
+        traj_b, occ_b = model_inference.infer(query_points=q, batch_size=3)   # inference_benchmark.py:38 (keyword form)
+        refined = od.refined_features(video.cpu(), feats, dsd)
+        t_ref, o_ref = oi.infer(refined, q.cpu(), head, geo, 0.7, 0.6)
+        assert t_np.shape == (6, T, 2) and o_np.dtype == bool
+        assert np.abs(t_np - t_ref.numpy()).max() <= 1e-3 and np.array_equal(o_np, o_ref.numpy())
+        t_ref_b, o_ref_b = oi.infer(refined, q.cpu(), head, geo, 0.7, 0.6, batch_size=3)
+        assert (traj_b.cpu() - t_ref_b).abs().max().item() <= 1e-3 and torch.equal(occ_b.cpu(), o_ref_b)
+    finally:
+        sys.path.pop(0)
+        for m in [k for k in list(sys.modules) if k == "models" or k.startswith("models.")]:
+            del sys.modules[m]
