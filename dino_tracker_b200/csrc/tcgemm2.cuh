@@ -90,29 +90,30 @@ __device__ __forceinline__ void mma2_commit_mc(uint64_t* bar) {
 
 constexpr int TC2_BM = 256, TC2_BN = 256;   // pair tile; each CTA owns 128 rows of A / D and 128 rows of B
 
-template <TcMode MODE>
+// EPI_WARPS / SCRATCH: epilogue warps of the kernel and whether it needs the per-warp transpose scratch (coalesced epilogues);
+// 8 warps with scratch trade one ring stage for it.
+template <TcMode MODE, int EPI_WARPS = 4, bool SCRATCH = true>
 struct Tc2Cfg {
   using Base = TcCfg<MODE, TC2_BN>;
   static constexpr int kABytes = 128 * 128, kBBytes = (TC2_BN / 2) * 128;
   static constexpr int kStageBytes = Base::kOps * (kABytes + kBBytes);
-  static constexpr int kStages = (Base::kOps == 2) ? 3 : 6;
+  static constexpr int kStages = (Base::kOps == 2) ? 3 : ((EPI_WARPS == 8 && SCRATCH) ? 5 : 6);
   // no alignment slack: the kernel has no static shared memory, so the dynamic array starts 1024-byte aligned (trap otherwise)
-  // (the KB saved lets two head CTAs sit next to a correlation-GEMM CTA, inference.cu phase C)
-  static constexpr int kSmem = kStages * kStageBytes + 256 + (Base::kOps == 1 ? TC_EPI_SCRATCH : 0);
+  static constexpr int kSmem = kStages * kStageBytes + 256 + ((Base::kOps == 1 && SCRATCH) ? (EPI_WARPS / 4) * TC_EPI_SCRATCH : 0);
   static constexpr uint32_t kIdesc = tc::make_idesc(Base::kFmt, TC2_BM, TC2_BN);
 };
 
 // pb.tile_start: prefix of ceil(m / 256) per group.  Same Epi contract as tc_gemm_kernel.
-// EPI_WARPS = 4: warps 2..5 own one TMEM lane quadrant each (all 256 columns of a tile); EPI_WARPS = 8 (direct epilogues only):
-// two warps per quadrant, each covering 128 columns -- the epilogue functor then sees "tiles" of 128 columns
-// (tile_end's n_tile index = 2 * (n0 / 256) + half).  Launch with 64 + 32 * EPI_WARPS threads.
+// EPI_WARPS = 4: warps 2..5 own one TMEM lane quadrant each (all 256 columns of a tile); EPI_WARPS = 8: two warps per
+// quadrant, each covering 128 columns -- a direct epilogue functor then sees "tiles" of 128 columns (tile_end's n_tile index
+// = 2 * (n0 / 256) + half).  Launch with 64 + 32 * EPI_WARPS threads and Tc2Cfg<MODE, EPI_WARPS, scratch>::kSmem.
 template <TcMode MODE, class Epi, int EPI_WARPS = 4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcProblem pb,
                 Epi epi) {
   using Base = TcCfg<MODE, TC2_BN>;
-  using Cfg = Tc2Cfg<MODE>;
+  using Cfg = Tc2Cfg<MODE, EPI_WARPS, EPI_WARPS == 4 || EpiCoalesced<Epi>::value>;
   constexpr int BN = TC2_BN;
   extern __shared__ uint8_t smem_raw[];   // no static shared memory in this kernel: the dynamic window starts 1 KB-aligned
   uint8_t* smem = smem_raw;
@@ -125,7 +126,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* epi_scratch = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
   static_assert(!EpiCoalesced<Epi>::value || Base::kOps == 1, "coalesced epilogues need the scratch of the single-pass modes");
-  static_assert(EPI_WARPS == 4 || (EPI_WARPS == 8 && !EpiCoalesced<Epi>::value), "8 epilogue warps: direct epilogues only");
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "4 or 8 epilogue warps");
   constexpr int EPI_COLS = BN / (EPI_WARPS / 4);   // columns of a tile one epilogue warp covers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -383,13 +383,16 @@ static int plan(const Plan& pl, int n_groups, int rows, int row_stride, int row_
 template <class Epi>
 static int run_gemm_pair(const void* A, uint64_t a_rows, const void* Bm, uint64_t b_rows, int K, const Plan& pl,
                          int max_tiles, const Epi& epi, int prof_cls, cudaStream_t st) {
+  // 8 epilogue warps (two per TMEM lane quadrant): the fused epilogues (GELU, LayerScale + residual, head scatter) run on
+  // warps that have their scheduler to themselves, so their latency chains, not the MMAs, paced these GEMMs with 4 warps
+  constexpr int kEpiWarps = 8;
   using Base = TcCfg<TcMode::F16, TC2_BN>;
-  using Cfg = Tc2Cfg<TcMode::F16>;
+  using Cfg = Tc2Cfg<TcMode::F16, kEpiWarps, true>;
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_2d(&tmA, A, a_rows, K, 128, Base::kBK, TMAP_F16))) return rc;
   if ((rc = make_tmap_3d(&tmB, Bm, 1, b_rows, K, TC2_BN / 2, Base::kBK, TMAP_F16))) return rc;
-  auto kern = tc_gemm2_kernel<TcMode::F16, Epi>;
+  auto kern = tc_gemm2_kernel<TcMode::F16, Epi, kEpiWarps>;
   static PerDev<bool> attr_dev;
   bool& attr = attr_dev.get();
   if (!attr) {
@@ -403,7 +406,7 @@ static int run_gemm_pair(const void* A, uint64_t a_rows, const void* Bm, uint64_
   int pairs = max_tiles * cdiv((int)b_rows, TC2_BN);
   int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
   ProfRange pr(prof_cls, st);
-  kern<<<grid, TC_THREADS, Cfg::kSmem, st>>>(tmA, tmA, tmB, tmB, pb, epi);
+  kern<<<grid, 64 + 32 * kEpiWarps, Cfg::kSmem, st>>>(tmA, tmA, tmB, tmB, pb, epi);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }

@@ -75,7 +75,7 @@ struct CoarseEpi {
 int launch_xw_coarse(const FeatView& fv, const void* desc_hi, int desc_rows, const float* desc_norm, const int* grp_frame,
                      const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
                      int max_tiles, const XwChunk& xc, cudaStream_t st) {
-  using Cfg = Tc2Cfg<TcMode::F16>;
+  using Cfg = Tc2Cfg<TcMode::F16, 8, false>;
   using Base = TcCfg<TcMode::F16, TC2_BN>;
   static_assert(TC2_BN == 2 * XW_TILE, "coarse keys are per half GEMM tile (8 epilogue warps)");
   CUtensorMap tmA, tmB;
