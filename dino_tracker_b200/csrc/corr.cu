@@ -247,7 +247,9 @@ int launch_corr_maps(const FeatView& fv, const float* desc, int desc_rows, const
                      cudaStream_t st, const CorrAssist& assist) {
   if (n_groups <= 0 || total_maps <= 0) return DINOTRK_OK;
   unsigned long long* tkeys = fv.tensor() ? assist.tkeys : nullptr;
-  const int tile_rows = fv.tensor() ? (assist.small_tiles ? 128 : corr_tc_tile_rows()) : BM;   // rows per GEMM M tile
+  // rows per GEMM M tile: 256 (CTA pairs) by default; 128-row single-CTA tiles when no group can fill more than half a
+  // pair tile (10-128 points per call: Tracker.forward-sized batches, small query sets) or when the caller asks for them
+  const int tile_rows = fv.tensor() ? ((assist.small_tiles || max_group_m <= 128) ? 128 : corr_tc_tile_rows()) : BM;
   const int n_tiles = cdiv(fv.P, CORR_TILE);
   const float* tpc = fv.tpc;
   const float* norms = fv.norms;
