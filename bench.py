@@ -696,9 +696,10 @@ def stream_probe(model, mi, lib, _lib, args, peaks):
     T, C = args.T, args.C
     out = {}
     for qb in (1, 8, 9, 32, 128, 256):
-        desc = torch.randn(qb, C, device=dev)
+        # one descriptor row per map (the entry point's contract): the Q_b descriptors repeated for every frame
+        desc = torch.randn(qb, C, device=dev).repeat(T, 1).contiguous()
         dn = desc.norm(dim=1).contiguous()
-        grp = torch.stack([torch.arange(T), torch.zeros(T, dtype=torch.long), torch.full((T,), qb),
+        grp = torch.stack([torch.arange(T), torch.arange(T) * qb, torch.full((T,), qb),
                            torch.arange(T) * qb]).to(torch.int32).to(dev).contiguous()
         stride = lib.dinotrk_map_stride(ctypes.byref(model._geom))
         maps = torch.empty(T * qb, stride, device=dev)
@@ -717,7 +718,7 @@ def stream_probe(model, mi, lib, _lib, args, peaks):
         for _ in range(5):
             run()
         prof = _lib.profile_collect(); _lib.profile_enable(False)
-        if "corr_stream" in prof:      # <= 8 descriptors per frame: the HBM-bound streaming kernel (exact fp32)
+        if qb <= 8:                    # <= 8 descriptors per frame: the HBM-bound streaming kernel (exact fp32)
             ms_total, n = prof["corr_stream"]
             nbytes = T * P * C * 4 + T * P * 4 + qb * C * 4 + qb * T * 8
             gbs = nbytes / (ms_total / n / 1000.0) / 1e9

@@ -435,7 +435,7 @@ static XwAsync* xw_async() {
       if (cudaEventCreateWithFlags(&xa.done[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&xa.freed[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
-    if (cudaHostAlloc(&xa.host_cnt, (2 * XW_RING + 16) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&xa.host_cnt, (2 * XW_RING + 16 + 4) * sizeof(int), cudaHostAllocDefault) != cudaSuccess) return nullptr;
     xa.state = 1;
   }
   return xa.state == 1 ? &xa : nullptr;
@@ -563,6 +563,7 @@ size_t dinotrk_infer_workspace_bytes(int T, int C, const dinotrk_geom* g, int N,
   x += xw_chunk_bytes((int)chx, (int)max_cells_chunk, cdiv(g->h * g->w, XW_TILE), gcap);
   b += XW_RING * x;
   b += 2 * align_up((size_t)N * T * C * 2, 256) + 2 * align_up((size_t)N * T * 4, 256);   // unique descriptors (hi, lo, norm, flag)
+  b += align_up((size_t)T * g->h * g->w * 4, 256) + 256;                                  // reciprocal token norms, smallest norm
   b += align_up((size_t)N * T * nb * 16 + 64, 256);                         // cells of all chunks
   b += align_up(infer_max_chunks(T, N, ch) * (gcap + 1) * 4, 256);         // coarse tile prefixes per chunk
   {
@@ -664,6 +665,8 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
   __half* u_lo = ar.take<__half>((size_t)N * T * C);
   float* u_norm = ar.take<float>((size_t)N * T);
   int* u_flag = ar.take<int>((size_t)N * T);
+  float* d_rnorms = ar.take<float>((size_t)T * P);
+  unsigned* d_minnorm = ar.take<unsigned>(4);
   for (int k = 0; k < XW_RING; ++k) {
     xr[k].norm = ar.take<float>(ch);
     xr[k].split = ar.take<float>(corr_tc_workspace_bytes(ch, C) / 4);
@@ -778,10 +781,20 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
     if (pathsel == 0) use_xw = false;
     XwAsync* xa = use_xw ? xw_async() : nullptr;
     if (!xa) use_xw = false;
+    if (xa) {   // reciprocal token norms for the coarse epilogue + the smallest norm of the video (the host reads it below)
+      int rcn = launch_xw_rnorms(fv, d_rnorms, d_minnorm, st);
+      if (rcn) return rcn;
+      DTK_CUDA(cudaMemcpyAsync(xa->host_cnt + 2 * XW_RING + 16, d_minnorm, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    }
     if (xa && n_chunks_A > 0)
       DTK_CUDA(cudaMemcpyAsync(xa->host_cnt + 2 * XW_RING, d_cntA, (size_t)n_chunks_A * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTK_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)T * sizeof(int), cudaMemcpyDeviceToHost, st));
     DTK_CUDA(cudaStreamSynchronize(st));  // the one host sync: sizes of the anchor work lists
+    if (use_xw) {   // a (near-)zero token anywhere voids the coarse pass's error bound (xwin.cuh: XW_MIN_NORM)
+      float mn;
+      memcpy(&mn, xa->host_cnt + 2 * XW_RING + 16, sizeof(float));
+      if (!(mn >= XW_MIN_NORM)) use_xw = false;
+    }
     if (use_xw && pathsel < 0 && n_chunks_A > 0) {
       // head weights the certificate cannot handle send (almost) every map to the full-map kernels anyway: the trajectory
       // phase just showed it; skip the exact-window attempt then.  (Depends on the weights and the video only.)
@@ -900,7 +913,7 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
         const XwCells cells = cells_of(k);
         if (ovl) DTK_CUDA(cudaStreamWaitEvent(st, xa->sample[k % XW_RING], 0));
         if ((rc = launch_xw_coarse(fv, hi_of(x, cm.used), cm.used, x.norm, gp.f, gp.r, gp.m, gp.map0, d_tiles + k * (gcap + 1),
-                                   cm.n_groups, cm.used / TC2_BM_ROWS + cm.n_groups, x.xc, st))) return rc;
+                                   cm.n_groups, cm.used / TC2_BM_ROWS + cm.n_groups, x.xc, st, d_rnorms))) return rc;
         if ((rc = launch_xw_plan(cells, x.norm, cm.n_groups, *g, x.xc, st, cm.used))) return rc;
         if ((rc = launch_xw_gemm(fv, *g, hi_of(x, cm.used), lo_of(x, cm.used), cm.used, cells, x.xc, st))) return rc;
         if ((rc = launch_xw_head(fv, *g, *hw, cells, x.norm, gp.map0, cm.used, x.out_index, anchors, 2, 0, x.xc, st, cm.n_groups)))

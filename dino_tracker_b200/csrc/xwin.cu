@@ -17,7 +17,7 @@ int make_tmap_4d(CUtensorMap* map, const void* base, const uint64_t dims[4], con
 // key1 = bits(max) << 32 | (0x7fffffff - first token holding it), max2 = second largest value (>= 0).  Values are the same
 // expression as the exact path, relu(acc / max(|d| |F|, 1e-8)), with a fast division (its error is part of XW_EPS).
 struct CoarseEpi {
-  const float* norms;
+  const float* rnorms;     // [T][P] 1 / |F[t][p]| (xw_rnorm_kernel; every norm is >= XW_MIN_NORM on this path)
   const float* desc_norm;
   const int* grp_frame;
   const int* grp_row0;
@@ -25,14 +25,15 @@ struct CoarseEpi {
   unsigned long long* key1;
   float* max2;
   int n_tiles, P;
-  // The epilogue warps are alone on their schedulers, so every dependent instruction costs its full latency: the 32 values of
-  // a column block are formed as 32 independent chains (all norm loads first), and the (max, first token, second value)
-  // statistics run in four interleaved branch-free accumulators (columns = lane of the accumulator mod 4), merged per tile.
-  struct State { float m1[4], m2[4]; int tok[4]; float dn; };
+  // The epilogue warps have their schedulers (almost) to themselves, so every dependent instruction costs its full latency:
+  // the 32 values of a column block are formed as 32 independent chains (all loads first), and the (max, first token, second
+  // value) statistics run in four interleaved branch-free accumulators (columns = accumulator mod 4), merged per tile.
+  // Per element only u = acc * (1 / |F|) is formed; the row's positive factor 1 / |d| (and the ReLU) are applied to the two
+  // statistics at the end of the tile -- multiplication by a positive constant does not change which token holds the maximum.
+  struct State { float m1[4], m2[4]; int tok[4]; };
   __device__ __forceinline__ void tile_begin(State& s) const {
 #pragma unroll
-    for (int a = 0; a < 4; ++a) { s.m1[a] = -1.f; s.m2[a] = -1.f; s.tok[a] = 0x7fffffff; }
-    s.dn = -1.f;
+    for (int a = 0; a < 4; ++a) { s.m1[a] = -INFINITY; s.m2[a] = -INFINITY; s.tok[a] = 0x7fffffff; }
   }
   __device__ __forceinline__ void tile_end(State& s, int g, int r, int nt) const {
     if (nt >= n_tiles) return;   // second half of the last GEMM tile lies completely past the end of the map
@@ -45,22 +46,18 @@ struct CoarseEpi {
       tok = take ? s.tok[a] : tok;
       m1 = fmaxf(m1, s.m1[a]);
     }
+    const float rdn = __fdividef(1.f, fmaxf(desc_norm[grp_row0[g] + r], XW_MIN_NORM));
     const size_t o = (size_t)(grp_map0[g] + r) * n_tiles + nt;
-    key1[o] = ((unsigned long long)__float_as_uint(fmaxf(m1, 0.f)) << 32) | (unsigned)(0x7fffffff - tok);
-    max2[o] = fmaxf(m2, 0.f);
+    key1[o] = ((unsigned long long)__float_as_uint(fmaxf(m1 * rdn, 0.f)) << 32) | (unsigned)(0x7fffffff - tok);
+    max2[o] = fmaxf(m2 * rdn, 0.f);
   }
   __device__ __forceinline__ void operator()(State& s, int g, int r, int col0, const float (&f)[32], int ncols) const {
-    if (s.dn < 0.f) s.dn = desc_norm[grp_row0[g] + r];
-    const float dn = s.dn;
-    const float* fn = norms + (size_t)grp_frame[g] * P + col0;
+    const float* rn = rnorms + (size_t)grp_frame[g] * P + col0;
     float t[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t[i] = __ldg(fn + (i < ncols ? i : 0));
+    for (int i = 0; i < 32; ++i) t[i] = __ldg(rn + (i < ncols ? i : 0));
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float v = fmaxf(__fdividef(f[i], fmaxf(dn * t[i], 1e-8f)), 0.f);
-      t[i] = i < ncols ? v : -1.f;      // columns past the end of the map never win
-    }
+    for (int i = 0; i < 32; ++i) t[i] = i < ncols ? f[i] * t[i] : -INFINITY;      // columns past the end of the map never win
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const int a = i & 3;
@@ -72,9 +69,31 @@ struct CoarseEpi {
   }
 };
 
+// rnorms[i] = 1 / norms[i]; *min_bits = bit pattern of the smallest norm (norms are >= 0: the bit pattern orders like the value)
+__global__ void xw_rnorm_kernel(const float* __restrict__ norms, float* __restrict__ rnorms, size_t n, unsigned* __restrict__ min_bits) {
+  float mn = INFINITY;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = norms[i];
+    rnorms[i] = __fdiv_rn(1.f, fmaxf(v, XW_MIN_NORM));
+    mn = fminf(mn, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(min_bits, __float_as_uint(fmaxf(mn, 0.f)));
+}
+
+int launch_xw_rnorms(const FeatView& fv, float* rnorms, unsigned* min_bits, cudaStream_t st) {
+  const size_t n = (size_t)fv.T * fv.P;
+  DTK_CUDA(cudaMemsetAsync(min_bits, 0x7f, sizeof(unsigned), st));   // 0x7f7f7f7f: a huge positive float
+  ProfRange pr(PROF_XW_PLAN, st);
+  xw_rnorm_kernel<<<148 * 4, 256, 0, st>>>(fv.norms, rnorms, n, min_bits);
+  DTK_LAUNCHED();
+  return DINOTRK_OK;
+}
+
 int launch_xw_coarse(const FeatView& fv, const void* desc_hi, int desc_rows, const float* desc_norm, const int* grp_frame,
                      const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
-                     int max_tiles, const XwChunk& xc, cudaStream_t st) {
+                     int max_tiles, const XwChunk& xc, cudaStream_t st, const float* rnorms) {
   using Cfg = Tc2Cfg<TcMode::F16, 8, false>;
   using Base = TcCfg<TcMode::F16, TC2_BN>;
   static_assert(TC2_BN == 2 * XW_TILE, "coarse keys are per half GEMM tile (8 epilogue warps)");
@@ -90,7 +109,7 @@ int launch_xw_coarse(const FeatView& fv, const void* desc_hi, int desc_rows, con
     attr = true;
   }
   TcProblem pb{grp_frame, grp_row0, grp_m, tile_start, n_groups, fv.P, fv.C};
-  CoarseEpi epi{fv.norms, desc_norm, grp_frame, grp_row0, grp_map0, xc.key1, xc.max2, cdiv(fv.P, XW_TILE), fv.P};
+  CoarseEpi epi{rnorms, desc_norm, grp_frame, grp_row0, grp_map0, xc.key1, xc.max2, cdiv(fv.P, XW_TILE), fv.P};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -147,7 +166,7 @@ xw_cand_kernel(int n_maps, const float* __restrict__ desc_norm, int n_groups, in
       ncand += __popc(cm);
     }
     // a (near-)zero map has no meaningful arg-max candidates; a tiny descriptor norm voids the error bound
-    amb = amb || ncand > XW_MAX_CAND || !(gmax > 4.f * XW_EPS) || !(desc_norm[map] >= 1e-6f);
+    amb = amb || ncand > XW_MAX_CAND || !(gmax > 4.f * XW_EPS) || !(desc_norm[map] >= XW_MIN_NORM);
     if (lane >= ncand && lane < XW_MAX_CAND) cand[(size_t)map * XW_MAX_CAND + lane] = -1;
     if (lane == 0) pinfo[map] = amb ? -1 - ptok : ptok;
   }

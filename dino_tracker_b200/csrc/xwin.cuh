@@ -33,6 +33,9 @@ constexpr int XW_PARTS = 3, XW_PART_ROWS = 7, XW_PART_N = 160;   // 3 N-parts of
 constexpr int XW_COLS = XW_PARTS * XW_PART_N;                    // accumulator columns per map (raw dump pitch)
 constexpr int XW_MAX_CELL = 128;      // rows (source frames) per cell = UMMA M
 constexpr int XW_MAX_CAND = 4;
+constexpr float XW_MIN_NORM = 1e-4f;  // the coarse pass forms acc / (|d| |F|) without the reference's max(|d| |F|, 1e-8) clamp: both
+                                      // norms must be >= 1e-4 (smaller descriptor norms -> ambiguous map, smaller token norms
+                                      // anywhere in the video -> the whole call takes the full-map pipeline)
 constexpr int XW_TILE = 128;          // tokens per coarse key (the coarse GEMM's 8 epilogue warps cover 128 columns each)
 
 // column of box token (by, bx) in a map's accumulator row
@@ -63,7 +66,9 @@ size_t xw_chunk_bytes(int chunk_maps, int max_cells, int n_tiles, int gcap);
 // Coarse GEMM over the chunk's groups (tile_start: prefix of ceil(m / 256) per group, all groups wide).
 int launch_xw_coarse(const FeatView& fv, const void* desc_hi, int desc_rows, const float* desc_norm, const int* grp_frame,
                      const int* grp_row0, const int* grp_m, const int* grp_map0, const int* tile_start, int n_groups,
-                     int max_tiles, const XwChunk& xc, cudaStream_t st);
+                     int max_tiles, const XwChunk& xc, cudaStream_t st, const float* rnorms);
+// rnorms = 1 / |F| for the coarse epilogue; *min_bits = bit pattern of the smallest token norm of the video
+int launch_xw_rnorms(const FeatView& fv, float* rnorms, unsigned* min_bits, cudaStream_t st);
 int launch_xw_plan(const XwCells& cells, const float* desc_norm, int n_groups, const dinotrk_geom& g, const XwChunk& xc,
                    cudaStream_t st, int n_maps);
 int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_hi, const void* desc_lo, int desc_rows,

@@ -94,13 +94,14 @@ def test_chunking_and_stream_modes_do_not_change_a_bit():
 def test_adversarial_inputs_fall_back_correctly():
     """(a) duplicated frames content inside a frame: exact ties between two far-apart tokens -> ambiguous maps;
     (b) pure-noise features: the arg-maxes of a cell scatter over the whole frame -> windows leave the box;
-    (c) an all-zero frame: zero maps.  All must come out as the full-map pipeline computes them."""
+    (c) zero descriptors (a query on a frame whose features vanish in one corner region is not possible without (d));
+    (d) an all-zero frame (token norms below XW_MIN_NORM void the coarse bound): the whole call must take the full-map
+    pipeline even when the exact-window one is requested.  All must come out as the full-map pipeline computes them."""
     geo = Geometry(H=140, W=182)            # 19 x 25 tokens: smaller than the 21-row box in one direction
     T, C = 6, 64
     feats, _ = synth.shifted_field_features(T, C, geo.h, geo.w, seed=90, noise=0.1, max_shift=1)
     feats[2, :, 3, 4] = feats[2, :, 12, 20]                    # (a) an exact duplicate token in frame 2
     feats[3] = synth.random_features(1, C, geo.h, geo.w, seed=91)[0]   # (b) frame 3 is noise
-    feats[5] = 0.0                                             # (c)
     head = synth.head_weights("sharp", seed=9)
     q = synth.lattice_query_points(4, 3, geo.H, geo.W, t_q=[0, 1, 2, 4] * 3, margin=14.0, jitter_seed=9)
     q[0, :2] = torch.tensor([7.0 + 7 * 20, 7.0 + 7 * 12])      # sits on the duplicated token of frame 2
@@ -111,6 +112,15 @@ def test_adversarial_inputs_fall_back_correctly():
         d = _agree(xw, full)
         print(f"adversarial: exact-window vs full-map max |dxy| = {d:.2e} px; {st}")
         assert st["full_map"] > 0                                # the fallbacks were exercised
+    t_ref, o_ref, aux = oi.infer(feats, q, head, geo, 0.7, 0.6, return_all=True)
+    assert (xw["traj"].cpu() - aux["trajs"]).abs().max().item() <= XY_TOL
+    assert torch.equal(xw["occ"].bool().cpu(), o_ref)
+    # (d) a frame of zeros: no coarse pass at all
+    feats[5] = 0.0
+    full, _ = _run(feats, head, q, geo, 0)
+    xw, st = _run(feats, head, q, geo, 1)
+    assert st["pipeline"] == "full-map" and st["exact_window"] == 0
+    _agree(xw, full)
     t_ref, o_ref, aux = oi.infer(feats, q, head, geo, 0.7, 0.6, return_all=True)
     assert (xw["traj"].cpu() - aux["trajs"]).abs().max().item() <= XY_TOL
     assert torch.equal(xw["occ"].bool().cpu(), o_ref)

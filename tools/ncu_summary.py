@@ -4,7 +4,7 @@ import io
 import subprocess
 import sys
 
-KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+KEEP = ["Kernel Name", "gpu__time_duration.sum", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -18,10 +18,15 @@ KEEP = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
 
 
 def main():
+    """ncu_summary.py report.ncu-rep out.csv [kernel-name substring]: with a substring only the launches of that kernel."""
     src, dst = sys.argv[1], sys.argv[2]
+    only = sys.argv[3] if len(sys.argv) > 3 else None
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[0]
+    if only is not None:
+        k = hdr.index("Kernel Name")
+        rows = rows[:2] + [r for r in rows[2:] if only in r[k]]
     with open(dst, "w") as f:
         f.write(f"# ncu --set full --clock-control none, source {src}\n")
         f.write("metric,unit," + ",".join(f"launch{i}" for i in range(len(rows) - 2)) + "\n")
