@@ -60,9 +60,11 @@ def _delta_weights(model, seed=5):
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for name, p in sorted(model.delta_dino.named_parameters()):
-            if p.dim() > 1:
+            if p.dim() > 1:      # convolution kernels
                 fan = p[0].numel()
                 p.copy_(((torch.rand(p.shape, generator=g) * 2 - 1) / fan ** 0.5 * (0.05 if "layers.12" in name else 1.0)).to(p.device))
+            elif name.split(".")[1] in ("0", "4", "8", "12"):   # convolution biases (default init draws from the global RNG)
+                p.copy_(((torch.rand(p.shape, generator=g) * 2 - 1) * 0.05).to(p.device))
 
 
 def _frames(T, seed, dev):
