@@ -681,6 +681,8 @@ int dinotrk_infer(const dinotrk_features* feat, const dinotrk_geom* g,
     x.slow_list = ar.take<int>(ch);
     x.box_org = ar.take<int2>((size_t)ch + 2);
     x.xbox = ar.take<float>((size_t)ch * XW_COLS);
+    x.win = ar.take<float>((size_t)ch * 256);
+    x.hin = ar.take<int2>(ch);
     x.slow_cnt = ar.take<int>(gcap + 2);
   }
   const int cell_nb = (T + XW_MAX_CELL - 1) / XW_MAX_CELL;

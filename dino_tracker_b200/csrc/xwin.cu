@@ -500,24 +500,16 @@ struct XhParams {
 // zero padding anywhere: the per-position bounds tests drop out -- the common case away from the frame border).
 template <bool INTERIOR>
 __device__ __forceinline__ void xw_refine(const XhParams& hp, const dinotrk_head_weights& wts, float* __restrict__ mm,
-                                          float* __restrict__ hh_, const float* __restrict__ xr, const float* __restrict__ fn,
-                                          float dn, int2 org, int arow, int acol, int lane, float& mout, float& zmax,
-                                          float (&tot)[5]) {
+                                          float* __restrict__ hh_, const float (&wv)[8], int arow, int acol, int lane,
+                                          float& zmax, float (&tot)[5]) {
   const int h = hp.h, w = hp.w;
   const int c8 = lane & 7, pg = lane >> 3;
-  // ---- exact input window (15 x 15, zero outside the map) + exact part of m_out ----
+  // ---- input window (15 x 15 exact values, zero outside the map; extracted by xw_window_kernel, 16-float rows) ----
 #pragma unroll
-  for (int q = 0; q < (XWM * 16 + 31) / 32; ++q) {
+  for (int q = 0; q < 8; ++q) {
     const int i = lane + 32 * q;
     const int y = i >> 4, x = i & 15;
-    const int r = arow - 7 + y, c = acol - 7 + x;
-    float v = 0.f;
-    if (y < XWM && x < XWM && (INTERIOR || (r >= 0 && r < h && c >= 0 && c < w))) {
-      const int tok = r * w + c;
-      v = fmaxf(__fdiv_rn(__ldg(xr + xw_col(r - org.x, c - org.y)), fmaxf(__fmul_rn(dn, __ldg(fn + tok)), 1e-8f)), 0.f);
-      if (!(abs(r - arow) <= 3 && abs(c - acol) <= 3)) mout = fmaxf(mout, v);
-    }
-    if (y < XWM && x < XWM) mm[y * XH_MP + x] = v;
+    if (y < XWM && x < XWM) mm[y * XH_MP + x] = wv[q];
   }
   __syncwarp();
   // ---- refiner.  Lane = (channel c8 of the current half of 8, row group pg).  Hidden layer: the lane's channel on the
@@ -621,7 +613,6 @@ __device__ __forceinline__ void xw_refine(const XhParams& hp, const dinotrk_head
     zmax = fmaxf(zmax, z[q]);
   }
   zmax = warp_max(zmax);
-  mout = warp_max(mout);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float e = valid[q] ? expf(z[q] - zmax) : 0.f;
@@ -631,59 +622,111 @@ __device__ __forceinline__ void xw_refine(const XhParams& hp, const dinotrk_head
   }
 }
 
+// (a) window extraction: one warp per map, no shared memory, many warps per SM -- every load here is a dependent gather
+// (candidates -> box accumulators / token norms), so this part wants parallelism, not registers.  Writes the 15 x 15 exact
+// window as [15][16] floats and hin = (exact first arg-max token or -1 for a map the plan queued, m_out bits).
+constexpr int XWIN_PITCH = 256;
+__global__ void __launch_bounds__(256)
+xw_window_kernel(int n_maps, int h, int w, int P, int n_tiles, const float* __restrict__ norms, const float* __restrict__ desc_norm,
+                 const int* __restrict__ cell_frame, const int* __restrict__ cell_of, const int2* __restrict__ box_org,
+                 const int* __restrict__ stat, const int* __restrict__ cand, const unsigned long long* __restrict__ key1,
+                 const float* __restrict__ max2, const float* __restrict__ xbox, float* __restrict__ win, int2* __restrict__ hin) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int map = gw; map < n_maps; map += nw) {
+    if (stat[map] != 0) {
+      if (lane == 0) hin[map] = make_int2(-1, 0);
+      continue;
+    }
+    const int cell = cell_of[map];
+    const int2 org = box_org[cell];
+    const float* fn = norms + (size_t)cell_frame[cell] * P;
+    const float* xr = xbox + (size_t)map * XW_COLS;
+    const float dn = desc_norm[map];
+    // exact first arg-max among the candidates (every lane, redundantly: <= 4 loads)
+    const int4 cd = __ldg(reinterpret_cast<const int4*>(cand) + map);
+    const int ct[4] = {cd.x, cd.y, cd.z, cd.w};
+    float best = -1.f;
+    int amax = -1;
+#pragma unroll
+    for (int q = 0; q < XW_MAX_CAND; ++q)
+      if (ct[q] >= 0) {
+        const int tr = ct[q] / w, tcn = ct[q] - tr * w;
+        const float v = fmaxf(__fdiv_rn(__ldg(xr + xw_col(tr - org.x, tcn - org.y)), fmaxf(__fmul_rn(dn, __ldg(fn + ct[q])), 1e-8f)), 0.f);
+        if (v > best || (v == best && ct[q] < amax)) { best = v; amax = ct[q]; }
+      }
+    const int arow = amax / w, acol = amax - arow * w;
+    // coarse bound on everything outside the window, from the tile keys
+    float mout = 0.f;
+    for (int t = lane; t < n_tiles; t += 32) {
+      const unsigned long long k = __ldg(key1 + (size_t)map * n_tiles + t);
+      const int tk = 0x7fffffff - (int)(k & 0xffffffffu);
+      const int tr = tk / w, tcn = tk - tr * w;
+      const bool in_core = abs(tr - arow) <= 3 && abs(tcn - acol) <= 3;
+      const float b = in_core ? __ldg(max2 + (size_t)map * n_tiles + t) : __uint_as_float((unsigned)(k >> 32));
+      mout = fmaxf(mout, b + XW_EPS);
+    }
+    // exact window + exact part of m_out
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = lane + 32 * q;
+      const int y = i >> 4, x = i & 15;
+      const int r = arow - 7 + y, c = acol - 7 + x;
+      float v = 0.f;
+      if (y < XWM && x < XWM && r >= 0 && r < h && c >= 0 && c < w) {
+        v = fmaxf(__fdiv_rn(__ldg(xr + xw_col(r - org.x, c - org.y)), fmaxf(__fmul_rn(dn, __ldg(fn + r * w + c)), 1e-8f)), 0.f);
+        if (!(abs(r - arow) <= 3 && abs(c - acol) <= 3)) mout = fmaxf(mout, v);
+      }
+      win[(size_t)map * XWIN_PITCH + i] = v;
+    }
+    mout = warp_max(mout);
+    if (lane == 0) hin[map] = make_int2(amax, __float_as_int(mout));
+  }
+}
+
+// (b) refiner + softmax sums + certificate: one warp per map; the next map's window (8 coalesced loads per lane) and
+// arg-max are in flight while the current map is refined.
 __global__ void __launch_bounds__(XH_WARPS * 32, 3)
-xw_head_kernel(int n_maps, XhParams hp, dinotrk_head_weights wts, const float* __restrict__ norms,
-               const float* __restrict__ desc_norm, const int* __restrict__ cell_frame, const int* __restrict__ cell_group,
-               const int* __restrict__ grp_map0, const int* __restrict__ cell_of, const int2* __restrict__ box_org,
-               const int* __restrict__ stat, const int* __restrict__ cand, const unsigned long long* __restrict__ key1,
-               const float* __restrict__ max2, const float* __restrict__ xbox, const int* __restrict__ out_index,
-               float* __restrict__ out, int* __restrict__ slow_cnt, int* __restrict__ slow_list, int n_groups) {
+xw_head_kernel(int n_maps, XhParams hp, dinotrk_head_weights wts, const int* __restrict__ cell_group, const int* __restrict__ grp_map0,
+               const int* __restrict__ cell_of, const float* __restrict__ win, const int2* __restrict__ hin,
+               const int* __restrict__ out_index, float* __restrict__ out, int* __restrict__ slow_cnt, int* __restrict__ slow_list,
+               int n_groups) {
   extern __shared__ __align__(16) float xh_smem[];     // per warp [input window: 256 | hidden window: 1352]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float* mm = xh_smem + XH_W2 + wid * XH_PER_WARP;
   float* hh_ = mm + XH_MWIN;
   const int h = hp.h, w = hp.w, P = hp.P;
-  const int c8 = lane & 7, pg = lane >> 3;
+  const int stride = gridDim.x * XH_WARPS;
 
-  for (int map = blockIdx.x * XH_WARPS + wid; map < n_maps; map += gridDim.x * XH_WARPS) {
-    const int cell = cell_of[map];
-    const int g = cell_group[cell];
-    bool slow = stat[map] != 0;
-    int amax = 0;
-    float mout = 0.f, zmax = 0.f;
+  int map = blockIdx.x * XH_WARPS + wid;
+  float wnext[8];
+  int2 hnext = make_int2(-1, 0);
+  if (map < n_maps) {
+    hnext = __ldg(hin + map);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) wnext[q] = __ldg(win + (size_t)map * XWIN_PITCH + lane + 32 * q);
+  }
+  for (; map < n_maps; map += stride) {
+    float wv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) wv[q] = wnext[q];
+    const int2 hcur = hnext;
+    if (map + stride < n_maps) {
+      hnext = __ldg(hin + map + stride);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) wnext[q] = __ldg(win + (size_t)(map + stride) * XWIN_PITCH + lane + 32 * q);
+    }
+    const bool slow = hcur.x < 0;
+    const int amax = hcur.x;
+    const float mout = __int_as_float(hcur.y);
+    float zmax = 0.f;
     float tot[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (!slow) {
-      const int2 org = box_org[cell];
-      const float* fn = norms + (size_t)cell_frame[cell] * P;
-      const float* xr = xbox + (size_t)map * XW_COLS;
-      const float dn = desc_norm[map];
-      // ---- exact first arg-max among the candidates (every lane, redundantly: <= 4 loads) ----
-      float best = -1.f;
-      amax = -1;
-#pragma unroll
-      for (int q = 0; q < XW_MAX_CAND; ++q) {
-        const int tok = __ldg(cand + (size_t)map * XW_MAX_CAND + q);
-        if (tok >= 0) {
-          const int tr = tok / w, tcn = tok - tr * w;
-          const float v = fmaxf(__fdiv_rn(__ldg(xr + xw_col(tr - org.x, tcn - org.y)), fmaxf(__fmul_rn(dn, __ldg(fn + tok)), 1e-8f)), 0.f);
-          if (v > best || (v == best && tok < amax)) { best = v; amax = tok; }
-        }
-      }
       const int arow = amax / w, acol = amax - arow * w;
-      // ---- coarse bound on everything outside the window, from the tile keys ----
-      for (int t = lane; t < hp.n_tiles; t += 32) {
-        const unsigned long long k = __ldg(key1 + (size_t)map * hp.n_tiles + t);
-        const int tk = 0x7fffffff - (int)(k & 0xffffffffu);
-        const int tr = tk / w, tcn = tk - tr * w;
-        const bool in_core = abs(tr - arow) <= 3 && abs(tcn - acol) <= 3;
-        const float b = in_core ? __ldg(max2 + (size_t)map * hp.n_tiles + t) : __uint_as_float((unsigned)(k >> 32));
-        mout = fmaxf(mout, b + XW_EPS);
-      }
-      // ---- window, refiner, softmax sums ----
       if (arow >= 7 && arow + 7 < h && acol >= 7 && acol + 7 < w)
-        xw_refine<true>(hp, wts, mm, hh_, xr, fn, dn, org, arow, acol, lane, mout, zmax, tot);
+        xw_refine<true>(hp, wts, mm, hh_, wv, arow, acol, lane, zmax, tot);
       else
-        xw_refine<false>(hp, wts, mm, hh_, xr, fn, dn, org, arow, acol, lane, mout, zmax, tot);
+        xw_refine<false>(hp, wts, mm, hh_, wv, arow, acol, lane, zmax, tot);
 #pragma unroll
       for (int q = 0; q < 5; ++q) tot[q] = warp_sum(tot[q]);
     }
@@ -708,6 +751,7 @@ xw_head_kernel(int n_maps, XhParams hp, dinotrk_head_weights wts, const float* _
         const size_t oi = (size_t)(out_index ? out_index[map] : map) * hp.out_stride;
         out[oi] = nx; out[oi + 1] = ny;
       } else {
+        const int g = cell_group[cell_of[map]];
         const int pos = atomicAdd(slow_cnt + g, 1);
         slow_list[grp_map0[g] + pos] = map;
         atomicAdd(slow_cnt + n_groups, 1);
@@ -745,8 +789,14 @@ int launch_xw_head(const FeatView& fv, const dinotrk_geom& g, const dinotrk_head
     attr = true;
   }
   ProfRange pr(PROF_XW_HEAD, st);
-  xw_head_kernel<<<grid, XH_WARPS * 32, XH_SMEM, st>>>(n_maps, hp, hw, fv.norms, desc_norm, cells.frame, cells.group, grp_map0,
-                                                 xc.cell_of, xc.box_org, xc.stat, xc.cand, xc.key1, xc.max2, xc.xbox, out_index,
+  {
+    int wgrid = cdiv(n_maps, 8);
+    if (wgrid > sms * 8) wgrid = sms * 8;
+    xw_window_kernel<<<wgrid, 256, 0, st>>>(n_maps, g.h, g.w, hp.P, hp.n_tiles, fv.norms, desc_norm, cells.frame, xc.cell_of, xc.box_org,
+                                            xc.stat, xc.cand, xc.key1, xc.max2, xc.xbox, xc.win, xc.hin);
+    DTK_LAUNCHED();
+  }
+  xw_head_kernel<<<grid, XH_WARPS * 32, XH_SMEM, st>>>(n_maps, hp, hw, cells.group, grp_map0, xc.cell_of, xc.win, xc.hin, out_index,
                                                  out, xc.slow_cnt, xc.slow_list, n_groups);
   DTK_LAUNCHED();
   return DINOTRK_OK;
@@ -813,6 +863,7 @@ size_t xw_chunk_bytes(int chunk_maps, int max_cells, int n_tiles, int gcap) {
   b += align_up(ch * XW_MAX_CAND * 4, 256) + 4 * align_up(ch * 4, 256);                // cand, stat, pinfo, cell_of, slow_list
   b += align_up((size_t)max_cells * 8, 256);                                           // box_org
   b += align_up(ch * XW_COLS * 4, 256);                                                // xbox
+  b += align_up(ch * 256 * 4, 256) + align_up(ch * 8, 256);                            // win, hin
   b += align_up((size_t)(gcap + 2) * 4, 256);                                          // slow_cnt
   return b + 2048;
 }

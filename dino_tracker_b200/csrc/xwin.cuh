@@ -16,8 +16,9 @@
 //   3. exact GEMM    per cell, the fp32-faithful split-precision contraction (lo*hi + hi*lo + hi*hi, same operation
 //                    sequence as the full-map GEMM) of the cell's descriptors against the box's 441 tokens only:
 //                    5.4 % of the map.  Raw accumulators go to a [map][480] buffer (1.9 KB per map instead of 32 KB).
-//   4. head          one warp per map: exact arg-max among the candidates, exact window, refiner, softmax sums on the
-//                    11 x 11 box, certificate with the bound from (1); writes the track point.
+//   4. head          two kernels, one warp per map each: (a) exact arg-max among the candidates + the exact 15 x 15 window
+//                    + m_out (dependent gathers: many warps per SM), (b) refiner, softmax sums on the 11 x 11 box, certificate
+//                    with the bound from (1); writes the track point.
 //   Maps that are ambiguous, do not fit their cell's box or fail the certificate are queued and re-done by the full-map
 //   path (split-precision GEMM over all tokens + head kernels of head.cu) -- results never depend on the coarse values.
 #pragma once
@@ -50,6 +51,8 @@ struct XwChunk {          // device buffers of one chunk in flight (all sized fo
   int* cell_of;               // [maps] cell index
   int2* box_org;              // [cells] (first box row, first box column); x = INT_MIN: skip the cell
   float* xbox;                // [maps][XW_COLS] raw split-precision accumulators of the box tokens
+  float* win;                 // [maps][256] exact 15 x 15 windows ([15][16] floats, zero outside the map)
+  int2* hin;                  // [maps] (exact first arg-max token or -1, bits of m_out)
   int* slow_cnt;              // [n_groups + 1] per group count of queued maps; [n_groups] = total
   int* slow_list;             // [maps] group g's queue lives at [grp_map0[g], grp_map0[g] + slow_cnt[g])
 };
