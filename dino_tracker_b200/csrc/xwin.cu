@@ -482,11 +482,12 @@ int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_h
 //                                             per tile: (its max token inside the core ? second value : max) + XW_EPS)
 // and either the track point or a place in the group's full-map queue.
 constexpr int XH_WARPS = 8;
-constexpr int XH_MP = 17;      // input window pitch
-constexpr int XH_HP = 8;       // hidden window [position][8 channels]: the 4 row groups of a warp hit disjoint bank octets
+constexpr int XH_MP = 18;      // input window pitch (float2 units, even: 16-byte loads of two positions; 4 row groups -> 4 bank quads)
 constexpr int XWM = 15, XWH = 13, XWB = 11;
-constexpr int XH_W2 = 0, XH_MWIN = 256, XH_PER_WARP = XH_MWIN + 1352;      // floats (XWM * XH_MP = 255, XWH^2 * XH_HP = 1352)
-constexpr int XH_SMEM = (XH_W2 + XH_WARPS * XH_PER_WARP) * 4;
+constexpr int XH_MWIN = 544;   // floats: the 15 x 15 input window with every value stored twice (XWM * XH_MP * 2 = 540)
+constexpr int XH_PER_WARP = XH_MWIN + XWH * XWH * 16;      // + hidden window [position][8 channel pairs (c, c + 8)]
+constexpr int XH_WTAB = 20 * 16;                           // floats: refiner weights as pairs [w1 k = 0..8 | b1 | w2 k = 0..8 | -][8 pairs]
+constexpr int XH_SMEM = (XH_WTAB + XH_WARPS * XH_PER_WARP) * 4;
 
 struct XhParams {
   int h, w, P, n_tiles;
@@ -499,93 +500,86 @@ struct XhParams {
 // Window, refiner and softmax sums of one map (one warp).  INTERIOR: the 15 x 15 window lies inside the token grid (no
 // zero padding anywhere: the per-position bounds tests drop out -- the common case away from the frame border).
 template <bool INTERIOR>
-__device__ __forceinline__ void xw_refine(const XhParams& hp, const dinotrk_head_weights& wts, float* __restrict__ mm,
-                                          float* __restrict__ hh_, const float (&wv)[8], int arow, int acol, int lane,
+__device__ __forceinline__ void xw_refine(const XhParams& hp, const float2* __restrict__ wtab, float b2, float2* __restrict__ mm2,
+                                          float2* __restrict__ hh2, const float (&wv)[8], int arow, int acol, int lane,
                                           float& zmax, float (&tot)[5]) {
   const int h = hp.h, w = hp.w;
-  const int c8 = lane & 7, pg = lane >> 3;
-  // ---- input window (15 x 15 exact values, zero outside the map; extracted by xw_window_kernel, 16-float rows) ----
+  const int cp = lane & 7, pg = lane >> 3;
+  // ---- input window (15 x 15 exact values, zero outside the map; extracted by xw_window_kernel, 16-float rows), every
+  // value as the pair (v, v): the packed FMAs below take it straight from one 64-bit shared-memory load ----
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int i = lane + 32 * q;
     const int y = i >> 4, x = i & 15;
-    if (y < XWM && x < XWM) mm[y * XH_MP + x] = wv[q];
+    if (y < XWM && x < XWM) mm2[y * XH_MP + x] = make_float2(wv[q], wv[q]);
   }
   __syncwarp();
-  // ---- refiner.  Lane = (channel c8 of the current half of 8, row group pg).  Hidden layer: the lane's channel on the
-  // rows pg, pg + 4, ... of the 13 x 13 window, a 3 x 3 input window sliding along the row (weights in registers), stored
-  // [position][8 channels].  Output layer: the SAME lane layout -- the lane accumulates its channel's contribution to
-  // the logits of box rows pg, pg + 4, pg + 8 (again sliding along the row: 3 new shared-memory words per 9 FMAs), both
-  // halves into the same accumulators; the 8 channel lanes of a row group are then summed by shuffles.  (Thread = pixel
-  // with float4 reads of [position][channel] costs 4x the shared-memory wavefronts, which is what bounds this kernel.)
-  float acc[3 * XWB];
+  // ---- refiner on packed fp32 FMAs (FFMA2: two IEEE fp32 FMAs per issue slot; this kernel is issue-bound).  Lane =
+  // (channel pair cp = channels (cp, cp + 8), row group pg).  Hidden layer: the lane's two channels on the rows pg, pg + 4,
+  // ... of the 13 x 13 window, a 3 x 3 input window sliding along the row (weights in registers), stored [position][pair].
+  // Output layer: the SAME lane layout -- the lane forms its two channels' contribution to the logits of box rows pg,
+  // pg + 4, pg + 8 (again sliding along the row: 3 new 64-bit shared-memory words per 9 packed FMAs); the pair is folded
+  // and the 8 pair lanes of a row group are summed by shuffles.
+  {
+    float2 w1r[9];
 #pragma unroll
-  for (int q = 0; q < 3 * XWB; ++q) acc[q] = 0.f;
-#pragma unroll 1
-  for (int hf = 0; hf < 2; ++hf) {
-    const int ch = hf * 8 + c8;
-    {
-      float w1r[9];
+    for (int k = 0; k < 9; ++k) w1r[k] = wtab[k * 8 + cp];
+    const float2 b1r = wtab[9 * 8 + cp];
+    for (int y = pg; y < XWH; y += 4) {
+      const int r = arow - 6 + y;
+      const bool row_in = r >= 0 && r < h;
+      const float2* m0 = mm2 + y * XH_MP;
+      // the three input rows of this hidden row, two positions per 16-byte load (positions 15, 16, 17 of a row are padding)
+      float2 in0[16], in1[16], in2[16];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) w1r[k] = wts.w1[ch][k];
-      const float b1r = wts.b1[ch];
-      for (int y = pg; y < XWH; y += 4) {
-        const int r = arow - 6 + y;
-        const bool row_in = r >= 0 && r < h;
-        const float* m0 = mm + y * XH_MP;
-        float i00 = m0[0], i01 = m0[1], i10 = m0[XH_MP], i11 = m0[XH_MP + 1], i20 = m0[2 * XH_MP], i21 = m0[2 * XH_MP + 1];
+      for (int x = 0; x < 16; x += 2) {
+        const float4 q0 = *reinterpret_cast<const float4*>(m0 + x);
+        const float4 q1 = *reinterpret_cast<const float4*>(m0 + XH_MP + x);
+        const float4 q2 = *reinterpret_cast<const float4*>(m0 + 2 * XH_MP + x);
+        in0[x] = make_float2(q0.x, q0.y); in0[x + 1] = make_float2(q0.z, q0.w);
+        in1[x] = make_float2(q1.x, q1.y); in1[x + 1] = make_float2(q1.z, q1.w);
+        in2[x] = make_float2(q2.x, q2.y); in2[x + 1] = make_float2(q2.z, q2.w);
+      }
 #pragma unroll
-        for (int x = 0; x < XWH; ++x) {
-          const float i02 = m0[x + 2], i12 = m0[XH_MP + x + 2], i22 = m0[2 * XH_MP + x + 2];
-          float a = b1r;
-          a = fmaf(w1r[0], i00, a); a = fmaf(w1r[1], i01, a); a = fmaf(w1r[2], i02, a);
-          a = fmaf(w1r[3], i10, a); a = fmaf(w1r[4], i11, a); a = fmaf(w1r[5], i12, a);
-          a = fmaf(w1r[6], i20, a); a = fmaf(w1r[7], i21, a); a = fmaf(w1r[8], i22, a);
-          const int c = acol - 6 + x;
-          hh_[(y * XWH + x) * XH_HP + c8] = (INTERIOR || (row_in && c >= 0 && c < w)) ? fmaxf(a, 0.f) : 0.f;
-          i00 = i01; i01 = i02; i10 = i11; i11 = i12; i20 = i21; i21 = i22;
-        }
+      for (int x = 0; x < XWH; ++x) {
+        // three short chains per output (one per input row) instead of one chain of nine dependent FMAs
+        float2 a0 = __ffma2_rn(w1r[0], in0[x], b1r), a1 = __fmul2_rn(w1r[3], in1[x]), a2 = __fmul2_rn(w1r[6], in2[x]);
+        a0 = __ffma2_rn(w1r[1], in0[x + 1], a0); a1 = __ffma2_rn(w1r[4], in1[x + 1], a1); a2 = __ffma2_rn(w1r[7], in2[x + 1], a2);
+        a0 = __ffma2_rn(w1r[2], in0[x + 2], a0); a1 = __ffma2_rn(w1r[5], in1[x + 2], a1); a2 = __ffma2_rn(w1r[8], in2[x + 2], a2);
+        const float2 a = __fadd2_rn(__fadd2_rn(a0, a1), a2);
+        const int c = acol - 6 + x;
+        const bool in = INTERIOR || (row_in && c >= 0 && c < w);
+        hh2[(y * XWH + x) * 8 + cp] = in ? make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)) : make_float2(0.f, 0.f);
       }
     }
-    __syncwarp();
-    {
-      float w2r[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) w2r[k] = wts.w2[ch][k];
-#pragma unroll
-      for (int yi = 0; yi < 3; ++yi) {
-        const int y = pg + 4 * yi;
-        if (y < XWB) {
-          const float* h0 = hh_ + (y * XWH) * XH_HP + c8;
-          float i00 = h0[0], i01 = h0[XH_HP], i10 = h0[XWH * XH_HP], i11 = h0[(XWH + 1) * XH_HP];
-          float i20 = h0[2 * XWH * XH_HP], i21 = h0[(2 * XWH + 1) * XH_HP];
-#pragma unroll
-          for (int x = 0; x < XWB; ++x) {
-            const float i02 = h0[(x + 2) * XH_HP], i12 = h0[(XWH + x + 2) * XH_HP], i22 = h0[(2 * XWH + x + 2) * XH_HP];
-            float a = acc[yi * XWB + x];
-            a = fmaf(w2r[0], i00, a); a = fmaf(w2r[1], i01, a); a = fmaf(w2r[2], i02, a);
-            a = fmaf(w2r[3], i10, a); a = fmaf(w2r[4], i11, a); a = fmaf(w2r[5], i12, a);
-            a = fmaf(w2r[6], i20, a); a = fmaf(w2r[7], i21, a); a = fmaf(w2r[8], i22, a);
-            acc[yi * XWB + x] = a;
-            i00 = i01; i01 = i02; i10 = i11; i11 = i12; i20 = i21; i21 = i22;
-          }
-        }
-      }
-    }
-    __syncwarp();
   }
-  // sum over the 8 channel lanes (and thereby over the 16 channels); lane c8 == x & 7 publishes pixel (y, x)
-  float* zb = mm;                                  // the input window is dead: reuse it for the 121 logits
+  __syncwarp();
+  float* zb = reinterpret_cast<float*>(mm2);       // the input window is dead: reuse it for the 121 logits
+  {
+    float2 w2r[9];
 #pragma unroll
-  for (int yi = 0; yi < 3; ++yi) {
-    const int y = pg + 4 * yi;
+    for (int k = 0; k < 9; ++k) w2r[k] = wtab[(10 + k) * 8 + cp];
 #pragma unroll
-    for (int x = 0; x < XWB; ++x) {
-      float v = acc[yi * XWB + x];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      if (y < XWB && c8 == (x & 7)) zb[y * XWB + x] = v + wts.b2;
+    for (int yi = 0; yi < 3; ++yi) {
+      const int y = pg + 4 * yi;
+      const bool row_ok = y < XWB;                  // (row group 3 has no third row; its lanes still take part in the shuffles)
+      const float2* h0 = hh2 + ((row_ok ? y : 0) * XWH) * 8 + cp;
+      float2 i00 = h0[0], i01 = h0[8], i10 = h0[XWH * 8], i11 = h0[(XWH + 1) * 8];
+      float2 i20 = h0[2 * XWH * 8], i21 = h0[(2 * XWH + 1) * 8];
+#pragma unroll
+      for (int x = 0; x < XWB; ++x) {
+        const float2 i02 = h0[(x + 2) * 8], i12 = h0[(XWH + x + 2) * 8], i22 = h0[(2 * XWH + x + 2) * 8];
+        float2 a0 = __fmul2_rn(w2r[0], i00), a1 = __fmul2_rn(w2r[3], i10), a2 = __fmul2_rn(w2r[6], i20);
+        a0 = __ffma2_rn(w2r[1], i01, a0); a1 = __ffma2_rn(w2r[4], i11, a1); a2 = __ffma2_rn(w2r[7], i21, a2);
+        a0 = __ffma2_rn(w2r[2], i02, a0); a1 = __ffma2_rn(w2r[5], i12, a1); a2 = __ffma2_rn(w2r[8], i22, a2);
+        const float2 a = __fadd2_rn(__fadd2_rn(a0, a1), a2);
+        float v = a.x + a.y;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (row_ok && cp == (x & 7)) zb[y * XWB + x] = v + b2;
+        i00 = i01; i01 = i02; i10 = i11; i11 = i12; i20 = i21; i21 = i22;
+      }
     }
   }
   __syncwarp();
@@ -686,15 +680,28 @@ xw_window_kernel(int n_maps, int h, int w, int P, int n_tiles, const float* __re
 
 // (b) refiner + softmax sums + certificate: one warp per map; the next map's window (8 coalesced loads per lane) and
 // arg-max are in flight while the current map is refined.
-__global__ void __launch_bounds__(XH_WARPS * 32, 3)
+__global__ void __launch_bounds__(XH_WARPS * 32, 2)
 xw_head_kernel(int n_maps, XhParams hp, dinotrk_head_weights wts, const int* __restrict__ cell_group, const int* __restrict__ grp_map0,
                const int* __restrict__ cell_of, const float* __restrict__ win, const int2* __restrict__ hin,
                const int* __restrict__ out_index, float* __restrict__ out, int* __restrict__ slow_cnt, int* __restrict__ slow_list,
                int n_groups) {
-  extern __shared__ __align__(16) float xh_smem[];     // per warp [input window: 256 | hidden window: 1352]
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float* mm = xh_smem + XH_W2 + wid * XH_PER_WARP;
-  float* hh_ = mm + XH_MWIN;
+  extern __shared__ __align__(16) float xh_smem[];     // [weights table: 320] then per warp [input window pairs: 544 | hidden window: 2704]
+  // (the warp index through a shuffle: the compiler then knows that everything derived from it -- the map index, the
+  // loop trip count, the branches on the map's state -- is warp-uniform and keeps the shuffles below plain SHFLs instead
+  // of wrapping each in a WARPSYNC.COLLECTIVE sequence)
+  const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  float2* wtab = reinterpret_cast<float2*>(xh_smem);
+  float2* mm = reinterpret_cast<float2*>(xh_smem + XH_WTAB + wid * XH_PER_WARP);
+  float2* hh_ = reinterpret_cast<float2*>(xh_smem + XH_WTAB + wid * XH_PER_WARP + XH_MWIN);
+  // refiner weights as channel pairs (c, c + 8) in shared memory: a lane-indexed read of the constant bank serialises over
+  // its 8 distinct addresses in the address-divergence unit (55 % busy in the capture before this table existed)
+  if (threadIdx.x < 19 * 8) {
+    const int k = threadIdx.x >> 3, c = threadIdx.x & 7;
+    wtab[threadIdx.x] = k < 9    ? make_float2(wts.w1[c][k], wts.w1[c + 8][k])
+                        : k == 9 ? make_float2(wts.b1[c], wts.b1[c + 8])
+                                 : make_float2(wts.w2[c][k - 10], wts.w2[c + 8][k - 10]);
+  }
+  __syncthreads();
   const int h = hp.h, w = hp.w, P = hp.P;
   const int stride = gridDim.x * XH_WARPS;
 
@@ -724,9 +731,9 @@ xw_head_kernel(int n_maps, XhParams hp, dinotrk_head_weights wts, const int* __r
     if (!slow) {
       const int arow = amax / w, acol = amax - arow * w;
       if (arow >= 7 && arow + 7 < h && acol >= 7 && acol + 7 < w)
-        xw_refine<true>(hp, wts, mm, hh_, wv, arow, acol, lane, zmax, tot);
+        xw_refine<true>(hp, wtab, wts.b2, mm, hh_, wv, arow, acol, lane, zmax, tot);
       else
-        xw_refine<false>(hp, wts, mm, hh_, wv, arow, acol, lane, zmax, tot);
+        xw_refine<false>(hp, wtab, wts.b2, mm, hh_, wv, arow, acol, lane, zmax, tot);
 #pragma unroll
       for (int q = 0; q < 5; ++q) tot[q] = warp_sum(tot[q]);
     }
@@ -781,7 +788,7 @@ int launch_xw_head(const FeatView& fv, const dinotrk_geom& g, const dinotrk_head
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = cdiv(n_maps, XH_WARPS);
-  if (grid > sms * 3) grid = sms * 3;
+  if (grid > sms * 2) grid = sms * 2;
   static PerDev<bool> attr_dev;
   bool& attr = attr_dev.get();
   if (!attr) {
