@@ -58,6 +58,10 @@ SIGNATURES = {
     "dinotrk_corr_maps": (c_int, [POINTER(Features), POINTER(Geom), _P, _P, _P, _P, _P, _P, c_int, c_int, c_int,
                                   _P, _P, c_size_t, _P]),
     "dinotrk_head": (c_int, [_P, c_int, POINTER(Geom), POINTER(HeadWeights), _P, _P, c_int, c_int, _P, _P, _P]),
+    "dinotrk_sample_backward": (c_int, [c_int, c_int, POINTER(Geom), _P, c_int, _P, c_int, c_int, _P, _P, _P]),
+    "dinotrk_track_backward_workspace_bytes": (c_size_t, [c_int, c_int, POINTER(Geom)]),
+    "dinotrk_track_backward": (c_int, [POINTER(Features), POINTER(Geom), POINTER(HeadWeights), _P, _P, c_int, _P, _P, _P, _P, _P,
+                                       _P, c_int, _P, _P, _P, c_size_t, _P]),
     "dinotrk_infer_workspace_bytes": (c_size_t, [c_int, c_int, POINTER(Geom), c_int, c_int]),
     "dinotrk_infer_set_overlap": (c_int, [c_int]),
     "dinotrk_infer_set_path": (c_int, [c_int]),

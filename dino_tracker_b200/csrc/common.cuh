@@ -42,7 +42,7 @@ extern unsigned long long g_launches;
 enum ProfClass {
   PROF_SAMPLE = 0, PROF_CORR_GEMM, PROF_CORR_STREAM, PROF_HEAD, PROF_COS, PROF_ANCHOR_LIST, PROF_OCCLUSION,
   PROF_PACK, PROF_CONV, PROF_BLUR, PROF_ALIGN, PROF_MISC, PROF_BB, PROF_VIT_GEMM, PROF_VIT_ATTN, PROF_VIT_MISC, PROF_HEAD_FULL,
-  PROF_XW_COARSE, PROF_XW_PLAN, PROF_XW_GEMM, PROF_XW_HEAD,
+  PROF_XW_COARSE, PROF_XW_PLAN, PROF_XW_GEMM, PROF_XW_HEAD, PROF_TRAIN_BWD,
   PROF_COUNT
 };
 extern bool g_prof_on;

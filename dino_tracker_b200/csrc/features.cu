@@ -96,7 +96,7 @@ unsigned long long dinotrk_launch_count(void) { return dtk::g_launches; }
 static const char* kProfNames[PROF_COUNT] = {"sample", "corr_gemm", "corr_stream", "head", "traj_cos", "anchor_lists",
                                               "occlusion", "pack", "delta_conv", "delta_blur", "delta_align", "misc",
                                               "best_buddies", "vit_gemm", "vit_attn", "vit_misc", "head_full",
-                                              "xw_coarse_gemm", "xw_plan", "xw_exact_gemm", "xw_head"};
+                                              "xw_coarse_gemm", "xw_plan", "xw_exact_gemm", "xw_head", "train_backward"};
 int dinotrk_profile_classes(void) { return PROF_COUNT; }
 const char* dinotrk_profile_class_name(int cls) { return (cls >= 0 && cls < PROF_COUNT) ? kProfNames[cls] : ""; }
 void dinotrk_profile_enable(int on) { dtk::g_prof_on = on != 0; }

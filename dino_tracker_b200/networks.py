@@ -3,14 +3,17 @@
 ``DeltaDINO`` mirrors ``models/networks/delta_dino.py`` (keys ``layers.{0,4,8,12}.{weight,bias}``,
 ``layers.{1,5,9,13}.*`` BatchNorm, ``layers.{3,7,11}.filt``) and ``TrackerHead`` mirrors
 ``models/networks/tracker_head.py`` (keys ``cnn_refiner.{0,2}.{weight,bias}``), so the reference's
-checkpoints load bit-for-bit.  Neither module runs torch arithmetic in ``forward``: they fold /
-normalise their weights once per parameter version and hand them to the CUDA kernels.
+checkpoints load bit-for-bit.  Without autograd neither module runs torch arithmetic: they fold / normalise their
+weights once per parameter version and hand them to the CUDA kernels.  With autograd (the training step,
+``dino_tracker.py:405-429``) the refiner's weight normalisation and the delta-DINO CNN (train-mode BatchNorm, cuDNN
+convolutions) are torch graphs -- library code feeding the hand-written tracker forward / backward of ``train.py``.
 """
 import ctypes
 import math
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib
 
@@ -25,6 +28,13 @@ class NormalizedConv2d(nn.Module):
         nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
         fan_in = in_channels * kernel_size * kernel_size
         nn.init.uniform_(self.bias, -1 / math.sqrt(fan_in), 1 / math.sqrt(fan_in))
+
+    def normalized_weight_graph(self):
+        """The same normalisation as a torch graph on the parameter's device (training: the gradient of the
+        normalised weights, produced by ``dinotrk_track_backward``, flows back to ``weight`` through it)."""
+        s = self.weight.sum(dim=[2, 3], keepdim=True)
+        s = torch.where(s.abs() < 1e-8, torch.sign(s) * 1e-8, s)
+        return self.weight / s
 
     def normalized_weight(self):
         """conv_norm.py:34-46: w / sum_{3x3} w, |sum| < 1e-8 -> sign(sum) * 1e-8."""
@@ -72,6 +82,10 @@ class _BlurPoolParams(nn.Module):
         a = torch.tensor([1.0, 3.0, 3.0, 1.0])
         f = a[:, None] * a[None, :]
         self.register_buffer("filt", (f / f.sum())[None, None].repeat(channels, 1, 1, 1))
+
+    def forward(self, x):
+        """Autograd (training) path only: reflect pad (1, 2, 1, 2), depthwise 4 x 4 binomial filter, stride 2."""
+        return F.conv2d(F.pad(x, (1, 2, 1, 2), mode="reflect"), self.filt, stride=2, groups=x.shape[1])
 
 
 class DeltaDINO(nn.Module):
@@ -207,8 +221,29 @@ class DeltaDINO(nn.Module):
                     peers, len(peer_ptrs), first_frame + i, _lib.stream_ptr()), "delta_refine_allgather")
         return refined, norms
 
+    def wants_graph(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def forward_graph(self, x, vit_hw, vit_patch_size=14):
+        """Training path of models/networks/delta_dino.py:53-61 as a torch graph: the layer stack (BatchNorm in the
+        module's current mode) and the bilinear alignment of models/utils.py:7-45 (grid without gradient)."""
+        for layer in self.layers:
+            x = layer(x)
+        n_h, n_w = x.shape[-2:]
+        cnn_stride = self.get_total_stride()
+        axes = []
+        for n_c, n_v in ((n_w, vit_hw[1]), (n_h, vit_hw[0])):
+            c_br = (n_c - 1) * cnn_stride
+            v = torch.arange(n_v, dtype=x.dtype, device=x.device) * self.vit_stride + vit_patch_size / 2.
+            axes.append(-1. - (1. / c_br) + (2. * v / c_br))
+        gx, gy = torch.meshgrid(axes[0], axes[1], indexing="xy")
+        grid = torch.stack([gx, gy], dim=-1)[None].expand(x.shape[0], -1, -1, -1)
+        return F.grid_sample(x, grid=grid, mode="bilinear", padding_mode="border", align_corners=True)
+
     def forward(self, x, vit_features):
         """models/networks/delta_dino.py:53-61: returns the aligned residual B x C x h x w."""
+        if self.wants_graph():
+            return self.forward_graph(x.float(), vit_features.shape[-2:])
         B, C, h, w = vit_features.shape
         geom = _lib.make_geom(x.shape[-2], x.shape[-1], 14, self.vit_stride, 35)
         zeros = torch.zeros(B, h * w, C, device=vit_features.device, dtype=torch.float32)

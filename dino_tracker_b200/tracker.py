@@ -3,8 +3,11 @@
 Same constructor kwargs, attributes, ``forward`` / ``load_weights`` / ``cache_refined_embeddings`` /
 ``sample_embeddings`` signatures and state-dict keys as the reference (``models/tracker.py:17-180,
 303-325``), so ``dino_tracker.py::get_model`` and ``ModelInference`` use it unchanged.  All arithmetic is
-in the CUDA kernels; this file only owns tensors and forwards calls.  The training-only
-cycle-consistency methods (``models/tracker.py:182-301``) are out of scope.
+in the CUDA kernels; this file only owns tensors and forwards calls.  With gradients enabled (the training step of
+``dino_tracker.py:405-429``) ``forward`` builds a graph: delta-DINO as torch ops, the tracker as one autograd node
+with hand-written forward and backward kernels (``train.py``, ``csrc/train.cu``); ``get_point_predictions`` is the
+primitive the reference's cycle-consistency code (``models/tracker.py:182-301``) is written on.  The cycle-consistency
+sampling itself and the losses / optimiser loop of ``dino_tracker.py`` stay with the reference's trainer.
 
 Internal layout: features are kept token-major ``[T][P][C]`` (see include/dinotrk.h);
 ``refined_features`` / ``dino_embed_video`` expose zero-copy ``T x C x h x w`` views of them.
@@ -18,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import train as _train
 from .networks import DeltaDINO, TrackerHead
 from .range_normalizer import RangeNormalizer
 
@@ -54,7 +58,8 @@ class Tracker(nn.Module):
         self._refined_tpc = None
         self._refined_norms = None
         self._head_cache = (None, None)
-        self._local = None   # (refined tpc, norms) of the last uncached forward (training-style call)
+        self._local = None   # (refined tpc, norms) of the last uncached forward without a graph
+        self._graph = None   # (embeddings, raw, residual) of the last forward WITH a graph (training step)
 
         with torch.cuda.device(self._dev):
             if _adopt_tpc is not None:            # token-major features straight from the in-process ViT stage (no copy)
@@ -148,10 +153,15 @@ class Tracker(nn.Module):
     def get_refined_embeddings(self, frames_set_t, return_raw_embeddings=False):
         """models/tracker.py:113-129: refined = dino + align(delta_cnn(frames)) for the given frames."""
         idx = frames_set_t.to(self._dev).long()
-        tpc, _ = self._refined_for(idx)
-        refined = self._chw_view(tpc)
         raw = self.dino_embed_video[idx]
-        residual = refined - raw
+        if self.delta_dino.wants_graph():     # training: residual with delta-DINO's graph, batches of 8 frames (:118-123)
+            frames = _as_f32(self.video[idx.to(self.video.device)], self._dev)
+            residual = torch.cat([self.delta_dino(frames[i:i + 8], raw[i:i + 8]) for i in range(0, idx.shape[0], 8)], dim=0)
+            refined = raw + residual
+        else:
+            tpc, _ = self._refined_for(idx)
+            refined = self._chw_view(tpc)
+            residual = refined - raw
         if return_raw_embeddings:
             return refined, residual, raw
         return refined, residual
@@ -207,6 +217,8 @@ class Tracker(nn.Module):
     def sample_embeddings(self, embeddings, source_points):
         """models/tracker.py:96-111: embeddings T x C x h x w, source_points B x 3 = (x_n, y_n, t_index)
         with x_n, y_n in [-1, 1].  Returns B x C."""
+        if embeddings is not None and torch.is_grad_enabled() and embeddings.requires_grad:
+            return _train.sample_points(self, embeddings, source_points)      # contrastive losses, dino_tracker.py:215-220
         if embeddings is not None and self._refined_tpc is not None and \
                 embeddings.data_ptr() == self._refined_tpc.data_ptr():
             tpc = self._refined_tpc
@@ -256,6 +268,9 @@ class Tracker(nn.Module):
             if ih.numel() and (int(ih.min()) < 0 or int(ih.max()) >= n_set):
                 raise IndexError(f"{name} must index the frame set (size {n_set})")
         self._local = None
+        self._graph = None
+        if self._wants_graph(use_raw_features):
+            return self._forward_graph(inp, use_raw_features)
         tpc, norms, mode = self._features_for_forward(frames_set_t, use_raw_features)
         self._last_frames = (frames_set_t, use_raw_features)
         B = src_pts.shape[0]
@@ -286,11 +301,113 @@ class Tracker(nn.Module):
             _lib.ptr(ws), ws_bytes, _lib.stream_ptr(self._dev)), "corr_track")
         return out
 
+    # ------------------------------------------------------------------ training-step forward (graph)
+    def _wants_graph(self, use_raw_features):
+        if not torch.is_grad_enabled():
+            return False
+        if any(p.requires_grad for p in self.tracker_head.parameters()):
+            return True
+        return not use_raw_features and self._refined_tpc is None and self.delta_dino.wants_graph()
+
+    def _forward_graph(self, inp, use_raw_features):
+        """models/tracker.py:303-325 with autograd: same three sources of embeddings, kept (with their graph) as
+        ``frame_embeddings`` / ``raw_embeddings`` / ``residual_embeddings`` for the regularisation losses
+        (dino_tracker.py:136-146)."""
+        frames_set_t = inp[-1]
+        idx = frames_set_t.to(self._dev).long()
+        residual = None
+        if use_raw_features:
+            emb = raw = self.dino_embed_video[idx]
+        elif self._refined_tpc is not None:
+            emb, raw = self.refined_features[idx], self.dino_embed_video[idx]
+        else:
+            emb, residual, raw = self.get_refined_embeddings(frames_set_t, return_raw_embeddings=True)
+        self._graph = (emb, raw, residual)
+        self._last_frames = (frames_set_t, use_raw_features)
+        return self.get_point_predictions(inp, emb)
+
+    def get_point_predictions(self, inp, frame_embeddings):
+        """models/tracker.py:175-180: B x 2 in [-1, 1] from the frame set's embeddings N x C x h x w."""
+        return _train.track_points(self, frame_embeddings, inp)
+
+    # ------------------------------------------------------------------ cycle consistency (models/tracker.py:182-301)
+    @torch.no_grad()
+    def get_cycle_consistent_coords(self, frames_set_t, fg_masks):
+        """models/tracker.py:182-262.  ``cyc_n_frames`` random (source, target) slots of the frame set; per pair
+        ``cyc_batch_size_per_frame`` pixel positions of the source frame (share ``cyc_fg_points_ratio`` inside
+        ``fg_masks``), tracked source -> target -> source with the embeddings of the last forward; kept when they
+        return within ``cyc_thresh`` px.  Random draws in the reference's order (two ``randint`` on the frame set's
+        device, then per pair a foreground and a background ``randperm``)."""
+        dev = frames_set_t.device
+        n_set = frames_set_t.shape[0]
+        src_slots = torch.randint(n_set, (self.cyc_n_frames,), device=dev)
+        tgt_slots = torch.randint(n_set, (self.cyc_n_frames,), device=dev)
+        H, W = fg_masks.shape[-2:]
+        ys = torch.arange(H, device=fg_masks.device).float()
+        xs = torch.arange(W, device=fg_masks.device).float()
+        pixels = torch.stack([xs.repeat(H), ys.repeat_interleave(W)], dim=-1)        # row-major (x, y)
+        n_fg = int(self.cyc_batch_size_per_frame * self.cyc_fg_points_ratio)
+        n_bg = self.cyc_batch_size_per_frame - n_fg
+        emb = self.frame_embeddings
+        rows = {k: [] for k in ("source_points", "target_points", "cycle_points", "source_frame_indices",
+                                "target_frame_indices", "source_times", "target_times")}
+
+        def with_time(xy, t):
+            return torch.cat([xy, torch.full((xy.shape[0], 1), float(t), device=xy.device)], dim=-1)
+
+        def to_px(coords):
+            return self.range_normalizer.unnormalize(coords, src=(-1, 1), dims=[0, 1])
+
+        for s_slot, t_slot in zip(src_slots, tgt_slots):
+            t_src, t_tgt = frames_set_t[s_slot], frames_set_t[t_slot]
+            is_fg = (fg_masks[t_src] > 0).reshape(-1)
+            fg_px, bg_px = pixels[is_fg], pixels[~is_fg]
+            fg_px = fg_px[torch.randperm(fg_px.shape[0])[:n_fg]]
+            bg_px = bg_px[torch.randperm(bg_px.shape[0])[:n_bg]]
+            start = with_time(torch.cat([fg_px, bg_px], dim=0), t_src)
+            n = start.shape[0]
+            s_idx, t_idx = s_slot.repeat(n), t_slot.repeat(n)
+            there = with_time(to_px(self.get_point_predictions((start, s_idx, t_idx, frames_set_t), emb)), t_tgt)
+            back = to_px(self.get_point_predictions((there, t_idx, s_idx, frames_set_t), emb))
+            ok = torch.norm(start[:, :2] - back[:, :2], dim=1) <= self.cyc_thresh
+            m = int(ok.sum())
+            rows["source_points"].append(start[ok]); rows["target_points"].append(there[ok]); rows["cycle_points"].append(back[ok])
+            rows["source_frame_indices"].append(s_slot.repeat(m)); rows["target_frame_indices"].append(t_slot.repeat(m))
+            rows["source_times"].append(t_src.repeat(m)); rows["target_times"].append(t_tgt.repeat(m))
+        out = {k: torch.cat(v, dim=0) for k, v in rows.items()}
+        for name in ("source", "target"):
+            t3 = out.pop(f"{name}_times").unsqueeze(1).repeat(1, 3).float()
+            out[f"{name}_times_normalized"] = self.range_normalizer(t3, dst=(-1, 1), dims=[2])[:, 2]
+        return out
+
+    def get_cycle_consistent_preds(self, frames_set_t, fg_masks):
+        """models/tracker.py:264-301: redraw until at least one point survives the filter, then predict source -> target
+        and target -> source WITH the graph (the cycle-consistency loss of dino_tracker.py:346-353 trains on them)."""
+        while True:
+            cyc = self.get_cycle_consistent_coords(frames_set_t, fg_masks)
+            if cyc["source_points"].shape[0] > 0:
+                break
+        emb = self.frame_embeddings
+        fwd = self.get_point_predictions((cyc["source_points"], cyc["source_frame_indices"], cyc["target_frame_indices"],
+                                          frames_set_t), emb)
+        bwd = self.get_point_predictions((cyc["target_points"], cyc["target_frame_indices"], cyc["source_frame_indices"],
+                                          frames_set_t), emb)
+        return {
+            "source_coords": self.range_normalizer(cyc["source_points"], dst=[-1, 1]),
+            "target_coords": self.range_normalizer(cyc["target_points"], dst=[-1, 1]),
+            "source_target_coords": fwd[:, :2],
+            "target_source_coords": bwd[:, :2],
+            "cycle_consistency_dists": torch.norm(cyc["cycle_points"][:, :2] - cyc["source_points"][:, :2], dim=1),
+            "cycle_points": cyc["cycle_points"],
+        }
+
     # the reference stores gathered copies of the frame set on every call (models/tracker.py:322-323);
     # they are materialised lazily here (only training code reads them)
     @property
     def frame_embeddings(self):
         fs, raw = self._last_frames
+        if getattr(self, "_graph", None) is not None:
+            return self._graph[0]
         if not raw and self._local is not None:   # uncached forward: the refined embeddings of that frame set
             return self._chw_view(self._local[0])
         src = self.dino_embed_video if raw else self.refined_features
@@ -302,9 +419,13 @@ class Tracker(nn.Module):
         fs, raw = self._last_frames
         if raw:
             return None
+        if getattr(self, "_graph", None) is not None and self._graph[2] is not None:
+            return self._graph[2]
         return self.frame_embeddings - self.raw_embeddings
 
     @property
     def raw_embeddings(self):
         fs, _ = self._last_frames
+        if getattr(self, "_graph", None) is not None:
+            return self._graph[1]
         return self.dino_embed_video[fs.to(self._dev).long()]

@@ -120,6 +120,29 @@ int dinotrk_head(const float* maps, int n_maps, const dinotrk_geom* g,
                  const dinotrk_head_weights* hw, const int* out_index, float* out,
                  int out_stride, int out_mode, int* aux, int* scratch, void* stream);
 
+/* ---- training: reverse pass of the tracker forward (dino_tracker.py:405-429, models/tracker.py:170-180,303-325) -- */
+/* The forward of a training step is dinotrk_sample_descriptors + dinotrk_corr_maps + dinotrk_head (with aux) on the
+ * frame set's embeddings, with desc / desc_norm / maps / aux kept.  Given grad_out [B][2] = d loss / d coords (the
+ * normalised output of Tracker.forward), row j of points / desc / maps / aux / tgt_frame / grad_out describing map j:
+ *   grad_w   float[305] += d loss / d (w1[16][9] | b1[16] | w2[16][9] | b2), w1 / w2 the NORMALISED refiner weights of
+ *            dinotrk_head_weights (the spatial-sum normalisation of conv_norm.py:34-46 stays with the caller's autograd);
+ *   grad_tpc [T][P][C] += d loss / d feat->tpc, through the target maps (tracker.py:158-169) and through the sampled
+ *            source descriptors (tracker.py:96-111); NULL: embeddings without gradient (cached refined features).
+ * points [B][3] = (x_px, y_px, set slot) and frames_set [N] as given to dinotrk_sample_descriptors; tgt_frame [B] =
+ * the FRAME (index into feat) each map correlates against.  arg-max and disc mask carry no gradient (as in autograd).
+ * Accumulates with atomics: the caller zeroes grad_w / grad_tpc.  Syncs: no. */
+size_t dinotrk_track_backward_workspace_bytes(int B, int C, const dinotrk_geom* g);
+int dinotrk_track_backward(const dinotrk_features* feat, const dinotrk_geom* g, const dinotrk_head_weights* hw,
+                           const float* points, const int* frames_set, int N, const float* desc,
+                           const float* desc_norm, const int* tgt_frame, const float* maps, const int* aux,
+                           const float* grad_out, int B, float* grad_w, float* grad_tpc, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* Reverse pass of dinotrk_sample_descriptors alone (the contrastive losses sample refined embeddings with a graph,
+ * dino_tracker.py:215-220): grad_tpc [T][P][C] += the trilinear weights of every point times grad_desc [B][C]. */
+int dinotrk_sample_backward(int T, int C, const dinotrk_geom* g, const float* points, int B, const int* frames_set,
+                            int N, int points_normalized, const float* grad_desc, float* grad_tpc, void* stream);
+
 /* ---- inference driver (models/model_inference.py:97-216) ------------------------------- */
 /* query_points [N][3] (x, y, t) px; frame_batch = the reference's --batch-size (0 = whole
  * video).  Outputs: traj [N][T][3] (x, y, t); cos_sims [N][T]; anchors [N][T(a)][T(i)][2] valid

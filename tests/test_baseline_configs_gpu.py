@@ -235,7 +235,8 @@ def test_uncached_forward_twice_uses_fresh_split():
         src = torch.randint(0, 3, (B,), generator=g)
         tgt = torch.full((B,), 1, dtype=torch.long)          # > 8 maps on one frame: tensor-core GEMM path
         inp = (pts.to(DEV), src.to(DEV), tgt.to(DEV), frames_set.to(DEV))
-        out = m(inp).cpu()
+        with torch.no_grad():        # the inference kernels (with gradients enabled forward() builds the training graph)
+            out = m(inp).cpu()
         ref = ot.tracker_forward(feats, (pts, src, tgt, frames_set), head, geo)
         assert ((out - ref).abs() * scale).max().item() <= XY_TOL, fs
         # training-style consumers read the refined embeddings of the frame set (models/tracker.py:319-322)

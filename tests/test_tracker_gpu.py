@@ -181,7 +181,8 @@ def test_forward_matches_reference_vectors(name):
     model.cache_refined_embeddings()
     q = torch.from_numpy(g["query_points"]).to(DEV)
     inp = generate_trajectory_input(q[0], model.video)
-    out = model(inp)
+    with torch.no_grad():            # inference kernels (tests/test_train_gpu.py covers the graph path)
+        out = model(inp)
     scale = np.array([geo.W - 1, geo.H - 1]) / 2
     assert (np.abs(out.cpu().numpy() - g["forward0"]) * scale).max() <= XY_TOL
     # anchor-style input: sources in their own frames, one target
@@ -189,7 +190,8 @@ def test_forward_matches_reference_vectors(name):
     preds = torch.from_numpy(g["trajectories"][1]).to(DEV)
     fs = torch.cat([torch.tensor([2]), torch.arange(T)]).int().to(DEV)
     inp2 = (preds, torch.arange(1, T + 1, device=DEV), torch.zeros(T, dtype=torch.long, device=DEV), fs)
-    out2 = model(inp2).cpu()
+    with torch.no_grad():
+        out2 = model(inp2).cpu()
     ref2 = ot.tracker_forward(feats, (preds.cpu(), torch.arange(1, T + 1), torch.zeros(T, dtype=torch.long), fs.cpu()),
                               head, geo)
     assert ((out2 - ref2).abs() * torch.from_numpy(scale).float()).max().item() <= XY_TOL
