@@ -524,6 +524,7 @@ def run_b200(args):
         model = mi = None
     if args.stages and world == 1:
         line["stages"] = stage_timings(args, dev, _lib, peaks)
+        line["stages"]["train_step"] = train_step_stage(args, dev, _lib, bool(args.torch_cuda_baseline))
         fs = line["stages"]["per_video_feature_stage_s"]
         line["stages"]["query_points_per_s_from_pixels"] = nq / (fs + ms / args.steps / 1000.0)
     if args.cpu_baseline and world == 1:
@@ -679,6 +680,59 @@ def stage_timings(args, dev, _lib, peaks, vit_only=False):
     out["best_buddies"] = {"ordered_pairs_per_s": len(pairs) / (ms / 1000), "ms_per_ordered_pair": ms / len(pairs),
                            "tflops": 2.0 * P * P * args.C * len(pairs) / (ms / 1000) / 1e12, "kernel_ms_per_call": prof,
                            "math": "tcgen05 3xTF32 GEMM + top-2 epilogue + exact fp32 resolve"}
+    return out
+
+
+def train_step_stage(args, dev, _lib, torch_baseline):
+    """The tracker node of one training iteration (dino_tracker.py:405-411) at the reference's batch shape
+    (config/train.yaml: train_batch_size 512 points, batch_n_frames 4): forward with the graph and the CUDA reverse
+    pass down to d loss / d embeddings and d loss / d refiner weights, device-timed; beside it (optional) the same node
+    as PyTorch-CUDA autograd through the oracle's restatement (exact fp32) -- what the reference's trainer executes."""
+    from dino_tracker_b200 import Tracker
+    N, B = 4, 512
+    feats = synth_video_features(N, args.C, dev, seed=3, noise=args.noise)
+    head = head_weights_for(args.head)
+    m = Tracker(video=torch.zeros(N, 3, H, W, device=dev), dino_embed_video=feats, device=dev, delta_channels=[3, 8, 8, 8, args.C])
+    m.tracker_head.load_state_dict(head)
+    cg = torch.Generator().manual_seed(12)
+    pts = (torch.rand(B, 3, generator=cg) * torch.tensor([W - 1.0, H - 1.0, 0.0])).to(dev)
+    src = torch.randint(0, N, (B,), generator=cg).to(dev)
+    tgt = torch.randint(0, N, (B,), generator=cg).to(dev)
+    labels = (torch.rand(B, 2, generator=cg) * 2 - 1).to(dev)
+    fs = torch.arange(N, dtype=torch.int32, device=dev)
+    huber = torch.nn.HuberLoss(delta=1 / 32, reduction="none")
+
+    def run(forward, reps):
+        f_ms, b_ms = [], []
+        for i in range(reps + 1):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            loss = huber(forward(), labels).mean()
+            e[1].record()
+            loss.backward()
+            e[2].record(); torch.cuda.synchronize()
+            if i:       # first pass = warm-up
+                f_ms.append(e[0].elapsed_time(e[1])); b_ms.append(e[1].elapsed_time(e[2]))
+        return sum(f_ms) / reps, sum(b_ms) / reps
+
+    emb = feats.clone().requires_grad_(True)
+    _lib.profile_enable(True); _lib.profile_collect()
+    f_ms, b_ms = run(lambda: m.get_point_predictions((pts, src, tgt, fs), emb), 3)
+    prof = _lib.profile_collect(); _lib.profile_enable(False)
+    out = {"batch_points": B, "frames": N, "C": args.C, "forward_ms": f_ms, "backward_ms": b_ms,
+           "kernel_ms_per_step": {k: round(v[0] / 4, 3) for k, v in prof.items()},
+           "gradients": "embeddings [4][8107][C] + normalised refiner weights (305)",
+           "note": "tracker node only; delta-DINO's convolutions / BatchNorm of the training graph are torch (cuDNN) ops"}
+    if torch_baseline:
+        import oracle
+        from oracle import tracker as ot
+        oracle.use_exact_fp32()
+        geo = ot.Geometry(H=H, W=W)
+        f_o = feats.clone().requires_grad_(True)
+        head_o = {k: v.to(dev).requires_grad_(True) for k, v in head.items()}
+        tf_ms, tb_ms = run(lambda: ot.tracker_forward(f_o, (pts, src, tgt, fs), head_o, geo), 2)
+        out["torch_cuda_autograd"] = {"forward_ms": tf_ms, "backward_ms": tb_ms,
+                                      "speedup": (tf_ms + tb_ms) / (f_ms + b_ms)}
     return out
 
 
