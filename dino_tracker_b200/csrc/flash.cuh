@@ -2,15 +2,16 @@
 // head_dim^-1/2 * log2(e), so the softmax is exp2(s - max).
 //
 // One CTA per (frame*head, 128-query tile), two CTAs per SM; 192 threads:
-//   warp 0     : TMA producer (Q once; K_j [64 keys][64] and V^T_j [64][64 keys] through a 3-stage ring)
+//   warp 0     : TMA producer (Q once; K_j [64 keys][64] and V^T_j [64][64 keys] through a 4-stage ring)
 //   warp 1     : TMEM alloc + MMA issue.  S_j = Q K_j^T (kind::f16, M128 N64 K64) goes to one of TWO TMEM score buffers,
-//                so S_{j+1} is computed while the softmax warps work on S_j;  O += P_j V_j (M128 N80 K64) accumulates IN
-//                TMEM across all key tiles.  The V^T stage carries a 65th row of ones (written once, never touched by
+//                so S_{j+1} is computed while the softmax warps work on S_j;  O += P_j V_j (M128 N80 K64, A = P_j read
+//                FROM TENSOR MEMORY) accumulates IN TMEM across all key tiles.  The V^T stage carries a 65th row of ones (written once, never touched by
 //                the TMA), so accumulator column 64 is the softmax denominator sum_j P_j 1 - computed by the tensor
 //                core from the same fp16 P that multiplies V, at no issue-slot cost.
 //   warps 2..5 : softmax, thread = query row = TMEM lane.  Per key tile: one TMEM read of the 64 scores, row max
-//                (FMNMX3), p = exp2(s - m), fp16 P into one of two 128B-swizzled shared-memory tiles (A operand of the
-//                second MMA).  The running max m is LAZY: it only moves (and the TMEM accumulator is only rescaled,
+//                (FMNMX3), p = exp2(s - m), fp16 P stored back over the first 32 columns of the score buffer it came
+//                from (one tcgen05.st; no shared-memory tile, no generic->async proxy fence): S_{j+2}, the next writer of
+//                that buffer, is issued after P_j V_j and the tensor pipe executes in order.  The running max m is LAZY: it only moves (and the TMEM accumulator is only rescaled,
 //                tcgen05.ld -> multiply -> tcgen05.st) when some row of the warp would exceed it by 2^8, so after the
 //                first few tiles there is no per-tile accumulator traffic at all; p <= 256 keeps fp16 P in range, and
 //                the final O / l is independent of which m was used.  The exponentials are MUFU-bound (16/clk/SM
@@ -29,15 +30,14 @@ namespace dtk {
 constexpr int FA_POLY_DEFAULT = 0x88;   // 25 %
 constexpr int FA_BQ = 128, FA_BKV = 64, FA_D = 64, FA_THREADS = 192;
 constexpr int FA_NV = 80;                          // V^T tile rows = MMA N: 64 head dims, one row of ones, 15 rows of zeros
-constexpr int FA_KV_STAGES = 3;
+constexpr int FA_KV_STAGES = 4;
 constexpr int FA_SQ = FA_BQ * 128;                 // Q tile bytes (128 rows x 64 fp16)
 constexpr int FA_SK = FA_BKV * 128;                // K tile bytes
 constexpr int FA_SVT = FA_D * 128;                 // TMA-written part of the V^T tile
 constexpr int FA_SV = FA_NV * 128;                 // whole V^T tile
-constexpr int FA_SP = FA_BQ * 128;                 // P tile: [128 rows][64 keys] fp16
 constexpr int FA_STAGE = FA_SK + FA_SV;
-constexpr int FA_TMEM = 256;                       // S0 [0,64) S1 [64,128) O [128,208)
-constexpr int FA_SMEM = FA_SQ + FA_KV_STAGES * FA_STAGE + 2 * FA_SP + 256;   // extern smem is declared 1024-byte aligned
+constexpr int FA_TMEM = 256;                       // S0 [0,64) S1 [64,128) O [128,208); P_j = columns [0,32) of S_{j&1}
+constexpr int FA_SMEM = FA_SQ + FA_KV_STAGES * FA_STAGE + 256;   // extern smem is declared 1024-byte aligned
 constexpr float FA_RESCALE_STEP = 8.f;             // log2 units
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -54,6 +54,19 @@ __device__ __forceinline__ float poly_exp2(float x) {
   p = fmaf(p, f, 0.6932298f);
   p = fmaf(p, f, 1.f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// the same for two values at once on packed fp32 instructions (FADD2 / FFMA2: one issue slot per pair)
+__device__ __forceinline__ float2 poly_exp2x2(float2 x) {
+  x.x = fmaxf(x.x, -125.f); x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f), neg_magic = make_float2(-12582912.f, -12582912.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 r = __fadd2_rn(t, neg_magic);
+  const float2 f = __ffma2_rn(r, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(make_float2(0.055268917f, 0.055268917f), f, make_float2(0.24221092f, 0.24221092f));
+  p = __ffma2_rn(p, f, make_float2(0.6932298f, 0.6932298f));
+  p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
@@ -76,15 +89,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   extern __shared__ __align__(1024) uint8_t fa_smem[];
   uint8_t* sQ = fa_smem;
   uint8_t* sKV = sQ + FA_SQ;                 // stage s: K at sKV + s*FA_STAGE, V^T at + FA_SK
-  uint8_t* sP = sKV + FA_KV_STAGES * FA_STAGE;   // two P tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_SP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + FA_KV_STAGES * FA_STAGE);
   uint64_t* q_full = bars;           // 1
-  uint64_t* kv_full = bars + 1;      // [3]
-  uint64_t* kv_empty = bars + 4;     // [3]
-  uint64_t* s_full = bars + 7;       // [2]
-  uint64_t* p_ready = bars + 9;      // [2] (4 arrivals: one per softmax warp)
-  uint64_t* pv_done = bars + 11;     // [2] P V_j retired: P tile j&1 reusable, accumulator quiescent until p_ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* kv_full = bars + 1;                               // [FA_KV_STAGES]
+  uint64_t* kv_empty = kv_full + FA_KV_STAGES;                // [FA_KV_STAGES]
+  uint64_t* s_full = kv_empty + FA_KV_STAGES;                 // [2]
+  uint64_t* p_ready = s_full + 2;    // [2] (4 arrivals: one per softmax warp)
+  uint64_t* pv_done = p_ready + 2;   // [2] P V_j retired: accumulator quiescent until the next p_ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  static_assert((1 + 2 * FA_KV_STAGES + 6) * 8 + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, q0 = blockIdx.x * FA_BQ;
@@ -139,12 +152,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc::mma_ss<false>(tmem_base + buf * FA_BKV, tc::smem_desc_sw128(a + ks * 32), tc::smem_desc_sw128(b + ks * 32), kIdescS,
                           ks ? 1u : 0u);
     };
-    auto mma_O = [&](int s, int buf, bool acc) {   // O (+)= P [V | 1] : 4 k-steps over 64 keys
-      const uint32_t a = tc::smem_u32(sP + buf * FA_SP), b = tc::smem_u32(sKV + s * FA_STAGE + FA_SK);
+    auto mma_O = [&](int s, int buf, bool acc) {   // O (+)= P [V | 1] : 4 k-steps over 64 keys, P from tensor memory
+      const uint32_t b = tc::smem_u32(sKV + s * FA_STAGE + FA_SK);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        tc::mma_ss<false>(tmem_O, tc::smem_desc_sw128(a + ks * 32), tc::smem_desc_sw128(b + ks * 32), kIdescO,
-                          (acc || ks) ? 1u : 0u);
+        tc::mma_ts_f16(tmem_O, tmem_base + buf * FA_BKV + ks * 8, tc::smem_desc_sw128(b + ks * 32), kIdescO, (acc || ks) ? 1u : 0u);
     };
     tc::mbar_wait(q_full, 0);
     tc::mbar_wait(&kv_full[0], 0);
@@ -154,7 +166,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     int s = 0, s1 = 1, ph1 = 0;   // s: stage of tile j; s1 / ph1: stage and phase of tile j + 1
     for (int j = 0; j < n_kv; ++j) {
       if (j + 1 < n_kv) {
-        // score buffer (j+1)&1 was last read by the softmax of tile j-1, which arrived on p_ready before PV_{j-1} was issued
+        // score buffer (j+1)&1 held S_{j-1} and P_{j-1}: read by the softmax of tile j-1 (arrived on p_ready before
+        // PV_{j-1} was issued) and by PV_{j-1} itself, which precedes this MMA in the in-order tensor pipe
         tc::mbar_wait(&kv_full[s1], ph1);
         tc::fence_after_sync();
         if (tc::elect_one()) { mma_S(s1, (j + 1) & 1); tc::mma_commit(&s_full[(j + 1) & 1]); }
@@ -177,18 +190,23 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int row = quad * 32 + lane;                 // row inside the Q tile = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     float m_run = -INFINITY;
+    // The scores of tile j + 1 are requested from TMEM BEFORE the P tile of tile j is stored and published: the softmax
+    // warps are nearly alone on their schedulers (two per SMSP), so the TMEM read latency was fully exposed at the top
+    // of every tile (long-scoreboard stalls: 1.6 cycles per issued instruction in the capture of the unrotated loop).
+    uint32_t v[FA_BKV];
+    uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+    uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+    auto request_scores = [&](int jj) {
+      tc::mbar_wait(&s_full[jj & 1], (jj >> 1) & 1);
+      tc::fence_after_sync();
+      tc::tmem_ld32(tmem_base + lane_addr + (jj & 1) * FA_BKV, v0);
+      tc::tmem_ld32(tmem_base + lane_addr + (jj & 1) * FA_BKV + 32, v1);
+    };
+    request_scores(0);
     for (int j = 0; j < n_kv; ++j) {
       const int buf = j & 1, kbase = j * FA_BKV;
-      tc::mbar_wait(&s_full[buf], (j >> 1) & 1);
-      tc::fence_after_sync();
-      uint32_t v[FA_BKV];
-      {
-        uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-        uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-        tc::tmem_ld32(tmem_base + lane_addr + buf * FA_BKV, v0);
-        tc::tmem_ld32(tmem_base + lane_addr + buf * FA_BKV + 32, v1);
-        tc::tmem_ld_wait();
-      }
+      tc::tmem_ld_wait(v0);
+      tc::tmem_ld_wait(v1);
       if (kbase + FA_BKV > N1) {                      // only the last key tile needs masking
 #pragma unroll
         for (int i = 0; i < FA_BKV; ++i)
@@ -205,6 +223,15 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           m4[k] = fmaxf(m4[k], __uint_as_float(v[16 * k + 15]));
         }
         mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+      }
+      // publish P_{j-1}: its tcgen05.st was issued at the end of the previous iteration and had the score read and the
+      // max phase of this tile to land (the wait right behind the store cost its full latency on every tile).  S_{j+1} does
+      // not depend on this arrival (it is issued before P_{j-1} V_{j-1}), and the rescale below needs it to have happened.
+      if (j > 0) {
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&p_ready[(j - 1) & 1]);
       }
       // lazy running max: move it (and rescale the TMEM accumulator, row sums included) only on a 2^8 overshoot
       if (__any_sync(0xffffffffu, mx > m_run + FA_RESCALE_STEP)) {
@@ -234,27 +261,24 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       // p = exp2(s - m) as fp16 pairs
       uint32_t packed[FA_BKV / 2];
+      const float2 neg_m = make_float2(-m_run, -m_run);
 #pragma unroll
       for (int i = 0; i < FA_BKV; i += 2) {
-        const float x0 = __uint_as_float(v[i]) - m_run, x1 = __uint_as_float(v[i + 1]) - m_run;
-        float p0, p1;
-        if ((POLY >> ((i / 2) & 7)) & 1) { p0 = poly_exp2(x0); p1 = poly_exp2(x1); }
-        else { p0 = fast_exp2(x0); p1 = fast_exp2(x1); }
-        __half2 h = __floats2half2_rn(p0, p1);
+        const float2 x = __fadd2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), neg_m);   // one packed add
+        float2 pp;
+        if ((POLY >> ((i / 2) & 7)) & 1) pp = poly_exp2x2(x);
+        else pp = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+        __half2 h = __floats2half2_rn(pp.x, pp.y);
         packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
       }
-      if (j >= 2) tc::mbar_wait(&pv_done[buf], ((j - 2) >> 1) & 1);   // P tile `buf` was the A operand of PV_{j-2}
-      // fp16 P tile in the 128B-swizzled K-major layout: 64 keys = 8 chunks of 16 bytes per row
-      uint8_t* base = sP + buf * FA_SP + row * 128;
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        *reinterpret_cast<uint4*>(base + ((ch ^ (row & 7)) << 4)) =
-            make_uint4(packed[ch * 4], packed[ch * 4 + 1], packed[ch * 4 + 2], packed[ch * 4 + 3]);
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the MMA
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&p_ready[buf]);
+      if (j + 1 < n_kv) request_scores(j + 1);   // S_{j+1} was issued before PV_{j-1}: never waits on our own p_ready
+      // fp16 P over the first 32 columns of the score buffer (this thread's lane: its scores are already in registers)
+      tc::tmem_st32(tmem_base + lane_addr + buf * FA_BKV, packed);
     }
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&p_ready[(n_kv - 1) & 1]);
     // accumulator complete: normalise by the tensor-core row sum (column 64) and store
     tc::mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc::fence_after_sync();
