@@ -3,20 +3,20 @@
 //
 // One CTA per (frame*head, 128-query tile), two CTAs per SM; 192 threads:
 //   warp 0     : TMA producer (Q once; K_j [64 keys][64] and V^T_j [64][64 keys] through a 4-stage ring)
-//   warp 1     : TMEM alloc + MMA issue.  S_j = Q K_j^T (kind::f16, M128 N64 K64) goes to one of TWO TMEM score buffers,
-//                so S_{j+1} is computed while the softmax warps work on S_j;  O += P_j V_j (M128 N80 K64, A = P_j read
-//                FROM TENSOR MEMORY) accumulates IN TMEM across all key tiles.  The V^T stage carries a 65th row of ones (written once, never touched by
-//                the TMA), so accumulator column 64 is the softmax denominator sum_j P_j 1 - computed by the tensor
-//                core from the same fp16 P that multiplies V, at no issue-slot cost.
-//   warps 2..5 : softmax, thread = query row = TMEM lane.  Per key tile: one TMEM read of the 64 scores, row max
-//                (FMNMX3), p = exp2(s - m), fp16 P stored back over the first 32 columns of the score buffer it came
-//                from (one tcgen05.st; no shared-memory tile, no generic->async proxy fence): S_{j+2}, the next writer of
-//                that buffer, is issued after P_j V_j and the tensor pipe executes in order.  The running max m is LAZY: it only moves (and the TMEM accumulator is only rescaled,
-//                tcgen05.ld -> multiply -> tcgen05.st) when some row of the warp would exceed it by 2^8, so after the
-//                first few tiles there is no per-tile accumulator traffic at all; p <= 256 keeps fp16 P in range, and
-//                the final O / l is independent of which m was used.  The exponentials are MUFU-bound (16/clk/SM
-//                against 4 x 128 x 64-wide MMAs), so every FA_POLY_EVERY-th one is evaluated on the FMA pipe instead
-//                (Cody-Waite split + cubic, relative error 1.1e-4 < fp16 rounding of P).
+//   warp 1     : TMEM alloc + MMA issue.  S_j = Q K_j^T (kind::f16, M128 N64 K64) goes to one of TWO TMEM score buffers
+//                and is issued as soon as the softmax warps have READ S_{j-2} out of that buffer (s_free) -- two tiles
+//                ahead of its consumer, independent of the P V chain;  O += P_j V_j (M128 N64 K64, A = P_j read FROM
+//                TENSOR MEMORY) accumulates IN TMEM across all key tiles.
+//   warps 2..5 : softmax, thread = query row = TMEM lane.  Per key tile: the 64 scores (requested from TMEM one tile
+//                ahead), row max (FMNMX3), p = exp2(s - m), row sum in registers, fp16 P into one of two 32-column TMEM
+//                buffers (one tcgen05.st; no shared-memory tile, no generic->async proxy fence), published one tile
+//                later (the store has the next tile's score read and max phase to land).  The running max m is LAZY:
+//                it only moves (and the TMEM accumulator is only rescaled, tcgen05.ld -> multiply -> tcgen05.st) when
+//                some row of the warp would exceed it by 2^8, so after the first few tiles there is no per-tile
+//                accumulator traffic at all; p <= 256 keeps fp16 P in range, and the final O / l is independent of
+//                which m was used.  The exponentials are MUFU-bound (16/clk/SM against 4 x 128 x 64-wide MMAs), so a
+//                share of them (POLY) is evaluated on the FMA pipe instead (Cody-Waite split + cubic on packed fp32
+//                instructions, relative error 1.1e-4 < fp16 rounding of P).
 // The score matrix (8108 x 8108 per head) never leaves the SM.
 #pragma once
 #include <cuda_fp16.h>
@@ -29,14 +29,14 @@ namespace dtk {
 // POLY (template parameter of the kernel): bit k set -> the k-th fp16 pair of every 8 pairs takes the FMA-pipe exp2
 constexpr int FA_POLY_DEFAULT = 0x88;   // 25 %
 constexpr int FA_BQ = 128, FA_BKV = 64, FA_D = 64, FA_THREADS = 192;
-constexpr int FA_NV = 80;                          // V^T tile rows = MMA N: 64 head dims, one row of ones, 15 rows of zeros
+constexpr int FA_NV = 64;                          // V^T tile rows = MMA N: the 64 head dims
 constexpr int FA_KV_STAGES = 4;
 constexpr int FA_SQ = FA_BQ * 128;                 // Q tile bytes (128 rows x 64 fp16)
 constexpr int FA_SK = FA_BKV * 128;                // K tile bytes
 constexpr int FA_SVT = FA_D * 128;                 // TMA-written part of the V^T tile
 constexpr int FA_SV = FA_NV * 128;                 // whole V^T tile
 constexpr int FA_STAGE = FA_SK + FA_SV;
-constexpr int FA_TMEM = 256;                       // S0 [0,64) S1 [64,128) O [128,208); P_j = columns [0,32) of S_{j&1}
+constexpr int FA_TMEM = 256;                       // S0 [0,64) S1 [64,128) O [128,192) P0 [192,224) P1 [224,256)
 constexpr int FA_SMEM = FA_SQ + FA_KV_STAGES * FA_STAGE + 256;   // extern smem is declared 1024-byte aligned
 constexpr float FA_RESCALE_STEP = 8.f;             // log2 units
 
@@ -95,9 +95,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* kv_empty = kv_full + FA_KV_STAGES;                // [FA_KV_STAGES]
   uint64_t* s_full = kv_empty + FA_KV_STAGES;                 // [2]
   uint64_t* p_ready = s_full + 2;    // [2] (4 arrivals: one per softmax warp)
-  uint64_t* pv_done = p_ready + 2;   // [2] P V_j retired: accumulator quiescent until the next p_ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-  static_assert((1 + 2 * FA_KV_STAGES + 6) * 8 + 4 <= 256, "barrier block");
+  uint64_t* pv_done = p_ready + 2;   // [2] P V_j retired: P buffer j&1 reusable, accumulator quiescent until the next p_ready
+  uint64_t* s_free = pv_done + 2;    // [2] (4 arrivals) S_j is in the softmax warps' registers: its buffer may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  static_assert((1 + 2 * FA_KV_STAGES + 8) * 8 + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, q0 = blockIdx.x * FA_BQ;
@@ -108,25 +109,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV);
     tc::mbar_init(q_full, 1);
     for (int s = 0; s < FA_KV_STAGES; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_ready[s], 4); tc::mbar_init(&pv_done[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_ready[s], 4); tc::mbar_init(&pv_done[s], 1); tc::mbar_init(&s_free[s], 4);
+    }
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, FA_TMEM);
-  if (warp >= 2) {
-    // rows 64..79 of every V^T stage: ones (fp16 0x3C00) in row 64, zeros below; a constant row is swizzle-invariant
-    const int t = threadIdx.x - 64;   // 0..127: 3 stages x 16 rows x 8 chunks of 16 B = 384 chunks
-    for (int i = t; i < FA_KV_STAGES * 16 * 8; i += 128) {
-      const int s = i / 128, r = (i >> 3) & 15, ch = i & 7;
-      const uint32_t val = r == 0 ? 0x3C003C00u : 0u;
-      *reinterpret_cast<uint4*>(sKV + s * FA_STAGE + FA_SK + FA_SVT + r * 128 + ch * 16) = make_uint4(val, val, val, val);
-    }
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 2 * FA_BKV;
+  const uint32_t tmem_O = tmem_base + 2 * FA_BKV, tmem_P = tmem_O + FA_D;
   constexpr uint32_t kIdescS = tc::make_idesc(0, 128, FA_BKV);   // f16 inputs, fp32 accumulate
   constexpr uint32_t kIdescO = tc::make_idesc(0, 128, FA_NV);
 
@@ -152,37 +145,37 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc::mma_ss<false>(tmem_base + buf * FA_BKV, tc::smem_desc_sw128(a + ks * 32), tc::smem_desc_sw128(b + ks * 32), kIdescS,
                           ks ? 1u : 0u);
     };
-    auto mma_O = [&](int s, int buf, bool acc) {   // O (+)= P [V | 1] : 4 k-steps over 64 keys, P from tensor memory
+    auto mma_O = [&](int s, int buf, bool acc) {   // O (+)= P V : 4 k-steps over 64 keys, P from tensor memory
       const uint32_t b = tc::smem_u32(sKV + s * FA_STAGE + FA_SK);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
-        tc::mma_ts_f16(tmem_O, tmem_base + buf * FA_BKV + ks * 8, tc::smem_desc_sw128(b + ks * 32), kIdescO, (acc || ks) ? 1u : 0u);
+        tc::mma_ts_f16(tmem_O, tmem_P + buf * 32 + ks * 8, tc::smem_desc_sw128(b + ks * 32), kIdescO, (acc || ks) ? 1u : 0u);
     };
     tc::mbar_wait(q_full, 0);
-    tc::mbar_wait(&kv_full[0], 0);
-    tc::fence_after_sync();
-    if (tc::elect_one()) { mma_S(0, 0); tc::mma_commit(&s_full[0]); }
-    __syncwarp();
-    int s = 0, s1 = 1, ph1 = 0;   // s: stage of tile j; s1 / ph1: stage and phase of tile j + 1
+    for (int t = 0; t < 2 && t < n_kv; ++t) {          // S_0, S_1: both score buffers start empty
+      tc::mbar_wait(&kv_full[t], 0);
+      tc::fence_after_sync();
+      if (tc::elect_one()) { mma_S(t, t); tc::mma_commit(&s_full[t]); }
+      __syncwarp();
+    }
     for (int j = 0; j < n_kv; ++j) {
-      if (j + 1 < n_kv) {
-        // score buffer (j+1)&1 held S_{j-1} and P_{j-1}: read by the softmax of tile j-1 (arrived on p_ready before
-        // PV_{j-1} was issued) and by PV_{j-1} itself, which precedes this MMA in the in-order tensor pipe
-        tc::mbar_wait(&kv_full[s1], ph1);
+      if (j + 2 < n_kv) {
+        // S_{j+2} -> buffer j&1 the moment the softmax warps hold S_j in registers: two tiles before it is consumed
+        const int t = j + 2, st = t % FA_KV_STAGES;
+        tc::mbar_wait(&s_free[j & 1], (j >> 1) & 1);
+        tc::mbar_wait(&kv_full[st], (t / FA_KV_STAGES) & 1);
         tc::fence_after_sync();
-        if (tc::elect_one()) { mma_S(s1, (j + 1) & 1); tc::mma_commit(&s_full[(j + 1) & 1]); }
+        if (tc::elect_one()) { mma_S(st, j & 1); tc::mma_commit(&s_full[j & 1]); }
         __syncwarp();
       }
       tc::mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
       tc::fence_after_sync();
       if (tc::elect_one()) {
-        mma_O(s, j & 1, j > 0);
+        mma_O(j % FA_KV_STAGES, j & 1, j > 0);
         tc::mma_commit(&pv_done[j & 1]);
-        tc::mma_commit(&kv_empty[s]);
+        tc::mma_commit(&kv_empty[j % FA_KV_STAGES]);
       }
       __syncwarp();
-      s = s1;
-      if (++s1 == FA_KV_STAGES) { s1 = 0; ph1 ^= 1; }
     }
   } else {
     // ---------------- softmax: thread = query row ----------------
@@ -190,6 +183,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int row = quad * 32 + lane;                 // row inside the Q tile = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     float m_run = -INFINITY;
+    float2 l2 = make_float2(0.f, 0.f);                // row sum of p (two partial sums), rescaled with the accumulator
     // The scores of tile j + 1 are requested from TMEM BEFORE the P tile of tile j is stored and published: the softmax
     // warps are nearly alone on their schedulers (two per SMSP), so the TMEM read latency was fully exposed at the top
     // of every tile (long-scoreboard stalls: 1.6 cycles per issued instruction in the capture of the unrotated loop).
@@ -207,6 +201,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int buf = j & 1, kbase = j * FA_BKV;
       tc::tmem_ld_wait(v0);
       tc::tmem_ld_wait(v1);
+      tc::fence_before_sync();                        // S_j is in registers: the MMA warp may overwrite its buffer (S_{j+2})
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s_free[buf]);
       if (kbase + FA_BKV > N1) {                      // only the last key tile needs masking
 #pragma unroll
         for (int i = 0; i < FA_BKV; ++i)
@@ -249,12 +246,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tc::tmem_st32(tmem_O + lane_addr + c, o);
           }
-          uint32_t l16[16];
-          tc::tmem_ld16(tmem_O + lane_addr + FA_D, l16);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) l16[i] = __float_as_uint(__uint_as_float(l16[i]) * alpha);
-          tc::tmem_st16(tmem_O + lane_addr + FA_D, l16);
+          l2.x *= alpha; l2.y *= alpha;
           tc::tmem_st_wait();
         }
         m_run = m_new;
@@ -268,24 +260,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         float2 pp;
         if ((POLY >> ((i / 2) & 7)) & 1) pp = poly_exp2x2(x);
         else pp = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+        l2 = __fadd2_rn(l2, pp);
         __half2 h = __floats2half2_rn(pp.x, pp.y);
         packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
       }
       if (j + 1 < n_kv) request_scores(j + 1);   // S_{j+1} was issued before PV_{j-1}: never waits on our own p_ready
-      // fp16 P over the first 32 columns of the score buffer (this thread's lane: its scores are already in registers)
-      tc::tmem_st32(tmem_base + lane_addr + buf * FA_BKV, packed);
+      if (j >= 2) tc::mbar_wait(&pv_done[buf], ((j - 2) >> 1) & 1);   // P buffer `buf` was the A operand of PV_{j-2}
+      tc::tmem_st32(tmem_P + lane_addr + buf * 32, packed);
     }
     tc::tmem_st_wait();
     tc::fence_before_sync();
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(&p_ready[(n_kv - 1) & 1]);
-    // accumulator complete: normalise by the tensor-core row sum (column 64) and store
+    // accumulator complete: normalise by the row sum and store
     tc::mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc::fence_after_sync();
-    uint32_t l16[16];
-    tc::tmem_ld16(tmem_O + lane_addr + FA_D, l16);
-    tc::tmem_ld_wait();
-    const float inv = 1.f / __uint_as_float(l16[0]);
+    const float inv = 1.f / (l2.x + l2.y);
     const int qrow = q0 + row;
     const int b = bh / fp.heads, hd = bh - b * fp.heads;
     const size_t off = ((size_t)b * N1 + qrow) * fp.D + hd * FA_D;

@@ -55,6 +55,13 @@ struct TcCfg {
 template <class E, class = void> struct EpiCoalesced { static constexpr bool value = false; };
 template <class E> struct EpiCoalesced<E, std::enable_if_t<E::kCoalesced>> { static constexpr bool value = true; };
 
+// Read-modify-write epilogues (`static constexpr bool kPrefetch = true`) additionally provide
+// `float4 fetch(g, row, col)` and `vec4(g, row, col, acc, fetched)`: the coalesced loop then issues the 8 reads of a warp's
+// block before the first write (through one pointer the compiler must otherwise keep every load behind the previous
+// store, and each of the 64 round trips of a tile costs a full memory latency on warps that are alone on their scheduler).
+template <class E, class = void> struct EpiPrefetch { static constexpr bool value = false; };
+template <class E> struct EpiPrefetch<E, std::enable_if_t<E::kPrefetch>> { static constexpr bool value = true; };
+
 struct TcProblem {
   const int* grp_batch;    // [n_groups] B batch item (frame) of each group
   const int* grp_row0;     // [n_groups] first A row

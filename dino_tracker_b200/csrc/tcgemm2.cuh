@@ -257,11 +257,26 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const int c4 = (lane & 7) * 4, r4 = lane >> 3;
             const int row_base = m0 + (int)rank * 128 + quad * 32;
             if (c4 < ncols) {
+              if constexpr (EpiPrefetch<Epi>::value) {
+                float4 pre[8];
 #pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int rr = it * 4 + r4;
-                if (row_base + rr < pb.grp_m[g])
-                  epi.vec4(g, row_base + rr, n0 + c + c4, *reinterpret_cast<const float4*>(sw + rr * 36 + c4));
+                for (int it = 0; it < 8; ++it) {
+                  const int rr = it * 4 + r4;
+                  pre[it] = row_base + rr < pb.grp_m[g] ? epi.fetch(g, row_base + rr, n0 + c + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  const int rr = it * 4 + r4;
+                  if (row_base + rr < pb.grp_m[g])
+                    epi.vec4(g, row_base + rr, n0 + c + c4, *reinterpret_cast<const float4*>(sw + rr * 36 + c4), pre[it]);
+                }
+              } else {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  const int rr = it * 4 + r4;
+                  if (row_base + rr < pb.grp_m[g])
+                    epi.vec4(g, row_base + rr, n0 + c + c4, *reinterpret_cast<const float4*>(sw + rr * 36 + c4));
+                }
               }
             }
             __syncwarp();

@@ -277,7 +277,14 @@ struct EpiPV : EpiBase {
 // x[r][col] += ls[col] * (acc + bias[col])
 struct EpiResidual : EpiBase {
   static constexpr bool kCoalesced = true;
+  static constexpr bool kPrefetch = true;
   float* x; const float* bias; const float* ls; int D;
+  __device__ __forceinline__ float4 fetch(int, int r, int col) const { return *reinterpret_cast<const float4*>(x + (size_t)r * D + col); }
+  __device__ __forceinline__ void vec4(int, int r, int col, float4 v, float4 xv) const {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col)), ll = __ldg(reinterpret_cast<const float4*>(ls + col));
+    xv.x += (v.x + bb.x) * ll.x; xv.y += (v.y + bb.y) * ll.y; xv.z += (v.z + bb.z) * ll.z; xv.w += (v.w + bb.w) * ll.w;
+    *reinterpret_cast<float4*>(x + (size_t)r * D + col) = xv;
+  }
   __device__ __forceinline__ void vec4(int, int r, int col, float4 v) const {
     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col)), ll = __ldg(reinterpret_cast<const float4*>(ls + col));
     float4* o = reinterpret_cast<float4*>(x + (size_t)r * D + col);
@@ -298,6 +305,22 @@ struct EpiResidual : EpiBase {
   }
 };
 
+// 0.5 x (1 + erf(x / sqrt 2)) with erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, two MUFU + 9 FMA-pipe
+// instructions, branch-free): libdevice's erff is ~3x the instructions and made the fc1 epilogue, not its MMAs, pace that
+// GEMM.  The result is rounded to fp16 (relative 4.9e-4) right after.
+__device__ __forceinline__ float gelu_exact(float v) {
+  const float z = fabsf(v) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));      // one MUFU (1 ulp: below the 1.5e-7 of the fit)
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = fast_exp2(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p * t, e, 1.f);          // erf(|v| / sqrt 2)
+  return 0.5f * v + 0.5f * fabsf(v) * erf_abs;         // 0.5 v (1 + sign(v) erf(|v| / sqrt 2))
+}
+
 // h[r][col] = gelu(acc + bias[col])   (exact: 0.5 x (1 + erf(x / sqrt 2)))
 template <typename OutT>
 struct EpiGelu : EpiBase {
@@ -307,7 +330,7 @@ struct EpiGelu : EpiBase {
     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col));
     float t[4] = {v.x + bb.x, v.y + bb.y, v.z + bb.z, v.w + bb.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = 0.5f * t[j] * (1.f + erff(t[j] * 0.70710678118654752f));
+    for (int j = 0; j < 4; ++j) t[j] = sizeof(OutT) == 4 ? 0.5f * t[j] * (1.f + erff(t[j] * 0.70710678118654752f)) : gelu_exact(t[j]);
     if constexpr (sizeof(OutT) == 4) *reinterpret_cast<float4*>(h + (size_t)r * ld + col) = make_float4(t[0], t[1], t[2], t[3]);
     else *reinterpret_cast<uint2*>(h + (size_t)r * ld + col) = pack_half4(t[0], t[1], t[2], t[3]);
   }
@@ -422,11 +445,13 @@ static int launch_flash(const __half* q16, const __half* k16, const __half* v16,
   if ((rc = make_tmap_2d(&tmQ, q16, (uint64_t)B * heads * N1, HD, FA_BQ, HD, TMAP_F16))) return rc;
   if ((rc = make_tmap_3d(&tmK, k16, (uint64_t)B * heads, N1, HD, FA_BKV, HD, TMAP_F16))) return rc;
   if ((rc = make_tmap_3d(&tmV, v16, (uint64_t)B * heads, HD, N1, HD, 64, TMAP_F16, (uint64_t)N1p))) return rc;
-  // share of the exponentials evaluated on the FMA pipe (DTK_FA_POLY = 0 / 25 / 37 / 50 %, default 0)
+  // share of the exponentials evaluated on the FMA pipe (DTK_FA_POLY = 0 / 25 / 37 / 50 %, default 25)
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("DTK_FA_POLY");
-    poly = e ? atoi(e) : 0;   // measured on ViT-L (8108 tokens): the MUFU-only variant is the fastest
+    // measured on ViT-L (8108 tokens, 2 frames x 16 blocks): 0 % 11.3 ms, 25 % 10.2 ms, 37 % 10.3 ms, 50 % 10.9 ms -- since
+    // P goes through tensor memory the softmax warps are MUFU-bound enough for the packed polynomial to pay
+    poly = e ? atoi(e) : 25;
     DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0x88>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     DTK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0xA8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
