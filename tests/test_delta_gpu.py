@@ -45,9 +45,16 @@ def test_refined_features_match_reference_vectors(name):
     ref_norm = torch.from_numpy(refined).norm(dim=1).reshape(refined.shape[0], -1)
     assert torch.allclose(model._refined_norms.cpu(), ref_norm, rtol=1e-5)
     # DeltaDINO.forward returns the aligned residual (models/networks/delta_dino.py:53-61)
-    res = model.delta_dino(video[:1].to(DEV), dino[:1].to(DEV)).cpu()
+    with torch.no_grad():                        # the CUDA kernels (folded eval-mode BatchNorm)
+        res = model.delta_dino(video[:1].to(DEV), dino[:1].to(DEV)).cpu()
     ref_res = od.align_cnn_to_vit(od.delta_cnn(video[:1], sd), (geo.h, geo.w))
     assert (res - ref_res).abs().max().item() <= 5e-5
+    # with gradients enabled the same call is a torch graph (training step); in eval mode it is the same function
+    import oracle
+    oracle.use_exact_fp32()                      # torch's default lets cuDNN convolutions run in TF32
+    model.eval()
+    res_graph = model.delta_dino(video[:1].to(DEV), dino[:1].to(DEV))
+    assert res_graph.requires_grad and (res_graph.detach().cpu() - ref_res).abs().max().item() <= 5e-5
 
 
 def test_state_dict_keys_match_reference_checkpoint_format():
