@@ -214,8 +214,9 @@ struct EpiQKV : EpiBase {
 struct EpiQKV16 : EpiBase {
   static constexpr bool kCoalesced = true;
   __half* q; __half* k; __half* vT; const float* bias; int N1, D, heads, N1p; float qscale;
+  int direct_from = 1 << 30;   // columns >= direct_from take the thread-per-row call (host: 2 * D, or 0 = every column)
   // v goes out transposed ([d][n]): thread-per-row already writes consecutive n per lane -> keep the direct call there
-  __device__ __forceinline__ bool direct(int col0) const { return col0 >= 2 * D; }
+  __device__ __forceinline__ bool direct(int col0) const { return col0 >= direct_from; }
   __device__ __forceinline__ void vec4(int, int r, int col, float4 v) const {
     const int b = fast_div(r, N1), n = r - b * N1;
     const int which = (col >= D) + (col >= 2 * D), c = col - which * D, hd = c / HD, e0 = c - hd * HD;
@@ -326,6 +327,8 @@ template <typename OutT>
 struct EpiGelu : EpiBase {
   static constexpr bool kCoalesced = true;
   OutT* h; const float* bias; int ld;
+  int all_direct = 0;
+  __device__ __forceinline__ bool direct(int) const { return all_direct != 0; }
   __device__ __forceinline__ void vec4(int, int r, int col, float4 v) const {
     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col));
     float t[4] = {v.x + bb.x, v.y + bb.y, v.z + bb.z, v.w + bb.w};
@@ -342,7 +345,10 @@ struct EpiGelu : EpiBase {
       const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + (i < ncols ? i : 0)));
       const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { float v = f[i + j] + bv[j]; gl[i + j] = 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+      for (int j = 0; j < 4; ++j) {
+        const float v = f[i + j] + bv[j];
+        gl[i + j] = sizeof(OutT) == 4 ? 0.5f * v * (1.f + erff(v * 0.70710678118654752f)) : gelu_exact(v);
+      }
     }
     if constexpr (sizeof(OutT) == 4) {
 #pragma unroll
@@ -577,6 +583,8 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
       __half* v16 = reinterpret_cast<__half*>(vT);
       const int N1p8 = (int)align_up((size_t)N1, 8);
       EpiQKV16 eq{{}, q16, k16, v16, w[3], N1, D, heads, N1p8, 0.125f * 1.4426950408889634f};  // 1/sqrt(64) * log2(e)
+      static const int epi_direct = getenv("DTK_EPI_DIRECT") ? atoi(getenv("DTK_EPI_DIRECT")) : 0;
+      eq.direct_from = (epi_direct & 1) ? 0 : 2 * D;
       rc = pairs ? run_gemm_pair<EpiQKV16>(y16, rows, w[2], 3 * D, D, pl, pair_tiles, eq, PROF_VIT_GEMM, st)
          : f16 ? run_gemm<EpiQKV16, 256, TcMode::F16>(y16, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st)
                : run_gemm<EpiQKV16, 256>(y, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st);
@@ -615,8 +623,10 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
     }
     if ((rc = layernorm(w[7], w[8]))) return rc;
     if (pairs) {
-      if ((rc = run_gemm_pair<EpiGelu<__half>>(y16, rows, w[9], 4 * D, D, pl, pair_tiles, EpiGelu<__half>{{}, h16, w[10], 4 * D},
-                                               PROF_VIT_GEMM, st))) return rc;
+      EpiGelu<__half> eg{{}, h16, w[10], 4 * D};
+      static const int epi_direct2 = getenv("DTK_EPI_DIRECT") ? atoi(getenv("DTK_EPI_DIRECT")) : 0;
+      eg.all_direct = (epi_direct2 & 2) ? 1 : 0;
+      if ((rc = run_gemm_pair<EpiGelu<__half>>(y16, rows, w[9], 4 * D, D, pl, pair_tiles, eg, PROF_VIT_GEMM, st))) return rc;
       if ((rc = run_gemm_pair<EpiResidual>(h16, rows, w[11], D, 4 * D, pl, pair_tiles, EpiResidual{{}, x, w[12], w[13], D},
                                            PROF_VIT_GEMM, st))) return rc;
     } else if (f16) {

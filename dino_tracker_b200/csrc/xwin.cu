@@ -500,7 +500,7 @@ struct XhParams {
 // Window, refiner and softmax sums of one map (one warp).  INTERIOR: the 15 x 15 window lies inside the token grid (no
 // zero padding anywhere: the per-position bounds tests drop out -- the common case away from the frame border).
 template <bool INTERIOR>
-__device__ __forceinline__ void xw_refine(const XhParams& hp, const float2* __restrict__ wtab, float b2, float2* __restrict__ mm2,
+__device__ __forceinline__ void xw_refine(const XhParams& hp, const float2* __restrict__ wtab, float b2w, float2* __restrict__ mm2,
                                           float2* __restrict__ hh2, const float (&wv)[8], int arow, int acol, int lane,
                                           float& zmax, float (&tot)[5]) {
   const int h = hp.h, w = hp.w;
@@ -566,6 +566,8 @@ __device__ __forceinline__ void xw_refine(const XhParams& hp, const float2* __re
       const float2* h0 = hh2 + ((row_ok ? y : 0) * XWH) * 8 + cp;
       float2 i00 = h0[0], i01 = h0[8], i10 = h0[XWH * 8], i11 = h0[(XWH + 1) * 8];
       float2 i20 = h0[2 * XWH * 8], i21 = h0[(2 * XWH + 1) * 8];
+      float v[12];
+      v[11] = 0.f;
 #pragma unroll
       for (int x = 0; x < XWB; ++x) {
         const float2 i02 = h0[(x + 2) * 8], i12 = h0[(XWH + x + 2) * 8], i22 = h0[(2 * XWH + x + 2) * 8];
@@ -573,13 +575,28 @@ __device__ __forceinline__ void xw_refine(const XhParams& hp, const float2* __re
         a0 = __ffma2_rn(w2r[1], i01, a0); a1 = __ffma2_rn(w2r[4], i11, a1); a2 = __ffma2_rn(w2r[7], i21, a2);
         a0 = __ffma2_rn(w2r[2], i02, a0); a1 = __ffma2_rn(w2r[5], i12, a1); a2 = __ffma2_rn(w2r[8], i22, a2);
         const float2 a = __fadd2_rn(__fadd2_rn(a0, a1), a2);
-        float v = a.x + a.y;
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        if (row_ok && cp == (x & 7)) zb[y * XWB + x] = v + b2;
+        v[x] = a.x + a.y;
         i00 = i01; i01 = i02; i10 = i11; i11 = i12; i20 = i21; i21 = i22;
       }
+      // sum over the 8 pair lanes as a reduce-scatter (11 shuffles per row instead of 33): every halving step sends the
+      // half of the values the partner will own; afterwards lane cp holds logits 6 b2 + 3 b1 + {2 b0, 1 (b0 = 0 only)}
+      const bool b2 = cp & 4, b1 = cp & 2, b0 = cp & 1;
+      float u[6], w3[3];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float send = b2 ? v[j] : v[j + 6], keep = b2 ? v[j + 6] : v[j];
+        u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float send = b1 ? u[j] : u[j + 3], keep = b1 ? u[j + 3] : u[j];
+        w3[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      const float t0 = (b0 ? w3[2] : w3[0]) + __shfl_xor_sync(0xffffffffu, b0 ? w3[0] : w3[2], 1);
+      const float t1 = (b0 ? 0.f : w3[1]) + __shfl_xor_sync(0xffffffffu, b0 ? w3[1] : 0.f, 1);
+      const int idx0 = (b2 ? 6 : 0) + (b1 ? 3 : 0) + (b0 ? 2 : 0);
+      if (row_ok && idx0 < XWB) zb[y * XWB + idx0] = t0 + b2w;
+      if (row_ok && !b0) zb[y * XWB + idx0 + 1] = t1 + b2w;
     }
   }
   __syncwarp();

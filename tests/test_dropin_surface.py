@@ -46,6 +46,16 @@ def test_tracker_offers_everything_the_reference_touches():
                                   "cyc_n_frames", "cyc_batch_size_per_frame", "cyc_fg_points_ratio", "cyc_thresh"]
 
 
+def test_tracker_offers_everything_the_reference_trainer_touches():
+    """SURVEY 8f-4: every attribute / method dino_tracker.py::DINOTracker (training loop, losses, cycle-consistency and
+    contrastive helpers) uses on ``model``."""
+    from dino_tracker_b200.tracker import Tracker
+    have = _instance_attributes(Tracker)
+    missing = [a for a in SURFACE["trainer_tracker_attributes"] if a not in have]
+    assert not missing, missing
+    assert "get_point_predictions" in have and "get_cycle_consistent_coords" in have      # models/tracker.py:175-262
+
+
 def test_model_inference_offers_everything_the_reference_touches():
     from dino_tracker_b200 import model_inference as mi
     have = _instance_attributes(mi.ModelInference)

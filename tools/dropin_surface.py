@@ -5,7 +5,9 @@ present and otherwise checks the committed copy).
 Walked (AssafSinger94/dino-tracker @ 5b0f2b0): inference_grid.py, inference_benchmark.py (variables ``model``,
 ``model_inference``), dino_tracker.py::get_model / train_setup (``model``), models/model_inference.py (``self.model`` /
 ``model`` inside ModelInference and the module-level helpers -- what a drop-in Tracker must offer to the reference's
-ModelInference, and what a drop-in ModelInference must itself provide)."""
+ModelInference, and what a drop-in ModelInference must itself provide); and, separately (``trainer_tracker_attributes``),
+everything ANY method of dino_tracker.py::DINOTracker touches on ``model`` -- the training loop, its losses and the
+cycle-consistency / contrastive helpers."""
 import ast
 import json
 import os
@@ -45,6 +47,11 @@ def surface(ref):
     for node in ast.walk(dt):   # get_model / train_setup only (the training loop is out of scope)
         if isinstance(node, ast.FunctionDef) and node.name in ("get_model", "train_setup"):
             tracker |= attrs_on(node, {"model"})
+    trainer = set()
+    for node in ast.walk(dt):
+        if isinstance(node, ast.ClassDef) and node.name == "DINOTracker":
+            trainer |= attrs_on(node, {"model"})
+    trainer.discard("module")          # `model.module if hasattr(model, "module")`: DataParallel unwrapping, not a Tracker attribute
     minf = attrs_on(grid, {"model_inference"}) | attrs_on(bench, {"model_inference"})
     mi_kwargs = set()
     for tree in (grid, bench):
@@ -59,7 +66,8 @@ def surface(ref):
     module_funcs = sorted(n.name for n in mi.body if isinstance(n, ast.FunctionDef))
     mi_methods = sorted(n.name for c in mi.body if isinstance(c, ast.ClassDef) and c.name == "ModelInference"
                         for n in c.body if isinstance(n, ast.FunctionDef) and not n.name.startswith("__"))
-    return {"tracker_attributes": sorted(tracker), "tracker_ctor_kwargs": tracker_kwargs(dt),
+    return {"tracker_attributes": sorted(tracker), "trainer_tracker_attributes": sorted(trainer),
+            "tracker_ctor_kwargs": tracker_kwargs(dt),
             "model_inference_attributes": sorted(minf), "model_inference_ctor_kwargs": sorted(mi_kwargs),
             "infer_kwargs": sorted(infer_kwargs), "model_inference_module_functions": module_funcs,
             "model_inference_methods": mi_methods}
