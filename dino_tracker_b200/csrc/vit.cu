@@ -583,7 +583,7 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
       __half* v16 = reinterpret_cast<__half*>(vT);
       const int N1p8 = (int)align_up((size_t)N1, 8);
       EpiQKV16 eq{{}, q16, k16, v16, w[3], N1, D, heads, N1p8, 0.125f * 1.4426950408889634f};  // 1/sqrt(64) * log2(e)
-      static const int epi_direct = getenv("DTK_EPI_DIRECT") ? atoi(getenv("DTK_EPI_DIRECT")) : 0;
+      static const int epi_direct = getenv("DTK_EPI_DIRECT") ? atoi(getenv("DTK_EPI_DIRECT")) : 2;   // bit 0: q / k thread-per-row too (slower)
       eq.direct_from = (epi_direct & 1) ? 0 : 2 * D;
       rc = pairs ? run_gemm_pair<EpiQKV16>(y16, rows, w[2], 3 * D, D, pl, pair_tiles, eq, PROF_VIT_GEMM, st)
          : f16 ? run_gemm<EpiQKV16, 256, TcMode::F16>(y16, rows, w[2], 1, 3 * D, D, pl, 1, all_tiles, eq, PROF_VIT_GEMM, st)
@@ -624,7 +624,7 @@ int dinotrk_vit_forward(const float* frames, int B, const dinotrk_geom* g, const
     if ((rc = layernorm(w[7], w[8]))) return rc;
     if (pairs) {
       EpiGelu<__half> eg{{}, h16, w[10], 4 * D};
-      static const int epi_direct2 = getenv("DTK_EPI_DIRECT") ? atoi(getenv("DTK_EPI_DIRECT")) : 0;
+      static const int epi_direct2 = getenv("DTK_EPI_DIRECT") ? atoi(getenv("DTK_EPI_DIRECT")) : 2;  // bit 1: fp16 GELU rows written thread-per-row (64 B per thread, whole sectors; measured 6.46 -> 6.32 ms per 2 x 16 blocks)
       eg.all_direct = (epi_direct2 & 2) ? 1 : 0;
       if ((rc = run_gemm_pair<EpiGelu<__half>>(y16, rows, w[9], 4 * D, D, pl, pair_tiles, eg, PROF_VIT_GEMM, st))) return rc;
       if ((rc = run_gemm_pair<EpiResidual>(h16, rows, w[11], D, 4 * D, pl, pair_tiles, EpiResidual{{}, x, w[12], w[13], D},

@@ -260,21 +260,25 @@ int launch_xw_plan(const XwCells& cells, const float* desc_norm, int n_groups, c
 }
 
 // ====================================================================================================== 3. exact box GEMM
-// Persistent, warp-specialised (same roles as tc_gemm_kernel).  One "tile" = one cell: D[128 rows x 480 columns] in TMEM =
-// the cell's descriptors against the 21 x 21 box tokens (3 N-parts of 7 box rows), split precision (lo*hi + hi*lo + hi*hi
-// per K step, in the full-map GEMM's order).  A K-block of the descriptors (hi, lo) is loaded once and used by the three
-// parts; the box rows arrive as 4-D TMA boxes {64 channels, 21 columns, 7 rows, 1 frame} of the [T][h][w][C] feature video,
-// zero-filled outside the token grid.
-template <int AROWS>
+// Persistent, warp-specialised (same roles as tc_gemm_kernel).  One "tile" = one cell.  The BOX TOKENS are the UMMA M
+// operand (4 parts of 6 box rows = 126 of 128 rows) and the cell's descriptors the N operand (64 or 128 columns): a cell
+// of T = 50 maps fills 50 of 64 columns, where descriptors-as-rows filled 50 of 128 rows.  D[part][token][map] in TMEM
+// (4 x NB columns; two cells in flight for NB = 64), split precision (lo*hi + hi*lo + hi*hi per K step, in the full-map
+// GEMM's order).  A K-block of the descriptors (hi, lo) is loaded once and used by the four parts; the box rows arrive as
+// 4-D TMA boxes {64 channels, 21 columns, 6 rows, 1 frame} of the [T][h][w][C] feature video, zero-filled outside the
+// token grid.  Epilogue: TMEM lane = box token, so for every map the 32 lanes of a warp write 32 consecutive floats of
+// its accumulator row -- coalesced without a transpose.
+template <int NB>
 struct XwCfg {
   static constexpr int kBK = 64;                            // fp16 elements per 128-byte swizzle row
-  static constexpr int kABytes = AROWS * 128;               // one operand half (hi or lo) of the descriptor K-block
-  static constexpr int kAStage = 2 * kABytes, kAStages = 2;
-  static constexpr int kBBytes = XW_PART_N * 128;           // 160 rows reserved, 147 written
-  static constexpr int kBStage = 2 * kBBytes, kBStages = AROWS == 64 ? 4 : 3;
-  static constexpr int kBTx = 2 * XW_PART_ROWS * XW_BOX * 128;
-  static constexpr int kSmem = kAStages * kAStage + kBStages * kBStage + 256 + TC_EPI_SCRATCH;
-  static constexpr uint32_t kIdesc = tc::make_idesc(0, 128, XW_PART_N);
+  static constexpr int kTokBytes = 128 * 128;               // one operand half (hi or lo) of a token tile: 128 rows, 126 written
+  static constexpr int kTokStage = 2 * kTokBytes, kTokStages = NB == 64 ? 5 : 4;
+  static constexpr int kTokTx = 2 * XW_PART_TOK * 128;
+  static constexpr int kDescBytes = NB * 128;               // one operand half of the descriptor K-block
+  static constexpr int kDescStage = 2 * kDescBytes, kDescStages = 2;
+  static constexpr int kSmem = kDescStages * kDescStage + kTokStages * kTokStage + 256;
+  static constexpr int kAccCols = XW_PARTS * NB, kAccBufs = 512 / kAccCols;
+  static constexpr uint32_t kIdesc = tc::make_idesc(0, 128, NB);
 };
 
 namespace tc {
@@ -287,35 +291,35 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
 }
 }  // namespace tc
 
-template <int AROWS>
+template <int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-xw_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, XwCells cells,
+xw_gemm_kernel(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo,
+               const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ CUtensorMap tmT_lo, XwCells cells,
                const int2* __restrict__ box_org, float* __restrict__ xbox, int K) {
-  using Cfg = XwCfg<AROWS>;
+  using Cfg = XwCfg<NB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (tc::smem_u32(smem) & 1023u) __trap();   // no static shared memory in this kernel: the window starts 1 KB-aligned
-  uint8_t* a_ring = smem;
-  uint8_t* b_ring = smem + Cfg::kAStages * Cfg::kAStage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + Cfg::kBStages * Cfg::kBStage);
-  uint64_t* a_full = bars;                          // [2]
-  uint64_t* a_empty = a_full + Cfg::kAStages;       // [2]
-  uint64_t* b_full = a_empty + Cfg::kAStages;       // [kBStages]
-  uint64_t* b_empty = b_full + Cfg::kBStages;       // [kBStages]
-  uint64_t* tfull = b_empty + Cfg::kBStages;        // [1]
-  uint64_t* tempty = tfull + 1;                     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
-  float* epi_scratch = reinterpret_cast<float*>(b_ring + Cfg::kBStages * Cfg::kBStage + 256);
+  uint8_t* t_ring = smem;                                           // token tiles (UMMA A)
+  uint8_t* d_ring = smem + Cfg::kTokStages * Cfg::kTokStage;        // descriptor K-blocks (UMMA B)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(d_ring + Cfg::kDescStages * Cfg::kDescStage);
+  uint64_t* d_full = bars;                          // [2]
+  uint64_t* d_empty = d_full + Cfg::kDescStages;    // [2]
+  uint64_t* t_full = d_empty + Cfg::kDescStages;    // [kTokStages]
+  uint64_t* t_empty = t_full + Cfg::kTokStages;     // [kTokStages]
+  uint64_t* tfull = t_empty + Cfg::kTokStages;      // [2]
+  uint64_t* tempty = tfull + 2;                     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  static_assert((2 * Cfg::kDescStages + 2 * Cfg::kTokStages + 4) * 8 + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = (K + Cfg::kBK - 1) / Cfg::kBK;
 
   if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmA_hi); tc::prefetch_tmap(&tmA_lo); tc::prefetch_tmap(&tmB_hi); tc::prefetch_tmap(&tmB_lo);
-    for (int s = 0; s < Cfg::kAStages; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < Cfg::kBStages; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    tc::mbar_init(tfull, 1); tc::mbar_init(tempty, 4);
+    tc::prefetch_tmap(&tmD_hi); tc::prefetch_tmap(&tmD_lo); tc::prefetch_tmap(&tmT_hi); tc::prefetch_tmap(&tmT_lo);
+    for (int s = 0; s < Cfg::kDescStages; ++s) { tc::mbar_init(&d_full[s], 1); tc::mbar_init(&d_empty[s], 1); }
+    for (int s = 0; s < Cfg::kTokStages; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 4); }
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
@@ -327,106 +331,102 @@ xw_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (tc::elect_one()) {
-      int as = 0, aph = 0, bs = 0, bph = 0;
+      int ds = 0, dph = 0, ts = 0, tph = 0;
       for (int cell = blockIdx.x; cell < cells.n_cells; cell += gridDim.x) {
         const int2 org = box_org[cell];
         if (org.y == INT_MIN) continue;            // every map of the cell takes the full-map path
-        const int arow = cells.row0[cell], frame = cells.frame[cell];
+        const int drow = cells.row0[cell], frame = cells.frame[cell];
         for (int kb = 0; kb < KB; ++kb) {
           const int k0 = kb * Cfg::kBK;
-          tc::mbar_wait(&a_empty[as], aph ^ 1);
-          uint8_t* sa = a_ring + as * Cfg::kAStage;
-          tc::mbar_expect_tx(&a_full[as], Cfg::kAStage);
-          tc::tma_load_2d(&tmA_hi, &a_full[as], sa, k0, arow);
-          tc::tma_load_2d(&tmA_lo, &a_full[as], sa + Cfg::kABytes, k0, arow);
-          if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
+          tc::mbar_wait(&d_empty[ds], dph ^ 1);
+          uint8_t* sd = d_ring + ds * Cfg::kDescStage;
+          tc::mbar_expect_tx(&d_full[ds], Cfg::kDescStage);
+          tc::tma_load_2d(&tmD_hi, &d_full[ds], sd, k0, drow);
+          tc::tma_load_2d(&tmD_lo, &d_full[ds], sd + Cfg::kDescBytes, k0, drow);
+          if (++ds == Cfg::kDescStages) { ds = 0; dph ^= 1; }
           for (int part = 0; part < XW_PARTS; ++part) {
-            tc::mbar_wait(&b_empty[bs], bph ^ 1);
-            uint8_t* sb = b_ring + bs * Cfg::kBStage;
-            tc::mbar_expect_tx(&b_full[bs], Cfg::kBTx);
-            tc::tma_load_4d(&tmB_hi, &b_full[bs], sb, k0, org.y, org.x + part * XW_PART_ROWS, frame);
-            tc::tma_load_4d(&tmB_lo, &b_full[bs], sb + Cfg::kBBytes, k0, org.y, org.x + part * XW_PART_ROWS, frame);
-            if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+            tc::mbar_wait(&t_empty[ts], tph ^ 1);
+            uint8_t* st = t_ring + ts * Cfg::kTokStage;
+            tc::mbar_expect_tx(&t_full[ts], Cfg::kTokTx);
+            tc::tma_load_4d(&tmT_hi, &t_full[ts], st, k0, org.y, org.x + part * XW_PART_ROWS, frame);
+            tc::tma_load_4d(&tmT_lo, &t_full[ts], st + Cfg::kTokBytes, k0, org.y, org.x + part * XW_PART_ROWS, frame);
+            if (++ts == Cfg::kTokStages) { ts = 0; tph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    int as = 0, aph = 0, bs = 0, bph = 0, it = 0;
+    int ds = 0, dph = 0, ts = 0, tph = 0, it = 0;
     for (int cell = blockIdx.x; cell < cells.n_cells; cell += gridDim.x) {
       if (box_org[cell].y == INT_MIN) continue;
-      tc::mbar_wait(tempty, (it & 1) ^ 1);
+      const int buf = it % Cfg::kAccBufs, use = it / Cfg::kAccBufs;
+      tc::mbar_wait(&tempty[buf], (use & 1) ^ 1);
       tc::fence_after_sync();
       for (int kb = 0; kb < KB; ++kb) {
-        tc::mbar_wait(&a_full[as], aph);
-        const uint32_t sa = tc::smem_u32(a_ring + as * Cfg::kAStage);
+        tc::mbar_wait(&d_full[ds], dph);
+        const uint32_t sd = tc::smem_u32(d_ring + ds * Cfg::kDescStage);
         for (int part = 0; part < XW_PARTS; ++part) {
-          tc::mbar_wait(&b_full[bs], bph);
+          tc::mbar_wait(&t_full[ts], tph);
           tc::fence_after_sync();
           if (tc::elect_one()) {
-            const uint32_t sb = tc::smem_u32(b_ring + bs * Cfg::kBStage);
-            const uint32_t tmem_d = tmem_base + part * XW_PART_N;
+            const uint32_t st = tc::smem_u32(t_ring + ts * Cfg::kTokStage);
+            const uint32_t tmem_d = tmem_base + buf * Cfg::kAccCols + part * NB;
 #pragma unroll
             for (int ks = 0; ks < Cfg::kBK / 16; ++ks) {
               const uint32_t koff = ks * 32;
-              const uint64_t a_hi = tc::smem_desc_sw128(sa + koff), a_lo = tc::smem_desc_sw128(sa + Cfg::kABytes + koff);
-              const uint64_t b_hi = tc::smem_desc_sw128(sb + koff), b_lo = tc::smem_desc_sw128(sb + Cfg::kBBytes + koff);
+              const uint64_t t_hi = tc::smem_desc_sw128(st + koff), t_lo = tc::smem_desc_sw128(st + Cfg::kTokBytes + koff);
+              const uint64_t d_hi = tc::smem_desc_sw128(sd + koff), d_lo = tc::smem_desc_sw128(sd + Cfg::kDescBytes + koff);
               const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-              tc::mma_ss<false>(tmem_d, a_lo, b_hi, Cfg::kIdesc, first);   // same order as tc_gemm_kernel (F16X3)
-              tc::mma_ss<false>(tmem_d, a_hi, b_lo, Cfg::kIdesc, 1u);
-              tc::mma_ss<false>(tmem_d, a_hi, b_hi, Cfg::kIdesc, 1u);
+              tc::mma_ss<false>(tmem_d, t_hi, d_lo, Cfg::kIdesc, first);   // desc_lo * tok_hi, desc_hi * tok_lo, desc_hi * tok_hi:
+              tc::mma_ss<false>(tmem_d, t_lo, d_hi, Cfg::kIdesc, 1u);      // the product order of tc_gemm_kernel (F16X3)
+              tc::mma_ss<false>(tmem_d, t_hi, d_hi, Cfg::kIdesc, 1u);
             }
-            tc::mma_commit(&b_empty[bs]);
+            tc::mma_commit(&t_empty[ts]);
             if (part == XW_PARTS - 1) {
-              tc::mma_commit(&a_empty[as]);
-              if (kb == KB - 1) tc::mma_commit(tfull);
+              tc::mma_commit(&d_empty[ds]);
+              if (kb == KB - 1) tc::mma_commit(&tfull[buf]);
             }
           }
           __syncwarp();
-          if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+          if (++ts == Cfg::kTokStages) { ts = 0; tph ^= 1; }
         }
-        if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
+        if (++ds == Cfg::kDescStages) { ds = 0; dph ^= 1; }
       }
       ++it;
     }
   } else {
-    // ===================== epilogue: raw accumulator rows -> xbox (coalesced through a per-warp transpose) ==========
+    // ===================== epilogue: TMEM lane = box token -> xbox[map][token], coalesced along the tokens =====================
     const int quad = warp & 3;
-    float* sw = epi_scratch + (warp - 2) * (32 * 36);
     int it = 0;
     for (int cell = blockIdx.x; cell < cells.n_cells; cell += gridDim.x) {
       if (box_org[cell].y == INT_MIN) continue;
       const int m = cells.m[cell], map0 = cells.row0[cell];
-      tc::mbar_wait(tfull, it & 1);
+      const int buf = it % Cfg::kAccBufs, use = it / Cfg::kAccBufs;
+      tc::mbar_wait(&tfull[buf], use & 1);
       tc::fence_after_sync();
-      const int row_base = quad * 32;
-      if (row_base < m) {
-        const uint32_t taddr = tmem_base + ((uint32_t)row_base << 16);
+      const int tok = quad * 32 + lane;
 #pragma unroll 1
-        for (int c = 0; c < XW_COLS; c += 32) {
+      for (int part = 0; part < XW_PARTS; ++part) {
+        const int col = part * XW_PART_TOK + tok;
+        const bool ok = tok < XW_PART_TOK && col < XW_BOX * XW_BOX;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * Cfg::kAccCols + part * NB;
+        float* dst = xbox + (size_t)map0 * XW_COLS + col;
+#pragma unroll 1
+        for (int c = 0; c < NB && c < m; c += 32) {
           uint32_t v[32];
           tc::tmem_ld32(taddr + c, v);
           tc::tmem_ld_wait();
+          if (ok) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            *reinterpret_cast<float4*>(sw + lane * 36 + i) =
-                make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-          __syncwarp();
-          const int c4 = (lane & 7) * 4, r4 = lane >> 3;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int rr = q * 4 + r4;
-            if (row_base + rr < m)
-              *reinterpret_cast<float4*>(xbox + (size_t)(map0 + row_base + rr) * XW_COLS + c + c4) =
-                  *reinterpret_cast<const float4*>(sw + rr * 36 + c4);
+            for (int i = 0; i < 32; ++i)
+              if (c + i < m) dst[(size_t)(c + i) * XW_COLS] = __uint_as_float(v[i]);
           }
-          __syncwarp();
         }
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tempty);
+      if (lane == 0) tc::mbar_arrive(&tempty[buf]);
       ++it;
     }
   }
@@ -444,16 +444,16 @@ int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_h
   if (cells.n_cells <= 0) return DINOTRK_OK;
   DTK_CHECK_ARG(fv.C % 8 == 0 && cells.max_m <= XW_MAX_CELL, "exact-window GEMM: bad sizes");
   const bool small = cells.max_m <= 64;
-  const int arows = small ? 64 : 128;
-  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  const int nb = small ? 64 : 128;
+  CUtensorMap tD_hi, tD_lo, tT_hi, tT_lo;
   int rc;
-  if ((rc = make_tmap_2d(&tA_hi, desc_hi, desc_rows, fv.C, arows, 64, TMAP_F16))) return rc;
-  if ((rc = make_tmap_2d(&tA_lo, desc_lo, desc_rows, fv.C, arows, 64, TMAP_F16))) return rc;
+  if ((rc = make_tmap_2d(&tD_hi, desc_hi, desc_rows, fv.C, nb, 64, TMAP_F16))) return rc;
+  if ((rc = make_tmap_2d(&tD_lo, desc_lo, desc_rows, fv.C, nb, 64, TMAP_F16))) return rc;
   const uint64_t dims[4] = {(uint64_t)fv.C, (uint64_t)g.w, (uint64_t)g.h, (uint64_t)fv.T};
   const uint64_t strides[3] = {(uint64_t)fv.C * 2, (uint64_t)g.w * fv.C * 2, (uint64_t)fv.P * fv.C * 2};
   const uint32_t box[4] = {64, XW_BOX, XW_PART_ROWS, 1};
-  if ((rc = make_tmap_4d(&tB_hi, fv.hi, dims, strides, box, TMAP_F16))) return rc;
-  if ((rc = make_tmap_4d(&tB_lo, fv.lo, dims, strides, box, TMAP_F16))) return rc;
+  if ((rc = make_tmap_4d(&tT_hi, fv.hi, dims, strides, box, TMAP_F16))) return rc;
+  if ((rc = make_tmap_4d(&tT_lo, fv.lo, dims, strides, box, TMAP_F16))) return rc;
   static PerDev<bool> attr_dev;
   bool& attr = attr_dev.get();
   if (!attr) {
@@ -467,9 +467,9 @@ int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_h
   const int grid = cells.n_cells < sms ? cells.n_cells : sms;
   ProfRange pr(PROF_XW_GEMM, st);
   if (small)
-    xw_gemm_kernel<64><<<grid, TC_THREADS, XwCfg<64>::kSmem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, cells, xc.box_org, xc.xbox, fv.C);
+    xw_gemm_kernel<64><<<grid, TC_THREADS, XwCfg<64>::kSmem, st>>>(tD_hi, tD_lo, tT_hi, tT_lo, cells, xc.box_org, xc.xbox, fv.C);
   else
-    xw_gemm_kernel<128><<<grid, TC_THREADS, XwCfg<128>::kSmem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, cells, xc.box_org, xc.xbox, fv.C);
+    xw_gemm_kernel<128><<<grid, TC_THREADS, XwCfg<128>::kSmem, st>>>(tD_hi, tD_lo, tT_hi, tT_lo, cells, xc.box_org, xc.xbox, fv.C);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }

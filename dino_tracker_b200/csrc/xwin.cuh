@@ -15,7 +15,7 @@
 //                    21 x 21 token box around the cell's median arg-max holds every map's window.
 //   3. exact GEMM    per cell, the fp32-faithful split-precision contraction (lo*hi + hi*lo + hi*hi, same operation
 //                    sequence as the full-map GEMM) of the cell's descriptors against the box's 441 tokens only:
-//                    5.4 % of the map.  Raw accumulators go to a [map][480] buffer (1.9 KB per map instead of 32 KB).
+//                    5.4 % of the map.  Raw accumulators go to a [map][448] buffer (1.8 KB per map instead of 32 KB).
 //   4. head          two kernels, one warp per map each: (a) exact arg-max among the candidates + the exact 15 x 15 window
 //                    + m_out (dependent gathers: many warps per SM), (b) refiner, softmax sums on the 11 x 11 box, certificate
 //                    with the bound from (1); writes the track point.
@@ -30,9 +30,10 @@ namespace dtk {
 constexpr float XW_EPS = 1.1e-3f;     // bound on |coarse - exact| in cosine units (2^-10 + accumulation, rounded up)
 constexpr int XW_BOX = 21;            // box side (tokens); windows of maps whose arg-max lies within +-3 of the centre fit
 constexpr int XW_SLACK = 3;
-constexpr int XW_PARTS = 3, XW_PART_ROWS = 7, XW_PART_N = 160;   // 3 N-parts of 7 box rows (147 tokens, padded to 160)
-constexpr int XW_COLS = XW_PARTS * XW_PART_N;                    // accumulator columns per map (raw dump pitch)
-constexpr int XW_MAX_CELL = 128;      // rows (source frames) per cell = UMMA M
+constexpr int XW_PARTS = 4, XW_PART_ROWS = 6;                    // 4 M-parts of 6 box rows (126 tokens = 126 UMMA rows of 128)
+constexpr int XW_PART_TOK = XW_PART_ROWS * XW_BOX;
+constexpr int XW_COLS = 448;                                     // accumulator row pitch per map (441 box tokens, row-major)
+constexpr int XW_MAX_CELL = 128;      // maps (source frames) per cell = UMMA N (64 or 128)
 constexpr int XW_MAX_CAND = 4;
 constexpr float XW_MIN_NORM = 1e-4f;  // the coarse pass forms acc / (|d| |F|) without the reference's max(|d| |F|, 1e-8) clamp: both
                                       // norms must be >= 1e-4 (smaller descriptor norms -> ambiguous map, smaller token norms
@@ -40,7 +41,7 @@ constexpr float XW_MIN_NORM = 1e-4f;  // the coarse pass forms acc / (|d| |F|) w
 constexpr int XW_TILE = 128;          // tokens per coarse key (the coarse GEMM's 8 epilogue warps cover 128 columns each)
 
 // column of box token (by, bx) in a map's accumulator row
-__host__ __device__ inline int xw_col(int by, int bx) { return (by / XW_PART_ROWS) * XW_PART_N + (by % XW_PART_ROWS) * XW_BOX + bx; }
+__host__ __device__ inline int xw_col(int by, int bx) { return by * XW_BOX + bx; }
 
 struct XwChunk {          // device buffers of one chunk in flight (all sized for chunk_maps maps)
   unsigned long long* key1;   // [maps][n_tiles]  coarse maximum of a XW_TILE-token tile << 32 | (0x7fffffff - first token)
