@@ -274,6 +274,8 @@ struct XwCfg {
   static constexpr int kTokBytes = 128 * 128;               // one operand half (hi or lo) of a token tile: 128 rows, 126 written
   static constexpr int kTokStage = 2 * kTokBytes, kTokStages = NB == 64 ? 5 : 4;
   static constexpr int kTokTx = 2 * XW_PART_TOK * 128;
+  static constexpr int kLastRows = XW_BOX - (XW_PARTS - 1) * XW_PART_ROWS;     // the last part holds 3 box rows, not 6
+  static constexpr int kTokTxLast = 2 * kLastRows * XW_BOX * 128;
   static constexpr int kDescBytes = NB * 128;               // one operand half of the descriptor K-block
   static constexpr int kDescStage = 2 * kDescBytes, kDescStages = 2;
   static constexpr int kSmem = kDescStages * kDescStage + kTokStages * kTokStage + 256;
@@ -294,7 +296,8 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
 template <int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 xw_gemm_kernel(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant__ CUtensorMap tmD_lo,
-               const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ CUtensorMap tmT_lo, XwCells cells,
+               const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ CUtensorMap tmT_lo,
+               const __grid_constant__ CUtensorMap tmL_hi, const __grid_constant__ CUtensorMap tmL_lo, XwCells cells,
                const int2* __restrict__ box_org, float* __restrict__ xbox, int K) {
   using Cfg = XwCfg<NB>;
   extern __shared__ uint8_t smem_raw[];
@@ -317,6 +320,7 @@ xw_gemm_kernel(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmD_hi); tc::prefetch_tmap(&tmD_lo); tc::prefetch_tmap(&tmT_hi); tc::prefetch_tmap(&tmT_lo);
+    tc::prefetch_tmap(&tmL_hi); tc::prefetch_tmap(&tmL_lo);
     for (int s = 0; s < Cfg::kDescStages; ++s) { tc::mbar_init(&d_full[s], 1); tc::mbar_init(&d_empty[s], 1); }
     for (int s = 0; s < Cfg::kTokStages; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 4); }
@@ -347,9 +351,15 @@ xw_gemm_kernel(const __grid_constant__ CUtensorMap tmD_hi, const __grid_constant
           for (int part = 0; part < XW_PARTS; ++part) {
             tc::mbar_wait(&t_empty[ts], tph ^ 1);
             uint8_t* st = t_ring + ts * Cfg::kTokStage;
-            tc::mbar_expect_tx(&t_full[ts], Cfg::kTokTx);
-            tc::tma_load_4d(&tmT_hi, &t_full[ts], st, k0, org.y, org.x + part * XW_PART_ROWS, frame);
-            tc::tma_load_4d(&tmT_lo, &t_full[ts], st + Cfg::kTokBytes, k0, org.y, org.x + part * XW_PART_ROWS, frame);
+            if (part < XW_PARTS - 1) {
+              tc::mbar_expect_tx(&t_full[ts], Cfg::kTokTx);
+              tc::tma_load_4d(&tmT_hi, &t_full[ts], st, k0, org.y, org.x + part * XW_PART_ROWS, frame);
+              tc::tma_load_4d(&tmT_lo, &t_full[ts], st + Cfg::kTokBytes, k0, org.y, org.x + part * XW_PART_ROWS, frame);
+            } else {   // only the box rows that exist (this kernel runs at the L2 -> shared-memory bandwidth)
+              tc::mbar_expect_tx(&t_full[ts], Cfg::kTokTxLast);
+              tc::tma_load_4d(&tmL_hi, &t_full[ts], st, k0, org.y, org.x + part * XW_PART_ROWS, frame);
+              tc::tma_load_4d(&tmL_lo, &t_full[ts], st + Cfg::kTokBytes, k0, org.y, org.x + part * XW_PART_ROWS, frame);
+            }
             if (++ts == Cfg::kTokStages) { ts = 0; tph ^= 1; }
           }
         }
@@ -445,7 +455,7 @@ int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_h
   DTK_CHECK_ARG(fv.C % 8 == 0 && cells.max_m <= XW_MAX_CELL, "exact-window GEMM: bad sizes");
   const bool small = cells.max_m <= 64;
   const int nb = small ? 64 : 128;
-  CUtensorMap tD_hi, tD_lo, tT_hi, tT_lo;
+  CUtensorMap tD_hi, tD_lo, tT_hi, tT_lo, tL_hi, tL_lo;
   int rc;
   if ((rc = make_tmap_2d(&tD_hi, desc_hi, desc_rows, fv.C, nb, 64, TMAP_F16))) return rc;
   if ((rc = make_tmap_2d(&tD_lo, desc_lo, desc_rows, fv.C, nb, 64, TMAP_F16))) return rc;
@@ -454,6 +464,9 @@ int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_h
   const uint32_t box[4] = {64, XW_BOX, XW_PART_ROWS, 1};
   if ((rc = make_tmap_4d(&tT_hi, fv.hi, dims, strides, box, TMAP_F16))) return rc;
   if ((rc = make_tmap_4d(&tT_lo, fv.lo, dims, strides, box, TMAP_F16))) return rc;
+  const uint32_t box_last[4] = {64, XW_BOX, (uint32_t)XwCfg<64>::kLastRows, 1};
+  if ((rc = make_tmap_4d(&tL_hi, fv.hi, dims, strides, box_last, TMAP_F16))) return rc;
+  if ((rc = make_tmap_4d(&tL_lo, fv.lo, dims, strides, box_last, TMAP_F16))) return rc;
   static PerDev<bool> attr_dev;
   bool& attr = attr_dev.get();
   if (!attr) {
@@ -467,9 +480,9 @@ int launch_xw_gemm(const FeatView& fv, const dinotrk_geom& g, const void* desc_h
   const int grid = cells.n_cells < sms ? cells.n_cells : sms;
   ProfRange pr(PROF_XW_GEMM, st);
   if (small)
-    xw_gemm_kernel<64><<<grid, TC_THREADS, XwCfg<64>::kSmem, st>>>(tD_hi, tD_lo, tT_hi, tT_lo, cells, xc.box_org, xc.xbox, fv.C);
+    xw_gemm_kernel<64><<<grid, TC_THREADS, XwCfg<64>::kSmem, st>>>(tD_hi, tD_lo, tT_hi, tT_lo, tL_hi, tL_lo, cells, xc.box_org, xc.xbox, fv.C);
   else
-    xw_gemm_kernel<128><<<grid, TC_THREADS, XwCfg<128>::kSmem, st>>>(tD_hi, tD_lo, tT_hi, tT_lo, cells, xc.box_org, xc.xbox, fv.C);
+    xw_gemm_kernel<128><<<grid, TC_THREADS, XwCfg<128>::kSmem, st>>>(tD_hi, tD_lo, tT_hi, tT_lo, tL_hi, tL_lo, cells, xc.box_org, xc.xbox, fv.C);
   DTK_LAUNCHED();
   return DINOTRK_OK;
 }
