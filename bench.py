@@ -577,14 +577,16 @@ def kernel_roofline(name, stat, args, maps_per_step, peaks, clocks, path_stats=N
                 "note": "single kind::f16 pass over the hi halves: executed MMA FLOPs = algorithmic 2*maps*P*C; " + tensor_note,
                 "maps_per_launch": maps_per_launch, "ms_per_launch": avg_s * 1e3}
     if name == "xw_exact_gemm":
-        flops_exec = 2.0 * maps_per_launch * 480 * args.C * 3 * (128.0 / max(args.T if args.T <= 128 else 125, 1))
+        cell = max(args.T if args.T <= 128 else 125, 1)                 # maps per cell; UMMA N = 64 or 128 columns
+        flops_exec = 2.0 * maps_per_launch * 512 * args.C * 3 * ((64.0 if cell <= 64 else 128.0) / cell)
         flops_alg = 2.0 * maps_per_launch * 225 * args.C
         ach = flops_alg / avg_s / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_sustained"], "traffic": ncu_traffic("ncu_r2_xw_exact.csv"),
+                "frac": ach / peaks["tf_sustained"], "traffic": ncu_traffic("ncu_r2_final_xw.csv"),
                 "executed_mma_tflops": flops_exec / avg_s / 1e12,
                 "note": "algorithmic = the 15 x 15 window the head needs per map (2*225*C FLOPs); executed = 3 split-precision "
-                        "passes x 480 box columns x 128 UMMA rows per cell of T maps; " + tensor_note,
+                        "passes x 512 box-token rows (4 parts of 128, 441 used) x 64 UMMA columns per cell of T <= 64 maps; "
+                        "traffic: profiles/ncu_r2_final_xw.csv, first kernel; " + tensor_note,
                 "maps_per_launch": maps_per_launch, "ms_per_launch": avg_s * 1e3}
     if name in ("corr_gemm", "best_buddies", "vit_gemm", "delta_conv"):
         flops = 2.0 * maps_per_launch * P * args.C  # <d, F[p]> for every token of the target frame
