@@ -24,18 +24,22 @@ def blur_pool(x: torch.Tensor) -> torch.Tensor:
     return F.conv2d(F.pad(x, (1, 2, 1, 2), mode="reflect"), filt, stride=2, groups=C)
 
 
-def delta_cnn(frames: torch.Tensor, sd: dict) -> torch.Tensor:
+def delta_cnn(frames: torch.Tensor, sd: dict, bn_training: bool = False) -> torch.Tensor:
     """models/networks/delta_dino.py:22-46,53-55: [conv5x5 reflect -> BN(eval) -> ReLU ->
     BlurPool] x3, then conv5x5 dilation 2 (reflect pad 4) -> BN.  frames: B x 3 x H x W
-    raw [0,1] RGB (no ImageNet normalisation: models/tracker.py:115)."""
+    raw [0,1] RGB (no ImageNet normalisation: models/tracker.py:115).  ``bn_training``: BatchNorm on the batch
+    statistics of ``frames`` (the module in train mode, dino_tracker.py:133-134; running statistics are not updated here)."""
     x = frames
     for li, (ci, bi, dil) in enumerate(zip(CONV_IDX, BN_IDX, DILATIONS)):
         w = sd[f"layers.{ci}.weight"]
         k = w.shape[-1]
         pad = (k + (k - 1) * (dil - 1)) // 2
         x = F.conv2d(F.pad(x, (pad,) * 4, mode="reflect"), w, sd[f"layers.{ci}.bias"], dilation=dil)
-        x = F.batch_norm(x, sd[f"layers.{bi}.running_mean"], sd[f"layers.{bi}.running_var"],
-                         sd[f"layers.{bi}.weight"], sd[f"layers.{bi}.bias"], training=False, eps=BN_EPS)
+        if bn_training:
+            x = F.batch_norm(x, None, None, sd[f"layers.{bi}.weight"], sd[f"layers.{bi}.bias"], training=True, eps=BN_EPS)
+        else:
+            x = F.batch_norm(x, sd[f"layers.{bi}.running_mean"], sd[f"layers.{bi}.running_var"],
+                             sd[f"layers.{bi}.weight"], sd[f"layers.{bi}.bias"], training=False, eps=BN_EPS)
         if li < 3:
             x = blur_pool(torch.relu(x))
     return x
@@ -56,11 +60,11 @@ def align_cnn_to_vit(cnn: torch.Tensor, vit_hw, patch=14, vit_stride=7, cnn_stri
 
 
 def refined_features(video: torch.Tensor, dino: torch.Tensor, sd: dict, patch=14, stride=7,
-                     batch=8) -> torch.Tensor:
+                     batch=8, bn_training: bool = False) -> torch.Tensor:
     """models/tracker.py:113-129 (batches of 8 frames) -> dino + residual, T x C x h x w."""
     res = torch.zeros_like(dino)
     for i in range(0, video.shape[0], batch):
-        cnn = delta_cnn(video[i:i + batch], sd)
+        cnn = delta_cnn(video[i:i + batch], sd, bn_training)
         res[i:i + batch] = align_cnn_to_vit(cnn, dino.shape[-2:], patch, stride, 8)
     return dino + res
 

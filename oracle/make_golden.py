@@ -114,6 +114,55 @@ def gen_delta_case(name, H, W, T, channels, seed):
     print(name, "refined", tuple(refined.shape))
 
 
+TRAIN_CASE = dict(H=98, W=126, T=6, C=32, channels=[3, 8, 8, 8, 32], seed=51, frames_set=[5, 1, 3, 0], B=48)
+
+
+def train_case_inputs(cfg=TRAIN_CASE):
+    """Inputs of the training-step case, regenerable anywhere from the seed."""
+    from .tracker import Geometry
+    geo = Geometry(H=cfg["H"], W=cfg["W"])
+    feats, _ = synth.shifted_field_features(cfg["T"], cfg["C"], geo.h, geo.w, seed=cfg["seed"], noise=0.2, max_shift=2)
+    video = synth.random_video(cfg["T"], cfg["H"], cfg["W"], seed=cfg["seed"] + 1)
+    head = synth.head_weights("well", seed=cfg["seed"])
+    dsd = od.random_state_dict(cfg["channels"], torch.Generator().manual_seed(cfg["seed"] + 2), last_std=0.05)
+    g = torch.Generator().manual_seed(cfg["seed"] + 3)
+    n_set, B = len(cfg["frames_set"]), cfg["B"]
+    pts = torch.rand(B, 3, generator=g) * torch.tensor([cfg["W"] - 1.0, cfg["H"] - 1.0, 0.0])
+    src = torch.randint(0, n_set, (B,), generator=g)
+    tgt = torch.randint(0, n_set, (B,), generator=g)
+    labels = torch.rand(B, 2, generator=g) * 2 - 1
+    fs = torch.tensor(cfg["frames_set"], dtype=torch.int64)
+    return geo, feats, video, head, dsd, (pts, src, tgt, fs), labels
+
+
+def train_loss(coords, labels, frame_embeddings, raw_embeddings):
+    """The tracking loss of dino_tracker.py:30,411 plus the embedding-norm regulariser of :136-140 (weight 1e-2 here so
+    that its gradient is visible next to the tracking term)."""
+    huber = torch.nn.HuberLoss(delta=1 / 32, reduction="none")
+    reg = (frame_embeddings.norm(dim=1) / raw_embeddings.norm(dim=1) - 1).abs().mean()
+    return huber(coords, labels).mean() + 1e-2 * reg
+
+
+def gen_train_case(name, cfg=TRAIN_CASE):
+    """One training-step forward + backward of the LIVE reference in train mode (BatchNorm on batch statistics):
+    model(inputs) -> loss -> backward (dino_tracker.py:405-427), gradients of every trainable tensor + of the refined
+    embeddings."""
+    geo, feats, video, head, dsd, inp, labels = train_case_inputs(cfg)
+    model = ref_harness.build_reference_tracker(video, feats, head_sd=head, delta_sd=dsd, delta_channels=cfg["channels"])
+    model.train()
+    coords = model(inp)
+    model.frame_embeddings.retain_grad()
+    loss = train_loss(coords, labels, model.frame_embeddings, model.raw_embeddings)
+    loss.backward()
+    out = dict(coords=coords.detach().numpy(), loss=np.array(loss.item()), grad_frame_embeddings=model.frame_embeddings.grad.numpy())
+    for k, p in model.delta_dino.named_parameters():
+        out["grad.delta_dino." + k] = p.grad.numpy()
+    for k, p in model.tracker_head.named_parameters():
+        out["grad.tracker_head." + k] = p.grad.numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    print(name, "loss", loss.item(), "grad norms", {k: float(np.abs(v).max()) for k, v in out.items() if k.startswith("grad")})
+
+
 def gen_bb_case(name, H, W, T, C, seed):
     import argparse
     import tempfile
@@ -309,6 +358,7 @@ def main():
     gen_bb_nms_case("bb_nms_small", 154, 210, 3, 16, seed=32)
     gen_posembed_case("posembed", [(476, 854), (98, 126), (112, 140), (518, 518)], dim=6, n_pos=37, seed=41)
     gen_vit_case("vit_small")
+    gen_train_case("train_small")
 
 
 if __name__ == "__main__":

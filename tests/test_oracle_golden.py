@@ -195,3 +195,37 @@ def test_bb_peak_filter_closed_form_equals_greedy_nms():
         # (the stored r is the max over the two directions; compare the per-direction peaks)
         assert np.abs(vmax.numpy() - g[key + ".peak_affs"][:, 0]).max() <= 1e-6
         assert np.abs(second.numpy() - g[key + ".peak_affs"][:, 1]).max() <= 1e-6
+
+
+def _grad_close(got, want, rel=1e-4, floor=2e-7):
+    """max |got - want| <= rel * max |want|, with an absolute floor for gradients that are rounding noise in the reference
+    itself (convolution biases in front of a train-mode BatchNorm have an exactly-zero gradient)."""
+    return float(np.abs(got - want).max()) <= max(rel * float(np.abs(want).max()), floor)
+
+
+def test_training_step_gradients_match_reference():
+    """autograd through the oracle's chain (delta-DINO on batch statistics -> refined embeddings -> sample ->
+    correlation -> refiner -> soft-argmax -> Huber + norm regulariser) against the gradients the LIVE reference produced
+    for the same step in train mode (tests/golden/train_small.npz, oracle/make_golden.py::gen_train_case).  This pins the
+    checker the CUDA reverse pass is tested against (tests/test_train_gpu.py)."""
+    from oracle import make_golden as mg
+    g = np.load(os.path.join(GOLDEN_DIR, "train_small.npz"))
+    geo, feats, video, head, dsd, inp, labels = mg.train_case_inputs()
+    pts, src, tgt, fs = inp
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k and "filt" not in k else v)
+          for k, v in dsd.items()}
+    hd = {k: v.clone().requires_grad_(True) for k, v in head.items()}
+    raw = feats[fs]
+    refined = od.refined_features(video[fs], raw, sd, bn_training=True)
+    refined.retain_grad()
+    coords = ot.tracker_forward(refined, (pts, src, tgt, torch.arange(fs.shape[0], dtype=torch.int32)), hd, geo)
+    loss = mg.train_loss(coords, labels, refined, raw)
+    loss.backward()
+    assert np.abs(coords.detach().numpy() - g["coords"]).max() <= 2e-6
+    assert abs(loss.item() - float(g["loss"])) <= 1e-7
+    assert _grad_close(refined.grad.numpy(), g["grad_frame_embeddings"])
+    for k in g.files:
+        if k.startswith("grad.delta_dino."):
+            assert _grad_close(sd[k[len("grad.delta_dino."):]].grad.numpy(), g[k]), k
+        elif k.startswith("grad.tracker_head."):
+            assert _grad_close(hd[k[len("grad.tracker_head."):]].grad.numpy(), g[k], floor=1e-9), k

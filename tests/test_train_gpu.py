@@ -241,3 +241,37 @@ def test_cycle_consistent_preds_are_consistent_and_trainable():
     loss.backward()
     assert m.delta_dino.layers[12].weight.grad.abs().max().item() > 0
     assert m.tracker_head.cnn_refiner[0].weight.grad.abs().max().item() > 0
+
+
+def test_training_step_matches_reference_vectors():
+    """The step the LIVE reference ran on the CPU in train mode (tests/golden/train_small.npz: model(inputs) -> Huber +
+    norm regulariser -> backward, dino_tracker.py:405-427) through the drop-in Tracker on the GPU: coordinates, loss and the
+    gradient of every trainable tensor and of the refined embeddings."""
+    import os
+    from golden_util import GOLDEN_DIR
+    from oracle import make_golden as mg
+    from dino_tracker_b200 import Tracker
+    oracle.use_exact_fp32()                       # cuDNN convolutions of the delta-DINO graph in fp32, as the CPU reference
+    g = np.load(os.path.join(GOLDEN_DIR, "train_small.npz"))
+    cfg = mg.TRAIN_CASE
+    geo, feats, video, head, dsd, inp, labels = mg.train_case_inputs()
+    m = Tracker(video=video.to(DEV), dino_embed_video=feats, device=DEV, delta_channels=cfg["channels"])
+    m.tracker_head.load_state_dict(head)
+    m.delta_dino.load_state_dict(dsd)
+    m.train()
+    coords = m(tuple(t.to(DEV) for t in inp))
+    fe = m.frame_embeddings
+    fe.retain_grad()
+    loss = mg.train_loss(coords, labels.to(DEV), fe, m.raw_embeddings)
+    loss.backward()
+    scale = np.array([geo.W - 1, geo.H - 1]) / 2
+    assert (np.abs(coords.detach().cpu().numpy() - g["coords"]) * scale).max() <= XY_TOL
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6
+
+    def close(got, want, rel, floor):
+        return float(np.abs(got.detach().cpu().numpy() - want).max()) <= max(rel * float(np.abs(want).max()), floor)
+    assert close(fe.grad, g["grad_frame_embeddings"], GRAD_TOL, 1e-9)
+    for k, p in m.delta_dino.named_parameters():
+        assert close(p.grad, g["grad.delta_dino." + k], 5e-3, 2e-7), k      # (conv biases before a train-mode BN: exactly 0)
+    for k, p in m.tracker_head.named_parameters():
+        assert close(p.grad, g["grad.tracker_head." + k], GRAD_TOL, 1e-9), k
