@@ -124,6 +124,8 @@ class SampleFunction(torch.autograd.Function):
 
 def sample_points(tracker, emb_chw, pts):
     T, C, h, w = emb_chw.shape
+    if pts.shape[0] == 0:
+        return emb_chw.new_zeros(0, C)
     return SampleFunction.apply(emb_chw.permute(0, 2, 3, 1).reshape(T, h * w, C), pts, tracker)
 
 
@@ -132,6 +134,8 @@ def track_points(tracker, emb_chw, inp):
     embeddings, may require grad), inp as in ``Tracker.forward``.  Returns B x 2 in [-1, 1]."""
     src_pts, src_idx, tgt_idx, _ = inp
     N, C, h, w = emb_chw.shape
+    if src_pts.shape[0] == 0:                      # nothing to track (e.g. an empty cycle-consistency draw)
+        return emb_chw.new_zeros(0, 2)
     emb_tpc = emb_chw.permute(0, 2, 3, 1).reshape(N, h * w, C)
     head = tracker.tracker_head.cnn_refiner
     pts = torch.cat([src_pts.to(tracker._dev, torch.float32)[:, :2], src_idx.to(tracker._dev).to(torch.float32)[:, None]], dim=1)
