@@ -338,8 +338,8 @@ class Tracker(nn.Module):
         ``fg_masks``), tracked source -> target -> source with the embeddings of the last forward; kept when they
         return within ``cyc_thresh`` px.  Random draws in the reference's order (two ``randint`` on the frame set's
         device, then per pair a foreground and a background ``randperm``)."""
-        dev = frames_set_t.device
-        n_set = frames_set_t.shape[0]
+        dev = frames_set_t.device                    # the random draws live where the reference makes them:
+        n_set = frames_set_t.shape[0]                 # randint on the frame set's device, randperm on the host
         src_slots = torch.randint(n_set, (self.cyc_n_frames,), device=dev)
         tgt_slots = torch.randint(n_set, (self.cyc_n_frames,), device=dev)
         H, W = fg_masks.shape[-2:]
@@ -358,13 +358,13 @@ class Tracker(nn.Module):
         def to_px(coords):
             return self.range_normalizer.unnormalize(coords, src=(-1, 1), dims=[0, 1])
 
-        for s_slot, t_slot in zip(src_slots, tgt_slots):
-            t_src, t_tgt = frames_set_t[s_slot], frames_set_t[t_slot]
-            is_fg = (fg_masks[t_src] > 0).reshape(-1)
+        for s_slot, t_slot in zip(src_slots.to(self._dev), tgt_slots.to(self._dev)):
+            t_src, t_tgt = frames_set_t.to(self._dev)[s_slot], frames_set_t.to(self._dev)[t_slot]
+            is_fg = (fg_masks[int(t_src)] > 0).reshape(-1)
             fg_px, bg_px = pixels[is_fg], pixels[~is_fg]
             fg_px = fg_px[torch.randperm(fg_px.shape[0])[:n_fg]]
             bg_px = bg_px[torch.randperm(bg_px.shape[0])[:n_bg]]
-            start = with_time(torch.cat([fg_px, bg_px], dim=0), t_src)
+            start = with_time(torch.cat([fg_px, bg_px], dim=0).to(self._dev), t_src)
             n = start.shape[0]
             s_idx, t_idx = s_slot.repeat(n), t_slot.repeat(n)
             there = with_time(to_px(self.get_point_predictions((start, s_idx, t_idx, frames_set_t), emb)), t_tgt)

@@ -163,6 +163,44 @@ def gen_train_case(name, cfg=TRAIN_CASE):
     print(name, "loss", loss.item(), "grad norms", {k: float(np.abs(v).max()) for k, v in out.items() if k.startswith("grad")})
 
 
+CYC_CASE = dict(H=98, W=126, T=6, C=32, seed=61, frames_set=[0, 2, 3, 5], n_frames=3, per_frame=48, fg_ratio=0.7, thresh=20, rng=77)
+
+
+def cyc_case_inputs(cfg=CYC_CASE):
+    """Inputs of the cycle-consistency case (models/tracker.py:182-301)."""
+    from .tracker import Geometry
+    geo = Geometry(H=cfg["H"], W=cfg["W"])
+    feats, _ = synth.shifted_field_features(cfg["T"], cfg["C"], geo.h, geo.w, seed=cfg["seed"], noise=0.1, max_shift=1)
+    head = synth.head_weights("sharp", seed=cfg["seed"])
+    fg = torch.zeros(cfg["T"], cfg["H"], cfg["W"])
+    fg[:, 20:70, 30:100] = 1
+    fs = torch.tensor(cfg["frames_set"], dtype=torch.int64)
+    g = torch.Generator().manual_seed(cfg["seed"] + 1)
+    pts = torch.rand(8, 3, generator=g) * torch.tensor([cfg["W"] - 1.0, cfg["H"] - 1.0, 0.0])
+    inp = (pts, torch.randint(0, 4, (8,), generator=g), torch.randint(0, 4, (8,), generator=g), fs)
+    return geo, feats, head, fg, inp
+
+
+def gen_cycle_case(name, cfg=CYC_CASE):
+    """``Tracker.get_cycle_consistent_preds`` of the LIVE reference on the CPU (cached refined features = the synthetic
+    features: default-initialised delta-DINO has a zero residual), random draws seeded right before the call."""
+    geo, feats, head, fg, inp = cyc_case_inputs(cfg)
+    model = ref_harness.build_reference_tracker(torch.zeros(cfg["T"], 3, cfg["H"], cfg["W"]), feats, head_sd=head,
+                                                delta_channels=[3, 2, 2, 2, cfg["C"]])
+    model.cyc_n_frames, model.cyc_batch_size_per_frame = cfg["n_frames"], cfg["per_frame"]
+    model.cyc_fg_points_ratio, model.cyc_thresh = cfg["fg_ratio"], cfg["thresh"]
+    with torch.no_grad():
+        model.cache_refined_embeddings()
+        model(inp)                                   # the step's forward: its frame set's embeddings feed the cycle search
+        torch.manual_seed(cfg["rng"])
+        preds = model.get_cycle_consistent_preds(inp[-1], fg)
+    out = {k: v.detach().numpy() for k, v in preds.items()}
+    d = out["cycle_consistency_dists"]
+    assert d.shape[0] > 20 and d.max() < cfg["thresh"] - 0.5, (d.shape, d.max())     # no survivor near the threshold
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **out)
+    print(name, "survivors", d.shape[0], "of", cfg["n_frames"] * cfg["per_frame"], "max cycle distance", float(d.max()))
+
+
 def gen_bb_case(name, H, W, T, C, seed):
     import argparse
     import tempfile
@@ -359,6 +397,7 @@ def main():
     gen_posembed_case("posembed", [(476, 854), (98, 126), (112, 140), (518, 518)], dim=6, n_pos=37, seed=41)
     gen_vit_case("vit_small")
     gen_train_case("train_small")
+    gen_cycle_case("cycle_small")
 
 
 if __name__ == "__main__":

@@ -275,3 +275,38 @@ def test_training_step_matches_reference_vectors():
         assert close(p.grad, g["grad.delta_dino." + k], 5e-3, 2e-7), k      # (conv biases before a train-mode BN: exactly 0)
     for k, p in m.tracker_head.named_parameters():
         assert close(p.grad, g["grad.tracker_head." + k], GRAD_TOL, 1e-9), k
+
+
+def test_cycle_consistent_preds_match_reference_vectors():
+    """models/tracker.py:182-301 of the LIVE reference on the CPU (tests/golden/cycle_small.npz) vs the drop-in: frame set and
+    masks are given as host tensors, so the random draws (randint / randperm on the host generator) are the reference's --
+    same sampled pixels, same survivors; tracked coordinates within the parity bar."""
+    import os
+    from golden_util import GOLDEN_DIR
+    from oracle import make_golden as mg
+    from dino_tracker_b200 import Tracker
+    g = np.load(os.path.join(GOLDEN_DIR, "cycle_small.npz"))
+    cfg = mg.CYC_CASE
+    geo, feats, head, fg, inp = mg.cyc_case_inputs()
+    # (default-initialised delta-DINO: zero residual whatever its widths; the CUDA path wants multiples of 4)
+    m = Tracker(video=torch.zeros(cfg["T"], 3, cfg["H"], cfg["W"], device=DEV), dino_embed_video=feats, device=DEV,
+                delta_channels=[3, 4, 4, 4, cfg["C"]])
+    m.tracker_head.load_state_dict(head)
+    m.cyc_n_frames, m.cyc_batch_size_per_frame = cfg["n_frames"], cfg["per_frame"]
+    m.cyc_fg_points_ratio, m.cyc_thresh = cfg["fg_ratio"], cfg["thresh"]
+    with torch.no_grad():
+        m.cache_refined_embeddings()
+        m((inp[0].to(DEV), inp[1].to(DEV), inp[2].to(DEV), inp[3]))
+        torch.manual_seed(cfg["rng"])
+        preds = m.get_cycle_consistent_preds(inp[3], fg)          # host frame set + host masks: the reference's draws
+    got = {k: v.detach().cpu().numpy() for k, v in preds.items()}
+    assert got["source_coords"].shape == g["source_coords"].shape            # same survivors
+    assert np.abs(got["source_coords"] - g["source_coords"]).max() <= 1e-6   # same sampled pixels, same normalisation
+    to_px = np.array([geo.W - 1, geo.H - 1]) / 2
+    assert (np.abs(got["target_coords"][:, :2] - g["target_coords"][:, :2]) * to_px).max() <= XY_TOL
+    assert np.abs(got["target_coords"][:, 2] - g["target_coords"][:, 2]).max() <= 1e-6
+    assert (np.abs(got["source_target_coords"] - g["source_target_coords"]) * to_px).max() <= XY_TOL
+    # the way back starts from the (1e-3 px different) forward prediction: same bar plus that offset
+    assert (np.abs(got["target_source_coords"] - g["target_source_coords"]) * to_px).max() <= 2 * XY_TOL
+    assert np.abs(got["cycle_points"] - g["cycle_points"]).max() <= 2 * XY_TOL
+    assert np.abs(got["cycle_consistency_dists"] - g["cycle_consistency_dists"]).max() <= 3 * XY_TOL
